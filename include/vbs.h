@@ -1,0 +1,148 @@
+/*
+ * vbs.h - C ABI of libvbs_b200.so: the B200-native per-frame marker pipeline.
+ *
+ * The reference (UPM-ROB-Lab/Vision-basedSensor) has no FFI: its boundary for this path
+ * is a set of Python callables.  Each entry point below names the reference callable(s)
+ * it replaces (paths under /root/reference/code):
+ *   MD = Marker_Tracking/marker_detection.py
+ *   R3 = Marker_Calibration/3d_reconstruction.py
+ *   FD = ForceDistribution/ForceDistribution.py
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, no torch / C++ types.
+ *   - every function returns VBS_OK (0) or a negative vbs_status; vbs_last_error() gives text.
+ *   - the caller owns every frame / output buffer; the context owns only its scratch.
+ *   - one context = one GPU + one stream; not thread-safe; calls are asynchronous on the
+ *     context's stream unless stated otherwise, vbs_sync() waits and reports device-side errors.
+ *   - no CPU fallback anywhere: without a CUDA device vbs_create() fails.
+ */
+#ifndef VBS_H_
+#define VBS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum vbs_status {
+    VBS_OK = 0,
+    VBS_ERR_BAD_ARG = -1,   /* ValueError in the Python mirror (MD:38, R3:95,117)            */
+    VBS_ERR_CAPACITY = -2,  /* more labels / contours / rechecks than the context was sized for */
+    VBS_ERR_CUDA = -3,      /* CUDA runtime failure (no device, launch error, ...)            */
+    VBS_ERR_STATE = -4,     /* call order: e.g. 3D stage requested before vbs_set_camera       */
+    VBS_ERR_INTERNAL = -5   /* an invariant the parity argument relies on was violated         */
+} vbs_status;
+
+typedef struct vbs_ctx vbs_ctx;
+
+typedef struct vbs_config {
+    int32_t device;       /* CUDA ordinal                                                     */
+    int32_t height;       /* processed (cropped) frame height in pixels                        */
+    int32_t width;        /* processed (cropped) frame width in pixels                         */
+    int32_t channels;     /* 1 = gray, 3 = BGR (converted like cvtColor, MD:114)               */
+    int32_t max_batch;    /* frames per vbs_process_* call (scratch is sized for this)         */
+    int32_t max_markers;  /* capacity for labels / contours / markers per frame                */
+    int32_t max_refs;     /* capacity of the reference-state array                             */
+} vbs_config;
+
+/* Output block of one batch.  Every pointer may be NULL (that output is skipped).  For
+ * vbs_process_device they are device pointers, for vbs_process_host host pointers.
+ * B = batch, M = max_markers, R = number of reference entries set by vbs_set_reference. */
+typedef struct vbs_outputs {
+    int32_t *n_labels;    /* [B]        components of the ring-maxima image (MD:176)            */
+    double  *centres;     /* [B][M][2]  (row, col) centroids in label order (MD:181)            */
+    int32_t *n_markers;   /* [B]        markers returned by _marker_center (MD:249)             */
+    double  *marker_xy;   /* [B][M][2]  'center' = (x=col, y=row), reference output order       */
+    float   *marker_axes; /* [B][M][3]  major_axis, minor_axis, angle (MD:238-243)              */
+    int32_t *row_det;     /* [B][R]     index into the marker list, or -1 (MD:369-373)          */
+    double  *row_cxy;     /* [B][R][2]  Cx, Cy of the tracking row (MD:386-387)                 */
+    float   *row_axes;    /* [B][R][3]  major_axis, minor_axis, angle of the row (MD:388-390)   */
+    double  *pos3d;       /* [B][R][7]  X,Y,Z,dX,dY,dZ,displacement (R3:296-307)                */
+    uint8_t *pos_flags;   /* [B][R]     bit0: observation enters R3 (row present, major>=min),
+                                        bit1: 3D position valid, bit2: displacement row emitted */
+    double  *plane;       /* [B][4]     a, b, c, tilt_deg of the contact plane (FD:141-159)     */
+    int32_t *plane_n;     /* [B]        points that entered the plane fit                       */
+} vbs_outputs;
+
+/* stage images of the most recent batch, for stage-level parity checks (vbs_debug_stage) */
+typedef enum vbs_stage {
+    VBS_STAGE_AREA_MASK = 0,  /* uint8 [B][H][W] {0,255}  area_mask (MD:129)                   */
+    VBS_STAGE_MASK = 1,       /* uint8 [B][H][W] {0,1}    mask = ncc > 0.1 (MD:133)            */
+    VBS_STAGE_MAXIMA = 2,     /* uint8 [B][H][W] {0,1}    maxima (MD:172-174)                  */
+    VBS_STAGE_LABELS = 3,     /* int32 [B][H][W]          labeled (MD:176)                     */
+    VBS_STAGE_OPENED = 4,     /* uint8 [B][H][W] {0,255}  area_mask after the 5x5 open (MD:195)*/
+    VBS_STAGE_RECHECKS = 5    /* int32 [B]                pixels re-decided in float64         */
+} vbs_stage;
+
+/* lifetime ---------------------------------------------------------------------------------- */
+int  vbs_create(vbs_ctx **out, const vbs_config *cfg);      /* replaces MarkerTracker.__init__ (MD:15-31) */
+void vbs_destroy(vbs_ctx *ctx);                             /* replaces _cleanup (MD:470-474)             */
+const char *vbs_last_error(const vbs_ctx *ctx);
+int  vbs_set_stream(vbs_ctx *ctx, void *cuda_stream);       /* run on the caller's stream (0 = own stream) */
+int  vbs_sync(vbs_ctx *ctx);                                /* wait; returns device-side status of all work so far */
+const char *vbs_version(void);
+
+/* reference state ----------------------------------------------------------------------------
+ * replaces self.first_frame_markers (MD:31,289-347) + config['min_marker_distance'] (MD:359).
+ * Entries are matched in array order (= the reference's dict order).                          */
+int vbs_set_reference(vbs_ctx *ctx, int32_t n, const int32_t *row, const int32_t *col,
+                      const double *ox, const double *oy, double min_marker_distance);
+
+/* camera: replaces MarkerAnalysis.load_parameters results (R3:87-124) and Config (R3:21-24).
+ * K, R row-major 3x3; D = k1,k2,p1,p2,k3; all float32 like the reference stores them.         */
+int vbs_set_camera(vbs_ctx *ctx, const float K[9], const float D[5], const float R[9],
+                   const float T[3], double marker_diameter_mm, double min_marker_size_px,
+                   double max_displacement, int32_t warmup_frames);
+
+/* plane fit inputs: replaces df_ref / d_vert of process_marker_data (FD:173-204) and the
+ * 'plane' / 'shell' switch (FD:15,222).  n must equal the reference-array length.
+ *   ref_xyz  [n][3]  theoretical marker coordinates (FD:29-95)
+ *   start_xyz[n][3]  P_start of the tilted run (displacement = P(frame) - P_start)
+ *   d_vert   [n][3]  displacement of the vertical baseline run; NULL = zeros
+ *   use      [n]     1 = marker takes part (common_ids, FD:184); NULL = all                    */
+int vbs_set_plane(vbs_ctx *ctx, int32_t n, const double *ref_xyz, const double *start_xyz,
+                  const double *d_vert, const uint8_t *use, int32_t shell_mode, double scale);
+
+/* forget the last-seen observations (R3:252 marker_dict) and the first-frame number (R3:255). */
+int vbs_reset_sequence(vbs_ctx *ctx);
+/* last-seen table exchange for frame-sharded multi-GPU runs: [R][4] = u, v, diameter, frame (-1 = never) */
+int vbs_get_last_seen(vbs_ctx *ctx, double *host_table);
+int vbs_set_last_seen(vbs_ctx *ctx, const double *host_table);
+
+/* the hot path --------------------------------------------------------------------------------
+ * One call = MD:440-449 (crop view, _find_markers, _marker_center, _track_markers) for every
+ * frame of the batch, then R3:259-307 (undistort, 3D position, last-seen displacement) and
+ * FD:141-159 (plane tilt) when camera / plane inputs are set.
+ *   frames       first byte of the (cropped) first frame
+ *   frame_stride bytes between consecutive frames
+ *   row_pitch    bytes between consecutive rows
+ *   frameno0     frame number of the first frame of the batch (CSV column 'frameno')
+ * vbs_process_device: frames and outputs live in device memory, nothing is copied.
+ * vbs_process_host  : frames and outputs live in host memory (pinned for full speed); the
+ *                     H2D / D2H copies are part of the call, which returns after the results
+ *                     have landed.                                                              */
+int vbs_process_device(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int64_t frame_stride,
+                       int64_t row_pitch, int64_t frameno0, const vbs_outputs *out);
+int vbs_process_host(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int64_t frame_stride,
+                     int64_t row_pitch, int64_t frameno0, const vbs_outputs *out);
+
+/* stage-level entry points (same kernels, for the static-method mirrors) -----------------------
+ * vbs_find_markers : MarkerTracker._find_markers (MD:111-135): frames -> area_mask, mask (kept in ctx)
+ * vbs_marker_center: MarkerTracker._marker_center (MD:166-249) on masks supplied by the caller
+ *                    (uint8, device, [B][H][W]; mask nonzero = 1, area nonzero = 255)            */
+int vbs_find_markers(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int64_t frame_stride, int64_t row_pitch);
+int vbs_marker_center(vbs_ctx *ctx, const uint8_t *mask, const uint8_t *area_mask, int32_t batch,
+                      const vbs_outputs *out);
+
+/* copy one stage image of the most recent batch into dst (device memory, `bytes` capacity) */
+int vbs_debug_stage(vbs_ctx *ctx, int32_t stage, void *dst_device, size_t bytes);
+
+/* launch accounting for bench.py ("gpu_launches"): kernels launched by this context so far */
+int64_t vbs_kernel_launches(const vbs_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VBS_H_ */

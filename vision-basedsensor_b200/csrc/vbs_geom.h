@@ -1,0 +1,360 @@
+// vbs_geom.h - per-marker geometry shared by the CUDA kernels (device) and the host unit
+// tests (tests/hostcheck).  Everything here is scalar float64/float32 arithmetic written so
+// that it rounds like the library routine it stands in for.  Citations: MD = reference
+// code/Marker_Tracking/marker_detection.py, R3 = code/Marker_Calibration/3d_reconstruction.py,
+// FD = code/ForceDistribution/ForceDistribution.py.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define VBS_HD __host__ __device__ __forceinline__
+#else
+#define VBS_HD inline
+#endif
+
+namespace vbs {
+
+// ---- exact (non-contracted) float64 helpers -------------------------------------------------
+// nvcc contracts a*b+c into fma by default; the reference's NumPy / SciPy / OpenCV builds do
+// not (x86-64 baseline).  Where the last bit matters we spell the roundings out.
+VBS_HD double mul_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    volatile double r = a * b; return r;
+#endif
+}
+VBS_HD double add_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    volatile double r = a + b; return r;
+#endif
+}
+VBS_HD double sub_rn(double a, double b) { return add_rn(a, -b); }
+VBS_HD float fadd_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fadd_rn(a, b);
+#else
+    volatile float r = a + b; return r;
+#endif
+}
+VBS_HD float fsub_rn(float a, float b) { return fadd_rn(a, -b); }
+
+// ---- border following (cv2.findContours, RETR_EXTERNAL + CHAIN_APPROX_SIMPLE; MD:196) -------
+// Bits: functor  bool operator()(int x, int y)  -> foreground test, false outside the image.
+// Visitor: functor void operator()(int x, int y) called for every kept vertex, in contour order.
+// Start pixel = topmost-leftmost pixel of an 8-connected blob.  Returns the number of kept
+// vertices, or -1 if the step guard tripped (never on a consistent bit image).
+template <class Bits, class Visitor>
+VBS_HD int trace_external_simple(const Bits &fg, int x0, int y0, long long max_steps, Visitor &visit) {
+    const int DX[8] = {1, 1, 0, -1, -1, -1, 0, 1};
+    const int DY[8] = {0, -1, -1, -1, 0, 1, 1, 1};
+    int s = 4;
+    const int s_first_end = 4;
+    bool found = false;
+    // clockwise search for the "previous" border pixel
+    for (int it = 0; it < 8; ++it) {
+        s = (s - 1) & 7;
+        if (fg(x0 + DX[s], y0 + DY[s])) { found = true; break; }
+        if (s == s_first_end) break;
+    }
+    if (!found) { visit(x0, y0); return 1; }          // isolated pixel
+    const int x1 = x0 + DX[s], y1 = y0 + DY[s];
+    int x3 = x0, y3 = y0;
+    int prev_step = -1;
+    int kept = 0;
+    for (long long guard = 0; guard < max_steps; ++guard) {
+        int x4 = x3, y4 = y3;
+        for (int it = 0; it < 8; ++it) {              // counter-clockwise search for the next pixel
+            s = (s + 1) & 7;
+            x4 = x3 + DX[s]; y4 = y3 + DY[s];
+            if (fg(x4, y4)) break;
+        }
+        // (x3,y3) is a border point leaving with step s; the start point is always kept
+        if (prev_step < 0 || prev_step != s) { visit(x3, y3); ++kept; }
+        prev_step = s;
+        if (x4 == x0 && y4 == y0 && x3 == x1 && y3 == y1) return kept;
+        x3 = x4; y3 = y4;
+        s = (s + 4) & 7;
+    }
+    return -1;
+}
+
+// ---- streaming least squares by Givens rotations ---------------------------------------------
+// Rows arrive one at a time (the contour is re-traced, never stored); R is N x N upper
+// triangular, d the rotated right-hand side.  Replaces cv::solve(DECOMP_SVD) / SVBackSubst in
+// cv2.fitEllipse for full-rank systems (agreement ~1e-13 relative, outputs are float32).
+template <int N>
+struct GivensLsq {
+    double R[N][N];
+    double d[N];
+    VBS_HD void reset() {
+        for (int i = 0; i < N; ++i) { d[i] = 0.0; for (int j = 0; j < N; ++j) R[i][j] = 0.0; }
+    }
+    VBS_HD void add_row(double a[N], double beta) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 0; j < N; ++j) {
+            const double aj = a[j];
+            if (aj != 0.0) {
+                const double rjj = R[j][j];
+                const double h = hypot(rjj, aj);
+                const double c = rjj / h, sn = aj / h;
+                R[j][j] = h;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                for (int k = j + 1; k < N; ++k) {
+                    const double t = R[j][k];
+                    R[j][k] = c * t + sn * a[k];
+                    a[k] = c * a[k] - sn * t;
+                }
+                const double t = d[j];
+                d[j] = c * t + sn * beta;
+                beta = c * beta - sn * t;
+            }
+        }
+    }
+    // returns false when R is singular
+    VBS_HD bool solve(double x[N]) const {
+        for (int i = N - 1; i >= 0; --i) {
+            double acc = d[i];
+            for (int k = i + 1; k < N; ++k) acc -= R[i][k] * x[k];
+            if (R[i][i] == 0.0) return false;
+            x[i] = acc / R[i][i];
+        }
+        return true;
+    }
+};
+
+// ---- cv2.fitEllipse (MD:208) as four passes over the contour ---------------------------------
+struct EllipseResult {
+    float cx, cy, w, h, angle;   // exactly the RotatedRect cv2 returns
+    int ok;                      // 0 when the fit is degenerate (singular system / non-finite)
+};
+
+struct EllipsePassCentroid {     // pass 1: n and the float32 running sum in contour order
+    int n; float sx, sy;
+    VBS_HD void reset() { n = 0; sx = 0.f; sy = 0.f; }
+    VBS_HD void operator()(int x, int y) { sx = fadd_rn(sx, (float)x); sy = fadd_rn(sy, (float)y); ++n; }
+};
+struct EllipsePassScale {        // pass 2: s = sum |qx| + |qy| in float64 of float32 offsets
+    float cx, cy; double s;
+    VBS_HD void operator()(int x, int y) {
+        const float qx = fsub_rn((float)x, cx), qy = fsub_rn((float)y, cy);
+        s = add_rn(s, add_rn(fabs((double)qx), fabs((double)qy)));
+    }
+};
+struct EllipsePassConic {        // pass 3: [-px^2, -py^2, -px py, px, py] g = 10000
+    float cx, cy; double scale; GivensLsq<5> q;
+    VBS_HD void operator()(int x, int y) {
+        const double px = mul_rn((double)fsub_rn((float)x, cx), scale);
+        const double py = mul_rn((double)fsub_rn((float)y, cy), scale);
+        double a[5] = {-mul_rn(px, px), -mul_rn(py, py), -mul_rn(px, py), px, py};
+        q.add_row(a, 10000.0);
+    }
+};
+struct EllipsePassAxes {         // pass 4: [(px-r0)^2, (py-r1)^2, (px-r0)(py-r1)] h = 1
+    float cx, cy; double scale, r0, r1; GivensLsq<3> q;
+    VBS_HD void operator()(int x, int y) {
+        const double px = mul_rn((double)fsub_rn((float)x, cx), scale);
+        const double py = mul_rn((double)fsub_rn((float)y, cy), scale);
+        const double ex = sub_rn(px, r0), ey = sub_rn(py, r1);
+        double a[3] = {mul_rn(ex, ex), mul_rn(ey, ey), mul_rn(ex, ey)};
+        q.add_row(a, 1.0);
+    }
+};
+
+// Final stage of fitEllipse from h = (h0,h1,h2), the centre estimate and the scale.
+VBS_HD EllipseResult ellipse_from_fit(const double h[3], double r0, double r1, double scale, float cx, float cy) {
+    const double min_eps = 1e-8;
+    const double PI = 3.1415926535897932384626433832795;
+    EllipseResult e;
+    const double th = -0.5 * atan2(h[2], h[1] - h[0]);
+    double t;
+    if (fabs(h[2]) > min_eps) t = h[2] / sin(-2.0 * th);
+    else t = h[1] - h[0];
+    double a = fabs(h[0] + h[1] - t);
+    if (a > min_eps) a = sqrt(2.0 / a);
+    double b = fabs(h[0] + h[1] + t);
+    if (b > min_eps) b = sqrt(2.0 / b);
+    e.cx = fadd_rn((float)(r0 / scale), cx);
+    e.cy = fadd_rn((float)(r1 / scale), cy);
+    e.w = (float)(a * 2 / scale);
+    e.h = (float)(b * 2 / scale);
+    e.angle = 0.f;                                   // cv2 assigns the angle only when it swaps
+    if (e.w > e.h) {
+        const float tmp = e.w; e.w = e.h; e.h = tmp;
+        e.angle = (float)(90 + th * 180 / PI);
+    }
+    if (e.angle < -180) e.angle += 360;
+    if (e.angle > 360) e.angle -= 360;
+    e.ok = (isfinite(e.cx) && isfinite(e.cy) && isfinite(e.w) && isfinite(e.h) && isfinite(e.angle)) ? 1 : 0;
+    return e;
+}
+
+// 2x2 solve for the centre: [[2g0, g2],[g2, 2g1]] r = [g3, g4]  (cv::solve DECOMP_SVD in cv2)
+VBS_HD bool ellipse_centre_solve(const double g[5], double &r0, double &r1) {
+    const double a = 2 * g[0], b = g[2], c = g[2], d = 2 * g[1];
+    // Gaussian elimination with partial pivoting
+    if (fabs(a) >= fabs(c)) {
+        if (a == 0.0) return false;
+        const double m = c / a;
+        const double dd = d - m * b;
+        if (dd == 0.0) return false;
+        r1 = (g[4] - m * g[3]) / dd;
+        r0 = (g[3] - b * r1) / a;
+    } else {
+        const double m = a / c;
+        const double bb = b - m * d;
+        if (bb == 0.0) return false;
+        r1 = (g[3] - m * g[4]) / bb;
+        r0 = (g[4] - d * r1) / c;
+    }
+    return true;
+}
+
+// Whole fit for a blob given its start pixel (four traces).  n_out = kept vertices.
+template <class Bits>
+VBS_HD EllipseResult fit_ellipse_traced(const Bits &fg, int x0, int y0, long long max_steps, int &n_out) {
+    EllipseResult bad; bad.cx = bad.cy = bad.w = bad.h = bad.angle = 0.f; bad.ok = 0;
+    EllipsePassCentroid p1; p1.reset();
+    n_out = trace_external_simple(fg, x0, y0, max_steps, p1);
+    if (n_out < 5) return bad;                       // MD:204 len(contour) < 5 (and the guard case)
+    const float cx = p1.sx / (float)p1.n, cy = p1.sy / (float)p1.n;
+    EllipsePassScale p2; p2.cx = cx; p2.cy = cy; p2.s = 0.0;
+    trace_external_simple(fg, x0, y0, max_steps, p2);
+    const double FLT_EPS = 1.1920928955078125e-07;
+    const double scale = 100.0 / (p2.s > FLT_EPS ? p2.s : FLT_EPS);
+    EllipsePassConic p3; p3.cx = cx; p3.cy = cy; p3.scale = scale; p3.q.reset();
+    trace_external_simple(fg, x0, y0, max_steps, p3);
+    double g[5];
+    if (!p3.q.solve(g)) return bad;
+    double r0, r1;
+    if (!ellipse_centre_solve(g, r0, r1)) return bad;
+    EllipsePassAxes p4; p4.cx = cx; p4.cy = cy; p4.scale = scale; p4.r0 = r0; p4.r1 = r1; p4.q.reset();
+    trace_external_simple(fg, x0, y0, max_steps, p4);
+    double h[3];
+    if (!p4.q.solve(h)) return bad;
+    return ellipse_from_fit(h, r0, r1, scale, cx, cy);
+}
+
+// ---- cv2.pointPolygonTest(contour, (x, y), False) (MD:228) as an edge visitor ----------------
+// Feed the polygon vertices in order; finish() closes it.  result(): +1 inside, 0 on the border,
+// -1 outside.  The query point is rounded to float32 first (cv::Point2f), then either the
+// integer branch (int64 cross products) or the float branch (double cross products) is used.
+struct PointPolygon {
+    float fx, fy; bool is_int; long long ix, iy;
+    int first_x, first_y, prev_x, prev_y; int nv; int counter; bool on_edge;
+    VBS_HD void init(double x, double y) {
+        fx = (float)x; fy = (float)y;
+        const double rx = rint((double)fx), ry = rint((double)fy);
+        is_int = (rx == (double)fx) && (ry == (double)fy);
+        ix = (long long)rx; iy = (long long)ry;
+        nv = 0; counter = 0; on_edge = false;
+        first_x = first_y = prev_x = prev_y = 0;
+    }
+    VBS_HD void edge(int v0x, int v0y, int vx, int vy) {
+        if (is_int) {
+            if ((v0y <= iy && vy <= iy) || (v0y > iy && vy > iy) || (v0x < ix && vx < ix)) {
+                if (iy == vy && (ix == vx || (iy == v0y && ((v0x <= ix && ix <= vx) || (vx <= ix && ix <= v0x)))))
+                    on_edge = true;
+                return;
+            }
+            long long dist = (iy - v0y) * (long long)(vx - v0x) - (ix - v0x) * (long long)(vy - v0y);
+            if (dist == 0) { on_edge = true; return; }
+            if (vy < v0y) dist = -dist;
+            counter += dist > 0;
+        } else {
+            const float a0x = (float)v0x, a0y = (float)v0y, ax = (float)vx, ay = (float)vy;
+            if ((a0y <= fy && ay <= fy) || (a0y > fy && ay > fy) || (a0x < fx && ax < fx)) {
+                if (fy == ay && (fx == ax || (fy == a0y && ((a0x <= fx && fx <= ax) || (ax <= fx && fx <= a0x)))))
+                    on_edge = true;
+                return;
+            }
+            // (double)(pt.y - v0.y)*(v.x - v0.x) - (double)(pt.x - v0.x)*(v.y - v0.y): float32
+            // differences, first factor widened, products and difference in float64
+            double dist = sub_rn(mul_rn((double)fsub_rn(fy, a0y), (double)fsub_rn(ax, a0x)),
+                                 mul_rn((double)fsub_rn(fx, a0x), (double)fsub_rn(ay, a0y)));
+            if (dist == 0) { on_edge = true; return; }
+            if (ay < a0y) dist = -dist;
+            counter += dist > 0;
+        }
+    }
+    VBS_HD void operator()(int x, int y) {
+        if (nv == 0) { first_x = x; first_y = y; }
+        else edge(prev_x, prev_y, x, y);
+        prev_x = x; prev_y = y; ++nv;
+    }
+    VBS_HD int result() {
+        if (nv == 0) return -1;
+        edge(prev_x, prev_y, first_x, first_y);       // closing edge (cv2 starts with it)
+        if (on_edge) return 0;
+        return (counter & 1) ? 1 : -1;
+    }
+};
+
+// ---- cv2.undistortPoints(pts, K, D, None, K) (R3:187-193): exactly 5 iterations ---------------
+struct CameraF64 {
+    double fx, fy, cx, cy;          // float32 values widened
+    double k1, k2, p1, p2, k3;
+    double R[9], T[3];              // world->cam, float32 values widened
+    double f_avg;                   // float32((fx+fy)/2) widened        (R3:211)
+    double ratio;                   // float32(diam_mm / f_avg) widened  (R3:219)
+    double min_size, max_disp;
+};
+
+VBS_HD void undistort5(const CameraF64 &c, double u, double v, double &uo, double &vo) {
+    const double x0 = (u - c.cx) / c.fx, y0 = (v - c.cy) / c.fy;
+    double x = x0, y = y0;
+    for (int it = 0; it < 5; ++it) {
+        const double r2 = add_rn(mul_rn(x, x), mul_rn(y, y));
+        const double poly = add_rn(1.0, mul_rn(add_rn(mul_rn(add_rn(mul_rn(c.k3, r2), c.k2), r2), c.k1), r2));
+        const double icd = 1.0 / poly;
+        if (icd < 0) { x = x0; y = y0; break; }   // cv2 bails out on a negative factor
+        const double dx = add_rn(mul_rn(mul_rn(mul_rn(2.0, c.p1), x), y), mul_rn(c.p2, add_rn(r2, mul_rn(mul_rn(2.0, x), x))));
+        const double dy = add_rn(mul_rn(c.p1, add_rn(r2, mul_rn(mul_rn(2.0, y), y))), mul_rn(mul_rn(mul_rn(2.0, c.p2), x), y));
+        x = mul_rn(sub_rn(x0, dx), icd);
+        y = mul_rn(sub_rn(y0, dy), icd);
+    }
+    uo = add_rn(mul_rn(x, c.fx), c.cx);
+    vo = add_rn(mul_rn(y, c.fy), c.cy);
+}
+
+// ---- MarkerAnalysis._calculate_3d_position (R3:195-238) ---------------------------------------
+// returns false when the reference would raise (R < 1e-6 or non-finite result)
+VBS_HD bool position3d(const CameraF64 &c, double u, double v, double diam, double P[3]) {
+    const double du = u - c.cx, dv = v - c.cy;
+    const double rad = sqrt(add_rn(mul_rn(du, du), mul_rn(dv, dv)));
+    if (rad < 1e-6) return false;
+    const double d_eff = mul_rn(c.ratio, sqrt(add_rn(mul_rn(rad, rad), mul_rn(c.f_avg, c.f_avg))));
+    const double h = mul_rn(c.f_avg, d_eff / diam);
+    const double pc0 = sub_rn(mul_rn(h, du) / c.fx, c.T[0]);
+    const double pc1 = sub_rn(mul_rn(h, dv) / c.fy, c.T[1]);
+    const double pc2 = sub_rn(h, c.T[2]);
+    for (int i = 0; i < 3; ++i)       // R^T (Pc - T): column i of R
+        P[i] = add_rn(add_rn(mul_rn(c.R[0 * 3 + i], pc0), mul_rn(c.R[1 * 3 + i], pc1)), mul_rn(c.R[2 * 3 + i], pc2));
+    return isfinite(P[0]) && isfinite(P[1]) && isfinite(P[2]);
+}
+
+// ---- fit_plane_least_squares (FD:141-159): centred normal equations ---------------------------
+struct PlaneSums {
+    double n, sx, sy, sz;
+    VBS_HD void reset() { n = sx = sy = sz = 0.0; }
+};
+VBS_HD bool plane_solve(double n, double mx, double my, double mz, double sxx, double sxy, double syy,
+                        double sxz, double syz, double out[4]) {
+    const double PI = 3.1415926535897932384626433832795;
+    const double det = sxx * syy - sxy * sxy;
+    if (!(n >= 3.0) || det == 0.0 || !isfinite(det)) return false;
+    const double a = (sxz * syy - syz * sxy) / det;
+    const double b = (syz * sxx - sxz * sxy) / det;
+    out[0] = a; out[1] = b; out[2] = mz - a * mx - b * my;
+    out[3] = atan(sqrt(a * a + b * b)) * (180.0 / PI);
+    return true;
+}
+
+}  // namespace vbs
