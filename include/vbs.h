@@ -55,10 +55,11 @@ typedef struct vbs_outputs {
     double  *centres;     /* [B][M][2]  (row, col) centroids in label order (MD:181)            */
     int32_t *n_markers;   /* [B]        markers returned by _marker_center (MD:249)             */
     double  *marker_xy;   /* [B][M][2]  'center' = (x=col, y=row), reference output order       */
-    float   *marker_axes; /* [B][M][3]  major_axis, minor_axis, angle (MD:238-243)              */
+    double  *marker_axes; /* [B][M][3]  major_axis, minor_axis (float32 values) and angle, which the
+                                        reference forms in float64 as angle32 + 90 (MD:213-217,238-243)   */
     int32_t *row_det;     /* [B][R]     index into the marker list, or -1 (MD:369-373)          */
     double  *row_cxy;     /* [B][R][2]  Cx, Cy of the tracking row (MD:386-387)                 */
-    float   *row_axes;    /* [B][R][3]  major_axis, minor_axis, angle of the row (MD:388-390)   */
+    double  *row_axes;    /* [B][R][3]  major_axis, minor_axis, angle of the row (MD:388-390)   */
     double  *pos3d;       /* [B][R][7]  X,Y,Z,dX,dY,dZ,displacement (R3:296-307)                */
     uint8_t *pos_flags;   /* [B][R]     bit0: observation enters R3 (row present, major>=min),
                                         bit1: 3D position valid, bit2: displacement row emitted */
@@ -110,6 +111,8 @@ int vbs_reset_sequence(vbs_ctx *ctx);
 /* last-seen table exchange for frame-sharded multi-GPU runs: [R][4] = u, v, diameter, frame (-1 = never) */
 int vbs_get_last_seen(vbs_ctx *ctx, double *host_table);
 int vbs_set_last_seen(vbs_ctx *ctx, const double *host_table);
+/* frame-sharded runs: the warm-up window (R3:255-256) counts from the GLOBAL first frame number */
+int vbs_set_first_frame(vbs_ctx *ctx, int64_t first_frame);
 
 /* the hot path --------------------------------------------------------------------------------
  * One call = MD:440-449 (crop view, _find_markers, _marker_center, _track_markers) for every

@@ -1,0 +1,77 @@
+// ubench.cu - instruction-throughput probe for the pipes the marker pipeline leans on
+// (IDP.4A / IDP.2A / IMAD / FFMA / FFMA2 / DFMA / DADD / LOP3 and an IDP+FFMA mix).
+// Prints lane-ops per SM per clock assuming the SM clock nvidia-smi reports during the run.
+//   nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o ubench tools/ubench.cu && ./ubench
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+constexpr int ITERS = 2048;
+constexpr int NACC = 8;
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k(uint32_t *out, uint32_t seed) {
+    uint32_t a[NACC]; float fa[NACC]; double da[NACC];
+    const uint32_t x = threadIdx.x * 2654435761u + seed, y = x ^ 0x01020304u;
+    const float fx = 1.0f + 1e-7f * threadIdx.x, fy = 0.999999f;
+    const double dx = 1.0 + 1e-9 * threadIdx.x, dy = 0.999999999;
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) { a[i] = i + seed; fa[i] = i; da[i] = i; }
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) {
+            if (MODE == 0) a[i] = __dp4a(x + i, y, a[i]);
+            if (MODE == 1) a[i] = __dp2a_lo(x + i, y, a[i]);
+            if (MODE == 2) a[i] = a[i] * x + y;
+            if (MODE == 3) fa[i] = fmaf(fa[i], fx, fy);
+            if (MODE == 4) {   // packed fp32x2: two FMAs per instruction
+                float r0, r1;
+                asm volatile("{.reg .b64 ra,rb,rc,rd; mov.b64 ra,{%2,%3}; mov.b64 rb,{%4,%4}; mov.b64 rc,{%5,%5}; fma.rn.f32x2 rd,ra,rb,rc; mov.b64 {%0,%1},rd;}"
+                             : "=f"(r0), "=f"(r1) : "f"(fa[i]), "f"(fa[(i + 1) % NACC]), "f"(fx), "f"(fy));
+                fa[i] = r0; fa[(i + 1) % NACC] = r1;
+            }
+            if (MODE == 5) da[i] = fma(da[i], dx, dy);
+            if (MODE == 6) da[i] = da[i] + dx;
+            if (MODE == 7) a[i] = (a[i] & x) ^ (y | a[i]) ;
+            if (MODE == 8) { a[i] = __dp4a(x + i, y, a[i]); fa[i] = fmaf(fa[i], fx, fy); }
+            if (MODE == 9) a[i] = __funnelshift_r(a[i], x, 7) + 1;
+        }
+    }
+    uint32_t r = 0; float fr = 0; double dr = 0;
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) { r += a[i]; fr += fa[i]; dr += da[i]; }
+    if ((r ^ __float_as_uint(fr) ^ (uint32_t)__double2loint(dr)) == 0x12345678u) out[0] = r;
+}
+
+template <int MODE> double run(const char *name, double ops_per_iter, int sms, double mhz) {
+    uint32_t *d; cudaMalloc(&d, 4);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int grid = sms * 8;
+    k<MODE><<<grid, 256>>>(d, 1); cudaDeviceSynchronize();
+    cudaEventRecord(e0);
+    for (int r = 0; r < 5; ++r) k<MODE><<<grid, 256>>>(d, r);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    const double ops = 5.0 * grid * 256.0 * ITERS * NACC * ops_per_iter;
+    const double per_sm_clk = ops / (ms * 1e-3) / sms / (mhz * 1e6);
+    printf("%-10s %8.3f ms  %8.2f Tops/s  %7.1f lane-instr/SM/clk @%.0f MHz\n", name, ms / 5, ops / (ms * 1e-3) / 1e12, per_sm_clk, mhz);
+    cudaFree(d);
+    return per_sm_clk;
+}
+
+int main(int argc, char **argv) {
+    cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
+    double mhz = argc > 1 ? atof(argv[1]) : p.clockRate / 1000.0;
+    printf("%s, %d SMs, clock used for normalisation %.0f MHz (instructions counted, not MACs)\n", p.name, p.multiProcessorCount, mhz);
+    run<0>("IDP.4A", 1, p.multiProcessorCount, mhz);
+    run<1>("IDP.2A", 1, p.multiProcessorCount, mhz);
+    run<2>("IMAD", 1, p.multiProcessorCount, mhz);
+    run<3>("FFMA", 1, p.multiProcessorCount, mhz);
+    run<4>("FFMA2", 1, p.multiProcessorCount, mhz);
+    run<5>("DFMA", 1, p.multiProcessorCount, mhz);
+    run<6>("DADD", 1, p.multiProcessorCount, mhz);
+    run<7>("LOP3x2", 2, p.multiProcessorCount, mhz);
+    run<8>("IDP+FFMA", 2, p.multiProcessorCount, mhz);
+    run<9>("SHF+IADD", 2, p.multiProcessorCount, mhz);
+    return 0;
+}

@@ -1,0 +1,339 @@
+// k_blur.cu - K1: gray -> two fixed-point Gaussian blurs -> wrapping DoG -> inRange -> bit-packed
+// area mask + per-frame popcount.  Replaces MD:114-129 (cvtColor, GaussianBlur x2, uint8
+// subtraction, inRange) bit-exactly.
+//
+// One CTA marches down a 128-pixel-wide column strip.  Per step of 8 rows it
+//   1. stages 8 input rows (+ halo) in shared memory (REFLECT_101 resolved while loading),
+//   2. runs both horizontal passes with IDP.4A (u8 x u8 -> u32) on aligned words, the tap
+//      alignment of each of the 4 pixels a thread owns being folded into compile-time weights,
+//   3. packs vertically adjacent rows as u16 pairs into a ring of the last ~112 rows,
+//   4. runs both vertical passes with IDP.2A (u16 x u8 -> u32), 8 output rows per thread so
+//      every ring word is loaded once per 8 outputs,
+//   5. rounds, forms uint8(b_large - b_small + 15), range-tests and ballots 32 pixels per word.
+// Nothing but the 1 bit/pixel result leaves the SM.  No tensor cores: integer dot products only.
+#include <type_traits>
+#include <utility>
+#include "vbs_ctx.h"
+
+namespace {
+
+// ---- baked 8.8 fixed-point taps (cv2.GaussianBlur on CV_8U); verified against the host recipe
+// in vbs_check_taps() at context creation and against cv2 in tests/test_oracle_exact.py -------
+template <int K> struct Taps;
+template <> struct Taps<39> {
+    static __host__ __device__ constexpr int at(int j) {
+        constexpr int h[20] = {1, 1, 1, 2, 2, 3, 3, 5, 5, 6, 6, 8, 9, 10, 11, 11, 12, 13, 13, 12};
+        return (j < 0 || j >= 39) ? 0 : h[j < 20 ? j : 38 - j];
+    }
+};
+template <> struct Taps<101> {
+    static __host__ __device__ constexpr int at(int j) {
+        constexpr int h[51] = {0, 0, 1, 0, 0, 1, 0, 1, 0, 1, 1, 1, 0, 1, 1, 1, 2, 1, 1, 2, 2, 1, 2, 2, 3, 2,
+                               3, 2, 3, 3, 3, 3, 4, 4, 3, 4, 4, 4, 5, 4, 5, 4, 5, 5, 5, 5, 5, 5, 5, 5, 6};
+        return (j < 0 || j >= 101) ? 0 : h[j < 51 ? j : 100 - j];
+    }
+};
+template <> struct Taps<21> {
+    static __host__ __device__ constexpr int at(int j) {
+        constexpr int h[11] = {2, 3, 5, 7, 10, 12, 16, 18, 21, 23, 22};
+        return (j < 0 || j >= 21) ? 0 : h[j < 11 ? j : 20 - j];
+    }
+};
+template <> struct Taps<35> {
+    static __host__ __device__ constexpr int at(int j) {
+        constexpr int h[18] = {3, 4, 4, 5, 6, 6, 6, 7, 7, 8, 9, 9, 9, 10, 10, 10, 10, 10};
+        return (j < 0 || j >= 35) ? 0 : h[j < 18 ? j : 34 - j];
+    }
+};
+
+template <int K> __host__ __device__ constexpr uint32_t pack4(int j0) {
+    return (uint32_t)Taps<K>::at(j0) | ((uint32_t)Taps<K>::at(j0 + 1) << 8) |
+           ((uint32_t)Taps<K>::at(j0 + 2) << 16) | ((uint32_t)Taps<K>::at(j0 + 3) << 24);
+}
+
+template <int B, int E, class F> __device__ __forceinline__ void static_for(F &&f) {
+    if constexpr (B < E) {
+        f(std::integral_constant<int, B>{});
+        static_for<B + 1, E>(f);
+    }
+}
+
+constexpr int cdiv(int a, int b) { return (a + b - 1) / b; }
+constexpr int rup(int a, int b) { return cdiv(a, b) * b; }
+
+constexpr int TW = 128;       // strip width (pixels) = threads per CTA
+constexpr int RB = 8;         // rows per step
+
+template <int KS, int KL> struct Geo {
+    static constexpr int RL = KL / 2, RS = KS / 2;
+    static constexpr int HL = rup(RL, 4);                 // left/right halo, word aligned
+    static constexpr int TWORDS = (TW + 2 * HL) / 4;      // words per staged input row
+    static constexpr int NW = (3 + HL + RL) / 4 + 1;      // words a thread reads per row
+    static constexpr int PL = rup(RL, 2), PS = rup(RS, 2);
+    static constexpr int LEAD = cdiv(RL + PL, RB);        // horizontal steps ahead of the vertical pass
+    static constexpr int NGL = LEAD + 1;                  // ring groups (8 rows each), large kernel
+    static constexpr int NPL = (PL + RB + RL + 1) / 2;    // row pairs the large vertical pass reads
+    static constexpr int OFFS = (PL - PS) / 2;            // first pair of the small pass, relative
+    static constexpr int NPS = (PS + RB + RS + 1) / 2;    // row pairs the small vertical pass reads
+    static constexpr int GS0 = OFFS / 4;                  // first group the small pass touches
+    static constexpr int GS1 = (OFFS + NPS - 1) / 4;      // last group
+    static constexpr int NGS = NGL - GS0;                 // ring groups kept for the small kernel
+    static constexpr int PRE = cdiv(RB * TWORDS, TW);     // prefetch registers per thread
+    static constexpr size_t SMEM = (size_t)(NGL + NGS) * TW * 16 + (size_t)RB * TWORDS * 4;
+};
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = (i < 0) ? -i : 2 * (n - 1) - i;
+    return i;
+}
+
+template <bool BGR>
+__device__ __forceinline__ uint32_t load_px(const uint8_t *row, int x) {
+    if constexpr (BGR) {
+        const uint8_t *p = row + 3 * (size_t)x;
+        return (3735u * p[0] + 19235u * p[1] + 9798u * p[2] + 16384u) >> 15;   // cvtColor BGR2GRAY, MD:114
+    } else {
+        return row[x];
+    }
+}
+
+// one staged word = 4 horizontally adjacent gray pixels starting at image column col0
+template <bool BGR>
+__device__ __forceinline__ uint32_t load_word(const uint8_t *row, int col0, int W, bool aligned4) {
+    if (!BGR && aligned4 && col0 >= 0 && col0 + 3 < W)
+        return __ldg(reinterpret_cast<const uint32_t *>(row + col0));
+    uint32_t v = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) v |= load_px<BGR>(row, reflect101(col0 + b, W)) << (8 * b);
+    return v;
+}
+
+template <int KS, int KL, bool BGR>
+__global__ void __launch_bounds__(TW, 4)
+blur_area_kernel(const uint8_t *__restrict__ frames, int64_t frame_stride, int64_t row_pitch, int H, int W, int WW,
+                 int seg_rows, int lo, int hi, uint32_t *__restrict__ area_bits, uint32_t *__restrict__ area_count) {
+    using G = Geo<KS, KL>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint4 *ringL = reinterpret_cast<uint4 *>(smem_raw);                       // [NGL][TW]
+    uint4 *ringS = ringL + G::NGL * TW;                                       // [NGS][TW]
+    uint32_t *tile = reinterpret_cast<uint32_t *>(ringS + G::NGS * TW);       // [RB][TWORDS]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x0 = blockIdx.x * TW;
+    const int ys = blockIdx.y * seg_rows;
+    const int ye = min(H, ys + seg_rows);
+    const int f = blockIdx.z;
+    const uint8_t *fbase = frames + (size_t)f * frame_stride;
+    const bool aligned4 = ((reinterpret_cast<uintptr_t>(fbase) | (uintptr_t)row_pitch) & 3) == 0;
+    const int nk = (ye - ys + RB - 1) / RB;
+    const int nsteps = nk + G::LEAD;
+    uint32_t count = 0;
+
+    uint32_t pre[G::PRE];
+    auto fetch = [&](int m) {
+#pragma unroll
+        for (int i = 0; i < G::PRE; ++i) {
+            const int wi = tid + i * TW;
+            if (wi < RB * G::TWORDS) {
+                const int r = wi / G::TWORDS, wc = wi - r * G::TWORDS;
+                const int p = ys - G::PL + RB * m + r;
+                const uint8_t *row = fbase + (size_t)reflect101(p, H) * row_pitch;
+                pre[i] = load_word<BGR>(row, x0 - G::HL + 4 * wc, W, aligned4);
+            }
+        }
+    };
+    auto stash = [&]() {
+#pragma unroll
+        for (int i = 0; i < G::PRE; ++i) {
+            const int wi = tid + i * TW;
+            if (wi < RB * G::TWORDS) tile[wi] = pre[i];
+        }
+    };
+
+    fetch(0);
+    int gl = 0, gs = 0;          // ring group written by horizontal step m: m % NGL, m % NGS
+    for (int m = 0; m < nsteps; ++m) {
+        stash();
+        __syncthreads();
+        if (m + 1 < nsteps) fetch(m + 1);          // global loads of the next step fly during the math
+
+        // ---- horizontal passes: warp = row pair, lane = pixel quad ------------------------------
+        {
+            uint32_t outL[4], outS[4];
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const uint32_t *trow = tile + (2 * warp + half) * G::TWORDS + lane;
+                uint32_t x[G::NW];
+#pragma unroll
+                for (int w = 0; w < G::NW; ++w) x[w] = trow[w];
+                uint32_t aL[4] = {0, 0, 0, 0}, aS[4] = {0, 0, 0, 0};
+                static_for<0, 4>([&](auto S_) {
+                    constexpr int s = decltype(S_)::value;
+                    static_for<0, G::NW>([&](auto W_) {
+                        constexpr int w = decltype(W_)::value;
+                        constexpr uint32_t wl = pack4<KL>(4 * w - (G::HL - G::RL) - s);
+                        constexpr uint32_t ws = pack4<KS>(4 * w - (G::HL - G::RS) - s);
+                        if constexpr (wl != 0) aL[s] = __dp4a(x[w], wl, aL[s]);
+                        if constexpr (ws != 0) aS[s] = __dp4a(x[w], ws, aS[s]);
+                    });
+                });
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    if (half == 0) { outL[s] = aL[s]; outS[s] = aS[s]; }
+                    else { outL[s] |= aL[s] << 16; outS[s] |= aS[s] << 16; }
+                }
+            }
+            // ring element (group, column).e[warp]; rotate the column order per lane so the
+            // 32 lanes of one store hit 8 distinct banks instead of 2
+            uint32_t *dstL = reinterpret_cast<uint32_t *>(ringL + gl * TW) + warp;
+            uint32_t *dstS = reinterpret_cast<uint32_t *>(ringS + gs * TW) + warp;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int s = (j + (lane >> 1)) & 3;
+                const uint32_t vl = s == 0 ? outL[0] : s == 1 ? outL[1] : s == 2 ? outL[2] : outL[3];
+                const uint32_t vs = s == 0 ? outS[0] : s == 1 ? outS[1] : s == 2 ? outS[2] : outS[3];
+                dstL[(4 * lane + s) * 4] = vl;
+                dstS[(4 * lane + s) * 4] = vs;
+            }
+        }
+        __syncthreads();
+
+        // ---- vertical passes: thread = column, 8 output rows -----------------------------------
+        if (m >= G::LEAD) {
+            const int k = m - G::LEAD;
+            const int yb = ys + RB * k;
+            uint32_t accL[RB], accS[RB];
+#pragma unroll
+            for (int r = 0; r < RB; ++r) { accL[r] = 32768u; accS[r] = 32768u; }
+            // oldest live group of the large ring is (gl + 1) % NGL (written at step m - LEAD = k)
+            int g0 = gl + 1; if (g0 >= G::NGL) g0 -= G::NGL;
+            static_for<0, G::NGL>([&](auto G_) {
+                constexpr int g = decltype(G_)::value;
+                if constexpr (4 * g < G::NPL) {
+                    int gi = g0 + g; if (gi >= G::NGL) gi -= G::NGL;
+                    const uint4 v = ringL[gi * TW + tid];
+                    static_for<0, RB>([&](auto R_) {
+                        constexpr int r = decltype(R_)::value;
+                        constexpr uint32_t w01 = pack4<KL>(2 * (4 * g) - r - G::PL + G::RL);
+                        constexpr uint32_t w23 = pack4<KL>(2 * (4 * g + 2) - r - G::PL + G::RL);
+                        if constexpr ((w01 & 0xffffu) != 0) accL[r] = __dp2a_lo(v.x, w01, accL[r]);
+                        if constexpr ((w01 >> 16) != 0) accL[r] = __dp2a_hi(v.y, w01, accL[r]);
+                        if constexpr ((w23 & 0xffffu) != 0) accL[r] = __dp2a_lo(v.z, w23, accL[r]);
+                        if constexpr ((w23 >> 16) != 0) accL[r] = __dp2a_hi(v.w, w23, accL[r]);
+                    });
+                }
+            });
+            // small ring holds groups k+GS0 .. m; group written at step j sits in slot j % NGS
+            int s0 = gs + 1 + 0; if (s0 >= G::NGS) s0 -= G::NGS;       // slot of step m - NGS + 1 = k + GS0
+            static_for<G::GS0, G::GS1 + 1>([&](auto G_) {
+                constexpr int g = decltype(G_)::value;                 // group index relative to step k
+                int gi = s0 + (g - G::GS0); if (gi >= G::NGS) gi -= G::NGS;
+                const uint4 v = ringS[gi * TW + tid];
+                static_for<0, RB>([&](auto R_) {
+                    constexpr int r = decltype(R_)::value;
+                    // pair index relative to the small pass start: i = 4g + e - OFFS; tap = 2i - r - PS + RS
+                    constexpr uint32_t w01 = pack4<KS>(2 * (4 * g - G::OFFS) - r - G::PS + G::RS);
+                    constexpr uint32_t w23 = pack4<KS>(2 * (4 * g + 2 - G::OFFS) - r - G::PS + G::RS);
+                    if constexpr ((w01 & 0xffffu) != 0) accS[r] = __dp2a_lo(v.x, w01, accS[r]);
+                    if constexpr ((w01 >> 16) != 0) accS[r] = __dp2a_hi(v.y, w01, accS[r]);
+                    if constexpr ((w23 & 0xffffu) != 0) accS[r] = __dp2a_lo(v.z, w23, accS[r]);
+                    if constexpr ((w23 >> 16) != 0) accS[r] = __dp2a_hi(v.w, w23, accS[r]);
+                });
+            });
+            // round, wrapping DoG, inRange, 32 pixels per ballot word
+            const bool col_ok = (x0 + tid) < W;
+            uint32_t myword = 0;
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                const uint32_t bl = accL[r] >> 16, bs = accS[r] >> 16;
+                const uint32_t dog = (bl - bs + 15u) & 255u;             // uint8 wrap, MD:128
+                const bool in = col_ok && dog >= (uint32_t)lo && dog <= (uint32_t)hi;
+                const uint32_t word = __ballot_sync(0xffffffffu, in);
+                if (lane == r) myword = word;
+            }
+            const int wx = (x0 >> 5) + warp;
+            if (lane < RB && yb + lane < ye && wx < WW) {
+                area_bits[((size_t)f * H + (yb + lane)) * WW + wx] = myword;
+                count += __popc(myword);
+            }
+        }
+        if (++gl == G::NGL) gl = 0;
+        if (++gs == G::NGS) gs = 0;
+    }
+    // per-frame popcount -> mean of area_mask for the NCC (MD:153)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
+    if (lane == 0 && count) atomicAdd(area_count + f, count);
+}
+
+template <int KS, int KL>
+cudaError_t launch(vbs_ctx *ctx, const uint8_t *frames, int batch, int64_t frame_stride, int64_t row_pitch) {
+    using G = Geo<KS, KL>;
+    const int strips = (ctx->W + TW - 1) / TW;
+    // enough CTAs for ~8 waves of 4 CTAs/SM, but at least 64 output rows per segment
+    int vsegs = 1;
+    while ((long long)strips * batch * vsegs < 4096 && (ctx->H + vsegs) / (vsegs + 1) >= 64) ++vsegs;
+    int seg_rows = ((ctx->H + vsegs - 1) / vsegs + RB - 1) / RB * RB;
+    vsegs = (ctx->H + seg_rows - 1) / seg_rows;
+    dim3 grid(strips, vsegs, batch), block(TW);
+    cudaError_t e;
+    if (ctx->C == 3) {
+        auto kern = blur_area_kernel<KS, KL, true>;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM)) != cudaSuccess) return e;
+        kern<<<grid, block, G::SMEM, ctx->stream>>>(frames, frame_stride, row_pitch, ctx->H, ctx->W, ctx->WW, seg_rows,
+                                                    ctx->br.lo, ctx->br.hi, ctx->area_bits, ctx->area_count);
+    } else {
+        auto kern = blur_area_kernel<KS, KL, false>;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM)) != cudaSuccess) return e;
+        kern<<<grid, block, G::SMEM, ctx->stream>>>(frames, frame_stride, row_pitch, ctx->H, ctx->W, ctx->WW, seg_rows,
+                                                    ctx->br.lo, ctx->br.hi, ctx->area_bits, ctx->area_count);
+    }
+    ctx->launches += 1;
+    return cudaGetLastError();
+}
+
+template <int K> bool taps_match(const int *ref) {
+    for (int j = 0; j < K; ++j)
+        if (Taps<K>::at(j) != ref[j]) return false;
+    return true;
+}
+
+// host recipe of OpenCV's fixed-point Gaussian kernel: float64 taps, error diffusion from the
+// outside in (round half to even), the centre takes the remainder so the sum is exactly 256
+void host_taps(int ksize, double sigma, int *out) {
+    double k[128], sum = 0;
+    for (int i = 0; i < ksize; ++i) {
+        const double x = i - (ksize - 1) / 2.0;
+        k[i] = exp(-(x * x) / (2.0 * sigma * sigma));
+        sum += k[i];
+    }
+    double err = 0;
+    int acc = 0;
+    for (int i = 0; i < ksize / 2; ++i) {
+        const double adj = k[i] / sum * 256.0 + err;
+        const int v = (int)nearbyint(adj);
+        err = adj - v;
+        out[i] = out[ksize - 1 - i] = v;
+        acc += v;
+    }
+    out[ksize / 2] = 256 - 2 * acc;
+}
+
+}  // namespace
+
+int vbs_check_taps(std::string &err) {
+    int t[128];
+    host_taps(39, 8.0, t);    if (!taps_match<39>(t))  { err = "baked 39-tap kernel differs from the fixed-point recipe"; return -1; }
+    host_taps(101, 20.0, t);  if (!taps_match<101>(t)) { err = "baked 101-tap kernel differs from the fixed-point recipe"; return -1; }
+    host_taps(21, 4.56, t);   if (!taps_match<21>(t))  { err = "baked 21-tap kernel differs from the fixed-point recipe"; return -1; }
+    host_taps(35, 11.4, t);   if (!taps_match<35>(t))  { err = "baked 35-tap kernel differs from the fixed-point recipe"; return -1; }
+    return 0;
+}
+
+cudaError_t vbs_launch_blur(vbs_ctx *ctx, const uint8_t *frames, int batch, int64_t frame_stride, int64_t row_pitch) {
+    cudaError_t e = cudaMemsetAsync(ctx->area_count, 0, sizeof(uint32_t) * batch, ctx->stream);
+    if (e != cudaSuccess) return e;
+    if (ctx->big) return launch<39, 101>(ctx, frames, batch, frame_stride, row_pitch);
+    return launch<21, 35>(ctx, frames, batch, frame_stride, row_pitch);
+}

@@ -1,0 +1,171 @@
+// k_track3d.cu - K5b/K6/K7: batched per-marker kernels.
+//   track_kernel  : nearest detection per reference entry, first minimum, <= min distance   MD:349-396
+//   pos3d_kernel  : row filter + warm-up, undistortPoints (5 iterations), depth from the
+//                   apparent diameter, world transform                                       R3:172-176,185-238,255-260
+//   disp_kernel   : last-seen displacement along the frame axis                              R3:262-314
+//   plane_kernel  : deviation end points + least-squares plane + tilt                        FD:196-204,219-232,141-159
+#include "vbs_ctx.h"
+
+namespace {
+
+using namespace vbs;
+
+__global__ void track_kernel(const double *__restrict__ ref_xy, const double *__restrict__ marker_xy,
+                             const double *__restrict__ marker_axes, const int32_t *__restrict__ nmarkers, int32_t *__restrict__ row_det,
+                             double *__restrict__ row_cxy, double *__restrict__ row_axes, int R, int M, double min_dist, size_t total) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const size_t f = i / R;
+    const int r = (int)(i % R);
+    const double ox = ref_xy[2 * r], oy = ref_xy[2 * r + 1];
+    const int n = min(nmarkers[f], M);
+    const double *mk = marker_xy + f * (size_t)M * 2;
+    int best = -1;
+    double best_d = INFINITY;
+    for (int k = 0; k < n; ++k) {                // cdist(..)[0] then argmin: first minimum wins
+        const double dx = ox - mk[2 * k], dy = oy - mk[2 * k + 1];
+        const double d = __dsqrt_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)));
+        if (best < 0 || d < best_d) { best_d = d; best = k; }
+    }
+    if (best >= 0 && best_d > min_dist) best = -1;              // MD:372
+    row_det[i] = best;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    if (best >= 0) {
+        row_cxy[2 * i] = mk[2 * best]; row_cxy[2 * i + 1] = mk[2 * best + 1];
+        const double *ax = marker_axes + (f * (size_t)M + best) * 3;
+        row_axes[3 * i] = ax[0]; row_axes[3 * i + 1] = ax[1]; row_axes[3 * i + 2] = ax[2];
+    } else {
+        row_cxy[2 * i] = nan; row_cxy[2 * i + 1] = nan;
+        row_axes[3 * i] = nan; row_axes[3 * i + 1] = nan; row_axes[3 * i + 2] = nan;
+    }
+}
+
+__global__ void pos3d_kernel(CameraF64 cam, const int32_t *__restrict__ row_det, const double *__restrict__ row_cxy,
+                             const double *__restrict__ row_axes, double *__restrict__ obs, double *__restrict__ pos3d,
+                             uint8_t *__restrict__ flags, int R, int64_t frameno0, int64_t first_kept, size_t total) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const size_t f = i / R;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    uint8_t fl = 0;
+    double P[3] = {nan, nan, nan};
+    double u = nan, v = nan, d = nan;
+    const int64_t frameno = frameno0 + (int64_t)f;
+    if (row_det[i] >= 0 && row_axes[3 * i] >= cam.min_size && frameno >= first_kept) {   // R3:173, R3:255-256
+        d = row_axes[3 * i];                                                             // diameter = major_axis (R3:273)
+        undistort5(cam, row_cxy[2 * i], row_cxy[2 * i + 1], u, v);
+        fl = 1;
+        if (position3d(cam, u, v, d, P)) fl |= 2;
+        else { P[0] = P[1] = P[2] = nan; }
+    }
+    obs[3 * i] = u; obs[3 * i + 1] = v; obs[3 * i + 2] = d;
+    double *o = pos3d + 7 * i;
+    o[0] = P[0]; o[1] = P[1]; o[2] = P[2]; o[3] = nan; o[4] = nan; o[5] = nan; o[6] = nan;
+    flags[i] = fl;
+}
+
+// one thread per reference entry walks the frames of the batch in order
+__global__ void disp_kernel(CameraF64 cam, const double *__restrict__ obs, double *__restrict__ pos3d, uint8_t *__restrict__ flags,
+                            double *__restrict__ last_seen, int R, int batch, int64_t frameno0) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    double pu = last_seen[4 * r], pv = last_seen[4 * r + 1], pd = last_seen[4 * r + 2], pf = last_seen[4 * r + 3];
+    bool has = pf >= 0.0;
+    double Pp[3] = {0, 0, 0};
+    bool okp = has ? position3d(cam, pu, pv, pd, Pp) : false;
+    for (int f = 0; f < batch; ++f) {
+        const size_t i = (size_t)f * R + r;
+        uint8_t fl = flags[i];
+        if (!(fl & 1)) continue;
+        double *o = pos3d + 7 * i;
+        const bool okc = fl & 2;
+        if (has && okp && okc) {
+            const double dx = o[0] - Pp[0], dy = o[1] - Pp[1], dz = o[2] - Pp[2];
+            const double nrm = sqrt(dx * dx + dy * dy + dz * dz);
+            if (!(nrm > cam.max_disp)) {                                                  // R3:293
+                o[3] = dx; o[4] = dy; o[5] = dz; o[6] = nrm;
+                flags[i] = fl | 4;
+            }
+        }
+        has = true; okp = okc;
+        pu = obs[3 * i]; pv = obs[3 * i + 1]; pd = obs[3 * i + 2]; pf = (double)(frameno0 + f);
+        Pp[0] = o[0]; Pp[1] = o[1]; Pp[2] = o[2];
+    }
+    last_seen[4 * r] = pu; last_seen[4 * r + 1] = pv; last_seen[4 * r + 2] = pd; last_seen[4 * r + 3] = has ? pf : -1.0;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// one warp per frame
+__global__ void plane_kernel(const double *__restrict__ pos3d, const uint8_t *__restrict__ flags, const double *__restrict__ ref,
+                             const double *__restrict__ start, const double *__restrict__ dvert, const uint8_t *__restrict__ use,
+                             int shell, double scale, double *__restrict__ plane, int32_t *__restrict__ plane_n, int R, int batch) {
+    const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (f >= batch) return;
+    const int lane = threadIdx.x & 31;
+    auto point = [&](int r, double &X, double &Y, double &Z) -> bool {
+        const size_t i = (size_t)f * R + r;
+        if (!use[r] || !(flags[i] & 2)) return false;
+        const double *p = pos3d + 7 * i;
+        const double dx = (p[0] - start[3 * r]) - dvert[3 * r];           // d_tilt - d_vert (FD:196-203)
+        const double dy = (p[1] - start[3 * r + 1]) - dvert[3 * r + 1];
+        const double dz = (p[2] - start[3 * r + 2]) - dvert[3 * r + 2];
+        X = ref[3 * r] + dx * scale;                                      // FD:225-232
+        Y = ref[3 * r + 1] + dy * scale;
+        Z = (shell ? ref[3 * r + 2] : 0.0) + dz * scale;
+        return true;
+    };
+    double n = 0, sx = 0, sy = 0, sz = 0;
+    for (int r = lane; r < R; r += 32) {
+        double X, Y, Z;
+        if (point(r, X, Y, Z)) { n += 1; sx += X; sy += Y; sz += Z; }
+    }
+    n = warp_sum(n); sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
+    const double mx = sx / n, my = sy / n, mz = sz / n;
+    double sxx = 0, sxy = 0, syy = 0, sxz = 0, syz = 0;
+    for (int r = lane; r < R; r += 32) {
+        double X, Y, Z;
+        if (point(r, X, Y, Z)) {
+            const double x = X - mx, y = Y - my, z = Z - mz;
+            sxx += x * x; sxy += x * y; syy += y * y; sxz += x * z; syz += y * z;
+        }
+    }
+    sxx = warp_sum(sxx); sxy = warp_sum(sxy); syy = warp_sum(syy); sxz = warp_sum(sxz); syz = warp_sum(syz);
+    if (lane == 0) {
+        double out[4];
+        const double nan = __longlong_as_double(0x7ff8000000000000LL);
+        if (!plane_solve(n, mx, my, mz, sxx, sxy, syy, sxz, syz, out)) out[0] = out[1] = out[2] = out[3] = nan;
+        plane[4 * f] = out[0]; plane[4 * f + 1] = out[1]; plane[4 * f + 2] = out[2]; plane[4 * f + 3] = out[3];
+        plane_n[f] = (int32_t)n;
+    }
+}
+
+}  // namespace
+
+cudaError_t vbs_launch_track(vbs_ctx *ctx, int batch, int64_t frameno0) {
+    const int R = ctx->R;
+    if (R <= 0) return cudaSuccess;
+    const size_t total = (size_t)batch * R;
+    const unsigned g = (unsigned)((total + 127) / 128);
+    track_kernel<<<g, 128, 0, ctx->stream>>>(ctx->ref_xy, ctx->marker_xy, ctx->marker_axes, ctx->d_nmarkers, ctx->row_det, ctx->row_cxy,
+                                             ctx->row_axes, R, ctx->M, ctx->min_dist, total);
+    ctx->launches += 1;
+    if (ctx->have_cam) {
+        if (!ctx->have_first) { ctx->first_frame = frameno0; ctx->have_first = 1; }
+        const int64_t first_kept = ctx->first_frame + (ctx->warmup > 0 ? ctx->warmup : 0);
+        pos3d_kernel<<<g, 128, 0, ctx->stream>>>(ctx->cam, ctx->row_det, ctx->row_cxy, ctx->row_axes, ctx->obs, ctx->pos3d, ctx->pos_flags,
+                                                 R, frameno0, first_kept, total);
+        disp_kernel<<<(R + 63) / 64, 64, 0, ctx->stream>>>(ctx->cam, ctx->obs, ctx->pos3d, ctx->pos_flags, ctx->last_seen, R, batch, frameno0);
+        ctx->launches += 2;
+        if (ctx->have_plane) {
+            plane_kernel<<<(batch + 3) / 4, 128, 0, ctx->stream>>>(ctx->pos3d, ctx->pos_flags, ctx->pl_ref, ctx->pl_start, ctx->pl_dvert,
+                                                                   ctx->pl_use, ctx->shell, ctx->pscale, ctx->plane, ctx->plane_n, R, batch);
+            ctx->launches += 1;
+        }
+    }
+    return cudaGetLastError();
+}

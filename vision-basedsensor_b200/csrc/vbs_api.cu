@@ -1,0 +1,345 @@
+// vbs_api.cu - the C ABI of include/vbs.h: context lifetime, state setters, and the batch
+// entry points that chain the kernels on the context's stream.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include "vbs_ctx.h"
+
+namespace {
+
+template <class T> cudaError_t dalloc(T **p, size_t n) { *p = nullptr; return cudaMalloc((void **)p, (n ? n : 1) * sizeof(T)); }
+
+int fail(vbs_ctx *ctx, int code, const char *msg) { ctx->err = msg; return code; }
+
+int map_status(vbs_ctx *ctx, uint32_t st) {
+    if (!st) return VBS_OK;
+    std::string m = "device status:";
+    if (st & VBS_DEV_LABEL_OVERFLOW) m += " ring components exceed max_markers;";
+    if (st & VBS_DEV_CONTOUR_OVERFLOW) m += " opened blobs exceed max_markers;";
+    if (st & VBS_DEV_RECHECK_OVERFLOW) m += " float64 recheck list overflow;";
+    if (st & VBS_DEV_TRACE_GUARD) m += " border following did not close;";
+    if (st & VBS_DEV_MATCH_CONFLICT) m += " a centroid was matched by two contours;";
+    ctx->err = m;
+    if (st & (VBS_DEV_TRACE_GUARD | VBS_DEV_MATCH_CONFLICT)) return VBS_ERR_INTERNAL;
+    return VBS_ERR_CAPACITY;
+}
+
+void free_all(vbs_ctx *c) {
+    void *ptrs[] = {c->d_frames, c->area_bits, c->mask_bits, c->max_bits, c->open_bits, c->root_bits, c->area_count, c->thr_lut,
+                    c->d_n64, c->d_cn64, c->recheck, c->recheck_n, c->parent, c->parent2, c->rowcnt, c->rowoff, c->d_nlabels,
+                    c->d_ncont, c->lab_cnt, c->lab_sx, c->lab_sy, c->centres, c->croot, c->cell, c->claim, c->cmatch, c->d_nmarkers,
+                    c->marker_xy, c->marker_axes, c->ref_row, c->ref_col, c->ref_xy, c->row_det, c->row_cxy, c->row_axes, c->obs,
+                    c->pos3d, c->pos_flags, c->last_seen, c->pl_ref, c->pl_start, c->pl_dvert, c->pl_use, c->plane, c->plane_n,
+                    c->d_status};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (c->h_status) cudaFreeHost(c->h_status);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+}
+
+// run the detection chain on frames already in device memory
+int run_detection(vbs_ctx *ctx, const uint8_t *frames, int batch, int64_t frame_stride, int64_t row_pitch) {
+    VBS_CUDA(vbs_launch_blur(ctx, frames, batch, frame_stride, row_pitch));
+    VBS_CUDA(vbs_launch_ncc(ctx, batch));
+    return VBS_OK;
+}
+int run_centres(vbs_ctx *ctx, int batch) {
+    VBS_CUDA(vbs_launch_morph(ctx, batch));
+    VBS_CUDA(vbs_launch_components(ctx, batch));
+    VBS_CUDA(vbs_launch_contours(ctx, batch));
+    return VBS_OK;
+}
+
+struct CopyPlan { void *dst; const void *src; size_t bytes; };
+
+int plan_outputs(vbs_ctx *ctx, const vbs_outputs *out, int batch, CopyPlan *plan) {
+    int n = 0;
+    const size_t B = batch, M = ctx->M, R = ctx->R;
+    if (!out) return 0;
+    auto add = [&](void *dst, const void *src, size_t bytes) { if (dst && bytes) plan[n++] = CopyPlan{dst, src, bytes}; };
+    add(out->n_labels, ctx->d_nlabels, B * sizeof(int32_t));
+    add(out->centres, ctx->centres, B * M * 2 * sizeof(double));
+    add(out->n_markers, ctx->d_nmarkers, B * sizeof(int32_t));
+    add(out->marker_xy, ctx->marker_xy, B * M * 2 * sizeof(double));
+    add(out->marker_axes, ctx->marker_axes, B * M * 3 * sizeof(double));
+    if (R > 0) {
+        add(out->row_det, ctx->row_det, B * R * sizeof(int32_t));
+        add(out->row_cxy, ctx->row_cxy, B * R * 2 * sizeof(double));
+        add(out->row_axes, ctx->row_axes, B * R * 3 * sizeof(double));
+        if (ctx->have_cam) {
+            add(out->pos3d, ctx->pos3d, B * R * 7 * sizeof(double));
+            add(out->pos_flags, ctx->pos_flags, B * R);
+            if (ctx->have_plane) {
+                add(out->plane, ctx->plane, B * 4 * sizeof(double));
+                add(out->plane_n, ctx->plane_n, B * sizeof(int32_t));
+            }
+        }
+    }
+    return n;
+}
+
+int process_common(vbs_ctx *ctx, const uint8_t *d_frames, int batch, int64_t frame_stride, int64_t row_pitch, int64_t frameno0,
+                   const vbs_outputs *out, cudaMemcpyKind kind) {
+    int rc;
+    if ((rc = run_detection(ctx, d_frames, batch, frame_stride, row_pitch)) != VBS_OK) return rc;
+    if ((rc = run_centres(ctx, batch)) != VBS_OK) return rc;
+    VBS_CUDA(vbs_launch_track(ctx, batch, frameno0));
+    CopyPlan plan[16];
+    const int n = plan_outputs(ctx, out, batch, plan);
+    for (int i = 0; i < n; ++i) VBS_CUDA(cudaMemcpyAsync(plan[i].dst, plan[i].src, plan[i].bytes, kind, ctx->stream));
+    ctx->last_batch = batch;
+    return VBS_OK;
+}
+
+int check_batch(vbs_ctx *ctx, const void *frames, int batch) {
+    if (!ctx) return VBS_ERR_BAD_ARG;
+    if (!frames) return fail(ctx, VBS_ERR_BAD_ARG, "frames is NULL");
+    if (batch < 1 || batch > ctx->B) return fail(ctx, VBS_ERR_BAD_ARG, "batch must be in [1, max_batch]");
+    return VBS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *vbs_version(void) { return "vbs_b200 0.1.0 (sm_100a)"; }
+
+int vbs_create(vbs_ctx **out, const vbs_config *cfg) {
+    if (!out || !cfg) return VBS_ERR_BAD_ARG;
+    *out = nullptr;
+    if (cfg->height < 8 || cfg->width < 8 || (cfg->channels != 1 && cfg->channels != 3) || cfg->max_batch < 1 ||
+        cfg->max_markers < 1 || cfg->max_refs < 0)
+        return VBS_ERR_BAD_ARG;
+    vbs_ctx *ctx = new (std::nothrow) vbs_ctx();
+    if (!ctx) return VBS_ERR_CUDA;
+    ctx->cfg = *cfg;
+    ctx->H = cfg->height; ctx->W = cfg->width; ctx->WW = (cfg->width + 31) / 32; ctx->C = cfg->channels;
+    ctx->B = cfg->max_batch; ctx->M = cfg->max_markers; ctx->Rcap = cfg->max_refs;
+    ctx->big = cfg->height > 480;                                             // MD:117
+    ctx->br = ctx->big ? VbsBranch{39, 101, 80, 13.0, 20, 200, 14} : VbsBranch{21, 35, 33, 7.4, 35, 180, 8};
+    ctx->min_dist = 20.0;
+    ctx->first_frame = 0; ctx->have_first = 0;
+    *out = ctx;                                    // returned even on failure so vbs_last_error works; caller destroys
+    if (vbs_check_taps(ctx->err) != 0) return VBS_ERR_INTERNAL;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(ctx, VBS_ERR_CUDA, "no CUDA device (this library has no CPU path)");
+    VBS_CUDA(cudaSetDevice(cfg->device));
+    VBS_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    const size_t B = ctx->B, H = ctx->H, W = ctx->W, WW = ctx->WW, M = ctx->M, R = ctx->Rcap;
+    const size_t nbits = B * H * WW;
+    VBS_CUDA(dalloc(&ctx->area_bits, nbits)); VBS_CUDA(dalloc(&ctx->mask_bits, nbits)); VBS_CUDA(dalloc(&ctx->max_bits, nbits));
+    VBS_CUDA(dalloc(&ctx->open_bits, nbits)); VBS_CUDA(dalloc(&ctx->root_bits, nbits));
+    VBS_CUDA(dalloc(&ctx->area_count, B));
+    VBS_CUDA(dalloc(&ctx->thr_lut, (size_t)ctx->br.tl * ctx->br.tl + 1));
+    VBS_CUDA(dalloc(&ctx->d_n64, 96)); VBS_CUDA(dalloc(&ctx->d_cn64, 160));
+    ctx->recheck_cap = 16384;
+    VBS_CUDA(dalloc(&ctx->recheck, B * ctx->recheck_cap)); VBS_CUDA(dalloc(&ctx->recheck_n, B));
+    VBS_CUDA(dalloc(&ctx->parent, B * H * W)); VBS_CUDA(dalloc(&ctx->parent2, B * H * W));
+    VBS_CUDA(dalloc(&ctx->rowcnt, B * H)); VBS_CUDA(dalloc(&ctx->rowoff, B * H));
+    VBS_CUDA(dalloc(&ctx->d_nlabels, B)); VBS_CUDA(dalloc(&ctx->d_ncont, B));
+    VBS_CUDA(dalloc(&ctx->lab_cnt, B * M)); VBS_CUDA(dalloc(&ctx->lab_sx, B * M)); VBS_CUDA(dalloc(&ctx->lab_sy, B * M));
+    VBS_CUDA(dalloc(&ctx->centres, B * M * 2));
+    VBS_CUDA(dalloc(&ctx->croot, B * M)); VBS_CUDA(dalloc(&ctx->cell, B * M * 6)); VBS_CUDA(dalloc(&ctx->claim, B * M));
+    VBS_CUDA(dalloc(&ctx->cmatch, B * M));
+    VBS_CUDA(dalloc(&ctx->d_nmarkers, B)); VBS_CUDA(dalloc(&ctx->marker_xy, B * M * 2)); VBS_CUDA(dalloc(&ctx->marker_axes, B * M * 3));
+    VBS_CUDA(dalloc(&ctx->ref_row, R)); VBS_CUDA(dalloc(&ctx->ref_col, R)); VBS_CUDA(dalloc(&ctx->ref_xy, R * 2));
+    VBS_CUDA(dalloc(&ctx->row_det, B * R)); VBS_CUDA(dalloc(&ctx->row_cxy, B * R * 2)); VBS_CUDA(dalloc(&ctx->row_axes, B * R * 3));
+    VBS_CUDA(dalloc(&ctx->obs, B * R * 3)); VBS_CUDA(dalloc(&ctx->pos3d, B * R * 7)); VBS_CUDA(dalloc(&ctx->pos_flags, B * R));
+    VBS_CUDA(dalloc(&ctx->last_seen, R * 4));
+    VBS_CUDA(dalloc(&ctx->pl_ref, R * 3)); VBS_CUDA(dalloc(&ctx->pl_start, R * 3)); VBS_CUDA(dalloc(&ctx->pl_dvert, R * 3));
+    VBS_CUDA(dalloc(&ctx->pl_use, R)); VBS_CUDA(dalloc(&ctx->plane, B * 4)); VBS_CUDA(dalloc(&ctx->plane_n, B));
+    VBS_CUDA(dalloc(&ctx->d_status, 1));
+    VBS_CUDA(cudaMemset(ctx->d_status, 0, sizeof(uint32_t)));
+    VBS_CUDA(cudaHostAlloc((void **)&ctx->h_status, sizeof(uint32_t), cudaHostAllocDefault));
+    *ctx->h_status = 0;
+    VBS_CUDA(vbs_ncc_setup(ctx));
+    return vbs_reset_sequence(ctx);
+}
+
+void vbs_destroy(vbs_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->cfg.device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    free_all(ctx);
+    delete ctx;
+}
+
+const char *vbs_last_error(const vbs_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int vbs_set_stream(vbs_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return VBS_ERR_BAD_ARG;
+    VBS_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return VBS_OK;
+}
+
+int vbs_sync(vbs_ctx *ctx) {
+    if (!ctx) return VBS_ERR_BAD_ARG;
+    VBS_CUDA(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    VBS_CUDA(cudaMemsetAsync(ctx->d_status, 0, sizeof(uint32_t), ctx->stream));
+    VBS_CUDA(cudaStreamSynchronize(ctx->stream));
+    const uint32_t st = *ctx->h_status;
+    *ctx->h_status = 0;
+    return map_status(ctx, st);
+}
+
+int vbs_set_reference(vbs_ctx *ctx, int32_t n, const int32_t *row, const int32_t *col, const double *ox, const double *oy,
+                      double min_marker_distance) {
+    if (!ctx) return VBS_ERR_BAD_ARG;
+    if (n < 0 || n > ctx->Rcap) return fail(ctx, VBS_ERR_BAD_ARG, "reference count exceeds max_refs");
+    if (n > 0 && (!row || !col || !ox || !oy)) return fail(ctx, VBS_ERR_BAD_ARG, "NULL reference array");
+    VBS_CUDA(cudaStreamSynchronize(ctx->stream));
+    double *xy = new double[2 * (size_t)(n ? n : 1)];
+    for (int i = 0; i < n; ++i) { xy[2 * i] = ox[i]; xy[2 * i + 1] = oy[i]; }
+    cudaError_t e = cudaMemcpy(ctx->ref_xy, xy, sizeof(double) * 2 * n, cudaMemcpyHostToDevice);
+    delete[] xy;
+    VBS_CUDA(e);
+    VBS_CUDA(cudaMemcpy(ctx->ref_row, row, sizeof(int32_t) * n, cudaMemcpyHostToDevice));
+    VBS_CUDA(cudaMemcpy(ctx->ref_col, col, sizeof(int32_t) * n, cudaMemcpyHostToDevice));
+    ctx->R = n; ctx->min_dist = min_marker_distance;
+    ctx->have_plane = 0;
+    return vbs_reset_sequence(ctx);
+}
+
+int vbs_set_camera(vbs_ctx *ctx, const float K[9], const float D[5], const float R[9], const float T[3], double marker_diameter_mm,
+                   double min_marker_size_px, double max_displacement, int32_t warmup_frames) {
+    if (!ctx || !K || !D || !R || !T) return VBS_ERR_BAD_ARG;
+    if (!(K[0] > 0) || !(K[4] > 0)) return fail(ctx, VBS_ERR_BAD_ARG, "Focal lengths must be positive");   // R3:94-95
+    vbs::CameraF64 c;
+    c.fx = K[0]; c.fy = K[4]; c.cx = K[2]; c.cy = K[5];
+    c.k1 = D[0]; c.k2 = D[1]; c.p1 = D[2]; c.p2 = D[3]; c.k3 = D[4];
+    for (int i = 0; i < 9; ++i) c.R[i] = R[i];
+    for (int i = 0; i < 3; ++i) c.T[i] = T[i];
+    // NumPy-2 scalar promotion at R3:211,219: float32 + float32, / python int -> float32;
+    // python float / float32 -> float32
+    volatile float favg = (K[0] + K[4]) / 2.0f;
+    volatile float ratio = (float)marker_diameter_mm / favg;
+    c.f_avg = favg; c.ratio = ratio;
+    c.min_size = min_marker_size_px; c.max_disp = max_displacement;
+    ctx->cam = c; ctx->have_cam = 1; ctx->warmup = warmup_frames;
+    return vbs_reset_sequence(ctx);
+}
+
+int vbs_set_plane(vbs_ctx *ctx, int32_t n, const double *ref_xyz, const double *start_xyz, const double *d_vert, const uint8_t *use,
+                  int32_t shell_mode, double scale) {
+    if (!ctx) return VBS_ERR_BAD_ARG;
+    if (n != ctx->R || n <= 0) return fail(ctx, VBS_ERR_BAD_ARG, "plane arrays must match the reference array length");
+    if (!ref_xyz || !start_xyz) return fail(ctx, VBS_ERR_BAD_ARG, "NULL plane array");
+    VBS_CUDA(cudaStreamSynchronize(ctx->stream));
+    VBS_CUDA(cudaMemcpy(ctx->pl_ref, ref_xyz, sizeof(double) * 3 * n, cudaMemcpyHostToDevice));
+    VBS_CUDA(cudaMemcpy(ctx->pl_start, start_xyz, sizeof(double) * 3 * n, cudaMemcpyHostToDevice));
+    if (d_vert) VBS_CUDA(cudaMemcpy(ctx->pl_dvert, d_vert, sizeof(double) * 3 * n, cudaMemcpyHostToDevice));
+    else VBS_CUDA(cudaMemset(ctx->pl_dvert, 0, sizeof(double) * 3 * n));
+    if (use) VBS_CUDA(cudaMemcpy(ctx->pl_use, use, n, cudaMemcpyHostToDevice));
+    else VBS_CUDA(cudaMemset(ctx->pl_use, 1, n));
+    ctx->shell = shell_mode ? 1 : 0; ctx->pscale = scale; ctx->have_plane = 1;
+    return VBS_OK;
+}
+
+int vbs_reset_sequence(vbs_ctx *ctx) {
+    if (!ctx) return VBS_ERR_BAD_ARG;
+    const int R = ctx->Rcap;
+    VBS_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (R > 0) {
+        double *t = new double[4 * (size_t)R];
+        for (int i = 0; i < R; ++i) { t[4 * i] = t[4 * i + 1] = t[4 * i + 2] = 0.0; t[4 * i + 3] = -1.0; }
+        cudaError_t e = cudaMemcpy(ctx->last_seen, t, sizeof(double) * 4 * R, cudaMemcpyHostToDevice);
+        delete[] t;
+        VBS_CUDA(e);
+    }
+    ctx->have_first = 0; ctx->first_frame = 0;
+    return VBS_OK;
+}
+
+int vbs_get_last_seen(vbs_ctx *ctx, double *host_table) {
+    if (!ctx || !host_table) return VBS_ERR_BAD_ARG;
+    VBS_CUDA(cudaStreamSynchronize(ctx->stream));
+    VBS_CUDA(cudaMemcpy(host_table, ctx->last_seen, sizeof(double) * 4 * ctx->R, cudaMemcpyDeviceToHost));
+    return VBS_OK;
+}
+
+int vbs_set_last_seen(vbs_ctx *ctx, const double *host_table) {
+    if (!ctx || !host_table) return VBS_ERR_BAD_ARG;
+    VBS_CUDA(cudaStreamSynchronize(ctx->stream));
+    VBS_CUDA(cudaMemcpy(ctx->last_seen, host_table, sizeof(double) * 4 * ctx->R, cudaMemcpyHostToDevice));
+    return VBS_OK;
+}
+
+int vbs_set_first_frame(vbs_ctx *ctx, int64_t first_frame) {       // frame-sharded runs: warm-up counts from the global first frame
+    if (!ctx) return VBS_ERR_BAD_ARG;
+    ctx->first_frame = first_frame; ctx->have_first = 1;
+    return VBS_OK;
+}
+
+int vbs_process_device(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int64_t frame_stride, int64_t row_pitch, int64_t frameno0,
+                       const vbs_outputs *out) {
+    int rc = check_batch(ctx, frames, batch);
+    if (rc != VBS_OK) return rc;
+    if (row_pitch < (int64_t)ctx->W * ctx->C) return fail(ctx, VBS_ERR_BAD_ARG, "row_pitch smaller than a row");
+    return process_common(ctx, frames, batch, frame_stride, row_pitch, frameno0, out, cudaMemcpyDeviceToDevice);
+}
+
+int vbs_process_host(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int64_t frame_stride, int64_t row_pitch, int64_t frameno0,
+                     const vbs_outputs *out) {
+    int rc = check_batch(ctx, frames, batch);
+    if (rc != VBS_OK) return rc;
+    const size_t rowb = (size_t)ctx->W * ctx->C, fb = rowb * ctx->H;
+    if (row_pitch < (int64_t)rowb) return fail(ctx, VBS_ERR_BAD_ARG, "row_pitch smaller than a row");
+    if (!ctx->d_frames) {
+        ctx->frames_bytes = fb * ctx->B;
+        VBS_CUDA(cudaMalloc((void **)&ctx->d_frames, ctx->frames_bytes));
+    }
+    if ((size_t)row_pitch == rowb && (size_t)frame_stride == fb) {
+        VBS_CUDA(cudaMemcpyAsync(ctx->d_frames, frames, fb * batch, cudaMemcpyHostToDevice, ctx->stream));
+    } else {                                           // crop view (MD:85): one strided copy per frame
+        for (int f = 0; f < batch; ++f)
+            VBS_CUDA(cudaMemcpy2DAsync(ctx->d_frames + fb * f, rowb, frames + (size_t)frame_stride * f, (size_t)row_pitch, rowb, ctx->H,
+                                       cudaMemcpyHostToDevice, ctx->stream));
+    }
+    rc = process_common(ctx, ctx->d_frames, batch, (int64_t)fb, (int64_t)rowb, frameno0, out, cudaMemcpyDeviceToHost);
+    if (rc != VBS_OK) return rc;
+    return vbs_sync(ctx);
+}
+
+int vbs_find_markers(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int64_t frame_stride, int64_t row_pitch) {
+    int rc = check_batch(ctx, frames, batch);
+    if (rc != VBS_OK) return rc;
+    ctx->last_batch = batch;
+    return run_detection(ctx, frames, batch, frame_stride, row_pitch);
+}
+
+int vbs_marker_center(vbs_ctx *ctx, const uint8_t *mask, const uint8_t *area_mask, int32_t batch, const vbs_outputs *out) {
+    int rc = check_batch(ctx, mask, batch);
+    if (rc != VBS_OK) return rc;
+    if (!area_mask) return fail(ctx, VBS_ERR_BAD_ARG, "area_mask is NULL");
+    VBS_CUDA(vbs_launch_pack_masks(ctx, mask, area_mask, batch));
+    if ((rc = run_centres(ctx, batch)) != VBS_OK) return rc;
+    CopyPlan plan[16];
+    vbs_outputs o = *out;
+    o.row_det = nullptr; o.row_cxy = nullptr; o.row_axes = nullptr; o.pos3d = nullptr; o.pos_flags = nullptr; o.plane = nullptr; o.plane_n = nullptr;
+    const int n = plan_outputs(ctx, &o, batch, plan);
+    for (int i = 0; i < n; ++i) VBS_CUDA(cudaMemcpyAsync(plan[i].dst, plan[i].src, plan[i].bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->last_batch = batch;
+    return VBS_OK;
+}
+
+int vbs_debug_stage(vbs_ctx *ctx, int32_t stage, void *dst_device, size_t bytes) {
+    if (!ctx || !dst_device) return VBS_ERR_BAD_ARG;
+    const int batch = ctx->last_batch;
+    if (batch <= 0) return fail(ctx, VBS_ERR_STATE, "no batch processed yet");
+    const size_t npx = (size_t)batch * ctx->H * ctx->W;
+    if (stage == VBS_STAGE_RECHECKS) {
+        if (bytes < sizeof(int32_t) * batch) return fail(ctx, VBS_ERR_BAD_ARG, "destination too small");
+        VBS_CUDA(cudaMemcpyAsync(dst_device, ctx->recheck_n, sizeof(int32_t) * batch, cudaMemcpyDeviceToDevice, ctx->stream));
+        return VBS_OK;
+    }
+    const size_t need = npx * (stage == VBS_STAGE_LABELS ? 4 : 1);
+    if (bytes < need) return fail(ctx, VBS_ERR_BAD_ARG, "destination too small");
+    VBS_CUDA(vbs_launch_unpack(ctx, stage, dst_device, batch));
+    return VBS_OK;
+}
+
+int64_t vbs_kernel_launches(const vbs_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,99 @@
+// vbs_ctx.h - internal context and launcher declarations of libvbs_b200 (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include "../../include/vbs.h"
+#include "vbs_geom.h"
+
+// device-side status bits (OR-ed into ctx->d_status by kernels)
+enum : uint32_t {
+    VBS_DEV_LABEL_OVERFLOW = 1u << 0,    // more ring components than max_markers
+    VBS_DEV_CONTOUR_OVERFLOW = 1u << 1,  // more opened blobs than max_markers
+    VBS_DEV_RECHECK_OVERFLOW = 1u << 2,  // float64 recheck list full
+    VBS_DEV_TRACE_GUARD = 1u << 3,       // border following did not close
+    VBS_DEV_MATCH_CONFLICT = 1u << 4,    // one centroid claimed by two contours
+};
+
+struct VbsBranch {       // constants that switch on the frame height (MD:117-126,129,170)
+    int ks, kl;          // blur sizes: 21/35 or 39/101
+    int tl;              // template length 33 / 80
+    double tsigma;       // 7.4 / 13
+    int lo, hi;          // inRange bounds 35..180 / 20..200
+    int nb;              // max/min filter size 8 / 14
+};
+
+struct vbs_ctx {
+    vbs_config cfg;
+    int H, W, WW, C, B, M, Rcap;
+    int big;                         // 1: height > 480 branch
+    VbsBranch br;
+    cudaStream_t stream, own_stream;
+    std::string err;
+    int64_t launches;
+
+    // frame staging for the host entry point
+    uint8_t *d_frames; size_t frames_bytes;
+    // bit images [B][H][WW]
+    uint32_t *area_bits, *mask_bits, *max_bits, *open_bits, *root_bits;
+    uint32_t *area_count;            // [B] set pixels of area_mask
+    // NCC tables
+    float *thr_lut;                  // [tl*tl+1] interior threshold on G as a function of S
+    double *d_n64;                   // [tl] template factor n
+    double *d_cn64;                  // [tl+1+16] guarded prefix sums of n
+    double st2;                      // (sum n^2)^2 - 1/L^2
+    int2 *recheck; uint32_t *recheck_n; int recheck_cap;   // float64 recheck list [B][cap]
+    // union-find scratch
+    int32_t *parent, *parent2;       // [B][H*W] ring maxima / opened image (fg + bg)
+    int32_t *rowcnt, *rowoff;        // [B][H]
+    int32_t *d_nlabels, *d_ncont;    // [B]
+    // ring components
+    uint32_t *lab_cnt; unsigned long long *lab_sx, *lab_sy;   // [B][M]
+    double *centres;                 // [B][M][2] (row, col)
+    // contours / ellipses, slot = contour order (descending start pixel)
+    int32_t *croot;                  // [B][M] start pixel index
+    double *cell;                    // [B][M][6] cx, cy, major, minor, angle, valid
+    int32_t *claim;                  // [B][M] how many contours matched each centroid
+    int32_t *cmatch;                 // [B][M] matched label index or -1
+    // outputs kept on device
+    int32_t *d_nmarkers;             // [B]
+    double *marker_xy;               // [B][M][2]
+    double *marker_axes;             // [B][M][3]
+    // reference state
+    int R; double min_dist;
+    int32_t *ref_row, *ref_col; double *ref_xy;
+    int32_t *row_det; double *row_cxy; double *row_axes;  // [B][R]...
+    double *obs;                     // [B][R][3] undistorted u, v and diameter of each observation
+    // camera / 3D
+    int have_cam; vbs::CameraF64 cam; int warmup; int64_t first_frame; int have_first;
+    double *pos3d; uint8_t *pos_flags;      // [B][R][7], [B][R]
+    double *last_seen;                       // [R][4] u, v, diameter, frame
+    // plane
+    int have_plane; int shell; double pscale;
+    double *pl_ref, *pl_start, *pl_dvert; uint8_t *pl_use;
+    double *plane; int32_t *plane_n;         // [B][4], [B]
+    uint32_t *d_status; uint32_t *h_status;  // device flag word, pinned host mirror
+    int32_t *d_nrecheck;                     // [B] recheck counts (debug)
+    int last_batch;
+};
+
+#define VBS_CUDA(call)                                                                   \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess) {                                                         \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);               \
+            return VBS_ERR_CUDA;                                                         \
+        }                                                                                \
+    } while (0)
+
+// launchers (each returns a cudaError_t from cudaGetLastError after the launches)
+cudaError_t vbs_launch_blur(vbs_ctx *ctx, const uint8_t *frames, int batch, int64_t frame_stride, int64_t row_pitch);
+cudaError_t vbs_launch_ncc(vbs_ctx *ctx, int batch);
+cudaError_t vbs_ncc_setup(vbs_ctx *ctx);
+cudaError_t vbs_launch_morph(vbs_ctx *ctx, int batch);
+cudaError_t vbs_launch_components(vbs_ctx *ctx, int batch);
+cudaError_t vbs_launch_contours(vbs_ctx *ctx, int batch);
+cudaError_t vbs_launch_track(vbs_ctx *ctx, int batch, int64_t frameno0);
+cudaError_t vbs_launch_pack_masks(vbs_ctx *ctx, const uint8_t *mask, const uint8_t *area, int batch);
+cudaError_t vbs_launch_unpack(vbs_ctx *ctx, int stage, void *dst, int batch);
+int vbs_check_taps(std::string &err);       // baked integer taps == host recipe

@@ -1,0 +1,251 @@
+"""Batched host-side driver of the CUDA marker pipeline (thin: no arithmetic in Python).
+
+``MarkerPipeline`` owns one C context (= one GPU, one stream).  Frames go in as
+``[B, H, W]`` / ``[B, H, W, 3]`` uint8, either a CUDA ``torch`` tensor (nothing is
+copied) or a host ``numpy`` array (the H2D / D2H copies are part of the call); results
+come back as a :class:`BatchResult` of arrays on the same side.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import capi
+
+
+@dataclass
+class BatchResult:
+    """SoA outputs of one batch (device torch tensors or host numpy arrays)."""
+    frameno0: int
+    n_labels: object      # [B] int32
+    centres: object       # [B, M, 2] float64 (row, col)
+    n_markers: object     # [B] int32
+    marker_xy: object     # [B, M, 2] float64 (x, y)
+    marker_axes: object   # [B, M, 3] float64 major, minor, angle
+    row_det: object = None      # [B, R] int32
+    row_cxy: object = None      # [B, R, 2]
+    row_axes: object = None     # [B, R, 3]
+    pos3d: object = None        # [B, R, 7]
+    pos_flags: object = None    # [B, R] uint8
+    plane: object = None        # [B, 4]
+    plane_n: object = None      # [B]
+
+    def to_host(self) -> "BatchResult":
+        def cv(a):
+            return a.cpu().numpy() if hasattr(a, "cpu") else a
+        return BatchResult(self.frameno0, *[cv(getattr(self, k)) for k in
+                                            ("n_labels", "centres", "n_markers", "marker_xy", "marker_axes", "row_det", "row_cxy",
+                                             "row_axes", "pos3d", "pos_flags", "plane", "plane_n")])
+
+    def markers(self, f: int) -> list:
+        """Marker dicts of frame ``f`` exactly as ``_marker_center`` returns them (MD:238-243)."""
+        h = self if isinstance(self.n_markers, np.ndarray) else self.to_host()
+        n = int(h.n_markers[f])
+        return [{"center": (h.marker_xy[f, k, 0], h.marker_xy[f, k, 1]), "major_axis": float(h.marker_axes[f, k, 0]),
+                 "minor_axis": float(h.marker_axes[f, k, 1]), "angle": float(h.marker_axes[f, k, 2])} for k in range(n)]
+
+
+class MarkerPipeline:
+    def __init__(self, height: int, width: int, channels: int = 1, max_batch: int = 32, max_markers: int = 1024,
+                 max_refs: int = 1024, device: int = 0):
+        self.H, self.W, self.C = int(height), int(width), int(channels)
+        self.B, self.M, self.Rcap = int(max_batch), int(max_markers), int(max_refs)
+        self.device = int(device)
+        self.R = 0
+        self.have_cam = False
+        self.have_plane = False
+        self._ctx = C.c_void_p()
+        cfg = capi.VbsConfig(self.device, self.H, self.W, self.C, self.B, self.M, self.Rcap)
+        code = capi.lib.vbs_create(C.byref(self._ctx), C.byref(cfg))
+        if code != capi.VBS_OK:
+            ctx, self._ctx = self._ctx, C.c_void_p()
+            try:
+                capi.check(ctx if ctx else None, code)
+            finally:
+                if ctx:
+                    capi.lib.vbs_destroy(ctx)
+        self.ref_rows = self.ref_cols = None
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None):
+            capi.lib.vbs_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def sync(self):
+        capi.check(self._ctx, capi.lib.vbs_sync(self._ctx))
+
+    def use_stream(self, cuda_stream_ptr: int):
+        capi.check(self._ctx, capi.lib.vbs_set_stream(self._ctx, C.c_void_p(cuda_stream_ptr)))
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(capi.lib.vbs_kernel_launches(self._ctx))
+
+    # -- state ------------------------------------------------------------------------------
+    def set_reference(self, rows, cols, ox, oy, min_marker_distance: float = 20.0):
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        cols = np.ascontiguousarray(cols, dtype=np.int32)
+        ox = np.ascontiguousarray(ox, dtype=np.float64)
+        oy = np.ascontiguousarray(oy, dtype=np.float64)
+        n = len(rows)
+        capi.check(self._ctx, capi.lib.vbs_set_reference(self._ctx, n, rows.ctypes.data, cols.ctypes.data, ox.ctypes.data,
+                                                         oy.ctypes.data, float(min_marker_distance)))
+        self.R = n
+        self.ref_rows, self.ref_cols, self.ref_ox, self.ref_oy = rows, cols, ox, oy
+        self.have_plane = False
+
+    def set_camera(self, K, D, R, T, marker_diameter_mm: float = 2.0, min_marker_size_px: float = 5.0,
+                   max_displacement: float = 50.0, warmup_frames: int = 100):
+        K = np.ascontiguousarray(K, dtype=np.float32).reshape(9)
+        D = np.ascontiguousarray(np.asarray(D, dtype=np.float32).reshape(-1)[:5])
+        R = np.ascontiguousarray(R, dtype=np.float32).reshape(9)
+        T = np.ascontiguousarray(T, dtype=np.float32).reshape(3)
+        capi.check(self._ctx, capi.lib.vbs_set_camera(self._ctx, K.ctypes.data, D.ctypes.data, R.ctypes.data, T.ctypes.data,
+                                                      float(marker_diameter_mm), float(min_marker_size_px),
+                                                      float(max_displacement), int(warmup_frames)))
+        self.have_cam = True
+
+    def set_plane(self, ref_xyz, start_xyz, d_vert=None, use=None, shell: bool = False, scale: float = 1.0):
+        ref_xyz = np.ascontiguousarray(ref_xyz, dtype=np.float64)
+        start_xyz = np.ascontiguousarray(start_xyz, dtype=np.float64)
+        dv = None if d_vert is None else np.ascontiguousarray(d_vert, dtype=np.float64)
+        us = None if use is None else np.ascontiguousarray(use, dtype=np.uint8)
+        capi.check(self._ctx, capi.lib.vbs_set_plane(self._ctx, len(ref_xyz), ref_xyz.ctypes.data, start_xyz.ctypes.data,
+                                                     dv.ctypes.data if dv is not None else None,
+                                                     us.ctypes.data if us is not None else None, int(bool(shell)), float(scale)))
+        self.have_plane = True
+
+    def reset_sequence(self):
+        capi.check(self._ctx, capi.lib.vbs_reset_sequence(self._ctx))
+
+    def get_last_seen(self) -> np.ndarray:
+        t = np.zeros((self.R, 4), dtype=np.float64)
+        capi.check(self._ctx, capi.lib.vbs_get_last_seen(self._ctx, t.ctypes.data))
+        return t
+
+    def set_last_seen(self, table):
+        t = np.ascontiguousarray(table, dtype=np.float64)
+        assert t.shape == (self.R, 4)
+        capi.check(self._ctx, capi.lib.vbs_set_last_seen(self._ctx, t.ctypes.data))
+
+    def set_first_frame(self, frameno: int):
+        capi.check(self._ctx, capi.lib.vbs_set_first_frame(self._ctx, int(frameno)))
+
+    # -- output allocation --------------------------------------------------------------------
+    def _alloc(self, batch: int, on_device: bool):
+        B, M, R = batch, self.M, self.R
+        shapes = {"n_labels": ((B,), "int32"), "centres": ((B, M, 2), "float64"), "n_markers": ((B,), "int32"),
+                  "marker_xy": ((B, M, 2), "float64"), "marker_axes": ((B, M, 3), "float64")}
+        if R > 0:
+            shapes.update({"row_det": ((B, R), "int32"), "row_cxy": ((B, R, 2), "float64"), "row_axes": ((B, R, 3), "float64")})
+            if self.have_cam:
+                shapes.update({"pos3d": ((B, R, 7), "float64"), "pos_flags": ((B, R), "uint8")})
+                if self.have_plane:
+                    shapes.update({"plane": ((B, 4), "float64"), "plane_n": ((B,), "int32")})
+        arrays, out = {}, capi.VbsOutputs()
+        if on_device:
+            import torch
+            dev = torch.device("cuda", self.device)
+            for k, (shp, dt) in shapes.items():
+                arrays[k] = torch.empty(shp, dtype=getattr(torch, dt), device=dev)
+                setattr(out, k, arrays[k].data_ptr())
+        else:
+            for k, (shp, dt) in shapes.items():
+                arrays[k] = np.empty(shp, dtype=dt)
+                setattr(out, k, arrays[k].ctypes.data)
+        return arrays, out
+
+    # -- hot path -------------------------------------------------------------------------------
+    def _geometry(self, frames):
+        shp = tuple(frames.shape)
+        want = (self.H, self.W) if self.C == 1 else (self.H, self.W, self.C)
+        if len(shp) == len(want):
+            shp = (1,) + shp
+        if shp[1:] != want:
+            raise ValueError(f"frames must be [B,{','.join(map(str, want))}] uint8, got {tuple(frames.shape)}")
+        if shp[0] > self.B:
+            raise ValueError(f"batch {shp[0]} exceeds max_batch {self.B}")
+        return shp[0]
+
+    def process(self, frames, frameno0: int = 0, out: Optional[tuple] = None) -> BatchResult:
+        """Run the whole path on one batch.  CUDA tensor in -> device results (asynchronous, call
+        :meth:`sync` before trusting them); numpy in -> host results (synchronous)."""
+        batch = self._geometry(frames)
+        rowb = self.W * self.C
+        if isinstance(frames, np.ndarray):
+            if frames.dtype != np.uint8:
+                raise ValueError("frames must be uint8")
+            fr = np.ascontiguousarray(frames)
+            arrays, o = out if out is not None else self._alloc(batch, False)
+            capi.check(self._ctx, capi.lib.vbs_process_host(self._ctx, fr.ctypes.data, batch, rowb * self.H, rowb, int(frameno0),
+                                                            C.byref(o)))
+        else:
+            import torch
+            if frames.dtype != torch.uint8 or not frames.is_cuda:
+                raise ValueError("frames must be a CUDA uint8 tensor (or a host numpy array)")
+            fr = frames.contiguous()
+            arrays, o = out if out is not None else self._alloc(batch, True)
+            self._keep = fr
+            capi.check(self._ctx, capi.lib.vbs_process_device(self._ctx, fr.data_ptr(), batch, rowb * self.H, rowb, int(frameno0),
+                                                              C.byref(o)))
+        return BatchResult(frameno0=int(frameno0), **arrays)
+
+    def alloc_outputs(self, batch: int, on_device: bool):
+        """Pre-allocate an output block to reuse across calls (pass as ``out=``)."""
+        return self._alloc(batch, on_device)
+
+    def process_host_ptr(self, ptr: int, batch: int, frame_stride: int, row_pitch: int, frameno0: int, out):
+        """Host frames by raw pointer (pinned staging buffers, crop views): MD:85 crop is a pointer + pitch."""
+        capi.check(self._ctx, capi.lib.vbs_process_host(self._ctx, C.c_void_p(ptr), batch, frame_stride, row_pitch, int(frameno0),
+                                                        C.byref(out[1])))
+        return BatchResult(frameno0=int(frameno0), **out[0])
+
+    def find_markers(self, frames):
+        """Device frames -> (mask, area_mask) uint8 device tensors, like ``_find_markers`` (MD:111-135)."""
+        import torch
+        batch = self._geometry(frames)
+        fr = frames.contiguous()
+        rowb = self.W * self.C
+        capi.check(self._ctx, capi.lib.vbs_find_markers(self._ctx, fr.data_ptr(), batch, rowb * self.H, rowb))
+        return self.debug_stage(capi.STAGE_MASK, batch), self.debug_stage(capi.STAGE_AREA_MASK, batch)
+
+    def marker_center(self, mask, area_mask) -> BatchResult:
+        """Device masks [B,H,W] uint8 -> marker lists, like ``_marker_center`` (MD:166-249)."""
+        import torch
+        batch = mask.shape[0]
+        m = (mask != 0).to(torch.uint8).contiguous()
+        a = (area_mask != 0).to(torch.uint8).contiguous()
+        saveR = self.R
+        arrays, o = self._alloc(batch, True)
+        capi.check(self._ctx, capi.lib.vbs_marker_center(self._ctx, m.data_ptr(), a.data_ptr(), batch, C.byref(o)))
+        keep = {k: arrays[k] for k in ("n_labels", "centres", "n_markers", "marker_xy", "marker_axes")}
+        return BatchResult(frameno0=0, **keep)
+
+    def debug_stage(self, stage: int, batch: int):
+        import torch
+        dev = torch.device("cuda", self.device)
+        if stage == capi.STAGE_RECHECKS:
+            t = torch.empty((batch,), dtype=torch.int32, device=dev)
+        elif stage == capi.STAGE_LABELS:
+            t = torch.empty((batch, self.H, self.W), dtype=torch.int32, device=dev)
+        else:
+            t = torch.empty((batch, self.H, self.W), dtype=torch.uint8, device=dev)
+        capi.check(self._ctx, capi.lib.vbs_debug_stage(self._ctx, stage, t.data_ptr(), t.numel() * t.element_size()))
+        self.sync()
+        return t
