@@ -142,6 +142,12 @@ int vbs_marker_center(vbs_ctx *ctx, const uint8_t *mask, const uint8_t *area_mas
 /* copy one stage image of the most recent batch into dst (device memory, `bytes` capacity) */
 int vbs_debug_stage(vbs_ctx *ctx, int32_t stage, void *dst_device, size_t bytes);
 
+/* per-stage device timing for bench.py's roofline: CUDA events on the context's stream around
+ * each stage of vbs_process_*.  ms[7] = accumulated milliseconds of blur+DoG, NCC, morphology,
+ * components, contours+ellipse, tracking+3D+plane, output copies; *calls = batches accumulated. */
+int vbs_set_profiling(vbs_ctx *ctx, int32_t enable);
+int vbs_get_stage_ms(vbs_ctx *ctx, double ms[7], int64_t *calls);
+
 /* launch accounting for bench.py ("gpu_launches"): kernels launched by this context so far */
 int64_t vbs_kernel_launches(const vbs_ctx *ctx);
 

@@ -34,6 +34,7 @@ void free_all(vbs_ctx *c) {
                     c->d_status};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (c->h_status) cudaFreeHost(c->h_status);
+    for (cudaEvent_t e : c->ev) if (e) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
 }
 
@@ -78,15 +79,43 @@ int plan_outputs(vbs_ctx *ctx, const vbs_outputs *out, int batch, CopyPlan *plan
     return n;
 }
 
+int prof_collect(vbs_ctx *ctx) {               // fold the previous batch's events into the totals
+    if (!ctx->prof_pending) return VBS_OK;
+    VBS_CUDA(cudaEventSynchronize(ctx->ev[VBS_NSTAGES]));
+    for (int i = 0; i < VBS_NSTAGES; ++i) {
+        float ms = 0.f;
+        VBS_CUDA(cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]));
+        ctx->stage_ms[i] += ms;
+    }
+    ctx->stage_calls += 1;
+    ctx->prof_pending = 0;
+    return VBS_OK;
+}
+
+#define VBS_MARK(i) do { if (ctx->profiling) VBS_CUDA(cudaEventRecord(ctx->ev[i], ctx->stream)); } while (0)
+
 int process_common(vbs_ctx *ctx, const uint8_t *d_frames, int batch, int64_t frame_stride, int64_t row_pitch, int64_t frameno0,
                    const vbs_outputs *out, cudaMemcpyKind kind) {
     int rc;
-    if ((rc = run_detection(ctx, d_frames, batch, frame_stride, row_pitch)) != VBS_OK) return rc;
-    if ((rc = run_centres(ctx, batch)) != VBS_OK) return rc;
+    if (ctx->profiling && (rc = prof_collect(ctx)) != VBS_OK) return rc;
+    VBS_MARK(0);
+    VBS_CUDA(vbs_launch_blur(ctx, d_frames, batch, frame_stride, row_pitch));
+    VBS_MARK(1);
+    VBS_CUDA(vbs_launch_ncc(ctx, batch));
+    VBS_MARK(2);
+    VBS_CUDA(vbs_launch_morph(ctx, batch));
+    VBS_MARK(3);
+    VBS_CUDA(vbs_launch_components(ctx, batch));
+    VBS_MARK(4);
+    VBS_CUDA(vbs_launch_contours(ctx, batch));
+    VBS_MARK(5);
     VBS_CUDA(vbs_launch_track(ctx, batch, frameno0));
+    VBS_MARK(6);
     CopyPlan plan[16];
     const int n = plan_outputs(ctx, out, batch, plan);
     for (int i = 0; i < n; ++i) VBS_CUDA(cudaMemcpyAsync(plan[i].dst, plan[i].src, plan[i].bytes, kind, ctx->stream));
+    VBS_MARK(7);
+    if (ctx->profiling) ctx->prof_pending = 1;
     ctx->last_batch = batch;
     return VBS_OK;
 }
@@ -341,5 +370,23 @@ int vbs_debug_stage(vbs_ctx *ctx, int32_t stage, void *dst_device, size_t bytes)
 }
 
 int64_t vbs_kernel_launches(const vbs_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int vbs_set_profiling(vbs_ctx *ctx, int32_t enable) {
+    if (!ctx) return VBS_ERR_BAD_ARG;
+    if (enable && !ctx->ev[0])
+        for (int i = 0; i <= VBS_NSTAGES; ++i) VBS_CUDA(cudaEventCreate(&ctx->ev[i]));
+    if (!enable) { int rc = prof_collect(ctx); if (rc != VBS_OK) return rc; }
+    ctx->profiling = enable ? 1 : 0;
+    return VBS_OK;
+}
+
+int vbs_get_stage_ms(vbs_ctx *ctx, double ms[7], int64_t *calls) {
+    if (!ctx || !ms) return VBS_ERR_BAD_ARG;
+    int rc = prof_collect(ctx);
+    if (rc != VBS_OK) return rc;
+    for (int i = 0; i < VBS_NSTAGES; ++i) ms[i] = ctx->stage_ms[i];
+    if (calls) *calls = ctx->stage_calls;
+    return VBS_OK;
+}
 
 }  // extern "C"

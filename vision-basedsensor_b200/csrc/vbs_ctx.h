@@ -75,7 +75,12 @@ struct vbs_ctx {
     uint32_t *d_status; uint32_t *h_status;  // device flag word, pinned host mirror
     int32_t *d_nrecheck;                     // [B] recheck counts (debug)
     int last_batch;
+    // optional per-stage timing (events on the context's stream)
+    int profiling, prof_pending;
+    cudaEvent_t ev[8];
+    double stage_ms[7]; int64_t stage_calls;
 };
+enum { VBS_NSTAGES = 7 };   // blur, ncc, morph, components, contours, track3d, output copies
 
 #define VBS_CUDA(call)                                                                   \
     do {                                                                                 \

@@ -97,6 +97,18 @@ class MarkerPipeline:
     def kernel_launches(self) -> int:
         return int(capi.lib.vbs_kernel_launches(self._ctx))
 
+    STAGES = ("blur_dog_area", "ncc_mask", "morphology", "components", "contours_ellipse", "track_3d_plane", "output_copies")
+
+    def set_profiling(self, on: bool):
+        capi.check(self._ctx, capi.lib.vbs_set_profiling(self._ctx, int(bool(on))))
+
+    def stage_ms(self):
+        """(dict stage -> accumulated ms, batches accumulated) since profiling was switched on."""
+        ms = (C.c_double * 7)()
+        calls = C.c_int64()
+        capi.check(self._ctx, capi.lib.vbs_get_stage_ms(self._ctx, ms, C.byref(calls)))
+        return dict(zip(self.STAGES, list(ms))), int(calls.value)
+
     # -- state ------------------------------------------------------------------------------
     def set_reference(self, rows, cols, ox, oy, min_marker_distance: float = 20.0):
         rows = np.ascontiguousarray(rows, dtype=np.int32)
