@@ -20,11 +20,8 @@ def f32_ulps(a, b):
 
 def grid_reference(markers0, cols):
     """Reference-state array = detections of frame 0 in ascending raster order, ids (i//cols, i%cols)."""
-    pts = np.array([m["center"] for m in markers0])
-    order = np.lexsort((pts[:, 0], np.round(pts[:, 1] / 20.0)))
-    pts = pts[order]
-    keys = [(i // cols, i % cols) for i in range(len(pts))]
-    return keys, pts
+    from vbs_b200 import reference_state
+    return reference_state.grid_ids(np.array([m["center"] for m in markers0]), cols)
 
 
 def oracle_frames(frames, ref_keys=None, ref_xy=None, min_dist=20.0, frameno0=0):

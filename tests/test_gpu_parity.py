@@ -1,0 +1,257 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI, against (1) the committed golden
+outputs of the unmodified reference, (2) the oracle port on seeded frames incl. edge cases, and
+(3) size-independent properties at BASELINE.json's full batch size.
+
+Tolerances (stated once): masks, labels, counts, IDs, marker order, centroids: bit-exact.
+Ellipse axes: <= 2 float32 ulp.  Angle: <= 1e-3 deg mod 180.  3D positions / displacements:
+<= 1e-9 mm.  Plane tilt: <= 1e-4 deg (north_star), observed ~1e-14.
+"""
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+import parity_util as pu
+import vbs_b200  # noqa: F401
+from vbs_b200 import capi, pipeline, synth, reference_state
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+warnings.filterwarnings("ignore")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def torch_cuda(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def unpack(bits, W):
+    return np.unpackbits(bits, axis=-1)[..., :W]
+
+
+# ---------------------------------------------------------------------------------------------
+# 1. golden vectors produced by the reference itself
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["tiny_4x5", "small_6x8", "ring65_crop"])
+def test_cuda_reproduces_reference_golden(name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    frames = g["frames"]
+    B, H, W = frames.shape
+    keys = [tuple(k) for k in g["ref_keys"].tolist()]
+    R = len(keys)
+    with pipeline.MarkerPipeline(H, W, 1, max_batch=B, max_markers=256, max_refs=R) as pipe:
+        pipe.set_reference([k[0] for k in keys], [k[1] for k in keys], g["ref_xy"][:, 0], g["ref_xy"][:, 1], 20.0)
+        pipe.set_camera(g["K"], g["D"], g["R"], g["T"], 2.0, 5.0, 50.0, warmup_frames=0)
+        res = pipe.process(torch_cuda(frames), 0)
+        pipe.sync()
+        h = res.to_host()
+        for stage, key, on in ((capi.STAGE_AREA_MASK, "area_bits", 255), (capi.STAGE_MASK, "mask_bits", 1), (capi.STAGE_OPENED, "opened_bits", 255)):
+            got = pipe.debug_stage(stage, B).cpu().numpy()
+            assert np.array_equal(got, unpack(g[key], W) * on), key
+        assert np.array_equal(pipe.debug_stage(capi.STAGE_LABELS, B).cpu().numpy(), g["labeled"].astype(np.int32))
+        assert h.n_labels.tolist() == g["n_labels"].tolist()
+        assert h.n_markers.tolist() == g["n_markers"].tolist()
+        for f in range(B):
+            n = int(g["n_markers"][f])
+            assert np.array_equal(h.marker_xy[f, :n], g["marker_xy"][f, :n])                     # order + bit-exact centroids
+            assert pu.f32_ulps(h.marker_axes[f, :n, :2], g["marker_axes"][f, :n, :2]).max() <= 2.0
+            da = np.abs(h.marker_axes[f, :n, 2] - g["marker_axes"][f, :n, 2]) % 180.0
+            assert np.minimum(da, 180 - da).max() <= 1e-3
+        # tracking rows (CSV contract MD:380-391): same (frameno,row,col) set, same Cx/Cy
+        want = {(int(r[0]), int(r[1]), int(r[2])): r for r in g["rows"]}
+        got_rows = 0
+        for f in range(B):
+            for r, k in enumerate(keys):
+                key = (f, k[0], k[1])
+                assert (h.row_det[f, r] >= 0) == (key in want), key
+                if key in want:
+                    got_rows += 1
+                    assert h.row_cxy[f, r, 0] == want[key][5] and h.row_cxy[f, r, 1] == want[key][6]
+        assert got_rows == len(want)
+        # 3D rows (R3:296-307)
+        want3 = {(int(r[0]), int(r[1]), int(r[2])): r[3:] for r in g["rows3d"]}
+        n3 = 0
+        for f in range(B):
+            for r, k in enumerate(keys):
+                key = (f, k[0], k[1])
+                emitted = bool(h.pos_flags[f, r] & 4)
+                assert emitted == (key in want3), key
+                if emitted:
+                    n3 += 1
+                    assert np.abs(h.pos3d[f, r] - want3[key]).max() <= 1e-9
+        assert n3 == len(want3)
+        # plane of the last frame against the reference's own fit_plane_least_squares (tilt <= 1e-4 deg)
+        start = np.nan_to_num(h.pos3d[0, :, :3])
+        pipe.set_plane(g["ref_xyz"], start, None)
+        pipe.reset_sequence()
+        res = pipe.process(torch_cuda(frames), 0)
+        pipe.sync()
+        pl = res.to_host().plane[B - 1]
+        assert abs(pl[3] - g["plane"][3]) <= 1e-4 and np.abs(pl[:3] - g["plane"][:3]).max() <= 1e-9
+
+
+# ---------------------------------------------------------------------------------------------
+# 2. seeded frames against the oracle port, incl. ragged sizes and BGR input
+# ---------------------------------------------------------------------------------------------
+def run_against_oracle(frames, cols, channels=1, max_markers=512, with3d=True):
+    H, W = frames.shape[1:3]
+    ora0 = pu.oracle_frames(frames[:1])
+    m0 = ora0[0]["markers"]
+    keys, xy = pu.grid_reference(m0, max(cols, 1)) if m0 else ([], np.zeros((0, 2)))
+    oracle = pu.oracle_frames(frames, keys, xy, 20.0)
+    with pipeline.MarkerPipeline(H, W, channels, max_batch=len(frames), max_markers=max_markers, max_refs=max(len(keys), 1)) as pipe:
+        if keys:
+            pipe.set_reference([k[0] for k in keys], [k[1] for k in keys], xy[:, 0], xy[:, 1], 20.0)
+        K, D, R, T = synth.synthetic_camera()
+        K = K.copy(); K[0, 2] = W / 2 + 3.1; K[1, 2] = H / 2 - 2.3
+        if keys and with3d:
+            pipe.set_camera(K, D, R, T, 2.0, 5.0, 50.0, warmup_frames=0)
+        res = pipe.process(torch_cuda(frames), 0)
+        pipe.sync()
+        rep = pu.compare_detection(pipe, frames, res, oracle)
+        if keys:
+            rep.update(pu.compare_rows(res, oracle, keys))
+            if with3d:
+                rows3d, pos = pu.oracle_3d(oracle, port.Camera(K, D, R, T), warmup=0)
+                rep.update(pu.compare_3d(res, keys, rows3d, pos))
+        pu.assert_report(rep)
+    return rep
+
+
+@pytest.mark.parametrize("name,n", [("tiny_4x5", 3), ("small_6x8", 3)])
+def test_grid_frames_match_oracle(name, n):
+    run_against_oracle(synth.workload_frames(name, n, seed0=100), synth.WORKLOADS[name][3])
+
+
+def test_bgr_input_matches_oracle():
+    fr = synth.workload_frames("small_6x8", 2, seed0=7)
+    bgr = np.repeat(fr[..., None], 3, axis=3).copy()
+    bgr[..., 0] = np.clip(bgr[..., 0].astype(int) + 9, 0, 255)
+    bgr[..., 2] = np.clip(bgr[..., 2].astype(int) - 11, 0, 255)
+    run_against_oracle(bgr, 8, channels=3)
+
+
+@pytest.mark.parametrize("h,w,rows,cols,pitch,rad", [(301, 357, 4, 5, 56.0, 6.0), (563, 645, 6, 8, 60.0, 11.0), (481, 130, 5, 1, 62.0, 11.0)])
+def test_ragged_sizes_match_oracle(h, w, rows, cols, pitch, rad):
+    """H not a multiple of 8, W not a multiple of 32/128, a strip narrower than the halo."""
+    centres = synth.grid_layout(h, w, rows, cols, pitch)
+    frames = np.stack([synth.render_frame(h, w, centres, rad, seed=s) for s in (1, 2)])
+    run_against_oracle(frames, cols)
+
+
+def test_edge_cases_match_oracle():
+    h, w = 520, 600
+    rng = np.random.default_rng(5)
+    blank = np.full((h, w), 170, np.uint8)
+    dark = np.full((h, w), 12, np.uint8)
+    single = synth.render_frame(h, w, np.array([[300.0, 260.0]]), 11.0, seed=3)
+    border = synth.render_frame(h, w, np.array([[4.0, 5.0], [595.0, 300.0], [300.0, 516.0], [120.0, 130.0], [2.0, 300.0]]), 11.0, seed=4, jitter=0)
+    noise = np.clip(rng.normal(128, 60, (h, w)), 0, 255).astype(np.uint8)
+    bright = synth.render_frame(h, w, synth.grid_layout(h, w, 4, 5, 90.0), 11.0, seed=6)
+    bright = (255 - bright.astype(int)).clip(0, 255).astype(np.uint8)          # bright markers: exercises the uint8 wrap (MD:128)
+    touching = synth.render_frame(h, w, np.array([[200.0, 200.0], [222.0, 200.0], [400.0, 300.0], [400.0, 323.0]]), 11.0, seed=8, jitter=0)
+    frames = np.stack([blank, dark, single, border, noise, bright, touching])
+    run_against_oracle(frames, 1, max_markers=4096, with3d=False)
+
+
+def test_capacity_overflow_is_reported():
+    h, w = 520, 600
+    noise = np.clip(np.random.default_rng(5).normal(128, 60, (1, h, w)), 0, 255).astype(np.uint8)
+    n = len(port.find_markers_frame(noise[0], t := {})) or t.get("n_labels", 0)
+    if t.get("n_labels", 0) < 9:
+        pytest.skip("noise frame did not produce enough components")
+    with pipeline.MarkerPipeline(h, w, 1, max_batch=1, max_markers=8, max_refs=1) as pipe:
+        pipe.process(torch_cuda(noise), 0)
+        with pytest.raises(capi.VbsError, match="exceed max_markers"):
+            pipe.sync()
+
+
+def test_bad_arguments_raise_value_error():
+    with pytest.raises(ValueError):
+        pipeline.MarkerPipeline(4, 4)
+    with pipeline.MarkerPipeline(560, 640, 1, max_batch=1, max_markers=64, max_refs=4) as pipe:
+        with pytest.raises(ValueError):
+            pipe.set_reference(np.arange(9), np.arange(9), np.zeros(9), np.zeros(9))
+        with pytest.raises(ValueError):
+            pipe.process(np.zeros((2, 560, 640), np.uint8))
+        with pytest.raises(ValueError, match="Focal lengths must be positive"):
+            pipe.set_camera(np.zeros((3, 3)), np.zeros(5), np.eye(3), np.zeros(3))
+
+
+# ---------------------------------------------------------------------------------------------
+# 3. stage entry points and the crop view
+# ---------------------------------------------------------------------------------------------
+def test_stage_entry_points_and_crop_pitch():
+    import torch
+    full = synth.workload_frames("small_6x8", 2, seed0=11)
+    H, W = full.shape[1:]
+    taps = {}
+    want = port.find_markers_frame(full[0], taps)
+    with pipeline.MarkerPipeline(H, W, 1, max_batch=2, max_markers=256, max_refs=1) as pipe:
+        mask, area = pipe.find_markers(torch_cuda(full))
+        assert np.array_equal(mask[0].cpu().numpy(), taps["mask"]) and np.array_equal(area[0].cpu().numpy(), taps["area_mask"])
+        res = pipe.marker_center(torch_cuda(np.stack([taps["mask"]] * 2)), torch_cuda(np.stack([taps["area_mask"]] * 2)))
+        pipe.sync()
+        assert res.markers(1) == want
+    # crop (MD:81-85) is a pointer + pitch at the boundary: no copy of the frame is made on the host
+    left, right, top, bottom = port.crop_box(W, H, (1 / 8, 1 / 8, 1 / 16, 0))
+    ch, cw = bottom - top, right - left
+    crop = np.ascontiguousarray(full[:, top:bottom, left:right])
+    want_c = [port.find_markers_frame(c) for c in crop]
+    with pipeline.MarkerPipeline(ch, cw, 1, max_batch=2, max_markers=256, max_refs=1) as pipe:
+        pin = torch.from_numpy(full).pin_memory()
+        outs = pipe.alloc_outputs(2, False)
+        res = pipe.process_host_ptr(pin.data_ptr() + top * W + left, 2, H * W, W, 0, outs)
+        assert [res.markers(f) for f in range(2)] == want_c
+
+
+# ---------------------------------------------------------------------------------------------
+# 4. BASELINE.json full size: oracle on unique frames + size-independent properties at batch 256
+# ---------------------------------------------------------------------------------------------
+def test_full_1080p_batch256_properties():
+    import torch
+    name, U, B = "1080p_20x20", 4, 256
+    H, W, rows, cols, _, _ = synth.WORKLOADS[name]
+    uniq = synth.workload_frames(name, U, seed0=0)
+    ora0 = pu.oracle_frames(uniq[:1])
+    keys, xy = pu.grid_reference(ora0[0]["markers"], cols)
+    oracle = pu.oracle_frames(uniq, keys, xy, 20.0)
+    K, D, R, T = synth.synthetic_camera()
+    batch = torch_cuda(np.tile(uniq, (B // U, 1, 1)))
+    with pipeline.MarkerPipeline(H, W, 1, max_batch=B, max_markers=1024, max_refs=len(keys)) as pipe:
+        pipe.set_reference([k[0] for k in keys], [k[1] for k in keys], xy[:, 0], xy[:, 1], 20.0)
+        pipe.set_camera(K, D, R, T, 2.0, 5.0, 50.0, warmup_frames=0)
+        res = pipe.process(batch, 0)
+        pipe.sync()
+        h = res.to_host()
+        # (a) the unique frames against the oracle (stages skipped at this size; rows / 3D checked)
+        first = pipeline.BatchResult(0, *[getattr(h, k)[:U] if getattr(h, k) is not None else None for k in
+                                          ("n_labels", "centres", "n_markers", "marker_xy", "marker_axes", "row_det", "row_cxy", "row_axes", "pos3d", "pos_flags", "plane", "plane_n")])
+        rep = pu.compare_detection(pipe, uniq, first, oracle, stages=False)
+        rep.update(pu.compare_rows(first, oracle, keys))
+        pu.assert_report(rep)
+        # (b) tiling invariance: frame i of the batch == frame i mod U, bit for bit
+        for k in ("n_labels", "n_markers", "marker_xy", "marker_axes", "row_det", "row_cxy"):
+            a = getattr(h, k)
+            assert np.array_equal(a, np.tile(a[:U], (B // U,) + (1,) * (a.ndim - 1)), equal_nan=True), k
+        assert (h.n_markers == rows * cols).all()
+        # (c) idempotence and batch-split invariance incl. the last-seen carry (R3:277,314)
+        pipe.reset_sequence()
+        again = pipe.process(batch, 0).to_host(); pipe.sync()
+        assert np.array_equal(again.pos3d, h.pos3d, equal_nan=True) and np.array_equal(again.pos_flags, h.pos_flags)
+        pipe.reset_sequence()
+        a = pipe.process(batch[:100], 0); pipe.sync(); a = a.to_host()
+        b = pipe.process(batch[100:], 100); pipe.sync(); b = b.to_host()
+        assert np.array_equal(np.concatenate([a.pos3d, b.pos3d]), h.pos3d, equal_nan=True)
+        assert np.array_equal(np.concatenate([a.pos_flags, b.pos_flags]), h.pos_flags)
+        # (d) displacement linearity: dX of frame f = X(f) - X(f-1) wherever both are valid
+        ok = (h.pos_flags[1:] & 4).astype(bool) & (h.pos_flags[:-1] & 2).astype(bool)
+        d = h.pos3d[1:, :, :3] - h.pos3d[:-1, :, :3]
+        assert np.abs((d - h.pos3d[1:, :, 3:6])[ok]).max() <= 1e-12
+        # (e) host entry point gives the same bytes as the device entry point
+        pipe.reset_sequence()
+        hh = pipe.process(np.ascontiguousarray(batch[:32].cpu().numpy()), 0)
+        assert np.array_equal(hh.marker_xy, h.marker_xy[:32]) and np.array_equal(hh.pos3d, h.pos3d[:32], equal_nan=True)
