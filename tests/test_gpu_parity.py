@@ -208,6 +208,47 @@ def test_stage_entry_points_and_crop_pitch():
         assert [res.markers(f) for f in range(2)] == want_c
 
 
+def _disk(img, cx, cy, r, v=1):
+    yy, xx = np.mgrid[:img.shape[0], :img.shape[1]]
+    img[(xx - cx) ** 2 + (yy - cy) ** 2 <= r * r] = v
+
+
+def nested_masks(h=520, w=640):
+    """Hand-made masks: a ring with a blob inside its hole (dropped by RETR_EXTERNAL), a blob inside
+    an OPEN cavity (kept), a contour with > 128 vertices (re-trace path), blobs touching the frame."""
+    area = np.zeros((h, w), np.uint8)
+    _disk(area, 150, 150, 60); _disk(area, 150, 150, 38, 0); _disk(area, 150, 150, 12)        # ring + nested disk
+    _disk(area, 440, 200, 75)                                                                  # long contour
+    area[330:430, 100:110] = 1; area[330:430, 190:200] = 1; area[420:430, 100:200] = 1          # U shape
+    _disk(area, 150, 370, 14)                                                                  # blob in the open cavity
+    _disk(area, 3, 250, 16); _disk(area, 636, 500, 15); _disk(area, 320, 517, 13)               # frame contact
+    _disk(area, 560, 420, 20); _disk(area, 560, 420, 6, 0)                                     # small hole, nothing inside
+    mask = np.zeros((h, w), np.uint8)
+    for cx, cy, r in ((150, 150, 22), (440, 200, 28), (150, 370, 22), (3, 250, 20), (636, 500, 20), (320, 517, 20), (560, 420, 24), (150, 92, 20)):
+        _disk(mask, cx, cy, r)
+    return mask, area * 255
+
+
+def test_marker_center_nested_holes_and_long_contours():
+    mask, area = nested_masks()
+    taps = {}
+    want = port.marker_center(mask, area, taps)
+    assert len(taps["contours"]) >= 7 and max(len(c) for c in taps["contours"]) > 128
+    with pipeline.MarkerPipeline(mask.shape[0], mask.shape[1], 1, max_batch=2, max_markers=64, max_refs=1) as pipe:
+        res = pipe.marker_center(torch_cuda(np.stack([mask, mask])), torch_cuda(np.stack([area, area])))
+        pipe.sync()
+        assert np.array_equal(pipe.debug_stage(capi.STAGE_OPENED, 2).cpu().numpy()[0], taps["opened"])
+        assert np.array_equal(pipe.debug_stage(capi.STAGE_LABELS, 2).cpu().numpy()[1], taps["labeled"])
+        for f in range(2):
+            got = res.markers(f)
+            assert len(got) == len(want) and len(want) >= 3
+            for a, b in zip(got, want):
+                assert a["center"] == b["center"]
+                assert pu.f32_ulps(a["major_axis"], b["major_axis"]) <= 2 and pu.f32_ulps(a["minor_axis"], b["minor_axis"]) <= 2
+                da = abs(a["angle"] - b["angle"]) % 180.0
+                assert min(da, 180 - da) <= 1e-3
+
+
 # ---------------------------------------------------------------------------------------------
 # 4. BASELINE.json full size: oracle on unique frames + size-independent properties at batch 256
 # ---------------------------------------------------------------------------------------------
@@ -240,7 +281,7 @@ def test_full_1080p_batch256_properties():
         assert (h.n_markers == rows * cols).all()
         # (c) idempotence and batch-split invariance incl. the last-seen carry (R3:277,314)
         pipe.reset_sequence()
-        again = pipe.process(batch, 0).to_host(); pipe.sync()
+        again = pipe.process(batch, 0); pipe.sync(); again = again.to_host()
         assert np.array_equal(again.pos3d, h.pos3d, equal_nan=True) and np.array_equal(again.pos_flags, h.pos_flags)
         pipe.reset_sequence()
         a = pipe.process(batch[:100], 0); pipe.sync(); a = a.to_host()

@@ -43,10 +43,26 @@ __device__ __forceinline__ int find_root(const int32_t *par, int i) {
     }
     return i;          // root index, or a negative terminal (OUTSIDE / encoded label)
 }
+// find with path halving (every visited node is re-pointed at its grandparent; links only ever
+// move towards smaller indices, so concurrent atomicMin links stay consistent)
+__device__ __forceinline__ int find_root_halving(int32_t *par, int i) {
+    if (i < 0) return i;
+    int p = par[i];
+    while (p != i) {
+        if (p < 0) return p;
+        const int g = par[p];
+        if (g == p) return p;
+        if (g < 0) return g;
+        par[i] = g;
+        i = g;
+        p = par[i];
+    }
+    return i;
+}
 __device__ void unite(int32_t *par, int a, int b) {
     for (;;) {
-        a = find_root(par, a);
-        b = find_root(par, b);
+        a = find_root_halving(par, a);
+        b = find_root_halving(par, b);
         if (a == b) return;
         if (a < b) { const int t = a; a = b; b = t; }
         const int old = atomicMin(par + a, b);      // a >= 0 here (a > b >= -1)
@@ -55,39 +71,43 @@ __device__ void unite(int32_t *par, int a, int b) {
     }
 }
 
+// word kernels: block (64, 4) = 64 words x 4 rows, grid (ceil(WW/64), ceil(H/4), batch)
+#define VBS_WORD_COORDS                                          \
+    const int wx = blockIdx.x * 64 + threadIdx.x;               \
+    const int y = blockIdx.y * 4 + threadIdx.y;                 \
+    const int f = blockIdx.z;                                   \
+    if (wx >= WW || y >= H) return;
+
 // ---- 1. every segment start becomes its own root ------------------------------------------------
-template <bool INV>
-__global__ void ccl_init_kernel(const uint32_t *__restrict__ bits, int32_t *__restrict__ parent, int H, int W, int WW, size_t nwords) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nwords) return;
-    const int wx = (int)(i % WW);
-    const size_t fy = i / WW;
-    const int y = (int)(fy % H);
-    const size_t f = fy / H;
-    const uint32_t w = get_bits<INV>(bits + f * (size_t)H * WW, y, wx, W, WW);
-    uint32_t starts = w & ~(w << 1);
-    int32_t *par = parent + f * (size_t)H * W;
+// FG: set bits.  BG (conditional on holes[f] != 0): cleared bits inside the image.
+template <bool FG, bool BG>
+__global__ void __launch_bounds__(256) ccl_init_kernel(const uint32_t *__restrict__ bits, int32_t *__restrict__ parent,
+                                                        const int32_t *__restrict__ holes, int H, int W, int WW) {
+    VBS_WORD_COORDS
+    const uint32_t raw = __ldg(bits + ((size_t)f * H + y) * WW + wx);
+    int32_t *par = parent + (size_t)f * H * W;
     const int base = y * W + 32 * wx;
-    while (starts) {
-        const int s = __ffs(starts) - 1;
-        starts &= starts - 1;
-        par[base + s] = base + s;
+    if (FG) {
+        uint32_t starts = raw & ~(raw << 1);
+        while (starts) { const int s = __ffs(starts) - 1; starts &= starts - 1; par[base + s] = base + s; }
+    }
+    if (BG && holes[f] != 0) {
+        const uint32_t w = ~raw & valid_mask(wx, W);
+        uint32_t starts = w & ~(w << 1);
+        while (starts) { const int s = __ffs(starts) - 1; starts &= starts - 1; par[base + s] = base + s; }
     }
 }
 
 // ---- 2. link segments that touch -----------------------------------------------------------------
 template <bool CONN8, bool INV, bool BORDER>
-__global__ void ccl_merge_kernel(const uint32_t *__restrict__ bits, int32_t *__restrict__ parent, int H, int W, int WW, size_t nwords) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nwords) return;
-    const int wx = (int)(i % WW);
-    const size_t fy = i / WW;
-    const int y = (int)(fy % H);
-    const size_t f = fy / H;
-    const uint32_t *img = bits + f * (size_t)H * WW;
+__global__ void __launch_bounds__(256) ccl_merge_kernel(const uint32_t *__restrict__ bits, int32_t *__restrict__ parent,
+                                                         const int32_t *__restrict__ holes, int H, int W, int WW) {
+    VBS_WORD_COORDS
+    if (INV && holes[f] == 0) return;          // no hole anywhere in this frame: background labels are not needed
+    const uint32_t *img = bits + (size_t)f * H * WW;
     const uint32_t w = get_bits<INV>(img, y, wx, W, WW);
     if (!w) return;
-    int32_t *par = parent + f * (size_t)H * W;
+    int32_t *par = parent + (size_t)f * H * W;
     const int base = y * W + 32 * wx;
     if ((w & 1u) && wx > 0) {
         const uint32_t pw = get_bits<INV>(img, y, wx - 1, W, WW);
@@ -124,19 +144,14 @@ __global__ void ccl_merge_kernel(const uint32_t *__restrict__ bits, int32_t *__r
     }
 }
 
-// ---- 3. flatten: every segment points at its root; mark roots ------------------------------------
-// FG image: root bits + per-row root counts.  BGTOO: also flatten the background segments.
-template <bool BGTOO>
-__global__ void ccl_roots_kernel(const uint32_t *__restrict__ bits, int32_t *__restrict__ parent, uint32_t *__restrict__ root_bits,
-                                 int32_t *__restrict__ rowcnt, int H, int W, int WW, size_t nwords) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nwords) return;
-    const int wx = (int)(i % WW);
-    const size_t fy = i / WW;
-    const int y = (int)(fy % H);
-    const size_t f = fy / H;
+// ---- 3. flatten: every segment points at its root; mark roots (root bits + per-row counts) --------
+__global__ void __launch_bounds__(256) ccl_roots_kernel(const uint32_t *__restrict__ bits, int32_t *__restrict__ parent,
+                                                         uint32_t *__restrict__ root_bits, int32_t *__restrict__ rowcnt,
+                                                         int H, int W, int WW) {
+    VBS_WORD_COORDS
+    const size_t i = ((size_t)f * H + y) * WW + wx;
     const uint32_t w = __ldg(bits + i);
-    int32_t *par = parent + f * (size_t)H * W;
+    int32_t *par = parent + (size_t)f * H * W;
     const int base = y * W + 32 * wx;
     uint32_t roots = 0;
     uint32_t starts = w & ~(w << 1);
@@ -148,17 +163,53 @@ __global__ void ccl_roots_kernel(const uint32_t *__restrict__ bits, int32_t *__r
         else par[base + s] = r;
     }
     root_bits[i] = roots;
-    if (roots) atomicAdd(rowcnt + f * H + y, __popc(roots));
-    if (BGTOO) {
-        const uint32_t bg = ~w & valid_mask(wx, W);
-        uint32_t bs = bg & ~(bg << 1);
-        while (bs) {
-            const int s = __ffs(bs) - 1;
-            bs &= bs - 1;
-            const int r = find_root(par, base + s);
-            if (r != base + s) par[base + s] = r;
-        }
+    if (roots) atomicAdd(rowcnt + (size_t)f * H + y, __popc(roots));
+}
+// background segments of frames with holes: point straight at the root (or at OUTSIDE)
+__global__ void __launch_bounds__(256) ccl_flatten_bg_kernel(const uint32_t *__restrict__ bits, int32_t *__restrict__ parent,
+                                                              const int32_t *__restrict__ holes, int H, int W, int WW) {
+    VBS_WORD_COORDS
+    if (holes[f] == 0) return;
+    const uint32_t bg = ~__ldg(bits + ((size_t)f * H + y) * WW + wx) & valid_mask(wx, W);
+    int32_t *par = parent + (size_t)f * H * W;
+    const int base = y * W + 32 * wx;
+    uint32_t bs = bg & ~(bg << 1);
+    while (bs) {
+        const int s = __ffs(bs) - 1;
+        bs &= bs - 1;
+        const int r = find_root(par, base + s);
+        if (r != base + s) par[base + s] = r;
     }
+}
+
+// ---- 3b. Euler number of the 8-connected foreground by bit quads ----------------------------------
+// 4 E = #Q1 - #Q3 - 2 #QD over all 2x2 windows of the zero-padded image (Gray's formula).  The
+// number of holes of the whole image is (#blobs - E); when it is 0 no blob can lie inside
+// another one, so the background labelling that RETR_EXTERNAL would need is skipped for the frame.
+__global__ void __launch_bounds__(256) euler_kernel(const uint32_t *__restrict__ bits, int32_t *__restrict__ euler4, int H, int W, int WW) {
+    const int wx = blockIdx.x * 64 + threadIdx.x;            // 0 .. WW (one extra all-zero column)
+    const int yy = (int)(blockIdx.y * 4 + threadIdx.y) - 1;  // top row of the quad: -1 .. H-1
+    const int f = blockIdx.z;
+    int v = 0;
+    if (wx <= WW && yy < H) {
+        const uint32_t *img = bits + (size_t)f * H * WW;
+        auto ld = [&](int y, int w) -> uint32_t { return (y >= 0 && y < H && w >= 0 && w < WW) ? __ldg(img + (size_t)y * WW + w) : 0u; };
+        const uint32_t b = ld(yy, wx), d = ld(yy + 1, wx);
+        const uint32_t a = (b << 1) | (ld(yy, wx - 1) >> 31), c = (d << 1) | (ld(yy + 1, wx - 1) >> 31);
+        const uint32_t x1 = a ^ b, x2 = c ^ d, n1 = a & b, n2 = c & d;
+        const uint32_t q1 = (x1 & ~x2 & ~n2) | (x2 & ~x1 & ~n1);
+        const uint32_t q3 = (x1 & n2) | (x2 & n1);
+        const uint32_t qd = x1 & x2 & ~(a ^ d);
+        v = __popc(q1) - __popc(q3) - 2 * __popc(qd);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (((threadIdx.y * 64 + threadIdx.x) & 31) == 0 && v) atomicAdd(euler4 + f, v);
+}
+
+__global__ void holes_kernel(const int32_t *__restrict__ euler4, const int32_t *__restrict__ ncont, int32_t *__restrict__ holes, int batch) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < batch) holes[f] = ncont[f] - euler4[f] / 4;
 }
 
 // ---- 4. exclusive scan of the per-row root counts (one CTA per frame) ----------------------------
@@ -230,18 +281,13 @@ __global__ void rank_roots_kernel(const uint32_t *__restrict__ root_bits, const 
 }
 
 // ---- 6. ring components: integer moments per label (MD:181 center_of_mass on a 0/1 mask) ---------
-__global__ void moments_kernel(const uint32_t *__restrict__ bits, const int32_t *__restrict__ parent, uint32_t *__restrict__ cnt,
-                               unsigned long long *__restrict__ sx, unsigned long long *__restrict__ sy, int H, int W, int WW, int M,
-                               size_t nwords) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nwords) return;
-    const uint32_t w = __ldg(bits + i);
+__global__ void __launch_bounds__(256) moments_kernel(const uint32_t *__restrict__ bits, const int32_t *__restrict__ parent,
+                                                       uint32_t *__restrict__ cnt, unsigned long long *__restrict__ sx,
+                                                       unsigned long long *__restrict__ sy, int H, int W, int WW, int M) {
+    VBS_WORD_COORDS
+    const uint32_t w = __ldg(bits + ((size_t)f * H + y) * WW + wx);
     if (!w) return;
-    const int wx = (int)(i % WW);
-    const size_t fy = i / WW;
-    const int y = (int)(fy % H);
-    const size_t f = fy / H;
-    const int32_t *par = parent + f * (size_t)H * W;
+    const int32_t *par = parent + (size_t)f * H * W;
     const int base = y * W + 32 * wx;
     uint32_t rem = w;
     while (rem) {
@@ -255,9 +301,9 @@ __global__ void moments_kernel(const uint32_t *__restrict__ bits, const int32_t 
         if (label < 0 || label >= M) continue;
         const unsigned len = __popc(seg);
         const unsigned long long xs = (unsigned long long)len * (unsigned)(32 * wx + s) + (unsigned long long)len * (len - 1) / 2;
-        atomicAdd(cnt + f * M + label, len);
-        atomicAdd(sx + f * M + label, xs);
-        atomicAdd(sy + f * M + label, (unsigned long long)len * (unsigned)y);
+        atomicAdd(cnt + (size_t)f * M + label, len);
+        atomicAdd(sx + (size_t)f * M + label, xs);
+        atomicAdd(sy + (size_t)f * M + label, (unsigned long long)len * (unsigned)y);
     }
 }
 
@@ -278,9 +324,10 @@ __global__ void centres_kernel(const uint32_t *__restrict__ cnt, const unsigned 
 
 cudaError_t vbs_launch_components(vbs_ctx *ctx, int batch) {
     const int H = ctx->H, W = ctx->W, WW = ctx->WW, M = ctx->M;
-    const size_t nwords = (size_t)batch * H * WW;
     const size_t nrows = (size_t)batch * H;
-    const unsigned gw = (unsigned)((nwords + 255) / 256);
+    const dim3 wb(64, 4);
+    const dim3 wg((WW + 63) / 64, (H + 3) / 4, batch);
+    const dim3 eg((WW + 1 + 63) / 64, (H + 1 + 3) / 4, batch);
     const unsigned gr = (unsigned)((nrows + 7) / 8);
     cudaStream_t st = ctx->stream;
     cudaError_t e;
@@ -289,23 +336,28 @@ cudaError_t vbs_launch_components(vbs_ctx *ctx, int batch) {
     if ((e = cudaMemsetAsync(ctx->lab_cnt, 0, sizeof(uint32_t) * (size_t)batch * M, st)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(ctx->lab_sx, 0, sizeof(unsigned long long) * (size_t)batch * M, st)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(ctx->lab_sy, 0, sizeof(unsigned long long) * (size_t)batch * M, st)) != cudaSuccess) return e;
-    ccl_init_kernel<false><<<gw, 256, 0, st>>>(ctx->max_bits, ctx->parent, H, W, WW, nwords);
-    ccl_merge_kernel<false, false, false><<<gw, 256, 0, st>>>(ctx->max_bits, ctx->parent, H, W, WW, nwords);
-    ccl_roots_kernel<false><<<gw, 256, 0, st>>>(ctx->max_bits, ctx->parent, ctx->root_bits, ctx->rowcnt, H, W, WW, nwords);
+    if ((e = cudaMemsetAsync(ctx->euler4, 0, sizeof(int32_t) * batch, st)) != cudaSuccess) return e;
+    ccl_init_kernel<true, false><<<wg, wb, 0, st>>>(ctx->max_bits, ctx->parent, nullptr, H, W, WW);
+    ccl_merge_kernel<false, false, false><<<wg, wb, 0, st>>>(ctx->max_bits, ctx->parent, nullptr, H, W, WW);
+    ccl_roots_kernel<<<wg, wb, 0, st>>>(ctx->max_bits, ctx->parent, ctx->root_bits, ctx->rowcnt, H, W, WW);
     row_scan_kernel<<<batch, 1024, 0, st>>>(ctx->rowcnt, ctx->rowoff, ctx->d_nlabels, H);
     rank_roots_kernel<0><<<gr, 256, 0, st>>>(ctx->root_bits, ctx->rowoff, ctx->d_nlabels, ctx->parent, nullptr, H, W, WW, M, nrows, ctx->d_status);
-    moments_kernel<<<gw, 256, 0, st>>>(ctx->max_bits, ctx->parent, ctx->lab_cnt, ctx->lab_sx, ctx->lab_sy, H, W, WW, M, nwords);
+    moments_kernel<<<wg, wb, 0, st>>>(ctx->max_bits, ctx->parent, ctx->lab_cnt, ctx->lab_sx, ctx->lab_sy, H, W, WW, M);
     centres_kernel<<<(unsigned)(((size_t)batch * M + 255) / 256), 256, 0, st>>>(ctx->lab_cnt, ctx->lab_sx, ctx->lab_sy, ctx->d_nlabels,
                                                                                 ctx->centres, M, (size_t)batch * M);
-    // ---- opened area mask: foreground 8-connected + background 4-connected in parent2 -------------
+    // ---- opened area mask: foreground 8-connected; background 4-connected only in frames with holes --
     if ((e = cudaMemsetAsync(ctx->rowcnt, 0, sizeof(int32_t) * nrows, st)) != cudaSuccess) return e;
-    ccl_init_kernel<false><<<gw, 256, 0, st>>>(ctx->open_bits, ctx->parent2, H, W, WW, nwords);
-    ccl_init_kernel<true><<<gw, 256, 0, st>>>(ctx->open_bits, ctx->parent2, H, W, WW, nwords);
-    ccl_merge_kernel<true, false, false><<<gw, 256, 0, st>>>(ctx->open_bits, ctx->parent2, H, W, WW, nwords);
-    ccl_merge_kernel<false, true, true><<<gw, 256, 0, st>>>(ctx->open_bits, ctx->parent2, H, W, WW, nwords);
-    ccl_roots_kernel<true><<<gw, 256, 0, st>>>(ctx->open_bits, ctx->parent2, ctx->root_bits, ctx->rowcnt, H, W, WW, nwords);
+    ccl_init_kernel<true, false><<<wg, wb, 0, st>>>(ctx->open_bits, ctx->parent2, nullptr, H, W, WW);
+    ccl_merge_kernel<true, false, false><<<wg, wb, 0, st>>>(ctx->open_bits, ctx->parent2, nullptr, H, W, WW);
+    euler_kernel<<<eg, wb, 0, st>>>(ctx->open_bits, ctx->euler4, H, W, WW);
+    ccl_roots_kernel<<<wg, wb, 0, st>>>(ctx->open_bits, ctx->parent2, ctx->root_bits, ctx->rowcnt, H, W, WW);
     row_scan_kernel<<<batch, 1024, 0, st>>>(ctx->rowcnt, ctx->rowoff, ctx->d_ncont, H);
     rank_roots_kernel<1><<<gr, 256, 0, st>>>(ctx->root_bits, ctx->rowoff, ctx->d_ncont, nullptr, ctx->croot, H, W, WW, M, nrows, ctx->d_status);
-    ctx->launches += 14;
+    holes_kernel<<<(batch + 127) / 128, 128, 0, st>>>(ctx->euler4, ctx->d_ncont, ctx->holes, batch);
+    // background pass: every thread of a hole-free frame returns at once
+    ccl_init_kernel<false, true><<<wg, wb, 0, st>>>(ctx->open_bits, ctx->parent2, ctx->holes, H, W, WW);
+    ccl_merge_kernel<false, true, true><<<wg, wb, 0, st>>>(ctx->open_bits, ctx->parent2, ctx->holes, H, W, WW);
+    ccl_flatten_bg_kernel<<<wg, wb, 0, st>>>(ctx->open_bits, ctx->parent2, ctx->holes, H, W, WW);
+    ctx->launches += 17;
     return cudaGetLastError();
 }

@@ -20,37 +20,76 @@ struct BitImage {                 // foreground test on a bit-packed frame, fals
     }
 };
 
-// cell = {cx, cy, major, minor, angle, valid}
-__global__ void contour_fit_kernel(const uint32_t *__restrict__ open_bits, const int32_t *__restrict__ parent2,
-                                   const int32_t *__restrict__ croot, const int32_t *__restrict__ ncont, double *__restrict__ cell,
-                                   int H, int W, int WW, int M, size_t total, uint32_t *status) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const size_t f = i / M;
-    const int slot = (int)(i % M);
-    double *out = cell + i * 6;
-    out[5] = 0.0;
+constexpr int PCAP = 128;          // stored vertices per contour; longer contours are re-traced instead
+
+// ---- 1. follow every external border once; keep its CHAIN_APPROX_SIMPLE vertices -----------------
+struct StoreVisitor {
+    uint32_t *dst; int n;
+    __device__ __forceinline__ void operator()(int x, int y) {
+        if (n < PCAP) dst[n] = (uint32_t)x | ((uint32_t)y << 16);
+        ++n;
+    }
+};
+
+// cpn[slot] = number of kept vertices (0: not an external contour, <0: trace guard tripped)
+__global__ void contour_trace_kernel(const uint32_t *__restrict__ open_bits, const int32_t *__restrict__ parent2,
+                                     const int32_t *__restrict__ croot, const int32_t *__restrict__ ncont,
+                                     const int32_t *__restrict__ holes, uint32_t *__restrict__ cpts, int32_t *__restrict__ cpn,
+                                     int H, int W, int WW, int M, uint32_t *status) {
+    const int f = blockIdx.y;
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= M) return;
+    const size_t i = (size_t)f * M + slot;
+    cpn[i] = 0;
     if (slot >= min(ncont[f], M)) return;
     const int idx = croot[i];
     const int y0 = idx / W, x0 = idx - y0 * W;
-    const uint32_t *img = open_bits + f * (size_t)H * WW;
-    // external <=> the background left of the start pixel is 4-connected to the outside
-    if (x0 > 0) {
+    const uint32_t *img = open_bits + (size_t)f * H * WW;
+    // external <=> the background left of the start pixel is 4-connected to the outside.  Frames
+    // whose opened image has no hole at all (Euler number == component count) skip the test.
+    if (x0 > 0 && holes[f] != 0) {
         const int xb = x0 - 1, wx = xb >> 5, b = xb & 31;
         const uint32_t bg = ~__ldg(img + (size_t)y0 * WW + wx) & valid_mask(wx, W);
         const uint32_t t = ~bg & ((2u << b) - 1u);
         const int s = t ? 32 - __clz(t) : 0;
-        const int32_t *par = parent2 + f * (size_t)H * W;
+        const int32_t *par = parent2 + (size_t)f * H * W;
         const int bidx = y0 * W + 32 * wx + s;
         int p = par[bidx];
         if (p >= 0 && p != bidx) p = par[p];
         if (p >= 0) return;                       // enclosed by another blob: RETR_EXTERNAL drops it
     }
     BitImage fg{img, H, W, WW};
+    StoreVisitor sv{cpts + i * PCAP, 0};
+    const int n = trace_external_simple(fg, x0, y0, 8LL * H * W + 16, sv);
+    if (n < 0) atomicOr(status, VBS_DEV_TRACE_GUARD);
+    cpn[i] = n;
+}
+
+// ---- 2. ellipse fit per contour (MD:203-220) -------------------------------------------------------
+// cell = {cx, cy, major, minor, angle, valid}
+__global__ void contour_fit_kernel(const uint32_t *__restrict__ open_bits, const int32_t *__restrict__ croot,
+                                   const uint32_t *__restrict__ cpts, const int32_t *__restrict__ cpn, double *__restrict__ cell,
+                                   int H, int W, int WW, int M) {
+    const int f = blockIdx.y;
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= M) return;
+    const size_t i = (size_t)f * M + slot;
+    double *out = cell + i * 6;
+    out[5] = 0.0;
+    const int n = cpn[i];
+    if (n < 5) return;                            // MD:204 (also: not external / guard)
     int npts = 0;
-    const EllipseResult e = fit_ellipse_traced(fg, x0, y0, 8LL * H * W + 16, npts);
-    if (npts < 0) { atomicOr(status, VBS_DEV_TRACE_GUARD); return; }
-    if (npts < 5 || !e.ok) return;                // MD:204
+    EllipseResult e;
+    if (n <= PCAP) {
+        StoredSource src{cpts + i * PCAP, n};
+        e = fit_ellipse_from(src, npts);
+    } else {                                      // long contour: replay by following the border again
+        const int idx = croot[i];
+        const int y0 = idx / W, x0 = idx - y0 * W;
+        BitImage fg{open_bits + (size_t)f * H * WW, H, W, WW};
+        e = fit_ellipse_traced(fg, x0, y0, 8LL * H * W + 16, npts);
+    }
+    if (!e.ok) return;
     double major, minor, ang;
     if (e.w > e.h) { major = e.w; minor = e.h; ang = (double)e.angle; }
     else { major = e.h; minor = e.w; ang = (double)e.angle + 90.0; }     // MD:212-217 (float64 sum)
@@ -58,14 +97,16 @@ __global__ void contour_fit_kernel(const uint32_t *__restrict__ open_bits, const
     out[0] = e.cx; out[1] = e.cy; out[2] = major; out[3] = minor; out[4] = ang; out[5] = 1.0;
 }
 
-// nearest centroid inside the contour polygon and inside the (minor/10)^2 gate (MD:222-237)
+// ---- 3. nearest centroid inside the contour polygon and inside the (minor/10)^2 gate (MD:222-237) --
 __global__ void match_kernel(const uint32_t *__restrict__ open_bits, const int32_t *__restrict__ croot,
+                             const uint32_t *__restrict__ cpts, const int32_t *__restrict__ cpn,
                              const double *__restrict__ cell, const double *__restrict__ centres,
                              const int32_t *__restrict__ nlabels, int32_t *__restrict__ cmatch, int32_t *__restrict__ claim,
-                             int H, int W, int WW, int M, size_t total, uint32_t *status) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const size_t f = i / M;
+                             int H, int W, int WW, int M, uint32_t *status) {
+    const int f = blockIdx.y;
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= M) return;
+    const size_t i = (size_t)f * M + slot;
     cmatch[i] = -1;
     const double *c = cell + i * 6;
     if (c[5] == 0.0) return;
@@ -73,24 +114,30 @@ __global__ void match_kernel(const uint32_t *__restrict__ open_bits, const int32
     const double tenth = c[3] / 10.0;
     const double gate = mul_rn(tenth, tenth);
     const int n = min(nlabels[f], M);
-    const int idx = croot[i];
-    const int y0 = idx / W, x0 = idx - y0 * W;
-    BitImage fg{open_bits + f * (size_t)H * WW, H, W, WW};
+    const int np = cpn[i];
     int best = -1;
     double best_d = INFINITY;
-    const double *cen = centres + f * (size_t)M * 2;
+    const double *cen = centres + (size_t)f * M * 2;
     for (int j = 0; j < n; ++j) {
         const double y = cen[2 * j], x = cen[2 * j + 1];
         const double dx = x - ecx, dy = y - ecy;
         const double d = add_rn(mul_rn(dx, dx), mul_rn(dy, dy));
         if (d < gate && d < best_d) {
             PointPolygon pp; pp.init(x, y);
-            trace_external_simple(fg, x0, y0, 8LL * H * W + 16, pp);
+            if (np <= PCAP) {
+                StoredSource src{cpts + i * PCAP, np};
+                src(pp);
+            } else {
+                const int idx = croot[i];
+                const int y0 = idx / W, x0 = idx - y0 * W;
+                BitImage fg{open_bits + (size_t)f * H * WW, H, W, WW};
+                trace_external_simple(fg, x0, y0, 8LL * H * W + 16, pp);
+            }
             if (pp.result() >= 0) { best = j; best_d = d; }
         }
     }
     cmatch[i] = best;
-    if (best >= 0 && atomicAdd(claim + f * M + best, 1) > 0) atomicOr(status, VBS_DEV_MATCH_CONFLICT);
+    if (best >= 0 && atomicAdd(claim + (size_t)f * M + best, 1) > 0) atomicOr(status, VBS_DEV_MATCH_CONFLICT);
 }
 
 // marker list in contour order (one warp per frame)
@@ -125,15 +172,17 @@ __global__ void compact_kernel(const double *__restrict__ cell, const int32_t *_
 
 cudaError_t vbs_launch_contours(vbs_ctx *ctx, int batch) {
     const size_t total = (size_t)batch * ctx->M;
-    const unsigned g = (unsigned)((total + 127) / 128);
     cudaError_t e = cudaMemsetAsync(ctx->claim, 0, sizeof(int32_t) * total, ctx->stream);
     if (e != cudaSuccess) return e;
-    contour_fit_kernel<<<g, 128, 0, ctx->stream>>>(ctx->open_bits, ctx->parent2, ctx->croot, ctx->d_ncont, ctx->cell, ctx->H, ctx->W,
-                                                   ctx->WW, ctx->M, total, ctx->d_status);
-    match_kernel<<<g, 128, 0, ctx->stream>>>(ctx->open_bits, ctx->croot, ctx->cell, ctx->centres, ctx->d_nlabels, ctx->cmatch, ctx->claim,
-                                             ctx->H, ctx->W, ctx->WW, ctx->M, total, ctx->d_status);
+    const dim3 grid((ctx->M + 63) / 64, batch);
+    contour_trace_kernel<<<grid, 64, 0, ctx->stream>>>(ctx->open_bits, ctx->parent2, ctx->croot, ctx->d_ncont, ctx->holes, ctx->cpts,
+                                                       ctx->cpn, ctx->H, ctx->W, ctx->WW, ctx->M, ctx->d_status);
+    contour_fit_kernel<<<grid, 64, 0, ctx->stream>>>(ctx->open_bits, ctx->croot, ctx->cpts, ctx->cpn, ctx->cell, ctx->H, ctx->W, ctx->WW,
+                                                     ctx->M);
+    match_kernel<<<grid, 64, 0, ctx->stream>>>(ctx->open_bits, ctx->croot, ctx->cpts, ctx->cpn, ctx->cell, ctx->centres, ctx->d_nlabels,
+                                               ctx->cmatch, ctx->claim, ctx->H, ctx->W, ctx->WW, ctx->M, ctx->d_status);
     compact_kernel<<<(batch + 3) / 4, 128, 0, ctx->stream>>>(ctx->cell, ctx->cmatch, ctx->centres, ctx->d_ncont, ctx->d_nmarkers,
                                                              ctx->marker_xy, ctx->marker_axes, ctx->M, batch);
-    ctx->launches += 3;
+    ctx->launches += 4;
     return cudaGetLastError();
 }

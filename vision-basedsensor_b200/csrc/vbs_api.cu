@@ -28,7 +28,7 @@ int map_status(vbs_ctx *ctx, uint32_t st) {
 void free_all(vbs_ctx *c) {
     void *ptrs[] = {c->d_frames, c->area_bits, c->mask_bits, c->max_bits, c->open_bits, c->root_bits, c->area_count, c->thr_lut,
                     c->d_n64, c->d_cn64, c->recheck, c->recheck_n, c->parent, c->parent2, c->rowcnt, c->rowoff, c->d_nlabels,
-                    c->d_ncont, c->lab_cnt, c->lab_sx, c->lab_sy, c->centres, c->croot, c->cell, c->claim, c->cmatch, c->d_nmarkers,
+                    c->d_ncont, c->lab_cnt, c->lab_sx, c->lab_sy, c->centres, c->croot, c->cell, c->claim, c->cmatch, c->cpts, c->cpn, c->euler4, c->holes, c->d_nmarkers,
                     c->marker_xy, c->marker_axes, c->ref_row, c->ref_col, c->ref_xy, c->row_det, c->row_cxy, c->row_axes, c->obs,
                     c->pos3d, c->pos_flags, c->last_seen, c->pl_ref, c->pl_start, c->pl_dvert, c->pl_use, c->plane, c->plane_n,
                     c->d_status};
@@ -171,6 +171,8 @@ int vbs_create(vbs_ctx **out, const vbs_config *cfg) {
     VBS_CUDA(dalloc(&ctx->centres, B * M * 2));
     VBS_CUDA(dalloc(&ctx->croot, B * M)); VBS_CUDA(dalloc(&ctx->cell, B * M * 6)); VBS_CUDA(dalloc(&ctx->claim, B * M));
     VBS_CUDA(dalloc(&ctx->cmatch, B * M));
+    VBS_CUDA(dalloc(&ctx->cpts, B * M * 128)); VBS_CUDA(dalloc(&ctx->cpn, B * M));
+    VBS_CUDA(dalloc(&ctx->euler4, B)); VBS_CUDA(dalloc(&ctx->holes, B));
     VBS_CUDA(dalloc(&ctx->d_nmarkers, B)); VBS_CUDA(dalloc(&ctx->marker_xy, B * M * 2)); VBS_CUDA(dalloc(&ctx->marker_axes, B * M * 3));
     VBS_CUDA(dalloc(&ctx->ref_row, R)); VBS_CUDA(dalloc(&ctx->ref_col, R)); VBS_CUDA(dalloc(&ctx->ref_xy, R * 2));
     VBS_CUDA(dalloc(&ctx->row_det, B * R)); VBS_CUDA(dalloc(&ctx->row_cxy, B * R * 2)); VBS_CUDA(dalloc(&ctx->row_axes, B * R * 3));

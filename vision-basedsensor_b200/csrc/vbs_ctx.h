@@ -55,6 +55,8 @@ struct vbs_ctx {
     double *cell;                    // [B][M][6] cx, cy, major, minor, angle, valid
     int32_t *claim;                  // [B][M] how many contours matched each centroid
     int32_t *cmatch;                 // [B][M] matched label index or -1
+    uint32_t *cpts; int32_t *cpn;    // [B][M][128] stored contour vertices (x | y<<16), [B][M] vertex counts
+    int32_t *euler4, *holes;         // [B] 4 x Euler number of the opened image; holes = blobs - Euler number
     // outputs kept on device
     int32_t *d_nmarkers;             // [B]
     double *marker_xy;               // [B][M][2]

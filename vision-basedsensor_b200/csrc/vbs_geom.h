@@ -49,19 +49,24 @@ VBS_HD float fsub_rn(float a, float b) { return fadd_rn(a, -b); }
 // vertices, or -1 if the step guard tripped (never on a consistent bit image).
 template <class Bits, class Visitor>
 VBS_HD int trace_external_simple(const Bits &fg, int x0, int y0, long long max_steps, Visitor &visit) {
-    const int DX[8] = {1, 1, 0, -1, -1, -1, 0, 1};
-    const int DY[8] = {0, -1, -1, -1, 0, 1, 1, 1};
+    // chain codes 0..7 = E,NE,N,NW,W,SW,S,SE; (dx+1, dy+1) packed 2 bits per code so the lookup is
+    // two shifts instead of an indexed local array
+    //   dx+1 = {2,2,1,0,0,0,1,2}   dy+1 = {1,0,0,0,1,2,2,2}
+    const unsigned PX = 2u | (2u << 2) | (1u << 4) | (0u << 6) | (0u << 8) | (0u << 10) | (1u << 12) | (2u << 14);
+    const unsigned PY = 1u | (0u << 2) | (0u << 4) | (0u << 6) | (1u << 8) | (2u << 10) | (2u << 12) | (2u << 14);
+#define VBS_DX(s_) ((int)((PX >> (2 * (s_))) & 3u) - 1)
+#define VBS_DY(s_) ((int)((PY >> (2 * (s_))) & 3u) - 1)
     int s = 4;
     const int s_first_end = 4;
     bool found = false;
     // clockwise search for the "previous" border pixel
     for (int it = 0; it < 8; ++it) {
         s = (s - 1) & 7;
-        if (fg(x0 + DX[s], y0 + DY[s])) { found = true; break; }
+        if (fg(x0 + VBS_DX(s), y0 + VBS_DY(s))) { found = true; break; }
         if (s == s_first_end) break;
     }
     if (!found) { visit(x0, y0); return 1; }          // isolated pixel
-    const int x1 = x0 + DX[s], y1 = y0 + DY[s];
+    const int x1 = x0 + VBS_DX(s), y1 = y0 + VBS_DY(s);
     int x3 = x0, y3 = y0;
     int prev_step = -1;
     int kept = 0;
@@ -69,7 +74,7 @@ VBS_HD int trace_external_simple(const Bits &fg, int x0, int y0, long long max_s
         int x4 = x3, y4 = y3;
         for (int it = 0; it < 8; ++it) {              // counter-clockwise search for the next pixel
             s = (s + 1) & 7;
-            x4 = x3 + DX[s]; y4 = y3 + DY[s];
+            x4 = x3 + VBS_DX(s); y4 = y3 + VBS_DY(s);
             if (fg(x4, y4)) break;
         }
         // (x3,y3) is a border point leaving with step s; the start point is always kept
@@ -80,6 +85,8 @@ VBS_HD int trace_external_simple(const Bits &fg, int x0, int y0, long long max_s
         s = (s + 4) & 7;
     }
     return -1;
+#undef VBS_DX
+#undef VBS_DY
 }
 
 // ---- streaming least squares by Givens rotations ---------------------------------------------
@@ -101,20 +108,22 @@ struct GivensLsq {
             const double aj = a[j];
             if (aj != 0.0) {
                 const double rjj = R[j][j];
-                const double h = hypot(rjj, aj);
-                const double c = rjj / h, sn = aj / h;
+                // explicit fma everywhere: host (-ffp-contract=off) and device round identically
+                const double h = sqrt(fma(aj, aj, rjj * rjj));
+                const double inv = 1.0 / h;
+                const double c = rjj * inv, sn = aj * inv;
                 R[j][j] = h;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
                 for (int k = j + 1; k < N; ++k) {
                     const double t = R[j][k];
-                    R[j][k] = c * t + sn * a[k];
-                    a[k] = c * a[k] - sn * t;
+                    R[j][k] = fma(c, t, sn * a[k]);
+                    a[k] = fma(c, a[k], -(sn * t));
                 }
                 const double t = d[j];
-                d[j] = c * t + sn * beta;
-                beta = c * beta - sn * t;
+                d[j] = fma(c, t, sn * beta);
+                beta = fma(c, beta, -(sn * t));
             }
         }
     }
@@ -122,7 +131,7 @@ struct GivensLsq {
     VBS_HD bool solve(double x[N]) const {
         for (int i = N - 1; i >= 0; --i) {
             double acc = d[i];
-            for (int k = i + 1; k < N; ++k) acc -= R[i][k] * x[k];
+            for (int k = i + 1; k < N; ++k) acc = fma(-R[i][k], x[k], acc);
             if (R[i][i] == 0.0) return false;
             x[i] = acc / R[i][i];
         }
@@ -217,29 +226,49 @@ VBS_HD bool ellipse_centre_solve(const double g[5], double &r0, double &r1) {
     return true;
 }
 
-// Whole fit for a blob given its start pixel (four traces).  n_out = kept vertices.
-template <class Bits>
-VBS_HD EllipseResult fit_ellipse_traced(const Bits &fg, int x0, int y0, long long max_steps, int &n_out) {
+// Whole fit.  `Source` replays the kept vertices of one contour in order:
+//   template <class V> int operator()(V &visitor) const   -> number of vertices (or -1)
+// (re-tracing the border, or reading back a stored vertex list).  n_out = kept vertices.
+template <class Source>
+VBS_HD EllipseResult fit_ellipse_from(const Source &src, int &n_out) {
     EllipseResult bad; bad.cx = bad.cy = bad.w = bad.h = bad.angle = 0.f; bad.ok = 0;
     EllipsePassCentroid p1; p1.reset();
-    n_out = trace_external_simple(fg, x0, y0, max_steps, p1);
+    n_out = src(p1);
     if (n_out < 5) return bad;                       // MD:204 len(contour) < 5 (and the guard case)
     const float cx = p1.sx / (float)p1.n, cy = p1.sy / (float)p1.n;
     EllipsePassScale p2; p2.cx = cx; p2.cy = cy; p2.s = 0.0;
-    trace_external_simple(fg, x0, y0, max_steps, p2);
+    src(p2);
     const double FLT_EPS = 1.1920928955078125e-07;
     const double scale = 100.0 / (p2.s > FLT_EPS ? p2.s : FLT_EPS);
     EllipsePassConic p3; p3.cx = cx; p3.cy = cy; p3.scale = scale; p3.q.reset();
-    trace_external_simple(fg, x0, y0, max_steps, p3);
+    src(p3);
     double g[5];
     if (!p3.q.solve(g)) return bad;
     double r0, r1;
     if (!ellipse_centre_solve(g, r0, r1)) return bad;
     EllipsePassAxes p4; p4.cx = cx; p4.cy = cy; p4.scale = scale; p4.r0 = r0; p4.r1 = r1; p4.q.reset();
-    trace_external_simple(fg, x0, y0, max_steps, p4);
+    src(p4);
     double h[3];
     if (!p4.q.solve(h)) return bad;
     return ellipse_from_fit(h, r0, r1, scale, cx, cy);
+}
+
+template <class Bits> struct TraceSource {            // replay by following the border again
+    const Bits &fg; int x0, y0; long long max_steps;
+    template <class V> VBS_HD int operator()(V &v) const { return trace_external_simple(fg, x0, y0, max_steps, v); }
+};
+struct StoredSource {                                 // replay a stored vertex list (x | y << 16)
+    const uint32_t *pts; int n;
+    template <class V> VBS_HD int operator()(V &v) const {
+        for (int i = 0; i < n; ++i) { const uint32_t p = pts[i]; v((int)(p & 0xffffu), (int)(p >> 16)); }
+        return n;
+    }
+};
+
+template <class Bits>
+VBS_HD EllipseResult fit_ellipse_traced(const Bits &fg, int x0, int y0, long long max_steps, int &n_out) {
+    TraceSource<Bits> src{fg, x0, y0, max_steps};
+    return fit_ellipse_from(src, n_out);
 }
 
 // ---- cv2.pointPolygonTest(contour, (x, y), False) (MD:228) as an edge visitor ----------------

@@ -212,11 +212,20 @@ class MarkerPipeline:
             if frames.dtype != torch.uint8 or not frames.is_cuda:
                 raise ValueError("frames must be a CUDA uint8 tensor (or a host numpy array)")
             fr = frames.contiguous()
+            self._follow_torch_stream()
             arrays, o = out if out is not None else self._alloc(batch, True)
             self._keep = fr
             capi.check(self._ctx, capi.lib.vbs_process_device(self._ctx, fr.data_ptr(), batch, rowb * self.H, rowb, int(frameno0),
                                                               C.byref(o)))
         return BatchResult(frameno0=int(frameno0), **arrays)
+
+    def _follow_torch_stream(self):
+        """Launch on torch's current stream so later torch ops on the results are stream-ordered."""
+        import torch
+        ptr = torch.cuda.current_stream(self.device).cuda_stream
+        if getattr(self, "_stream_ptr", None) != ptr:
+            self.use_stream(ptr)
+            self._stream_ptr = ptr
 
     def alloc_outputs(self, batch: int, on_device: bool):
         """Pre-allocate an output block to reuse across calls (pass as ``out=``)."""
@@ -233,6 +242,7 @@ class MarkerPipeline:
         import torch
         batch = self._geometry(frames)
         fr = frames.contiguous()
+        self._follow_torch_stream()
         rowb = self.W * self.C
         capi.check(self._ctx, capi.lib.vbs_find_markers(self._ctx, fr.data_ptr(), batch, rowb * self.H, rowb))
         return self.debug_stage(capi.STAGE_MASK, batch), self.debug_stage(capi.STAGE_AREA_MASK, batch)
@@ -243,7 +253,7 @@ class MarkerPipeline:
         batch = mask.shape[0]
         m = (mask != 0).to(torch.uint8).contiguous()
         a = (area_mask != 0).to(torch.uint8).contiguous()
-        saveR = self.R
+        self._follow_torch_stream()
         arrays, o = self._alloc(batch, True)
         capi.check(self._ctx, capi.lib.vbs_marker_center(self._ctx, m.data_ptr(), a.data_ptr(), batch, C.byref(o)))
         keep = {k: arrays[k] for k in ("n_labels", "centres", "n_markers", "marker_xy", "marker_axes")}
