@@ -139,6 +139,24 @@ int vbs_find_markers(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int64_t
 int vbs_marker_center(vbs_ctx *ctx, const uint8_t *mask, const uint8_t *area_mask, int32_t batch,
                       const vbs_outputs *out);
 
+/* table-level entry points: host arrays in and out, synchronous.  They run the same kernels as
+ * vbs_process_* on rows / points supplied by the caller, for the per-call mirrors of the reference:
+ * vbs_track_markers    : MarkerTracker._track_markers (MD:349-396) on one marker list
+ *                        xy [n][2], axes [n][3] -> row_det [R], row_cxy [R][2], row_axes [R][3]
+ * vbs_reconstruct_rows : MarkerAnalysis._track_markers (R3:240-316) + plane fit on tracking rows
+ *                        row_det [B][R] (>= 0: row present), row_cxy [B][R][2], row_axes [B][R][3]
+ * vbs_undistort_points : MarkerAnalysis._undistort_points (R3:185-193), uv [n][2]
+ * vbs_position_3d      : MarkerAnalysis._calculate_3d_position (R3:195-238), uvd [n][3] = u, v, diameter;
+ *                        ok[i] = 0 where the reference raises
+ * vbs_fit_plane        : fit_plane_least_squares (FD:141-159) -> a, b, c, tilt_deg                   */
+int vbs_track_markers(vbs_ctx *ctx, int32_t n, const double *marker_xy, const double *marker_axes, int32_t *row_det,
+                      double *row_cxy, double *row_axes);
+int vbs_reconstruct_rows(vbs_ctx *ctx, int32_t batch, int64_t frameno0, const int32_t *row_det, const double *row_cxy,
+                         const double *row_axes, double *pos3d, uint8_t *pos_flags, double *plane, int32_t *plane_n);
+int vbs_undistort_points(vbs_ctx *ctx, int32_t n, const double *uv, double *out);
+int vbs_position_3d(vbs_ctx *ctx, int32_t n, const double *uvd, double *P, uint8_t *ok);
+int vbs_fit_plane(vbs_ctx *ctx, int32_t n, const double *X, const double *Y, const double *Z, double out[4]);
+
 /* copy one stage image of the most recent batch into dst (device memory, `bytes` capacity) */
 int vbs_debug_stage(vbs_ctx *ctx, int32_t stage, void *dst_device, size_t bytes);
 

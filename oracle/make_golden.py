@@ -169,5 +169,43 @@ def main():
     run_case("ring65_crop", crops, 0, cam_for(bottom - top, right - left), layout="list")
 
 
+def video_case():
+    """Config-1 substitute (the demo mp4 is absent from the checkout): a lossless FFV1 ring video run
+    through the UNMODIFIED ``MarkerTracker(config).process()`` (MD:429-462); the CSV it writes is the golden."""
+    import cv2
+    import tempfile
+    import pandas as pd
+    md = refload.marker_detection()
+    full_h, full_w = 480, 640
+    centres = synth.ring_layout(full_h, full_w, px_per_mm=11.0, dy=15.0)
+    seq = synth.compression_sequence(full_h, full_w, centres, 6.0, 5, tilt=0.5, depth=1.0, seed0=40, noise_sigma=1.0)
+    os.makedirs(OUT, exist_ok=True)
+    vpath = os.path.join(OUT, "ring_video.avi")
+    wr = cv2.VideoWriter(vpath, cv2.VideoWriter_fourcc(*"FFV1"), 12.0, (full_w, full_h))
+    for f in seq:
+        wr.write(np.repeat(f[..., None], 3, axis=2))
+    wr.release()
+    cap = cv2.VideoCapture(vpath)
+    for f in seq:                                   # lossless round trip or the golden is meaningless
+        ok, fr = cap.read()
+        assert ok and np.array_equal(fr[..., 0], f) and np.array_equal(fr[..., 1], f)
+    cap.release()
+    tmp = tempfile.mkdtemp(prefix="vbs_vid_")
+    cfg = {"video_path": vpath, "output_dir": tmp, "crop_ratios": (1 / 8, 1 / 8, 1 / 16, 0), "num_layers": 5, "min_marker_distance": 20}
+    orig = md.cv2.destroyAllWindows
+    md.cv2.destroyAllWindows = lambda: None         # raises on headless OpenCV, after the CSV is saved (MD:474)
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            md.MarkerTracker(cfg).process()
+    finally:
+        md.cv2.destroyAllWindows = orig
+    df = pd.read_csv(os.path.join(tmp, "ring_video_markers.csv"))
+    df.to_csv(os.path.join(OUT, "ring_video_markers.csv"), index=False)
+    print(f"ring_video: {len(seq)} frames, {len(df)} CSV rows, keys {sorted(set(zip(df.row, df.col)))}, "
+          f"video {os.path.getsize(vpath) / 1e3:.0f} kB")
+
+
 if __name__ == "__main__":
     main()
+    video_case()

@@ -46,6 +46,11 @@ SYMBOLS = {
     "vbs_process_host": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.POINTER(VbsOutputs)]),
     "vbs_find_markers": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int64]),
     "vbs_marker_center": (C.c_int, [_P, _P, _P, C.c_int32, C.POINTER(VbsOutputs)]),
+    "vbs_track_markers": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P]),
+    "vbs_reconstruct_rows": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P, _P, _P, _P, _P, _P]),
+    "vbs_undistort_points": (C.c_int, [_P, C.c_int32, _P, _P]),
+    "vbs_position_3d": (C.c_int, [_P, C.c_int32, _P, _P, _P]),
+    "vbs_fit_plane": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P]),
     "vbs_debug_stage": (C.c_int, [_P, C.c_int32, _P, C.c_size_t]),
     "vbs_kernel_launches": (C.c_int64, [_P]),
     "vbs_set_profiling": (C.c_int, [_P, C.c_int32]),

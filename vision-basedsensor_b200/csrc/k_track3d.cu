@@ -144,7 +144,59 @@ __global__ void plane_kernel(const double *__restrict__ pos3d, const uint8_t *__
     }
 }
 
+__global__ void undistort_kernel(CameraF64 cam, const double *__restrict__ uv, double *__restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    undistort5(cam, uv[2 * i], uv[2 * i + 1], out[2 * i], out[2 * i + 1]);
+}
+__global__ void position_kernel(CameraF64 cam, const double *__restrict__ uvd, double *__restrict__ P, uint8_t *__restrict__ ok, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double p[3];
+    const bool good = position3d(cam, uvd[3 * i], uvd[3 * i + 1], uvd[3 * i + 2], p);
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    P[3 * i] = good ? p[0] : nan; P[3 * i + 1] = good ? p[1] : nan; P[3 * i + 2] = good ? p[2] : nan;
+    ok[i] = good ? 1 : 0;
+}
+// plain plane fit of n points (one warp)
+__global__ void plane_points_kernel(const double *__restrict__ X, const double *__restrict__ Y, const double *__restrict__ Z, int n,
+                                    double *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    double sx = 0, sy = 0, sz = 0;
+    for (int i = lane; i < n; i += 32) { sx += X[i]; sy += Y[i]; sz += Z[i]; }
+    sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
+    const double mx = sx / n, my = sy / n, mz = sz / n;
+    double sxx = 0, sxy = 0, syy = 0, sxz = 0, syz = 0;
+    for (int i = lane; i < n; i += 32) {
+        const double x = X[i] - mx, y = Y[i] - my, z = Z[i] - mz;
+        sxx += x * x; sxy += x * y; syy += y * y; sxz += x * z; syz += y * z;
+    }
+    sxx = warp_sum(sxx); sxy = warp_sum(sxy); syy = warp_sum(syy); sxz = warp_sum(sxz); syz = warp_sum(syz);
+    if (lane == 0) {
+        double r[4];
+        const double nan = __longlong_as_double(0x7ff8000000000000LL);
+        if (!plane_solve((double)n, mx, my, mz, sxx, sxy, syy, sxz, syz, r)) r[0] = r[1] = r[2] = r[3] = nan;
+        out[0] = r[0]; out[1] = r[1]; out[2] = r[2]; out[3] = r[3];
+    }
+}
+
 }  // namespace
+
+cudaError_t vbs_launch_undistort(vbs_ctx *ctx, const double *uv, double *out, int n) {
+    undistort_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->cam, uv, out, n);
+    ctx->launches += 1;
+    return cudaGetLastError();
+}
+cudaError_t vbs_launch_position(vbs_ctx *ctx, const double *uvd, double *P, uint8_t *ok, int n) {
+    position_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->cam, uvd, P, ok, n);
+    ctx->launches += 1;
+    return cudaGetLastError();
+}
+cudaError_t vbs_launch_plane_points(vbs_ctx *ctx, const double *X, const double *Y, const double *Z, int n, double *out) {
+    plane_points_kernel<<<1, 32, 0, ctx->stream>>>(X, Y, Z, n, out);
+    ctx->launches += 1;
+    return cudaGetLastError();
+}
 
 cudaError_t vbs_launch_track(vbs_ctx *ctx, int batch, int64_t frameno0) {
     const int R = ctx->R;
@@ -154,6 +206,15 @@ cudaError_t vbs_launch_track(vbs_ctx *ctx, int batch, int64_t frameno0) {
     track_kernel<<<g, 128, 0, ctx->stream>>>(ctx->ref_xy, ctx->marker_xy, ctx->marker_axes, ctx->d_nmarkers, ctx->row_det, ctx->row_cxy,
                                              ctx->row_axes, R, ctx->M, ctx->min_dist, total);
     ctx->launches += 1;
+    return vbs_launch_reconstruct(ctx, batch, frameno0);
+}
+
+// R3:240-316 + FD:138-162 on the tracking rows currently in ctx->row_* (batch x R)
+cudaError_t vbs_launch_reconstruct(vbs_ctx *ctx, int batch, int64_t frameno0) {
+    const int R = ctx->R;
+    if (R <= 0) return cudaSuccess;
+    const size_t total = (size_t)batch * R;
+    const unsigned g = (unsigned)((total + 127) / 128);
     if (ctx->have_cam) {
         if (!ctx->have_first) { ctx->first_frame = frameno0; ctx->have_first = 1; }
         const int64_t first_kept = ctx->first_frame + (ctx->warmup > 0 ? ctx->warmup : 0);

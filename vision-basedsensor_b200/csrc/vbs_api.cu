@@ -371,6 +371,94 @@ int vbs_debug_stage(vbs_ctx *ctx, int32_t stage, void *dst_device, size_t bytes)
     return VBS_OK;
 }
 
+// ---- table-level entry points (host arrays in / out; synchronous) --------------------------------
+namespace {
+struct Scratch {                       // small device staging buffer, freed on scope exit
+    void *p = nullptr;
+    ~Scratch() { if (p) cudaFree(p); }
+};
+}
+
+int vbs_track_markers(vbs_ctx *ctx, int32_t n, const double *marker_xy, const double *marker_axes, int32_t *row_det, double *row_cxy,
+                      double *row_axes) {
+    if (!ctx || n < 0 || (n > 0 && (!marker_xy || !marker_axes))) return VBS_ERR_BAD_ARG;
+    if (n > ctx->M) return fail(ctx, VBS_ERR_CAPACITY, "marker list exceeds max_markers");
+    if (ctx->R <= 0) return fail(ctx, VBS_ERR_STATE, "no reference array set");
+    VBS_CUDA(cudaMemcpyAsync(ctx->marker_xy, marker_xy, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
+    VBS_CUDA(cudaMemcpyAsync(ctx->marker_axes, marker_axes, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
+    VBS_CUDA(cudaMemcpyAsync(ctx->d_nmarkers, &n, sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    const int save_cam = ctx->have_cam;
+    ctx->have_cam = 0;                                  // tracking only: leave the 3D sequence state alone
+    cudaError_t e = vbs_launch_track(ctx, 1, 0);
+    ctx->have_cam = save_cam;
+    VBS_CUDA(e);
+    const size_t R = ctx->R;
+    if (row_det) VBS_CUDA(cudaMemcpyAsync(row_det, ctx->row_det, sizeof(int32_t) * R, cudaMemcpyDeviceToHost, ctx->stream));
+    if (row_cxy) VBS_CUDA(cudaMemcpyAsync(row_cxy, ctx->row_cxy, sizeof(double) * 2 * R, cudaMemcpyDeviceToHost, ctx->stream));
+    if (row_axes) VBS_CUDA(cudaMemcpyAsync(row_axes, ctx->row_axes, sizeof(double) * 3 * R, cudaMemcpyDeviceToHost, ctx->stream));
+    return vbs_sync(ctx);
+}
+
+int vbs_reconstruct_rows(vbs_ctx *ctx, int32_t batch, int64_t frameno0, const int32_t *row_det, const double *row_cxy,
+                         const double *row_axes, double *pos3d, uint8_t *pos_flags, double *plane, int32_t *plane_n) {
+    if (!ctx || !row_det || !row_cxy || !row_axes) return VBS_ERR_BAD_ARG;
+    if (batch < 1 || batch > ctx->B) return fail(ctx, VBS_ERR_BAD_ARG, "batch must be in [1, max_batch]");
+    if (ctx->R <= 0 || !ctx->have_cam) return fail(ctx, VBS_ERR_STATE, "reference array and camera must be set first");
+    const size_t n = (size_t)batch * ctx->R;
+    VBS_CUDA(cudaMemcpyAsync(ctx->row_det, row_det, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+    VBS_CUDA(cudaMemcpyAsync(ctx->row_cxy, row_cxy, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
+    VBS_CUDA(cudaMemcpyAsync(ctx->row_axes, row_axes, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
+    VBS_CUDA(vbs_launch_reconstruct(ctx, batch, frameno0));
+    if (pos3d) VBS_CUDA(cudaMemcpyAsync(pos3d, ctx->pos3d, sizeof(double) * 7 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (pos_flags) VBS_CUDA(cudaMemcpyAsync(pos_flags, ctx->pos_flags, n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->have_plane) {
+        if (plane) VBS_CUDA(cudaMemcpyAsync(plane, ctx->plane, sizeof(double) * 4 * batch, cudaMemcpyDeviceToHost, ctx->stream));
+        if (plane_n) VBS_CUDA(cudaMemcpyAsync(plane_n, ctx->plane_n, sizeof(int32_t) * batch, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    return vbs_sync(ctx);
+}
+
+int vbs_undistort_points(vbs_ctx *ctx, int32_t n, const double *uv, double *out) {
+    if (!ctx || n < 0 || (n > 0 && (!uv || !out))) return VBS_ERR_BAD_ARG;
+    if (!ctx->have_cam) return fail(ctx, VBS_ERR_STATE, "camera not set");
+    if (n == 0) return VBS_OK;
+    Scratch s;
+    VBS_CUDA(cudaMalloc(&s.p, sizeof(double) * 4 * n));
+    double *d_in = (double *)s.p, *d_out = d_in + 2 * (size_t)n;
+    VBS_CUDA(cudaMemcpyAsync(d_in, uv, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
+    VBS_CUDA(vbs_launch_undistort(ctx, d_in, d_out, n));
+    VBS_CUDA(cudaMemcpyAsync(out, d_out, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    return vbs_sync(ctx);
+}
+
+int vbs_position_3d(vbs_ctx *ctx, int32_t n, const double *uvd, double *P, uint8_t *ok) {
+    if (!ctx || n < 0 || (n > 0 && (!uvd || !P || !ok))) return VBS_ERR_BAD_ARG;
+    if (!ctx->have_cam) return fail(ctx, VBS_ERR_STATE, "camera not set");
+    if (n == 0) return VBS_OK;
+    Scratch s;
+    VBS_CUDA(cudaMalloc(&s.p, sizeof(double) * 6 * n + n));
+    double *d_in = (double *)s.p, *d_P = d_in + 3 * (size_t)n;
+    uint8_t *d_ok = (uint8_t *)(d_P + 3 * (size_t)n);
+    VBS_CUDA(cudaMemcpyAsync(d_in, uvd, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
+    VBS_CUDA(vbs_launch_position(ctx, d_in, d_P, d_ok, n));
+    VBS_CUDA(cudaMemcpyAsync(P, d_P, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    VBS_CUDA(cudaMemcpyAsync(ok, d_ok, n, cudaMemcpyDeviceToHost, ctx->stream));
+    return vbs_sync(ctx);
+}
+
+int vbs_fit_plane(vbs_ctx *ctx, int32_t n, const double *X, const double *Y, const double *Z, double out[4]) {
+    if (!ctx || n < 1 || !X || !Y || !Z || !out) return VBS_ERR_BAD_ARG;
+    Scratch s;
+    VBS_CUDA(cudaMalloc(&s.p, sizeof(double) * (3 * (size_t)n + 4)));
+    double *dX = (double *)s.p, *dY = dX + n, *dZ = dY + n, *dO = dZ + n;
+    VBS_CUDA(cudaMemcpyAsync(dX, X, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    VBS_CUDA(cudaMemcpyAsync(dY, Y, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    VBS_CUDA(cudaMemcpyAsync(dZ, Z, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    VBS_CUDA(vbs_launch_plane_points(ctx, dX, dY, dZ, n, dO));
+    VBS_CUDA(cudaMemcpyAsync(out, dO, sizeof(double) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    return vbs_sync(ctx);
+}
+
 int64_t vbs_kernel_launches(const vbs_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 int vbs_set_profiling(vbs_ctx *ctx, int32_t enable) {

@@ -101,6 +101,10 @@ cudaError_t vbs_launch_morph(vbs_ctx *ctx, int batch);
 cudaError_t vbs_launch_components(vbs_ctx *ctx, int batch);
 cudaError_t vbs_launch_contours(vbs_ctx *ctx, int batch);
 cudaError_t vbs_launch_track(vbs_ctx *ctx, int batch, int64_t frameno0);
+cudaError_t vbs_launch_reconstruct(vbs_ctx *ctx, int batch, int64_t frameno0);
+cudaError_t vbs_launch_undistort(vbs_ctx *ctx, const double *uv, double *out, int n);
+cudaError_t vbs_launch_position(vbs_ctx *ctx, const double *uvd, double *P, uint8_t *ok, int n);
+cudaError_t vbs_launch_plane_points(vbs_ctx *ctx, const double *X, const double *Y, const double *Z, int n, double *out);
 cudaError_t vbs_launch_pack_masks(vbs_ctx *ctx, const uint8_t *mask, const uint8_t *area, int batch);
 cudaError_t vbs_launch_unpack(vbs_ctx *ctx, int stage, void *dst, int batch);
 int vbs_check_taps(std::string &err);       // baked integer taps == host recipe

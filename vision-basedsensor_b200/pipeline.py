@@ -259,6 +259,48 @@ class MarkerPipeline:
         keep = {k: arrays[k] for k in ("n_labels", "centres", "n_markers", "marker_xy", "marker_axes")}
         return BatchResult(frameno0=0, **keep)
 
+    # -- table-level calls (host arrays, synchronous) -------------------------------------------
+    def track_markers(self, markers: list):
+        """One marker list -> (row_det [R], row_cxy [R,2], row_axes [R,3]) like MD:349-396."""
+        n = len(markers)
+        xy = np.ascontiguousarray([m["center"] for m in markers], dtype=np.float64).reshape(n, 2)
+        ax = np.ascontiguousarray([[m["major_axis"], m["minor_axis"], m["angle"]] for m in markers], dtype=np.float64).reshape(n, 3)
+        det = np.empty(self.R, np.int32); cxy = np.empty((self.R, 2)); axes = np.empty((self.R, 3))
+        capi.check(self._ctx, capi.lib.vbs_track_markers(self._ctx, n, xy.ctypes.data, ax.ctypes.data, det.ctypes.data,
+                                                         cxy.ctypes.data, axes.ctypes.data))
+        return det, cxy, axes
+
+    def reconstruct_rows(self, row_det, row_cxy, row_axes, frameno0: int = 0):
+        """Dense tracking rows [B,R] -> (pos3d [B,R,7], flags [B,R], plane [B,4] | None), R3:240-316."""
+        det = np.ascontiguousarray(row_det, dtype=np.int32)
+        B = det.shape[0]
+        cxy = np.ascontiguousarray(row_cxy, dtype=np.float64); axes = np.ascontiguousarray(row_axes, dtype=np.float64)
+        pos = np.empty((B, self.R, 7)); fl = np.empty((B, self.R), np.uint8)
+        plane = np.empty((B, 4)) if self.have_plane else None
+        pn = np.empty(B, np.int32) if self.have_plane else None
+        capi.check(self._ctx, capi.lib.vbs_reconstruct_rows(self._ctx, B, int(frameno0), det.ctypes.data, cxy.ctypes.data, axes.ctypes.data,
+                                                            pos.ctypes.data, fl.ctypes.data, plane.ctypes.data if plane is not None else None,
+                                                            pn.ctypes.data if pn is not None else None))
+        return pos, fl, plane
+
+    def undistort_points(self, pts):
+        pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 2)
+        out = np.empty_like(pts)
+        capi.check(self._ctx, capi.lib.vbs_undistort_points(self._ctx, len(pts), pts.ctypes.data, out.ctypes.data))
+        return out
+
+    def position_3d(self, uvd):
+        uvd = np.ascontiguousarray(uvd, dtype=np.float64).reshape(-1, 3)
+        P = np.empty_like(uvd); ok = np.empty(len(uvd), np.uint8)
+        capi.check(self._ctx, capi.lib.vbs_position_3d(self._ctx, len(uvd), uvd.ctypes.data, P.ctypes.data, ok.ctypes.data))
+        return P, ok.astype(bool)
+
+    def fit_plane(self, X, Y, Z):
+        X = np.ascontiguousarray(X, dtype=np.float64); Y = np.ascontiguousarray(Y, dtype=np.float64); Z = np.ascontiguousarray(Z, dtype=np.float64)
+        out = np.empty(4)
+        capi.check(self._ctx, capi.lib.vbs_fit_plane(self._ctx, len(X), X.ctypes.data, Y.ctypes.data, Z.ctypes.data, out.ctypes.data))
+        return tuple(out)
+
     def debug_stage(self, stage: int, batch: int):
         import torch
         dev = torch.device("cuda", self.device)
