@@ -243,13 +243,12 @@ def main():
     R = pipe.R
     rec_bytes = B * (R * (7 * 8 + 1 + 4 + 2 * 8 + 3 * 8) + 4 * 8 + 4 + 4)
 
+    from vbs_b200 import sharding
+
     def gather(res):
         """NCCL gather of the per-frame records (3D field, flags, IDs, plane) to rank 0."""
-        if world == 1:
-            return
-        for t in (res.pos3d, res.pos_flags, res.row_det, res.plane):
-            lst = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
-            dist.gather(t, lst, dst=0)
+        if world > 1:
+            sharding.gather_records({"pos3d": res.pos3d, "pos_flags": res.pos_flags, "row_det": res.row_det, "plane": res.plane}, rank, world)
 
     def step(s):
         pipe.reset_sequence() if s == 0 else None

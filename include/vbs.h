@@ -111,6 +111,12 @@ int vbs_reset_sequence(vbs_ctx *ctx);
 /* last-seen table exchange for frame-sharded multi-GPU runs: [R][4] = u, v, diameter, frame (-1 = never) */
 int vbs_get_last_seen(vbs_ctx *ctx, double *host_table);
 int vbs_set_last_seen(vbs_ctx *ctx, const double *host_table);
+/* frame-sharded runs: a shard is processed with an empty last-seen table; once the table arriving
+ * from the preceding shards is known, this emits the one displacement row per reference entry that
+ * was missing (its first observation in the shard).  pos3d [N][R][7] / pos_flags [N][R] are the
+ * shard's device-resident outputs, incoming [R][4] is a host table as vbs_get_last_seen returns it. */
+int vbs_fix_displacement(vbs_ctx *ctx, double *pos3d_device, uint8_t *pos_flags_device, int64_t nframes,
+                         const double *incoming_host);
 /* frame-sharded runs: the warm-up window (R3:255-256) counts from the GLOBAL first frame number */
 int vbs_set_first_frame(vbs_ctx *ctx, int64_t first_frame);
 

@@ -43,8 +43,10 @@ def test_process_reproduces_reference_csv(tmp_path):
     tr = marker_detection.MarkerTracker(cfg)
     with contextlib.redirect_stdout(io.StringIO()):
         tr.process()
-    got = pd.read_csv(tr.output_csv)
-    want = pd.read_csv(os.path.join(GOLDEN, "ring_video_markers.csv"))
+    # pandas' default float parser is not correctly rounded (1-ulp errors): ask for the exact one
+    got = pd.read_csv(tr.output_csv, float_precision="round_trip")
+    want = pd.read_csv(os.path.join(GOLDEN, "ring_video_markers.csv"), float_precision="round_trip")
+    assert open(tr.output_csv).read().split("\n")[0] == open(os.path.join(GOLDEN, "ring_video_markers.csv")).read().split("\n")[0]
     assert list(got.columns) == list(want.columns) == ["frameno", "row", "col", "Ox", "Oy", "Cx", "Cy", "major_axis", "minor_axis", "angle"]
     assert len(got) == len(want)
     for c in ("frameno", "row", "col", "Ox", "Oy", "Cx", "Cy"):
@@ -81,7 +83,10 @@ def test_marker_analysis_matches_reference_golden():
     cam = port.Camera(g["K"], g["D"], g["R"], g["T"])
     pts = np.random.default_rng(0).uniform([0, 0], [480, 450], (200, 2))
     assert np.abs(an._undistort_points(pts) - port.undistort_points(cam, pts)).max() <= 1e-9
+    # float64 arguments, as R3:279-287 passes them (pandas values); with bare Python floats NumPy-2
+    # promotion would make the reference compute the whole formula in float32
     for u, v, d in ((100.3, 200.2, 13.1), (400.0, 50.5, 12.2)):
+        u, v, d = np.float64(u), np.float64(v), np.float64(d)
         assert np.abs(an._calculate_3d_position(u, v, d) - port.position_3d(cam, u, v, d)).max() <= 1e-9
     with pytest.raises(ValueError):
         an._calculate_3d_position(float(np.float32(g["K"][0, 2])), float(np.float32(g["K"][1, 2])), 12.0)

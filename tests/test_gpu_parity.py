@@ -296,3 +296,51 @@ def test_full_1080p_batch256_properties():
         pipe.reset_sequence()
         hh = pipe.process(np.ascontiguousarray(batch[:32].cpu().numpy()), 0)
         assert np.array_equal(hh.marker_xy, h.marker_xy[:32]) and np.array_equal(hh.pos3d, h.pos3d[:32], equal_nan=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# 5. frame sharding: N shards processed independently + last-seen exchange == one sequential run
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_run_is_byte_identical_to_single_run(world):
+    import torch
+    from vbs_b200 import sharding
+    h, w, rows, cols = 560, 640, 6, 8
+    centres = synth.grid_layout(h, w, rows, cols, 60.0)
+    seq = synth.compression_sequence(h, w, centres, 11.0, 19, tilt=0.4, depth=1.0, seed0=500)
+    # dropouts that straddle shard boundaries: paint two markers out for a few frames
+    for f in (4, 5, 9, 10, 11):
+        x, y = centres[13].astype(int); seq[f, y - 20:y + 20, x - 20:x + 20] = 170
+    for f in range(7, 15):
+        x, y = centres[30].astype(int); seq[f, y - 20:y + 20, x - 20:x + 20] = 170
+    K, D, R, T = synth.synthetic_camera()
+    K = K.copy(); K[0, 2] = w / 2 + 3.1; K[1, 2] = h / 2 - 2.3
+
+    def make():
+        p = pipeline.MarkerPipeline(h, w, 1, max_batch=len(seq), max_markers=256, max_refs=rows * cols)
+        p.set_reference([k[0] for k in keys], [k[1] for k in keys], xy[:, 0], xy[:, 1], 20.0)
+        p.set_camera(K, D, R, T, 2.0, 5.0, 50.0, warmup_frames=2)
+        p.set_first_frame(0)
+        return p
+
+    keys, xy = pu.grid_reference(port.find_markers_frame(seq[0]), cols)
+    dev = torch_cuda(seq)
+    with make() as p:
+        single = p.process(dev, 0); p.sync(); single = single.to_host()
+    assert (single.pos_flags & 4).any() and not (single.pos_flags[:, 13] & 1)[[4, 5, 9, 10, 11]].any()
+    pipes, results, tails = [], [], []
+    for r in range(world):
+        lo, hi = sharding.shard_bounds(len(seq), r, world)
+        p = make()
+        res = p.process(dev[lo:hi], lo); p.sync()
+        pipes.append(p); results.append(res); tails.append(p.get_last_seen())
+    for r in range(world):
+        inc = sharding.incoming_last_seen(np.stack(tails), r)
+        capi.check(pipes[r]._ctx, capi.lib.vbs_fix_displacement(pipes[r]._ctx, results[r].pos3d.data_ptr(), results[r].pos_flags.data_ptr(),
+                                                                results[r].pos3d.shape[0], inc.ctypes.data))
+    hosts = [r.to_host() for r in results]
+    for k in ("n_markers", "row_det", "row_cxy", "pos_flags", "pos3d"):
+        cat = np.concatenate([getattr(x, k) for x in hosts])
+        assert np.array_equal(cat, getattr(single, k), equal_nan=True), k
+    for p in pipes:
+        p.close()

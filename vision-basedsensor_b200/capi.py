@@ -42,6 +42,7 @@ SYMBOLS = {
     "vbs_get_last_seen": (C.c_int, [_P, _P]),
     "vbs_set_last_seen": (C.c_int, [_P, _P]),
     "vbs_set_first_frame": (C.c_int, [_P, C.c_int64]),
+    "vbs_fix_displacement": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
     "vbs_process_device": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.POINTER(VbsOutputs)]),
     "vbs_process_host": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.POINTER(VbsOutputs)]),
     "vbs_find_markers": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int64]),

@@ -94,6 +94,30 @@ __global__ void disp_kernel(CameraF64 cam, const double *__restrict__ obs, doubl
     last_seen[4 * r] = pu; last_seen[4 * r + 1] = pv; last_seen[4 * r + 2] = pd; last_seen[4 * r + 3] = has ? pf : -1.0;
 }
 
+// frame-sharded runs: a shard is first processed with an empty last-seen table, so the FIRST
+// observation of every reference entry in the shard has no displacement row yet.  Given the
+// last-seen table that arrives from the preceding shards, emit exactly that missing row.
+__global__ void fix_displacement_kernel(CameraF64 cam, double *__restrict__ pos3d, uint8_t *__restrict__ flags,
+                                        const double *__restrict__ incoming, int R, long long nframes) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    if (!(incoming[4 * r + 3] >= 0.0)) return;
+    double Pp[3];
+    const bool okp = position3d(cam, incoming[4 * r], incoming[4 * r + 1], incoming[4 * r + 2], Pp);
+    for (long long f = 0; f < nframes; ++f) {
+        const size_t i = (size_t)f * R + r;
+        const uint8_t fl = flags[i];
+        if (!(fl & 1)) continue;
+        if (okp && (fl & 2)) {
+            double *o = pos3d + 7 * i;
+            const double dx = o[0] - Pp[0], dy = o[1] - Pp[1], dz = o[2] - Pp[2];
+            const double nrm = sqrt(dx * dx + dy * dy + dz * dz);
+            if (!(nrm > cam.max_disp)) { o[3] = dx; o[4] = dy; o[5] = dz; o[6] = nrm; flags[i] = fl | 4; }
+        }
+        return;                                    // only the first observation was missing its predecessor
+    }
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -182,6 +206,11 @@ __global__ void plane_points_kernel(const double *__restrict__ X, const double *
 
 }  // namespace
 
+cudaError_t vbs_launch_fix_displacement(vbs_ctx *ctx, double *pos3d, uint8_t *flags, const double *incoming_dev, long long nframes) {
+    fix_displacement_kernel<<<(ctx->R + 63) / 64, 64, 0, ctx->stream>>>(ctx->cam, pos3d, flags, incoming_dev, ctx->R, nframes);
+    ctx->launches += 1;
+    return cudaGetLastError();
+}
 cudaError_t vbs_launch_undistort(vbs_ctx *ctx, const double *uv, double *out, int n) {
     undistort_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->cam, uv, out, n);
     ctx->launches += 1;

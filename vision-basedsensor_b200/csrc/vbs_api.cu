@@ -12,6 +12,11 @@ template <class T> cudaError_t dalloc(T **p, size_t n) { *p = nullptr; return cu
 
 int fail(vbs_ctx *ctx, int code, const char *msg) { ctx->err = msg; return code; }
 
+struct Scratch {                       // small device staging buffer, freed on scope exit
+    void *p = nullptr;
+    ~Scratch() { if (p) cudaFree(p); }
+};
+
 int map_status(vbs_ctx *ctx, uint32_t st) {
     if (!st) return VBS_OK;
     std::string m = "device status:";
@@ -297,6 +302,16 @@ int vbs_set_last_seen(vbs_ctx *ctx, const double *host_table) {
     return VBS_OK;
 }
 
+int vbs_fix_displacement(vbs_ctx *ctx, double *pos3d_device, uint8_t *pos_flags_device, int64_t nframes, const double *incoming_host) {
+    if (!ctx || !pos3d_device || !pos_flags_device || !incoming_host || nframes < 0) return VBS_ERR_BAD_ARG;
+    if (ctx->R <= 0 || !ctx->have_cam) return fail(ctx, VBS_ERR_STATE, "reference array and camera must be set first");
+    Scratch s;
+    VBS_CUDA(cudaMalloc(&s.p, sizeof(double) * 4 * ctx->R));
+    VBS_CUDA(cudaMemcpyAsync(s.p, incoming_host, sizeof(double) * 4 * ctx->R, cudaMemcpyHostToDevice, ctx->stream));
+    VBS_CUDA(vbs_launch_fix_displacement(ctx, pos3d_device, pos_flags_device, (const double *)s.p, nframes));
+    return vbs_sync(ctx);
+}
+
 int vbs_set_first_frame(vbs_ctx *ctx, int64_t first_frame) {       // frame-sharded runs: warm-up counts from the global first frame
     if (!ctx) return VBS_ERR_BAD_ARG;
     ctx->first_frame = first_frame; ctx->have_first = 1;
@@ -372,13 +387,6 @@ int vbs_debug_stage(vbs_ctx *ctx, int32_t stage, void *dst_device, size_t bytes)
 }
 
 // ---- table-level entry points (host arrays in / out; synchronous) --------------------------------
-namespace {
-struct Scratch {                       // small device staging buffer, freed on scope exit
-    void *p = nullptr;
-    ~Scratch() { if (p) cudaFree(p); }
-};
-}
-
 int vbs_track_markers(vbs_ctx *ctx, int32_t n, const double *marker_xy, const double *marker_axes, int32_t *row_det, double *row_cxy,
                       double *row_axes) {
     if (!ctx || n < 0 || (n > 0 && (!marker_xy || !marker_axes))) return VBS_ERR_BAD_ARG;

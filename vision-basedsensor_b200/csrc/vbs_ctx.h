@@ -102,6 +102,7 @@ cudaError_t vbs_launch_components(vbs_ctx *ctx, int batch);
 cudaError_t vbs_launch_contours(vbs_ctx *ctx, int batch);
 cudaError_t vbs_launch_track(vbs_ctx *ctx, int batch, int64_t frameno0);
 cudaError_t vbs_launch_reconstruct(vbs_ctx *ctx, int batch, int64_t frameno0);
+cudaError_t vbs_launch_fix_displacement(vbs_ctx *ctx, double *pos3d, uint8_t *flags, const double *incoming_dev, long long nframes);
 cudaError_t vbs_launch_undistort(vbs_ctx *ctx, const double *uv, double *out, int n);
 cudaError_t vbs_launch_position(vbs_ctx *ctx, const double *uvd, double *P, uint8_t *ok, int n);
 cudaError_t vbs_launch_plane_points(vbs_ctx *ctx, const double *X, const double *Y, const double *Z, int n, double *out);
