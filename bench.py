@@ -37,6 +37,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU-baseline budget (bounded sample)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--host-chunk", type=int, default=0, help="frames per chunk of the host path copy/compute overlap (0 = library default)")
     return ap.parse_args()
 
 
@@ -311,6 +312,8 @@ def main():
         pin = torch.from_numpy(host_frames).pin_memory()
         houts = pipe.alloc_outputs(B, False)
         pipe.reset_sequence()
+        if args.host_chunk:
+            pipe.set_host_chunk(args.host_chunk)
         for s in range(2):
             pipe.process_host_ptr(pin.data_ptr(), B, H * W, W, s * B, houts)
         barrier()

@@ -137,6 +137,9 @@ int vbs_process_device(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int64
 int vbs_process_host(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int64_t frame_stride,
                      int64_t row_pitch, int64_t frameno0, const vbs_outputs *out);
 
+/* frames per chunk of vbs_process_host's copy/compute overlap (0 = default 64) */
+int vbs_set_host_chunk(vbs_ctx *ctx, int32_t frames_per_chunk);
+
 /* stage-level entry points (same kernels, for the static-method mirrors) -----------------------
  * vbs_find_markers : MarkerTracker._find_markers (MD:111-135): frames -> area_mask, mask (kept in ctx)
  * vbs_marker_center: MarkerTracker._marker_center (MD:166-249) on masks supplied by the caller

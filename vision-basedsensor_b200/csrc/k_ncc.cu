@@ -42,7 +42,7 @@ template <int TL> struct Geo {
     static constexpr int HI = TL - 1 - OFF;               // 39 / 16
     static constexpr int LEAD = cdiv(TL - 1, RB);         // 10 / 4
     static constexpr int NG = LEAD + 1;                   // ring groups of 8 rows
-    static constexpr int UL = RB + TL - 1;                // union window of 8 adjacent pixels (bits)
+    static constexpr int UL = RB + TL - 1;                // widest union window the prefix table must cover
     static constexpr int CNX = 8 + UL + 9;                // guarded prefix table entries, index d+8
     static constexpr size_t SMEM = (size_t)NG * 2 * TWP * 16 + (size_t)NG * TWP * 8 + (size_t)CNX * 8;
 };
@@ -75,9 +75,18 @@ __device__ double border_threshold(int y, int x, int H, int W, double S, double 
     return m * g1 + (S - m * A) / L2 + 0.1 * sqrt(st2 * q) / (double)TL;
 }
 
+// 256 threads per 128-pixel strip.  Horizontal role: warp = row of the step, lane = pixel quad.
+// Vertical role: thread = (column, half); half h owns output rows 4h..4h+3 of the 8-row step and
+// reads the ring one 4-row unit later, so both halves run the same unrolled code.
+constexpr int NT = 256;
+constexpr int HPX = 4;      // pixels per thread in the horizontal pass
+constexpr int VR = 4;       // output rows per thread in the vertical pass
+
 template <int TL>
-__global__ void __launch_bounds__(TW, 4) ncc_mask_kernel(NccParams P) {
+__global__ void __launch_bounds__(NT, 3) ncc_mask_kernel(NccParams P) {
     using G = Geo<TL>;
+    constexpr int UL = HPX + TL - 1;                       // union window of 4 adjacent pixels (bits)
+    constexpr int NU = (VR + TL - 1 + 3) / 4;              // 4-row ring units one half reads
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *ringH = reinterpret_cast<float4 *>(smem_raw);                        // [NG*2][TWP]
     uint2 *ringB = reinterpret_cast<uint2 *>(ringH + G::NG * 2 * TWP);           // [NG][TWP]
@@ -91,15 +100,15 @@ __global__ void __launch_bounds__(TW, 4) ncc_mask_kernel(NccParams P) {
     const int H = P.H, W = P.W, WW = P.WW;
     const uint32_t *abits = P.area_bits + (size_t)f * H * WW;
     const double mfrac = (double)P.area_count[f] / P.hw;          // mean(area_mask)/255
-    for (int i = tid; i < G::CNX; i += TW) cn[i] = P.cn64[i];
+    for (int i = tid; i < G::CNX; i += NT) cn[i] = P.cn64[i];
 
     const int nk = (ye - ys + RB - 1) / RB;
     const int nsteps = nk + G::LEAD;
-    // horizontal role: row hr of the step, pixel octet ho
-    const int hr = tid >> 4, ho = tid & 15;
-    const int hcol = 8 * ho;                                        // strip-relative first column
+    const int hr = warp;                                            // horizontal role: row of the step
+    const int hcol = HPX * lane;                                    // strip-relative first column
     const int sb = x0 + hcol - G::OFF;                              // first bit of the union window
     const int wi0 = sb >> 5, bo = sb & 31;                          // arithmetic shift: floor
+    const int vcol = tid & (TW - 1), vhalf = tid >> 7;              // vertical role
 
     uint32_t pw[4];
     auto fetch = [&](int m) {
@@ -113,8 +122,7 @@ __global__ void __launch_bounds__(TW, 4) ncc_mask_kernel(NccParams P) {
             for (int i = 0; i < 4; ++i) pw[i] = 0u;
         }
     };
-    // vertical carry: S of the previous output row and the box row that left the window
-    int s_prev = 0; uint32_t hb_m1 = 0;
+    int s_prev = 0; uint32_t hb_m1 = 0;         // S of the previous output row and the box row that left the window
 
     fetch(0);
     __syncthreads();
@@ -126,16 +134,15 @@ __global__ void __launch_bounds__(TW, 4) ncc_mask_kernel(NccParams P) {
             uint32_t U1 = __funnelshift_r(pw[1], pw[2], bo);
             uint32_t U2 = __funnelshift_r(pw[2], pw[3], bo);
             if (m + 1 < nsteps) fetch(m + 1);
-            // keep UL bits, bit UL.. = 0
-            if constexpr (G::UL <= 64) { U2 = 0; U1 &= (G::UL == 64) ? 0xffffffffu : ((1u << (G::UL - 32)) - 1u); }
-            else { U2 &= (1u << (G::UL - 64)) - 1u; }
+            if constexpr (UL <= 64) { U2 = 0; U1 &= (UL == 64) ? 0xffffffffu : ((1u << (UL - 32)) - 1u); }
+            else { U2 &= (1u << (UL - 64)) - 1u; }
             // transitions: bit t set when bit(t) != bit(t-1)  (bit(-1) = 0, bit(UL) = 0)
             uint32_t T0 = U0 ^ (U0 << 1);
             uint32_t T1 = U1 ^ __funnelshift_l(U0, U1, 1);
             uint32_t T2 = U2 ^ __funnelshift_l(U1, U2, 1);
-            double acc[8];
+            double acc[HPX];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = 0.0;
+            for (int j = 0; j < HPX; ++j) acc[j] = 0.0;
             auto consume = [&](uint32_t T, uint32_t U, int base) {
                 while (T) {
                     const int b = __ffs(T) - 1;
@@ -143,7 +150,7 @@ __global__ void __launch_bounds__(TW, 4) ncc_mask_kernel(NccParams P) {
                     const bool is_start = (U >> b) & 1u;
                     const double *c = cn + (base + b + 8);           // cn[d + 8], d = t - j
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
+                    for (int j = 0; j < HPX; ++j) {
                         const double v = c[-j];
                         acc[j] += is_start ? -v : v;
                     }
@@ -151,43 +158,36 @@ __global__ void __launch_bounds__(TW, 4) ncc_mask_kernel(NccParams P) {
             };
             consume(T0, U0, 0);
             consume(T1, U1, 32);
-            consume(T2, U2, 64);
-            // box row: popcount of [j, j+TL-1]
+            if constexpr (UL > 64) consume(T2, U2, 64);
             auto bit = [&](int t) -> uint32_t {
                 return t < 32 ? (U0 >> t) & 1u : t < 64 ? (U1 >> (t - 32)) & 1u : (U2 >> (t - 64)) & 1u;
             };
-            uint32_t hb[8];
-            {
-                uint32_t c0;
-                if constexpr (TL >= 64) c0 = __popc(U0) + __popc(U1) + __popc(U2 & ((TL == 96) ? 0xffffffffu : ((1u << (TL - 64)) - 1u)));
-                else c0 = __popc(U0) + __popc(U1 & ((1u << (TL - 32)) - 1u));
-                hb[0] = c0;
+            uint32_t hb[HPX];
+            if constexpr (TL >= 64) hb[0] = __popc(U0) + __popc(U1) + __popc(U2 & ((1u << (TL - 64)) - 1u));
+            else hb[0] = __popc(U0) + __popc(U1 & ((1u << (TL - 32)) - 1u));
 #pragma unroll
-                for (int j = 1; j < 8; ++j) hb[j] = hb[j - 1] + bit(j - 1 + TL) - bit(j - 1);
-            }
-            // ring stores: H as float4 units [group*2 + hr/4][col + col/8].f[hr%4]; box as bytes
+            for (int j = 1; j < HPX; ++j) hb[j] = hb[j - 1] + bit(j - 1 + TL) - bit(j - 1);
+            // ring stores: H as float4 units [group*2 + hr/4][col + col/8].f[hr%4]; box rows as bytes
             float *dstH = reinterpret_cast<float *>(ringH + (gw * 2 + (hr >> 2)) * TWP) + (hr & 3);
             unsigned char *dstB = reinterpret_cast<unsigned char *>(ringB + gw * TWP) + hr;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int cp = hcol + j + ho;                        // (hcol + j) + (hcol + j)/8
+            for (int j = 0; j < HPX; ++j) {
+                const int c = hcol + j, cp = c + (c >> 3);
                 dstH[cp * 4] = (float)acc[j];
                 dstB[cp * 8] = (unsigned char)hb[j];
             }
         }
         __syncthreads();
 
-        // ---- vertical pass: thread = column, 8 output rows ----------------------------------------
+        // ---- vertical pass ---------------------------------------------------------------------------
         if (m >= G::LEAD) {
             const int k = m - G::LEAD;
             const int yb = ys + RB * k;
-            const int cp = tid + (tid >> 3);
+            const int cp = vcol + (vcol >> 3);
             int g0 = gw + 1; if (g0 >= G::NG) g0 -= G::NG;           // group of step k
-            float acc[RB];
-#pragma unroll
-            for (int r = 0; r < RB; ++r) acc[r] = 0.f;
+            // box sums of all 8 rows of the step (cheap; both halves run the same chain, no exchange)
             int S[RB];
-            auto box_at = [&](auto I_) -> int {                        // box row idx of the window (compile-time idx)
+            auto box_at = [&](auto I_) -> int {
                 constexpr int idx = decltype(I_)::value;
                 int gi = g0 + idx / 8; if (gi >= G::NG) gi -= G::NG;
                 const uint2 b = ringB[gi * TWP + cp];
@@ -206,36 +206,38 @@ __global__ void __launch_bounds__(TW, 4) ncc_mask_kernel(NccParams P) {
                 S[r] = S[r - 1] + box_at(std::integral_constant<int, r + TL - 1>{}) - box_at(std::integral_constant<int, r - 1>{});
             });
             s_prev = S[RB - 1]; hb_m1 = (uint32_t)box_at(std::integral_constant<int, RB - 1>{});
-            // Gaussian column sums: G(yb + r) = sum_a n[a] h[r + a]
-            static_for<0, G::NG>([&](auto G_) {
-                constexpr int g = decltype(G_)::value;
-                if constexpr (8 * g < RB + TL - 1) {
-                    int gi = g0 + g; if (gi >= G::NG) gi -= G::NG;
-                    const float4 v0 = ringH[(gi * 2 + 0) * TWP + cp];
-                    const float4 v1 = ringH[(gi * 2 + 1) * TWP + cp];
-                    const float hv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-                    static_for<0, 8>([&](auto E_) {
-                        constexpr int t = 8 * g + decltype(E_)::value;
-                        static_for<0, RB>([&](auto R_) {
-                            constexpr int r = decltype(R_)::value;
-                            constexpr int a = t - r;
-                            if constexpr (a >= 0 && a < TL) acc[r] = fmaf(c_n32[TL == 80][a], hv[t - 8 * g], acc[r]);
-                        });
+            // Gaussian column sums of this half: G(yb + 4h + r) = sum_a n[a] h[4h + r + a]
+            float acc[VR];
+#pragma unroll
+            for (int r = 0; r < VR; ++r) acc[r] = 0.f;
+            int u0 = 2 * g0 + vhalf; if (u0 >= 2 * G::NG) u0 -= 2 * G::NG;
+            static_for<0, NU>([&](auto U_) {
+                constexpr int u = decltype(U_)::value;
+                int ui = u0 + u; if (ui >= 2 * G::NG) ui -= 2 * G::NG;
+                const float4 v = ringH[ui * TWP + cp];
+                const float hv[4] = {v.x, v.y, v.z, v.w};
+                static_for<0, 4>([&](auto E_) {
+                    constexpr int t = 4 * u + decltype(E_)::value;
+                    static_for<0, VR>([&](auto R_) {
+                        constexpr int r = decltype(R_)::value;
+                        constexpr int a = t - r;
+                        if constexpr (a >= 0 && a < TL) acc[r] = fmaf(c_n32[TL == 80][a], hv[t - 4 * u], acc[r]);
                     });
-                }
+                });
             });
             // decision
-            const int x = x0 + tid;
+            const int x = x0 + vcol;
             const bool xin = x >= G::OFF && x + G::HI < W;
             uint32_t myword = 0;
 #pragma unroll
-            for (int r = 0; r < RB; ++r) {
-                const int y = yb + r;
+            for (int r = 0; r < VR; ++r) {
+                const int y = yb + VR * vhalf + r;
+                const int Sr = vhalf ? S[VR + r] : S[r];
                 bool on = false;
                 if (x < W && y < ye) {
                     float thr;
-                    if (xin && y >= G::OFF && y + G::HI < H) thr = __ldg(P.thr_lut + S[r]);
-                    else thr = (float)border_threshold<TL>(y, x, H, W, (double)S[r], mfrac, P.st2, cn);
+                    if (xin && y >= G::OFF && y + G::HI < H) thr = __ldg(P.thr_lut + Sr);
+                    else thr = (float)border_threshold<TL>(y, x, H, W, (double)Sr, mfrac, P.st2, cn);
                     const float d = acc[r] - thr;
                     on = d > 0.f;
                     if (fabsf(d) <= BAND) {          // float32 cannot decide: queue for the float64 pass
@@ -248,8 +250,9 @@ __global__ void __launch_bounds__(TW, 4) ncc_mask_kernel(NccParams P) {
                 const uint32_t word = __ballot_sync(0xffffffffu, on);
                 if (lane == r) myword = word;
             }
-            const int wx = (x0 >> 5) + warp;
-            if (lane < RB && yb + lane < ye && wx < WW) P.mask_bits[((size_t)f * H + (yb + lane)) * WW + wx] = myword;
+            const int wx = (x0 >> 5) + (vcol >> 5);
+            const int yw = yb + VR * vhalf + lane;
+            if (lane < VR && yw < ye && wx < WW) P.mask_bits[((size_t)f * H + yw) * WW + wx] = myword;
         }
         __syncthreads();
         if (++gw == G::NG) gw = 0;
@@ -325,7 +328,7 @@ template <int TL> cudaError_t launch(vbs_ctx *ctx, int batch, double st2) {
     if (e != cudaSuccess) return e;
     auto kern = ncc_mask_kernel<TL>;
     if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM)) != cudaSuccess) return e;
-    kern<<<dim3(strips, vsegs, batch), TW, G::SMEM, ctx->stream>>>(P);
+    kern<<<dim3(strips, vsegs, batch), NT, G::SMEM, ctx->stream>>>(P);
     ncc_recheck_kernel<TL><<<dim3(16, batch), 256, 0, ctx->stream>>>(P, ctx->d_n64, batch);
     ctx->launches += 2;
     return cudaGetLastError();

@@ -64,34 +64,53 @@ __global__ void pos3d_kernel(CameraF64 cam, const int32_t *__restrict__ row_det,
     flags[i] = fl;
 }
 
-// one thread per reference entry walks the frames of the batch in order
+// one warp per reference entry: lanes take 32 consecutive frames, the "previous observation" of a
+// frame is found with a ballot (nearest earlier lane) or carried over from the previous 32 frames
 __global__ void disp_kernel(CameraF64 cam, const double *__restrict__ obs, double *__restrict__ pos3d, uint8_t *__restrict__ flags,
                             double *__restrict__ last_seen, int R, int batch, int64_t frameno0) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= R) return;
-    double pu = last_seen[4 * r], pv = last_seen[4 * r + 1], pd = last_seen[4 * r + 2], pf = last_seen[4 * r + 3];
-    bool has = pf >= 0.0;
-    double Pp[3] = {0, 0, 0};
-    bool okp = has ? position3d(cam, pu, pv, pd, Pp) : false;
-    for (int f = 0; f < batch; ++f) {
-        const size_t i = (size_t)f * R + r;
-        uint8_t fl = flags[i];
-        if (!(fl & 1)) continue;
-        double *o = pos3d + 7 * i;
-        const bool okc = fl & 2;
-        if (has && okp && okc) {
-            const double dx = o[0] - Pp[0], dy = o[1] - Pp[1], dz = o[2] - Pp[2];
-            const double nrm = sqrt(dx * dx + dy * dy + dz * dz);
-            if (!(nrm > cam.max_disp)) {                                                  // R3:293
-                o[3] = dx; o[4] = dy; o[5] = dz; o[6] = nrm;
-                flags[i] = fl | 4;
+    const int lane = threadIdx.x & 31;
+    // carry = most recent observation before the current 32-frame window: -2 none, -1 the last-seen table, >= 0 a frame of this batch
+    int carry = last_seen[4 * r + 3] >= 0.0 ? -1 : -2;
+    double Pl[3] = {0, 0, 0};
+    bool okl = false;
+    if (carry == -1) okl = position3d(cam, last_seen[4 * r], last_seen[4 * r + 1], last_seen[4 * r + 2], Pl);
+    for (int f0 = 0; f0 < batch; f0 += 32) {
+        const int f = f0 + lane;
+        const size_t i = (size_t)(f < batch ? f : batch - 1) * R + r;
+        const uint8_t fl = f < batch ? flags[i] : 0;
+        const uint32_t has = __ballot_sync(0xffffffffu, fl & 1);
+        if (fl & 1) {
+            const uint32_t below = has & ((1u << lane) - 1u);
+            const int prev = below ? f0 + (31 - __clz(below)) : carry;
+            bool okp = false;
+            double Pp[3] = {0, 0, 0};
+            if (prev >= 0) {
+                const size_t j = (size_t)prev * R + r;
+                okp = flags[j] & 2;
+                Pp[0] = pos3d[7 * j]; Pp[1] = pos3d[7 * j + 1]; Pp[2] = pos3d[7 * j + 2];
+            } else if (prev == -1) {
+                okp = okl; Pp[0] = Pl[0]; Pp[1] = Pl[1]; Pp[2] = Pl[2];
+            }
+            if (prev != -2 && okp && (fl & 2)) {
+                double *o = pos3d + 7 * i;
+                const double dx = o[0] - Pp[0], dy = o[1] - Pp[1], dz = o[2] - Pp[2];
+                const double nrm = sqrt(dx * dx + dy * dy + dz * dz);
+                if (!(nrm > cam.max_disp)) {                                              // R3:293
+                    o[3] = dx; o[4] = dy; o[5] = dz; o[6] = nrm;
+                    flags[i] = fl | 4;                    // bit 2 is only read by the host
+                }
             }
         }
-        has = true; okp = okc;
-        pu = obs[3 * i]; pv = obs[3 * i + 1]; pd = obs[3 * i + 2]; pf = (double)(frameno0 + f);
-        Pp[0] = o[0]; Pp[1] = o[1]; Pp[2] = o[2];
+        if (has) carry = f0 + (31 - __clz(has));
+        __syncwarp();
     }
-    last_seen[4 * r] = pu; last_seen[4 * r + 1] = pv; last_seen[4 * r + 2] = pd; last_seen[4 * r + 3] = has ? pf : -1.0;
+    if (lane == 0 && carry >= 0) {
+        const size_t j = (size_t)carry * R + r;
+        last_seen[4 * r] = obs[3 * j]; last_seen[4 * r + 1] = obs[3 * j + 1]; last_seen[4 * r + 2] = obs[3 * j + 2];
+        last_seen[4 * r + 3] = (double)(frameno0 + carry);
+    }
 }
 
 // frame-sharded runs: a shard is first processed with an empty last-seen table, so the FIRST
@@ -249,7 +268,7 @@ cudaError_t vbs_launch_reconstruct(vbs_ctx *ctx, int batch, int64_t frameno0) {
         const int64_t first_kept = ctx->first_frame + (ctx->warmup > 0 ? ctx->warmup : 0);
         pos3d_kernel<<<g, 128, 0, ctx->stream>>>(ctx->cam, ctx->row_det, ctx->row_cxy, ctx->row_axes, ctx->obs, ctx->pos3d, ctx->pos_flags,
                                                  R, frameno0, first_kept, total);
-        disp_kernel<<<(R + 63) / 64, 64, 0, ctx->stream>>>(ctx->cam, ctx->obs, ctx->pos3d, ctx->pos_flags, ctx->last_seen, R, batch, frameno0);
+        disp_kernel<<<(R + 3) / 4, 128, 0, ctx->stream>>>(ctx->cam, ctx->obs, ctx->pos3d, ctx->pos_flags, ctx->last_seen, R, batch, frameno0);
         ctx->launches += 2;
         if (ctx->have_plane) {
             plane_kernel<<<(batch + 3) / 4, 128, 0, ctx->stream>>>(ctx->pos3d, ctx->pos_flags, ctx->pl_ref, ctx->pl_start, ctx->pl_dvert,

@@ -40,6 +40,8 @@ void free_all(vbs_ctx *c) {
     for (void *p : ptrs) if (p) cudaFree(p);
     if (c->h_status) cudaFreeHost(c->h_status);
     for (cudaEvent_t e : c->ev) if (e) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i) { if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]); }
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
 }
 
@@ -326,26 +328,81 @@ int vbs_process_device(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int64
     return process_common(ctx, frames, batch, frame_stride, row_pitch, frameno0, out, cudaMemcpyDeviceToDevice);
 }
 
+// Host frames in, host results out.  The batch is cut into chunks; chunk c+1 crosses PCIe on a
+// copy stream while chunk c is being processed (two staging buffers, events both ways), so the
+// call costs max(copy, compute) instead of their sum.
 int vbs_process_host(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int64_t frame_stride, int64_t row_pitch, int64_t frameno0,
                      const vbs_outputs *out) {
     int rc = check_batch(ctx, frames, batch);
     if (rc != VBS_OK) return rc;
     const size_t rowb = (size_t)ctx->W * ctx->C, fb = rowb * ctx->H;
     if (row_pitch < (int64_t)rowb) return fail(ctx, VBS_ERR_BAD_ARG, "row_pitch smaller than a row");
-    if (!ctx->d_frames) {
-        ctx->frames_bytes = fb * ctx->B;
+    const int CH = ctx->host_chunk > 0 ? (ctx->host_chunk < ctx->B ? ctx->host_chunk : ctx->B) : (ctx->B < 64 ? ctx->B : 64);
+    if (!ctx->d_frames || ctx->frames_bytes < 2 * fb * CH) {
+        if (ctx->d_frames) { VBS_CUDA(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->d_frames); ctx->d_frames = nullptr; }
+        ctx->frames_bytes = 2 * fb * CH;
         VBS_CUDA(cudaMalloc((void **)&ctx->d_frames, ctx->frames_bytes));
     }
-    if ((size_t)row_pitch == rowb && (size_t)frame_stride == fb) {
-        VBS_CUDA(cudaMemcpyAsync(ctx->d_frames, frames, fb * batch, cudaMemcpyHostToDevice, ctx->stream));
-    } else {                                           // crop view (MD:85): one strided copy per frame
-        for (int f = 0; f < batch; ++f)
-            VBS_CUDA(cudaMemcpy2DAsync(ctx->d_frames + fb * f, rowb, frames + (size_t)frame_stride * f, (size_t)row_pitch, rowb, ctx->H,
-                                       cudaMemcpyHostToDevice, ctx->stream));
+    if (!ctx->copy_stream) {
+        VBS_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            VBS_CUDA(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
+            VBS_CUDA(cudaEventCreateWithFlags(&ctx->ev_consumed[i], cudaEventDisableTiming));
+        }
     }
-    rc = process_common(ctx, ctx->d_frames, batch, (int64_t)fb, (int64_t)rowb, frameno0, out, cudaMemcpyDeviceToHost);
-    if (rc != VBS_OK) return rc;
+    const size_t M = ctx->M, R = ctx->R;
+    const int nchunks = (batch + CH - 1) / CH;
+    // the copy stream runs one chunk ahead of the compute stream
+    auto upload = [&](int c) -> int {
+        const int off = c * CH, n = batch - off < CH ? batch - off : CH, buf = c & 1;
+        uint8_t *dst = ctx->d_frames + (size_t)buf * fb * CH;
+        if (c >= 2) VBS_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[buf], 0));
+        const uint8_t *src = frames + (size_t)frame_stride * off;
+        if ((size_t)row_pitch == rowb && (size_t)frame_stride == fb) {
+            VBS_CUDA(cudaMemcpyAsync(dst, src, fb * n, cudaMemcpyHostToDevice, ctx->copy_stream));
+        } else {                                           // crop view (MD:85): one strided copy per frame
+            for (int f = 0; f < n; ++f)
+                VBS_CUDA(cudaMemcpy2DAsync(dst + fb * f, rowb, src + (size_t)frame_stride * f, (size_t)row_pitch, rowb, ctx->H,
+                                           cudaMemcpyHostToDevice, ctx->copy_stream));
+        }
+        VBS_CUDA(cudaEventRecord(ctx->ev_copied[buf], ctx->copy_stream));
+        return VBS_OK;
+    };
+    if ((rc = upload(0)) != VBS_OK) return rc;
+    for (int c = 0; c < nchunks; ++c) {
+        const int off = c * CH, n = batch - off < CH ? batch - off : CH, buf = c & 1;
+        uint8_t *dst = ctx->d_frames + (size_t)buf * fb * CH;
+        if (c + 1 < nchunks && (rc = upload(c + 1)) != VBS_OK) return rc;
+        VBS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[buf], 0));
+        vbs_outputs o;
+        std::memset(&o, 0, sizeof(o));
+        if (out) {
+            o = *out;
+            if (o.n_labels) o.n_labels += off;
+            if (o.centres) o.centres += (size_t)off * M * 2;
+            if (o.n_markers) o.n_markers += off;
+            if (o.marker_xy) o.marker_xy += (size_t)off * M * 2;
+            if (o.marker_axes) o.marker_axes += (size_t)off * M * 3;
+            if (o.row_det) o.row_det += (size_t)off * R;
+            if (o.row_cxy) o.row_cxy += (size_t)off * R * 2;
+            if (o.row_axes) o.row_axes += (size_t)off * R * 3;
+            if (o.pos3d) o.pos3d += (size_t)off * R * 7;
+            if (o.pos_flags) o.pos_flags += (size_t)off * R;
+            if (o.plane) o.plane += (size_t)off * 4;
+            if (o.plane_n) o.plane_n += off;
+        }
+        rc = process_common(ctx, dst, n, (int64_t)fb, (int64_t)rowb, frameno0 + off, out ? &o : nullptr, cudaMemcpyDeviceToHost);
+        if (rc != VBS_OK) return rc;
+        VBS_CUDA(cudaEventRecord(ctx->ev_consumed[buf], ctx->stream));
+    }
     return vbs_sync(ctx);
+}
+
+int vbs_set_host_chunk(vbs_ctx *ctx, int32_t frames_per_chunk) {
+    if (!ctx || frames_per_chunk < 0) return VBS_ERR_BAD_ARG;
+    VBS_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->host_chunk = frames_per_chunk;
+    return VBS_OK;
 }
 
 int vbs_find_markers(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int64_t frame_stride, int64_t row_pitch) {

@@ -33,7 +33,8 @@ struct vbs_ctx {
     int64_t launches;
 
     // frame staging for the host entry point
-    uint8_t *d_frames; size_t frames_bytes;
+    uint8_t *d_frames; size_t frames_bytes;      // two staging buffers of host_chunk frames
+    int host_chunk; cudaStream_t copy_stream; cudaEvent_t ev_copied[2], ev_consumed[2];
     // bit images [B][H][WW]
     uint32_t *area_bits, *mask_bits, *max_bits, *open_bits, *root_bits;
     uint32_t *area_count;            // [B] set pixels of area_mask

@@ -143,6 +143,10 @@ class MarkerPipeline:
                                                      us.ctypes.data if us is not None else None, int(bool(shell)), float(scale)))
         self.have_plane = True
 
+    def set_host_chunk(self, frames_per_chunk: int):
+        """Frames per chunk of the copy/compute overlap in the host entry point (0 = default 64)."""
+        capi.check(self._ctx, capi.lib.vbs_set_host_chunk(self._ctx, int(frames_per_chunk)))
+
     def reset_sequence(self):
         capi.check(self._ctx, capi.lib.vbs_reset_sequence(self._ctx))
 
@@ -178,8 +182,14 @@ class MarkerPipeline:
                 arrays[k] = torch.empty(shp, dtype=getattr(torch, dt), device=dev)
                 setattr(out, k, arrays[k].data_ptr())
         else:
+            # pinned host memory: D2H copies into pageable memory would block the host per chunk and
+            # defeat the copy/compute overlap of vbs_process_host
+            import torch
+            self._pinned = getattr(self, "_pinned", [])
             for k, (shp, dt) in shapes.items():
-                arrays[k] = np.empty(shp, dtype=dt)
+                t = torch.empty(shp, dtype=getattr(torch, dt), pin_memory=torch.cuda.is_available())
+                self._pinned.append(t)
+                arrays[k] = t.numpy()
                 setattr(out, k, arrays[k].ctypes.data)
         return arrays, out
 
