@@ -8,6 +8,7 @@
 
 constexpr int ITERS = 2048;
 constexpr int NACC = 8;
+__constant__ float c_w[128];
 
 template <int MODE>
 __global__ void __launch_bounds__(256) k(uint32_t *out, uint32_t seed) {
@@ -35,6 +36,8 @@ __global__ void __launch_bounds__(256) k(uint32_t *out, uint32_t seed) {
             if (MODE == 7) a[i] = (a[i] & x) ^ (y | a[i]) ;
             if (MODE == 8) { a[i] = __dp4a(x + i, y, a[i]); fa[i] = fmaf(fa[i], fx, fy); }
             if (MODE == 9) a[i] = __funnelshift_r(a[i], x, 7) + 1;
+            if (MODE == 10) { fa[i] = fmaf(c_w[i], fx, fa[i]); fa[i] = fmaf(c_w[i + 8], fy, fa[i]); fa[i] = fmaf(c_w[i + 16], fx, fa[i]); fa[i] = fmaf(c_w[i + 24], fy, fa[i]); }
+            if (MODE == 11) { fa[i] = fmaf(fx, fy, fa[i]); fa[i] = fmaf(fy, fx, fa[i]); fa[i] = fmaf(fx, fx, fa[i]); fa[i] = fmaf(fy, fy, fa[i]); }
         }
     }
     uint32_t r = 0; float fr = 0; double dr = 0;
@@ -73,5 +76,7 @@ int main(int argc, char **argv) {
     run<7>("LOP3x2", 2, p.multiProcessorCount, mhz);
     run<8>("IDP+FFMA", 2, p.multiProcessorCount, mhz);
     run<9>("SHF+IADD", 2, p.multiProcessorCount, mhz);
+    run<10>("FFMA c[]", 4, p.multiProcessorCount, mhz);
+    run<11>("FFMA reg", 4, p.multiProcessorCount, mhz);
     return 0;
 }

@@ -44,7 +44,8 @@ template <int TL> struct Geo {
     static constexpr int NG = LEAD + 1;                   // ring groups of 8 rows
     static constexpr int UL = RB + TL - 1;                // widest union window the prefix table must cover
     static constexpr int CNX = 8 + UL + 9;                // guarded prefix table entries, index d+8
-    static constexpr size_t SMEM = (size_t)NG * 2 * TWP * 16 + (size_t)NG * TWP * 8 + (size_t)CNX * 8;
+    static constexpr size_t SMEM = (size_t)NG * 2 * TWP * 16 + (size_t)NG * TWP * 8 + (size_t)(CNX + (CNX & 1)) * 8 + 4 * 112 * 4 +
+                                   2 * 4 * TW * 4 + 4 * TW * 4;
 };
 
 struct NccParams {
@@ -53,6 +54,7 @@ struct NccParams {
     const uint32_t *area_bits; const uint32_t *area_count;
     uint32_t *mask_bits;
     const float *thr_lut; const double *cn64;      // cn64[d+8] = Cn[clamp(d,0,TL)]
+    const int *cnfix;                              // [4][112] fixed-point copies: cnfix[s][k] = round(2^30 cn64[k+s])
     int2 *recheck; uint32_t *recheck_n; int recheck_cap;
     uint32_t *status;
 };
@@ -63,7 +65,7 @@ __device__ __forceinline__ uint32_t ld_bits(const uint32_t *row, int wi, int WW)
 
 // threshold on G for a pixel whose window is clipped by the image border (float64)
 template <int TL>
-__device__ double border_threshold(int y, int x, int H, int W, double S, double m, double st2, const double *cn) {
+__device__ __noinline__ double border_threshold(int y, int x, int H, int W, double S, double m, double st2, const double *cn) {
     using G = Geo<TL>;
     const int ylo = max(0, G::OFF - y), yhi = min(TL - 1, H - 1 - y + G::OFF);
     const int xlo = max(0, G::OFF - x), xhi = min(TL - 1, W - 1 - x + G::OFF);
@@ -75,24 +77,32 @@ __device__ double border_threshold(int y, int x, int H, int W, double S, double 
     return m * g1 + (S - m * A) / L2 + 0.1 * sqrt(st2 * q) / (double)TL;
 }
 
-// 256 threads per 128-pixel strip.  Horizontal role: warp = row of the step, lane = pixel quad.
-// Vertical role: thread = (column, half); half h owns output rows 4h..4h+3 of the 8-row step and
-// reads the ring one 4-row unit later, so both halves run the same unrolled code.
+// 256 threads per 128-pixel strip, three phases per 8-row step:
+//  H  (threads 0..127): one (row, 8-pixel octet) item each.  Run transitions of the 87-bit union
+//     window are turned into h(x) with a FIXED-POINT prefix table (2^30 scale, int32 adds are exact
+//     and order-free); any 8 consecutive table entries come from two aligned LDS.128 (four shifted
+//     copies of the table).  Results go to the float ring (scale folded into the vertical weights).
+//  V  (all 256 threads): thread = (column, half); half h accumulates taps [h L/2, (h+1) L/2) of all
+//     8 output rows, so it reads only half of the ring; partial sums of the 4 rows the other half
+//     decides are swapped through shared memory together with the box sums.
+//  D  decision: LUT threshold on the box sum; a CTA-uniform fast path when the whole step is interior.
 constexpr int NT = 256;
-constexpr int HPX = 4;      // pixels per thread in the horizontal pass
-constexpr int VR = 4;       // output rows per thread in the vertical pass
+constexpr int VR = 4;                    // output rows each half decides
+constexpr int FIX_SHIFT = 30;            // fixed-point scale of the prefix table
+constexpr int FXN = 112;                 // entries per shifted copy of the fixed-point table (>= CNX + 3, multiple of 4)
 
 template <int TL>
 __global__ void __launch_bounds__(NT, 3) ncc_mask_kernel(NccParams P) {
     using G = Geo<TL>;
-    constexpr int UL = HPX + TL - 1;                       // union window of 4 adjacent pixels (bits)
-    constexpr int NU = (VR + TL - 1 + 3) / 4;              // 4-row ring units one half reads
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *ringH = reinterpret_cast<float4 *>(smem_raw);                        // [NG*2][TWP]
     uint2 *ringB = reinterpret_cast<uint2 *>(ringH + G::NG * 2 * TWP);           // [NG][TWP]
-    double *cn = reinterpret_cast<double *>(ringB + G::NG * TWP);                // [CNX]
+    double *cn = reinterpret_cast<double *>(ringB + G::NG * TWP);                // [CNX] float64 prefix sums (border formula)
+    int4 *fx = reinterpret_cast<int4 *>(cn + G::CNX + (G::CNX & 1));             // [4][FXN/4] shifted fixed-point copies
+    float *xbuf = reinterpret_cast<float *>(fx + FXN);                           // [2][VR][TW] partial sums in flight
+    int *sbuf = reinterpret_cast<int *>(xbuf + 2 * VR * TW);                     // [VR][TW] box sums for half 1
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int x0 = blockIdx.x * TW;
     const int ys = blockIdx.y * P.seg_rows;
     const int ye = min(P.H, ys + P.seg_rows);
@@ -101,16 +111,20 @@ __global__ void __launch_bounds__(NT, 3) ncc_mask_kernel(NccParams P) {
     const uint32_t *abits = P.area_bits + (size_t)f * H * WW;
     const double mfrac = (double)P.area_count[f] / P.hw;          // mean(area_mask)/255
     for (int i = tid; i < G::CNX; i += NT) cn[i] = P.cn64[i];
+    for (int i = tid; i < 4 * FXN; i += NT) reinterpret_cast<int *>(fx)[i] = P.cnfix[i];
 
     const int nk = (ye - ys + RB - 1) / RB;
     const int nsteps = nk + G::LEAD;
-    const int hr = warp;                                            // horizontal role: row of the step
-    const int hcol = HPX * lane;                                    // strip-relative first column
-    const int sb = x0 + hcol - G::OFF;                              // first bit of the union window
+    // horizontal role (threads 0..127): row hr of the step, pixel octet ho
+    const bool hrole = tid < TW;
+    const int hr = (tid >> 4) & 7, ho = tid & 15;
+    const int sb = x0 + 8 * ho - G::OFF;                            // first bit of the union window
     const int wi0 = sb >> 5, bo = sb & 31;                          // arithmetic shift: floor
     const int vcol = tid & (TW - 1), vhalf = tid >> 7;              // vertical role
+    const int cp = vcol + (vcol >> 3);
+    const bool strip_interior = x0 >= G::OFF && x0 + TW - 1 + G::HI < W;
 
-    uint32_t pw[4];
+    uint32_t pw[4] = {0, 0, 0, 0};
     auto fetch = [&](int m) {
         const int p = ys - G::OFF + RB * m + hr;
         if (p >= 0 && p < H) {
@@ -122,136 +136,189 @@ __global__ void __launch_bounds__(NT, 3) ncc_mask_kernel(NccParams P) {
             for (int i = 0; i < 4; ++i) pw[i] = 0u;
         }
     };
-    int s_prev = 0; uint32_t hb_m1 = 0;         // S of the previous output row and the box row that left the window
+    int s_prev = 0; uint32_t hb_m1 = 0;         // half 0: S of the previous output row and the box row that left the window
 
-    fetch(0);
+    if (hrole) fetch(0);
     __syncthreads();
     int gw = 0;                                  // ring group written by step m (m % NG)
     for (int m = 0; m < nsteps; ++m) {
-        // ---- horizontal pass on bits -------------------------------------------------------------
-        {
+        // ---- H: horizontal pass on bits ------------------------------------------------------------
+        if (hrole) {
             uint32_t U0 = __funnelshift_r(pw[0], pw[1], bo);
             uint32_t U1 = __funnelshift_r(pw[1], pw[2], bo);
             uint32_t U2 = __funnelshift_r(pw[2], pw[3], bo);
             if (m + 1 < nsteps) fetch(m + 1);
-            if constexpr (UL <= 64) { U2 = 0; U1 &= (UL == 64) ? 0xffffffffu : ((1u << (UL - 32)) - 1u); }
-            else { U2 &= (1u << (UL - 64)) - 1u; }
+            if constexpr (G::UL <= 64) { U2 = 0; U1 &= (G::UL == 64) ? 0xffffffffu : ((1u << (G::UL - 32)) - 1u); }
+            else { U2 &= (1u << (G::UL - 64)) - 1u; }
             // transitions: bit t set when bit(t) != bit(t-1)  (bit(-1) = 0, bit(UL) = 0)
-            uint32_t T0 = U0 ^ (U0 << 1);
-            uint32_t T1 = U1 ^ __funnelshift_l(U0, U1, 1);
-            uint32_t T2 = U2 ^ __funnelshift_l(U1, U2, 1);
-            double acc[HPX];
+            const uint32_t T0 = U0 ^ (U0 << 1);
+            const uint32_t T1 = U1 ^ __funnelshift_l(U0, U1, 1);
+            const uint32_t T2 = U2 ^ __funnelshift_l(U1, U2, 1);
+            int acc[8];
 #pragma unroll
-            for (int j = 0; j < HPX; ++j) acc[j] = 0.0;
-            auto consume = [&](uint32_t T, uint32_t U, int base) {
+            for (int j = 0; j < 8; ++j) acc[j] = 0;
+            auto consume = [&](uint32_t T, uint32_t Uw, int base) {
                 while (T) {
                     const int b = __ffs(T) - 1;
                     T &= T - 1;
-                    const bool is_start = (U >> b) & 1u;
-                    const double *c = cn + (base + b + 8);           // cn[d + 8], d = t - j
-#pragma unroll
-                    for (int j = 0; j < HPX; ++j) {
-                        const double v = c[-j];
-                        acc[j] += is_start ? -v : v;
-                    }
+                    const int sgn = ((Uw >> b) & 1u) ? -1 : 1;       // run start: -Cn, run end: +Cn
+                    const int i0 = base + b + 1;                     // table index of d = t - 7 (pixel j = 7)
+                    const int4 *src = fx + (i0 & 3) * (FXN / 4) + (i0 >> 2);
+                    const int4 lo = src[0], hi = src[1];
+                    acc[7] += sgn * lo.x; acc[6] += sgn * lo.y; acc[5] += sgn * lo.z; acc[4] += sgn * lo.w;
+                    acc[3] += sgn * hi.x; acc[2] += sgn * hi.y; acc[1] += sgn * hi.z; acc[0] += sgn * hi.w;
                 }
             };
             consume(T0, U0, 0);
             consume(T1, U1, 32);
-            if constexpr (UL > 64) consume(T2, U2, 64);
+            if constexpr (G::UL > 64) consume(T2, U2, 64);
             auto bit = [&](int t) -> uint32_t {
                 return t < 32 ? (U0 >> t) & 1u : t < 64 ? (U1 >> (t - 32)) & 1u : (U2 >> (t - 64)) & 1u;
             };
-            uint32_t hb[HPX];
+            uint32_t hb[8];
             if constexpr (TL >= 64) hb[0] = __popc(U0) + __popc(U1) + __popc(U2 & ((1u << (TL - 64)) - 1u));
             else hb[0] = __popc(U0) + __popc(U1 & ((1u << (TL - 32)) - 1u));
 #pragma unroll
-            for (int j = 1; j < HPX; ++j) hb[j] = hb[j - 1] + bit(j - 1 + TL) - bit(j - 1);
+            for (int j = 1; j < 8; ++j) hb[j] = hb[j - 1] + bit(j - 1 + TL) - bit(j - 1);
             // ring stores: H as float4 units [group*2 + hr/4][col + col/8].f[hr%4]; box rows as bytes
             float *dstH = reinterpret_cast<float *>(ringH + (gw * 2 + (hr >> 2)) * TWP) + (hr & 3);
             unsigned char *dstB = reinterpret_cast<unsigned char *>(ringB + gw * TWP) + hr;
 #pragma unroll
-            for (int j = 0; j < HPX; ++j) {
-                const int c = hcol + j, cp = c + (c >> 3);
-                dstH[cp * 4] = (float)acc[j];
-                dstB[cp * 8] = (unsigned char)hb[j];
+            for (int j = 0; j < 8; ++j) {
+                const int c = 9 * ho + j;                            // (8 ho + j) + (8 ho + j) / 8
+                dstH[c * 4] = (float)acc[j];                         // 2^30 h; the scale lives in the vertical weights
+                dstB[c * 8] = (unsigned char)hb[j];
             }
         }
         __syncthreads();
 
-        // ---- vertical pass ---------------------------------------------------------------------------
+        // ---- V: vertical pass ------------------------------------------------------------------------
         if (m >= G::LEAD) {
             const int k = m - G::LEAD;
             const int yb = ys + RB * k;
-            const int cp = vcol + (vcol >> 3);
             int g0 = gw + 1; if (g0 >= G::NG) g0 -= G::NG;           // group of step k
-            // box sums of all 8 rows of the step (cheap; both halves run the same chain, no exchange)
-            int S[RB];
-            auto box_at = [&](auto I_) -> int {
-                constexpr int idx = decltype(I_)::value;
-                int gi = g0 + idx / 8; if (gi >= G::NG) gi -= G::NG;
-                const uint2 b = ringB[gi * TWP + cp];
-                const uint32_t w = (idx % 8) < 4 ? b.x : b.y;
-                return (int)((w >> (8 * (idx % 4))) & 255u);
-            };
-            if (k == 0) {
-                int s = 0;
-                static_for<0, TL>([&](auto I_) { s += box_at(I_); });
-                S[0] = s;
-            } else {
-                S[0] = s_prev + box_at(std::integral_constant<int, TL - 1>{}) - (int)hb_m1;
-            }
-            static_for<1, RB>([&](auto R_) {
-                constexpr int r = decltype(R_)::value;
-                S[r] = S[r - 1] + box_at(std::integral_constant<int, r + TL - 1>{}) - box_at(std::integral_constant<int, r - 1>{});
-            });
-            s_prev = S[RB - 1]; hb_m1 = (uint32_t)box_at(std::integral_constant<int, RB - 1>{});
-            // Gaussian column sums of this half: G(yb + 4h + r) = sum_a n[a] h[4h + r + a]
-            float acc[VR];
+            // box sums of the 8 rows: half 0 runs the chain and hands rows 4..7 to half 1
+            int S[VR];
+            if (vhalf == 0) {
+                auto box_at = [&](auto I_) -> int {
+                    constexpr int idx = decltype(I_)::value;
+                    int gi = g0 + idx / 8; if (gi >= G::NG) gi -= G::NG;
+                    const uint2 b = ringB[gi * TWP + cp];
+                    const uint32_t w = (idx % 8) < 4 ? b.x : b.y;
+                    return (int)((w >> (8 * (idx % 4))) & 255u);
+                };
+                int S8[RB];
+                if (k == 0) {                   // first step of the segment: sum the whole window once (rolled: code size)
+                    int s = 0;
+#pragma unroll 1
+                    for (int t = 0; t < TL; ++t) {
+                        int gi = g0 + (t >> 3); if (gi >= G::NG) gi -= G::NG;
+                        s += reinterpret_cast<const unsigned char *>(ringB + gi * TWP + cp)[t & 7];
+                    }
+                    S8[0] = s;
+                } else {
+                    S8[0] = s_prev + box_at(std::integral_constant<int, TL - 1>{}) - (int)hb_m1;
+                }
+                static_for<1, RB>([&](auto R_) {
+                    constexpr int r = decltype(R_)::value;
+                    S8[r] = S8[r - 1] + box_at(std::integral_constant<int, r + TL - 1>{}) - box_at(std::integral_constant<int, r - 1>{});
+                });
+                s_prev = S8[RB - 1]; hb_m1 = (uint32_t)box_at(std::integral_constant<int, RB - 1>{});
 #pragma unroll
-            for (int r = 0; r < VR; ++r) acc[r] = 0.f;
-            int u0 = 2 * g0 + vhalf; if (u0 >= 2 * G::NG) u0 -= 2 * G::NG;
-            static_for<0, NU>([&](auto U_) {
-                constexpr int u = decltype(U_)::value;
-                int ui = u0 + u; if (ui >= 2 * G::NG) ui -= 2 * G::NG;
-                const float4 v = ringH[ui * TWP + cp];
-                const float hv[4] = {v.x, v.y, v.z, v.w};
-                static_for<0, 4>([&](auto E_) {
-                    constexpr int t = 4 * u + decltype(E_)::value;
-                    static_for<0, VR>([&](auto R_) {
-                        constexpr int r = decltype(R_)::value;
-                        constexpr int a = t - r;
-                        if constexpr (a >= 0 && a < TL) acc[r] = fmaf(c_n32[TL == 80][a], hv[t - 4 * u], acc[r]);
+                for (int r = 0; r < VR; ++r) { S[r] = S8[r]; sbuf[r * TW + vcol] = S8[VR + r]; }
+            }
+            // partial Gaussian column sums: taps [A0, A1) of all 8 rows; ring rows A0 .. A1+6
+            float part[RB];
+#pragma unroll
+            for (int r = 0; r < RB; ++r) part[r] = 0.f;
+            auto vpart = [&](auto H_) {
+                constexpr int hh = decltype(H_)::value;
+                constexpr int A0 = hh == 0 ? 0 : (TL + 1) / 2 / 4 * 4;          // tap split on a 4-row unit boundary
+                constexpr int A1 = hh == 0 ? (TL + 1) / 2 / 4 * 4 : TL;
+                constexpr int U0_ = A0 / 4, U1_ = (A1 - 1 + RB - 1) / 4;        // ring units touched
+                // units before the ring wraps use base 0, the others base 1 (= base 0 - ring size)
+                const int ub = 2 * g0;
+                const float4 *b0 = ringH + ub * TWP + cp;
+                const float4 *b1 = b0 - 2 * G::NG * TWP;
+                const int wrap_at = 2 * G::NG - ub;                            // first unit index that wraps
+                static_for<U0_, U1_ + 1>([&](auto U_) {
+                    constexpr int u = decltype(U_)::value;
+                    const float4 v = (u < wrap_at ? b0 : b1)[u * TWP];
+                    const float hv[4] = {v.x, v.y, v.z, v.w};
+                    static_for<0, 4>([&](auto E_) {
+                        constexpr int t = 4 * u + decltype(E_)::value;
+                        static_for<0, RB>([&](auto R_) {
+                            constexpr int r = decltype(R_)::value;
+                            constexpr int a = t - r;
+                            if constexpr (a >= A0 && a < A1) part[r] = fmaf(c_n32[TL == 80][a], hv[t - 4 * u], part[r]);
+                        });
                     });
                 });
-            });
-            // decision
-            const int x = x0 + vcol;
-            const bool xin = x >= G::OFF && x + G::HI < W;
-            uint32_t myword = 0;
+            };
+            if (vhalf == 0) vpart(std::integral_constant<int, 0>{}); else vpart(std::integral_constant<int, 1>{});
+            // swap: each half sends the partials of the 4 rows the other half decides
+            {
+                float *dst = xbuf + (vhalf * VR) * TW + vcol;
 #pragma unroll
-            for (int r = 0; r < VR; ++r) {
-                const int y = yb + VR * vhalf + r;
-                const int Sr = vhalf ? S[VR + r] : S[r];
-                bool on = false;
-                if (x < W && y < ye) {
-                    float thr;
-                    if (xin && y >= G::OFF && y + G::HI < H) thr = __ldg(P.thr_lut + Sr);
-                    else thr = (float)border_threshold<TL>(y, x, H, W, (double)Sr, mfrac, P.st2, cn);
-                    const float d = acc[r] - thr;
-                    on = d > 0.f;
-                    if (fabsf(d) <= BAND) {          // float32 cannot decide: queue for the float64 pass
-                        on = false;
-                        const uint32_t slot = atomicAdd(P.recheck_n + f, 1u);
-                        if (slot < (uint32_t)P.recheck_cap) P.recheck[(size_t)f * P.recheck_cap + slot] = make_int2(x, y);
-                        else atomicOr(P.status, VBS_DEV_RECHECK_OVERFLOW);
-                    }
+                for (int r = 0; r < VR; ++r) dst[r * TW] = vhalf ? part[r] : part[VR + r];
+            }
+            __syncthreads();
+            float acc[VR];
+            {
+                const float *src = xbuf + ((1 - vhalf) * VR) * TW + vcol;
+#pragma unroll
+                for (int r = 0; r < VR; ++r) {
+                    const float mine = vhalf ? part[VR + r] : part[r];
+                    const float other = src[r * TW];
+                    acc[r] = vhalf ? other + mine : mine + other;     // low taps first on both sides
                 }
-                const uint32_t word = __ballot_sync(0xffffffffu, on);
-                if (lane == r) myword = word;
+                if (vhalf) {
+#pragma unroll
+                    for (int r = 0; r < VR; ++r) S[r] = sbuf[r * TW + vcol];
+                }
+            }
+            // ---- D: decision --------------------------------------------------------------------------
+            const int x = x0 + vcol;
+            const int y0 = yb + VR * vhalf;
+            uint32_t myword = 0;
+            auto queue = [&](int y) {                 // float32 cannot decide: queue for the float64 pass
+                const uint32_t slot = atomicAdd(P.recheck_n + f, 1u);
+                if (slot < (uint32_t)P.recheck_cap) P.recheck[(size_t)f * P.recheck_cap + slot] = make_int2(x, y);
+                else atomicOr(P.status, VBS_DEV_RECHECK_OVERFLOW);
+            };
+            if (strip_interior && yb >= G::OFF && yb + RB - 1 + G::HI < H && yb + RB <= ye) {
+                // whole step inside the image: threshold is the table entry of the box sum
+                float thr[VR];
+#pragma unroll
+                for (int r = 0; r < VR; ++r) thr[r] = __ldg(P.thr_lut + S[r]);
+#pragma unroll
+                for (int r = 0; r < VR; ++r) {
+                    const float d = acc[r] - thr[r];
+                    bool on = d > 0.f;
+                    if (fabsf(d) <= BAND) { on = false; queue(y0 + r); }
+                    const uint32_t word = __ballot_sync(0xffffffffu, on);
+                    if (lane == r) myword = word;
+                }
+            } else {
+                const bool xin = x >= G::OFF && x + G::HI < W;
+#pragma unroll
+                for (int r = 0; r < VR; ++r) {
+                    const int y = y0 + r;
+                    bool on = false;
+                    if (x < W && y < ye) {
+                        float thr;
+                        if (xin && y >= G::OFF && y + G::HI < H) thr = __ldg(P.thr_lut + S[r]);
+                        else thr = (float)border_threshold<TL>(y, x, H, W, (double)S[r], mfrac, P.st2, cn);
+                        const float d = acc[r] - thr;
+                        on = d > 0.f;
+                        if (fabsf(d) <= BAND) { on = false; queue(y); }
+                    }
+                    const uint32_t word = __ballot_sync(0xffffffffu, on);
+                    if (lane == r) myword = word;
+                }
             }
             const int wx = (x0 >> 5) + (vcol >> 5);
-            const int yw = yb + VR * vhalf + lane;
+            const int yw = y0 + lane;
             if (lane < VR && yw < ye && wx < WW) P.mask_bits[((size_t)f * H + yw) * WW + wx] = myword;
         }
         __syncthreads();
@@ -321,7 +388,7 @@ template <int TL> cudaError_t launch(vbs_ctx *ctx, int batch, double st2) {
     vsegs = (ctx->H + P.seg_rows - 1) / P.seg_rows;
     P.st2 = st2; P.hw = (double)ctx->H * (double)ctx->W;
     P.area_bits = ctx->area_bits; P.area_count = ctx->area_count; P.mask_bits = ctx->mask_bits;
-    P.thr_lut = ctx->thr_lut; P.cn64 = ctx->d_cn64;
+    P.thr_lut = ctx->thr_lut; P.cn64 = ctx->d_cn64; P.cnfix = ctx->d_cnfix;
     P.recheck = ctx->recheck; P.recheck_n = ctx->recheck_n; P.recheck_cap = ctx->recheck_cap;
     P.status = ctx->d_status;
     cudaError_t e = cudaMemsetAsync(ctx->recheck_n, 0, sizeof(uint32_t) * batch, ctx->stream);
@@ -348,7 +415,8 @@ cudaError_t vbs_ncc_setup(vbs_ctx *ctx) {
     }
     double ss = 0;
     float n32[96] = {0};
-    for (int i = 0; i < TL; ++i) { n[i] = e[i] / sum; ss += n[i] * n[i]; n32[i] = (float)n[i]; }
+    // the horizontal pass hands over 2^30 h (fixed point): fold the exact power of two into the weights
+    for (int i = 0; i < TL; ++i) { n[i] = e[i] / sum; ss += n[i] * n[i]; n32[i] = (float)ldexp(n[i], -30); }
     const double L2 = (double)TL * TL;
     const double st2 = ss * ss - 1.0 / L2;
     ctx->st2 = st2;
@@ -365,6 +433,13 @@ cudaError_t vbs_ncc_setup(vbs_ctx *ctx) {
         lut[S] = (q > 0) ? (float)(S / L2 + 0.1 * sqrt(st2 * q) / (double)TL) : INFINITY;
     }
     cudaError_t err;
+    int fixt[4 * 112];
+    for (int sft = 0; sft < 4; ++sft)
+        for (int k2 = 0; k2 < 112; ++k2) {
+            const int idx = k2 + sft;
+            fixt[sft * 112 + k2] = idx < CNX ? (int)llrint(ldexp(cn[idx], 30)) : (int)llrint(ldexp(pre[TL], 30));
+        }
+    if ((err = cudaMemcpy(ctx->d_cnfix, fixt, sizeof(fixt), cudaMemcpyHostToDevice)) != cudaSuccess) { delete[] lut; return err; }
     if ((err = cudaMemcpy(ctx->d_n64, n, sizeof(double) * TL, cudaMemcpyHostToDevice)) != cudaSuccess) { delete[] lut; return err; }
     if ((err = cudaMemcpy(ctx->d_cn64, cn, sizeof(double) * CNX, cudaMemcpyHostToDevice)) != cudaSuccess) { delete[] lut; return err; }
     err = cudaMemcpy(ctx->thr_lut, lut, sizeof(float) * NL, cudaMemcpyHostToDevice);

@@ -32,7 +32,7 @@ int map_status(vbs_ctx *ctx, uint32_t st) {
 
 void free_all(vbs_ctx *c) {
     void *ptrs[] = {c->d_frames, c->area_bits, c->mask_bits, c->max_bits, c->open_bits, c->root_bits, c->area_count, c->thr_lut,
-                    c->d_n64, c->d_cn64, c->recheck, c->recheck_n, c->parent, c->parent2, c->rowcnt, c->rowoff, c->d_nlabels,
+                    c->d_n64, c->d_cn64, c->d_cnfix, c->recheck, c->recheck_n, c->parent, c->parent2, c->rowcnt, c->rowoff, c->d_nlabels,
                     c->d_ncont, c->lab_cnt, c->lab_sx, c->lab_sy, c->centres, c->croot, c->cell, c->claim, c->cmatch, c->cpts, c->cpn, c->euler4, c->holes, c->d_nmarkers,
                     c->marker_xy, c->marker_axes, c->ref_row, c->ref_col, c->ref_xy, c->row_det, c->row_cxy, c->row_axes, c->obs,
                     c->pos3d, c->pos_flags, c->last_seen, c->pl_ref, c->pl_start, c->pl_dvert, c->pl_use, c->plane, c->plane_n,
@@ -168,7 +168,7 @@ int vbs_create(vbs_ctx **out, const vbs_config *cfg) {
     VBS_CUDA(dalloc(&ctx->open_bits, nbits)); VBS_CUDA(dalloc(&ctx->root_bits, nbits));
     VBS_CUDA(dalloc(&ctx->area_count, B));
     VBS_CUDA(dalloc(&ctx->thr_lut, (size_t)ctx->br.tl * ctx->br.tl + 1));
-    VBS_CUDA(dalloc(&ctx->d_n64, 96)); VBS_CUDA(dalloc(&ctx->d_cn64, 160));
+    VBS_CUDA(dalloc(&ctx->d_n64, 96)); VBS_CUDA(dalloc(&ctx->d_cn64, 160)); VBS_CUDA(dalloc(&ctx->d_cnfix, 4 * 112));
     ctx->recheck_cap = 16384;
     VBS_CUDA(dalloc(&ctx->recheck, B * ctx->recheck_cap)); VBS_CUDA(dalloc(&ctx->recheck_n, B));
     VBS_CUDA(dalloc(&ctx->parent, B * H * W)); VBS_CUDA(dalloc(&ctx->parent2, B * H * W));

@@ -43,6 +43,7 @@ struct vbs_ctx {
     double *d_n64;                   // [tl] template factor n
     double *d_cn64;                  // [tl+1+16] guarded prefix sums of n
     double st2;                      // (sum n^2)^2 - 1/L^2
+    int *d_cnfix;                    // [4][112] shifted fixed-point (2^30) copies of the prefix sums
     int2 *recheck; uint32_t *recheck_n; int recheck_cap;   // float64 recheck list [B][cap]
     // union-find scratch
     int32_t *parent, *parent2;       // [B][H*W] ring maxima / opened image (fg + bg)
