@@ -63,18 +63,21 @@ __device__ __forceinline__ uint32_t ld_bits(const uint32_t *row, int wi, int WW)
     return (wi >= 0 && wi < WW) ? __ldg(row + wi) : 0u;
 }
 
-// threshold on G for a pixel whose window is clipped by the image border (float64)
+// threshold on G for a pixel whose window is clipped by the image border.  float32 is enough for the
+// filter: q <= L^4/4 ~ 1e7 is a sum of a few exactly representable integers times m, so thr carries
+// ~1e-6 relative error at worst; such pixels use the wider BAND_BORDER before the float64 re-decision.
+constexpr float BAND_BORDER = 2e-5f;
 template <int TL>
-__device__ __noinline__ double border_threshold(int y, int x, int H, int W, double S, double m, double st2, const double *cn) {
+__device__ __forceinline__ float border_threshold(int y, int x, int H, int W, float S, float m, float st2, const double *cn) {
     using G = Geo<TL>;
     const int ylo = max(0, G::OFF - y), yhi = min(TL - 1, H - 1 - y + G::OFF);
     const int xlo = max(0, G::OFF - x), xhi = min(TL - 1, W - 1 - x + G::OFF);
-    const double A = (double)(yhi - ylo + 1) * (double)(xhi - xlo + 1);
-    const double g1 = (cn[yhi + 1 + 8] - cn[ylo + 8]) * (cn[xhi + 1 + 8] - cn[xlo + 8]);
-    const double L2 = (double)(TL * TL);
-    const double q = S * (L2 - S) - 2.0 * m * S * (L2 - A) + m * m * A * (L2 - A);
-    if (!(q > 0.0)) return INFINITY;
-    return m * g1 + (S - m * A) / L2 + 0.1 * sqrt(st2 * q) / (double)TL;
+    const float A = (float)((yhi - ylo + 1) * (xhi - xlo + 1));
+    const float g1 = (float)(cn[yhi + 1 + 8] - cn[ylo + 8]) * (float)(cn[xhi + 1 + 8] - cn[xlo + 8]);
+    const float L2 = (float)(TL * TL);
+    const float q = S * (L2 - S) - 2.0f * m * S * (L2 - A) + m * m * A * (L2 - A);
+    if (!(q > 0.0f)) return INFINITY;
+    return m * g1 + (S - m * A) * (1.0f / L2) + (0.1f / (float)TL) * sqrtf(st2 * q);
 }
 
 // 256 threads per 128-pixel strip, three phases per 8-row step:
@@ -91,13 +94,19 @@ constexpr int VR = 4;                    // output rows each half decides
 constexpr int FIX_SHIFT = 30;            // fixed-point scale of the prefix table
 constexpr int FXN = 112;                 // entries per shifted copy of the fixed-point table (>= CNX + 3, multiple of 4)
 
+template <int TL> struct GeoR : Geo<TL> {
+    static constexpr int NR = Geo<TL>::NG;                // ring groups (a spare slot would save a barrier but costs the 3rd CTA/SM)
+    static constexpr size_t SMEM = (size_t)NR * 2 * TWP * 16 + (size_t)NR * TWP * 8 + (size_t)(Geo<TL>::CNX + (Geo<TL>::CNX & 1)) * 8 +
+                                   4 * 112 * 4 + 2 * 4 * TW * 4 + 4 * TW * 4;
+};
+
 template <int TL>
 __global__ void __launch_bounds__(NT, 3) ncc_mask_kernel(NccParams P) {
-    using G = Geo<TL>;
+    using G = GeoR<TL>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4 *ringH = reinterpret_cast<float4 *>(smem_raw);                        // [NG*2][TWP]
-    uint2 *ringB = reinterpret_cast<uint2 *>(ringH + G::NG * 2 * TWP);           // [NG][TWP]
-    double *cn = reinterpret_cast<double *>(ringB + G::NG * TWP);                // [CNX] float64 prefix sums (border formula)
+    float4 *ringH = reinterpret_cast<float4 *>(smem_raw);                        // [NR*2][TWP]
+    uint2 *ringB = reinterpret_cast<uint2 *>(ringH + G::NR * 2 * TWP);           // [NR][TWP]
+    double *cn = reinterpret_cast<double *>(ringB + G::NR * TWP);                // [CNX] float64 prefix sums (border formula)
     int4 *fx = reinterpret_cast<int4 *>(cn + G::CNX + (G::CNX & 1));             // [4][FXN/4] shifted fixed-point copies
     float *xbuf = reinterpret_cast<float *>(fx + FXN);                           // [2][VR][TW] partial sums in flight
     int *sbuf = reinterpret_cast<int *>(xbuf + 2 * VR * TW);                     // [VR][TW] box sums for half 1
@@ -109,7 +118,7 @@ __global__ void __launch_bounds__(NT, 3) ncc_mask_kernel(NccParams P) {
     const int f = blockIdx.z;
     const int H = P.H, W = P.W, WW = P.WW;
     const uint32_t *abits = P.area_bits + (size_t)f * H * WW;
-    const double mfrac = (double)P.area_count[f] / P.hw;          // mean(area_mask)/255
+    const float mfrac = (float)((double)P.area_count[f] / P.hw);  // mean(area_mask)/255
     for (int i = tid; i < G::CNX; i += NT) cn[i] = P.cn64[i];
     for (int i = tid; i < 4 * FXN; i += NT) reinterpret_cast<int *>(fx)[i] = P.cnfix[i];
 
@@ -140,7 +149,7 @@ __global__ void __launch_bounds__(NT, 3) ncc_mask_kernel(NccParams P) {
 
     if (hrole) fetch(0);
     __syncthreads();
-    int gw = 0;                                  // ring group written by step m (m % NG)
+    int gw = 0;                                  // ring slot written by step m (m % NR)
     for (int m = 0; m < nsteps; ++m) {
         // ---- H: horizontal pass on bits ------------------------------------------------------------
         if (hrole) {
@@ -196,13 +205,13 @@ __global__ void __launch_bounds__(NT, 3) ncc_mask_kernel(NccParams P) {
         if (m >= G::LEAD) {
             const int k = m - G::LEAD;
             const int yb = ys + RB * k;
-            int g0 = gw + 1; if (g0 >= G::NG) g0 -= G::NG;           // group of step k
+            int g0 = gw + 1; if (g0 >= G::NR) g0 -= G::NR;           // slot of step k = m - LEAD (NR = LEAD + 1)
             // box sums of the 8 rows: half 0 runs the chain and hands rows 4..7 to half 1
             int S[VR];
             if (vhalf == 0) {
                 auto box_at = [&](auto I_) -> int {
                     constexpr int idx = decltype(I_)::value;
-                    int gi = g0 + idx / 8; if (gi >= G::NG) gi -= G::NG;
+                    int gi = g0 + idx / 8; if (gi >= G::NR) gi -= G::NR;
                     const uint2 b = ringB[gi * TWP + cp];
                     const uint32_t w = (idx % 8) < 4 ? b.x : b.y;
                     return (int)((w >> (8 * (idx % 4))) & 255u);
@@ -212,7 +221,7 @@ __global__ void __launch_bounds__(NT, 3) ncc_mask_kernel(NccParams P) {
                     int s = 0;
 #pragma unroll 1
                     for (int t = 0; t < TL; ++t) {
-                        int gi = g0 + (t >> 3); if (gi >= G::NG) gi -= G::NG;
+                        int gi = g0 + (t >> 3); if (gi >= G::NR) gi -= G::NR;
                         s += reinterpret_cast<const unsigned char *>(ringB + gi * TWP + cp)[t & 7];
                     }
                     S8[0] = s;
@@ -239,8 +248,8 @@ __global__ void __launch_bounds__(NT, 3) ncc_mask_kernel(NccParams P) {
                 // units before the ring wraps use base 0, the others base 1 (= base 0 - ring size)
                 const int ub = 2 * g0;
                 const float4 *b0 = ringH + ub * TWP + cp;
-                const float4 *b1 = b0 - 2 * G::NG * TWP;
-                const int wrap_at = 2 * G::NG - ub;                            // first unit index that wraps
+                const float4 *b1 = b0 - 2 * G::NR * TWP;
+                const int wrap_at = 2 * G::NR - ub;                            // first unit index that wraps
                 static_for<U0_, U1_ + 1>([&](auto U_) {
                     constexpr int u = decltype(U_)::value;
                     const float4 v = (u < wrap_at ? b0 : b1)[u * TWP];
@@ -307,11 +316,12 @@ __global__ void __launch_bounds__(NT, 3) ncc_mask_kernel(NccParams P) {
                     bool on = false;
                     if (x < W && y < ye) {
                         float thr;
+                        float band = BAND;
                         if (xin && y >= G::OFF && y + G::HI < H) thr = __ldg(P.thr_lut + S[r]);
-                        else thr = (float)border_threshold<TL>(y, x, H, W, (double)S[r], mfrac, P.st2, cn);
+                        else { thr = border_threshold<TL>(y, x, H, W, (float)S[r], mfrac, (float)P.st2, cn); band = BAND_BORDER; }
                         const float d = acc[r] - thr;
                         on = d > 0.f;
-                        if (fabsf(d) <= BAND) { on = false; queue(y); }
+                        if (fabsf(d) <= band) { on = false; queue(y); }
                     }
                     const uint32_t word = __ballot_sync(0xffffffffu, on);
                     if (lane == r) myword = word;
@@ -321,8 +331,8 @@ __global__ void __launch_bounds__(NT, 3) ncc_mask_kernel(NccParams P) {
             const int yw = y0 + lane;
             if (lane < VR && yw < ye && wx < WW) P.mask_bits[((size_t)f * H + yw) * WW + wx] = myword;
         }
-        __syncthreads();
-        if (++gw == G::NG) gw = 0;
+        __syncthreads();                         // the next horizontal step overwrites the oldest ring group
+        if (++gw == G::NR) gw = 0;
     }
 }
 
@@ -378,7 +388,7 @@ __global__ void ncc_recheck_kernel(NccParams P, const double *__restrict__ n64, 
 }
 
 template <int TL> cudaError_t launch(vbs_ctx *ctx, int batch, double st2) {
-    using G = Geo<TL>;
+    using G = GeoR<TL>;
     NccParams P;
     P.H = ctx->H; P.W = ctx->W; P.WW = ctx->WW;
     const int strips = (ctx->W + TW - 1) / TW;
