@@ -43,7 +43,7 @@ typedef struct vbs_config {
     int32_t width;        /* processed (cropped) frame width in pixels                         */
     int32_t channels;     /* 1 = gray, 3 = BGR (converted like cvtColor, MD:114)               */
     int32_t max_batch;    /* frames per vbs_process_* call (scratch is sized for this)         */
-    int32_t max_markers;  /* capacity for labels / contours / markers per frame                */
+    int32_t max_markers;  /* capacity for labels / contours / markers per frame (<= 8192)      */
     int32_t max_refs;     /* capacity of the reference-state array                             */
 } vbs_config;
 
@@ -81,7 +81,8 @@ typedef enum vbs_stage {
 int  vbs_create(vbs_ctx **out, const vbs_config *cfg);      /* replaces MarkerTracker.__init__ (MD:15-31) */
 void vbs_destroy(vbs_ctx *ctx);                             /* replaces _cleanup (MD:470-474)             */
 const char *vbs_last_error(const vbs_ctx *ctx);
-int  vbs_set_stream(vbs_ctx *ctx, void *cuda_stream);       /* run on the caller's stream (0 = own stream) */
+int  vbs_set_stream(vbs_ctx *ctx, void *cuda_stream);       /* run on the caller's stream; 0 = the context's own
+                                                                non-blocking stream, cudaStreamLegacy (0x1) = the legacy default stream */
 int  vbs_sync(vbs_ctx *ctx);                                /* wait; returns device-side status of all work so far */
 const char *vbs_version(void);
 
@@ -137,6 +138,10 @@ int vbs_process_device(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int64
 int vbs_process_host(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int64_t frame_stride,
                      int64_t row_pitch, int64_t frameno0, const vbs_outputs *out);
 
+/* optional for vbs_process_device (default off; vbs_process_host always does it): cut a batch of >= 64
+ * frames into chunks and run the long detection kernels of chunk c+1 beside the short latency-bound
+ * kernels of chunk c on a second stream */
+int vbs_set_overlap(vbs_ctx *ctx, int32_t enable);
 /* frames per chunk of vbs_process_host's copy/compute overlap (0 = default 64) */
 int vbs_set_host_chunk(vbs_ctx *ctx, int32_t frames_per_chunk);
 

@@ -71,12 +71,21 @@ __device__ void unite(int32_t *par, int a, int b) {
     }
 }
 
-// word kernels: block (64, 4) = 64 words x 4 rows, grid (ceil(WW/64), ceil(H/4), batch)
+// word kernels (background pass): block (64, 4) = 64 words x 4 rows, grid (ceil(WW/64), ceil(H/4), batch)
 #define VBS_WORD_COORDS                                          \
     const int wx = blockIdx.x * 64 + threadIdx.x;               \
     const int y = blockIdx.y * 4 + threadIdx.y;                 \
     const int f = blockIdx.z;                                   \
     if (wx >= WW || y >= H) return;
+
+// quad kernels (foreground passes): one thread = 4 consecutive words (one 128-bit load; rows are padded
+// to a multiple of 4 words); block (16, 16), grid (ceil(WW/64), ceil(H/16), 2 * batch); z = 2 f + image,
+// image 0 = ring maxima (4-connected, parent), image 1 = opened area mask (8-connected, parent2)
+#define VBS_QUAD_COORDS                                          \
+    const int q = blockIdx.x * 16 + threadIdx.x;                \
+    const int y = blockIdx.y * 16 + threadIdx.y;                \
+    const int z = blockIdx.z, f = z >> 1, img = z & 1;          \
+    if (4 * q >= WW || y >= H) return;
 
 // ---- 1. every segment start becomes its own root ------------------------------------------------
 // FG: set bits.  BG (conditional on holes[f] != 0): cleared bits inside the image.
@@ -144,27 +153,6 @@ __global__ void __launch_bounds__(256) ccl_merge_kernel(const uint32_t *__restri
     }
 }
 
-// ---- 3. flatten: every segment points at its root; mark roots (root bits + per-row counts) --------
-__global__ void __launch_bounds__(256) ccl_roots_kernel(const uint32_t *__restrict__ bits, int32_t *__restrict__ parent,
-                                                         uint32_t *__restrict__ root_bits, int32_t *__restrict__ rowcnt,
-                                                         int H, int W, int WW) {
-    VBS_WORD_COORDS
-    const size_t i = ((size_t)f * H + y) * WW + wx;
-    const uint32_t w = __ldg(bits + i);
-    int32_t *par = parent + (size_t)f * H * W;
-    const int base = y * W + 32 * wx;
-    uint32_t roots = 0;
-    uint32_t starts = w & ~(w << 1);
-    while (starts) {
-        const int s = __ffs(starts) - 1;
-        starts &= starts - 1;
-        const int r = find_root(par, base + s);
-        if (r == base + s) roots |= 1u << s;
-        else par[base + s] = r;
-    }
-    root_bits[i] = roots;
-    if (roots) atomicAdd(rowcnt + (size_t)f * H + y, __popc(roots));
-}
 // background segments of frames with holes: point straight at the root (or at OUTSIDE)
 __global__ void __launch_bounds__(256) ccl_flatten_bg_kernel(const uint32_t *__restrict__ bits, int32_t *__restrict__ parent,
                                                               const int32_t *__restrict__ holes, int H, int W, int WW) {
@@ -182,7 +170,127 @@ __global__ void __launch_bounds__(256) ccl_flatten_bg_kernel(const uint32_t *__r
     }
 }
 
-// ---- 3b. Euler number of the 8-connected foreground by bit quads ----------------------------------
+
+// ---- foreground, both images in one launch ---------------------------------------------------------
+struct FgImages {
+    const uint32_t *bits[2];     // max_bits, open_bits
+    int32_t *parent[2];          // parent, parent2
+};
+
+template <bool CONN8>
+__device__ __forceinline__ void merge_word(int32_t *par, uint32_t w, uint32_t prev, uint32_t up, uint32_t upl, uint32_t upr, int base, int W) {
+    if ((w & 1u) && (prev >> 31)) unite(par, base, base - 32 + seg_start(prev, 31));
+    uint32_t rem = w;
+    while (rem) {
+        const int s = __ffs(rem) - 1;
+        const uint32_t seg = run_mask(w, s);
+        rem &= ~seg;
+        const int id = base + s;
+        uint32_t nb = seg;
+        if (CONN8) nb |= (seg << 1) | (seg >> 1);
+        uint32_t ov = up & nb;
+        while (ov) {
+            const int b = __ffs(ov) - 1;
+            const int us = seg_start(up, b);
+            ov &= ~run_mask(up, us);
+            unite(par, id, base - W + us);
+        }
+        if (CONN8) {
+            if ((seg & 1u) && (upl >> 31)) unite(par, id, base - W - 32 + seg_start(upl, 31));
+            if ((seg >> 31) && (upr & 1u)) unite(par, id, base - W + 32);
+        }
+    }
+}
+
+// one thread per word (a quad-per-thread version was 1.8x slower: the few busy threads serialise)
+__global__ void __launch_bounds__(256) fg_merge_kernel(FgImages im, int H, int W, int WW) {
+    const int wx = blockIdx.x * 64 + threadIdx.x;
+    const int y = blockIdx.y * 4 + threadIdx.y;
+    const int z = blockIdx.z, f = z >> 1, img = z & 1;
+    if (wx >= WW || y >= H) return;
+    const uint32_t *img_bits = im.bits[img] + (size_t)f * H * WW;
+    const uint32_t w = __ldg(img_bits + (size_t)y * WW + wx);
+    if (!w) return;
+    int32_t *par = im.parent[img] + (size_t)f * H * W;
+    const uint32_t prev = ((w & 1u) && wx > 0) ? __ldg(img_bits + (size_t)y * WW + wx - 1) : 0u;
+    uint32_t up = 0, upl = 0, upr = 0;
+    if (y > 0) {
+        const uint32_t *urow = img_bits + (size_t)(y - 1) * WW;
+        up = __ldg(urow + wx);
+        if (img) {                               // diagonal neighbours (8-connectivity)
+            upl = wx > 0 ? __ldg(urow + wx - 1) : 0u;
+            upr = wx + 1 < WW ? __ldg(urow + wx + 1) : 0u;
+        }
+    }
+    const int base = y * W + 32 * wx;
+    if (img) merge_word<true>(par, w, prev, up, upl, upr, base, W);
+    else merge_word<false>(par, w, prev, up, 0u, 0u, base, W);
+}
+
+// flatten + root discovery: a root takes the next slot of its (frame, image) list and encodes it
+// in place (parent[root] = -2 - slot); everybody else points at its root (or already at the code)
+__global__ void __launch_bounds__(256) fg_roots_kernel(FgImages im, int32_t *__restrict__ nroots, int32_t *__restrict__ rootlist,
+                                                        int H, int W, int WW, int M) {
+    VBS_QUAD_COORDS
+    const uint32_t *img_bits = im.bits[img] + (size_t)f * H * WW;
+    const uint4 w4 = __ldg(reinterpret_cast<const uint4 *>(img_bits + (size_t)y * WW) + q);
+    if (!(w4.x | w4.y | w4.z | w4.w)) return;
+    int32_t *par = im.parent[img] + (size_t)f * H * W;
+    const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int base = y * W + 32 * (4 * q + k);
+        uint32_t starts = w[k] & ~(w[k] << 1);
+        while (starts) {
+            const int s = __ffs(starts) - 1;
+            starts &= starts - 1;
+            const int r = find_root(par, base + s);
+            if (r == base + s) {
+                const int slot = atomicAdd(nroots + z, 1);
+                if (slot < M) { rootlist[(size_t)z * M + slot] = r; par[r] = -2 - slot; }
+            } else {
+                par[base + s] = r;
+            }
+        }
+    }
+}
+
+// ring components: integer moments per root slot (MD:181 center_of_mass on a 0/1 mask)
+__global__ void __launch_bounds__(256) moments_kernel(const uint32_t *__restrict__ bits, const int32_t *__restrict__ parent,
+                                                       uint32_t *__restrict__ cnt, unsigned long long *__restrict__ sx,
+                                                       unsigned long long *__restrict__ sy, int H, int W, int WW, int M) {
+    const int q = blockIdx.x * 16 + threadIdx.x;
+    const int y = blockIdx.y * 16 + threadIdx.y;
+    const int f = blockIdx.z;
+    if (4 * q >= WW || y >= H) return;
+    const uint4 w4 = __ldg(reinterpret_cast<const uint4 *>(bits + ((size_t)f * H + y) * WW) + q);
+    if (!(w4.x | w4.y | w4.z | w4.w)) return;
+    const int32_t *par = parent + (size_t)f * H * W;
+    const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int wx = 4 * q + k;
+        const int base = y * W + 32 * wx;
+        uint32_t rem = w[k];
+        while (rem) {
+            const int s = __ffs(rem) - 1;
+            const uint32_t seg = run_mask(w[k], s);
+            rem &= ~seg;
+            int p = par[base + s];
+            if (p >= 0) p = par[p];                 // non-root segments point at their root, which holds the code
+            if (p >= 0) continue;                   // root beyond capacity (flagged by the sort kernel)
+            const int slot = -2 - p;
+            if (slot < 0 || slot >= M) continue;
+            const unsigned len = __popc(seg);
+            const unsigned long long xs = (unsigned long long)len * (unsigned)(32 * wx + s) + (unsigned long long)len * (len - 1) / 2;
+            atomicAdd(cnt + (size_t)f * M + slot, len);
+            atomicAdd(sx + (size_t)f * M + slot, xs);
+            atomicAdd(sy + (size_t)f * M + slot, (unsigned long long)len * (unsigned)y);
+        }
+    }
+}
+
+// ---- Euler number of the 8-connected foreground by bit quads ----------------------------------------
 // 4 E = #Q1 - #Q3 - 2 #QD over all 2x2 windows of the zero-padded image (Gray's formula).  The
 // number of holes of the whole image is (#blobs - E); when it is 0 no blob can lie inside
 // another one, so the background labelling that RETR_EXTERNAL would need is skipped for the frame.
@@ -195,169 +303,98 @@ __global__ void __launch_bounds__(256) euler_kernel(const uint32_t *__restrict__
         const uint32_t *img = bits + (size_t)f * H * WW;
         auto ld = [&](int y, int w) -> uint32_t { return (y >= 0 && y < H && w >= 0 && w < WW) ? __ldg(img + (size_t)y * WW + w) : 0u; };
         const uint32_t b = ld(yy, wx), d = ld(yy + 1, wx);
-        const uint32_t a = (b << 1) | (ld(yy, wx - 1) >> 31), c = (d << 1) | (ld(yy + 1, wx - 1) >> 31);
-        const uint32_t x1 = a ^ b, x2 = c ^ d, n1 = a & b, n2 = c & d;
-        const uint32_t q1 = (x1 & ~x2 & ~n2) | (x2 & ~x1 & ~n1);
-        const uint32_t q3 = (x1 & n2) | (x2 & n1);
-        const uint32_t qd = x1 & x2 & ~(a ^ d);
-        v = __popc(q1) - __popc(q3) - 2 * __popc(qd);
+        if (b | d | (wx > 0 ? 1u : 0u)) {
+            const uint32_t a = (b << 1) | (ld(yy, wx - 1) >> 31), c = (d << 1) | (ld(yy + 1, wx - 1) >> 31);
+            const uint32_t x1 = a ^ b, x2 = c ^ d, n1 = a & b, n2 = c & d;
+            const uint32_t q1 = (x1 & ~x2 & ~n2) | (x2 & ~x1 & ~n1);
+            const uint32_t q3 = (x1 & n2) | (x2 & n1);
+            const uint32_t qd = x1 & x2 & ~(a ^ d);
+            v = __popc(q1) - __popc(q3) - 2 * __popc(qd);
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (((threadIdx.y * 64 + threadIdx.x) & 31) == 0 && v) atomicAdd(euler4 + f, v);
 }
 
-__global__ void holes_kernel(const int32_t *__restrict__ euler4, const int32_t *__restrict__ ncont, int32_t *__restrict__ holes, int batch) {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f < batch) holes[f] = ncont[f] - euler4[f] / 4;
-}
-
-// ---- 4. exclusive scan of the per-row root counts (one CTA per frame) ----------------------------
-__global__ void __launch_bounds__(1024) row_scan_kernel(const int32_t *__restrict__ rowcnt, int32_t *__restrict__ rowoff,
-                                                         int32_t *__restrict__ total, int H) {
-    __shared__ int32_t warp_sum[32];
-    __shared__ int32_t carry_s;
-    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int32_t *cnt = rowcnt + (size_t)f * H;
-    int32_t *off = rowoff + (size_t)f * H;
-    if (tid == 0) carry_s = 0;
+// ---- rank the roots of one (frame, image) in raster order: bitonic sort in shared memory -----------
+// image 0: label = rank -> slot2label, centroids in label order.  image 1: contour slot = n-1-rank -> croot, holes.
+__global__ void __launch_bounds__(1024) rank_kernel(const int32_t *__restrict__ nroots, const int32_t *__restrict__ rootlist,
+                                                     const int32_t *__restrict__ parent, const uint32_t *__restrict__ cnt,
+                                                     const unsigned long long *__restrict__ sx, const unsigned long long *__restrict__ sy,
+                                                     const int32_t *__restrict__ euler4, int32_t *__restrict__ slot2label,
+                                                     double *__restrict__ centres, int32_t *__restrict__ nlabels, int32_t *__restrict__ croot,
+                                                     int32_t *__restrict__ ncont, int32_t *__restrict__ holes, int H, int W, int M, int P2,
+                                                     uint32_t *status) {
+    extern __shared__ int32_t key[];
+    const int f = blockIdx.x, img = blockIdx.y, z = 2 * f + img, tid = threadIdx.x;
+    const int total = nroots[z];
+    const int n = min(total, M);
+    if (total > M && tid == 0) atomicOr(status, img == 0 ? VBS_DEV_LABEL_OVERFLOW : VBS_DEV_CONTOUR_OVERFLOW);
+    int P = 1;
+    while (P < n) P <<= 1;                                  // P <= P2 (shared memory is sized for P2)
+    for (int i = tid; i < P; i += blockDim.x) key[i] = i < n ? rootlist[(size_t)z * M + i] : 0x7fffffff;
     __syncthreads();
-    for (int y0 = 0; y0 < H; y0 += 1024) {
-        const int y = y0 + tid;
-        const int v = y < H ? cnt[y] : 0;
-        int incl = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        if (lane == 31) warp_sum[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            int ws = warp_sum[lane], wi = ws;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
-            warp_sum[lane] = wi - ws;          // exclusive prefix of warp totals
+    for (int k = 2; k <= P; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < P; i += blockDim.x) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const int a = key[i], b = key[l];
+                    if (((i & k) == 0) == (a > b)) { key[i] = b; key[l] = a; }
+                }
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        const int base = carry_s + warp_sum[warp];
-        if (y < H) off[y] = base + incl - v;
-        __syncthreads();
-        if (tid == 1023) carry_s = base + incl;
-        __syncthreads();
-    }
-    if (tid == 0) total[f] = carry_s;
-}
-
-// ---- 5. rank roots in raster order (one warp per row) --------------------------------------------
-// MODE 0 (ring maxima): parent[root] = -2 - label.       MODE 1 (contours): croot[n-1-rank] = root.
-template <int MODE>
-__global__ void rank_roots_kernel(const uint32_t *__restrict__ root_bits, const int32_t *__restrict__ rowoff,
-                                  const int32_t *__restrict__ total, int32_t *__restrict__ parent, int32_t *__restrict__ croot,
-                                  int H, int W, int WW, int M, size_t nrows, uint32_t *status) {
-    const size_t row = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= nrows) return;
-    const int lane = threadIdx.x & 31;
-    const int y = (int)(row % H);
-    const size_t f = row / H;
-    int carry = rowoff[row];
-    const int n = total[f];
-    if (n > M && lane == 0 && y == 0) atomicOr(status, MODE == 0 ? VBS_DEV_LABEL_OVERFLOW : VBS_DEV_CONTOUR_OVERFLOW);
-    for (int w0 = 0; w0 < WW; w0 += 32) {
-        const int wx = w0 + lane;
-        uint32_t r = wx < WW ? root_bits[row * WW + wx] : 0u;
-        const int c = __popc(r);
-        int incl = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        int rank = carry + incl - c;
-        while (r) {
-            const int b = __ffs(r) - 1;
-            r &= r - 1;
-            const int idx = y * W + 32 * wx + b;
-            if (MODE == 0) { if (rank < M) parent[f * (size_t)H * W + idx] = -2 - rank; }
-            else { const int slot = n - 1 - rank; if (slot < M) croot[f * (size_t)M + slot] = idx; }
-            ++rank;
+    if (img == 0) {
+        const int32_t *par = parent + (size_t)f * H * W;
+        for (int i = tid; i < n; i += blockDim.x) {
+            const int slot = -2 - par[key[i]];
+            slot2label[(size_t)f * M + slot] = i;
+            const size_t s = (size_t)f * M + slot;
+            const double c = (double)cnt[s];
+            centres[((size_t)f * M + i) * 2 + 0] = (double)sy[s] / c;     // row: exact integer sum, one float64 division
+            centres[((size_t)f * M + i) * 2 + 1] = (double)sx[s] / c;     // col
         }
-        carry += __shfl_sync(0xffffffffu, incl, 31);
+        if (tid == 0) nlabels[f] = total;
+    } else {
+        for (int i = tid; i < n; i += blockDim.x) croot[(size_t)f * M + (n - 1 - i)] = key[i];
+        if (tid == 0) { ncont[f] = total; holes[f] = total - euler4[f] / 4; }
     }
-}
-
-// ---- 6. ring components: integer moments per label (MD:181 center_of_mass on a 0/1 mask) ---------
-__global__ void __launch_bounds__(256) moments_kernel(const uint32_t *__restrict__ bits, const int32_t *__restrict__ parent,
-                                                       uint32_t *__restrict__ cnt, unsigned long long *__restrict__ sx,
-                                                       unsigned long long *__restrict__ sy, int H, int W, int WW, int M) {
-    VBS_WORD_COORDS
-    const uint32_t w = __ldg(bits + ((size_t)f * H + y) * WW + wx);
-    if (!w) return;
-    const int32_t *par = parent + (size_t)f * H * W;
-    const int base = y * W + 32 * wx;
-    uint32_t rem = w;
-    while (rem) {
-        const int s = __ffs(rem) - 1;
-        const uint32_t seg = run_mask(w, s);
-        rem &= ~seg;
-        int p = par[base + s];
-        if (p >= 0) p = par[p];                 // non-root segments point straight at their root
-        if (p >= 0) continue;                   // root beyond capacity (flagged elsewhere)
-        const int label = -2 - p;
-        if (label < 0 || label >= M) continue;
-        const unsigned len = __popc(seg);
-        const unsigned long long xs = (unsigned long long)len * (unsigned)(32 * wx + s) + (unsigned long long)len * (len - 1) / 2;
-        atomicAdd(cnt + (size_t)f * M + label, len);
-        atomicAdd(sx + (size_t)f * M + label, xs);
-        atomicAdd(sy + (size_t)f * M + label, (unsigned long long)len * (unsigned)y);
-    }
-}
-
-__global__ void centres_kernel(const uint32_t *__restrict__ cnt, const unsigned long long *__restrict__ sx,
-                               const unsigned long long *__restrict__ sy, const int32_t *__restrict__ total,
-                               double *__restrict__ centres, int M, size_t n) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const size_t f = i / M;
-    const int l = (int)(i % M);
-    if (l >= total[f]) return;
-    const double c = (double)cnt[i];
-    centres[2 * i + 0] = (double)sy[i] / c;     // row: exact integer sum, one float64 division
-    centres[2 * i + 1] = (double)sx[i] / c;     // col
 }
 
 }  // namespace
 
 cudaError_t vbs_launch_components(vbs_ctx *ctx, int batch) {
     const int H = ctx->H, W = ctx->W, WW = ctx->WW, M = ctx->M;
-    const size_t nrows = (size_t)batch * H;
     const dim3 wb(64, 4);
     const dim3 wg((WW + 63) / 64, (H + 3) / 4, batch);
     const dim3 eg((WW + 1 + 63) / 64, (H + 1 + 3) / 4, batch);
-    const unsigned gr = (unsigned)((nrows + 7) / 8);
+    const dim3 qb(16, 16);
+    const dim3 qg2((WW + 63) / 64, (H + 15) / 16, 2 * batch), qg1((WW + 63) / 64, (H + 15) / 16, batch);
     cudaStream_t st = ctx->stream;
     cudaError_t e;
-    // ---- ring maxima: 4-connected, labels in raster order, centroids -------------------------------
-    if ((e = cudaMemsetAsync(ctx->rowcnt, 0, sizeof(int32_t) * nrows, st)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(ctx->lab_cnt, 0, sizeof(uint32_t) * (size_t)batch * M, st)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(ctx->lab_sx, 0, sizeof(unsigned long long) * (size_t)batch * M, st)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(ctx->lab_sy, 0, sizeof(unsigned long long) * (size_t)batch * M, st)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(ctx->euler4, 0, sizeof(int32_t) * batch, st)) != cudaSuccess) return e;
-    ccl_init_kernel<true, false><<<wg, wb, 0, st>>>(ctx->max_bits, ctx->parent, nullptr, H, W, WW);
-    ccl_merge_kernel<false, false, false><<<wg, wb, 0, st>>>(ctx->max_bits, ctx->parent, nullptr, H, W, WW);
-    ccl_roots_kernel<<<wg, wb, 0, st>>>(ctx->max_bits, ctx->parent, ctx->root_bits, ctx->rowcnt, H, W, WW);
-    row_scan_kernel<<<batch, 1024, 0, st>>>(ctx->rowcnt, ctx->rowoff, ctx->d_nlabels, H);
-    rank_roots_kernel<0><<<gr, 256, 0, st>>>(ctx->root_bits, ctx->rowoff, ctx->d_nlabels, ctx->parent, nullptr, H, W, WW, M, nrows, ctx->d_status);
-    moments_kernel<<<wg, wb, 0, st>>>(ctx->max_bits, ctx->parent, ctx->lab_cnt, ctx->lab_sx, ctx->lab_sy, H, W, WW, M);
-    centres_kernel<<<(unsigned)(((size_t)batch * M + 255) / 256), 256, 0, st>>>(ctx->lab_cnt, ctx->lab_sx, ctx->lab_sy, ctx->d_nlabels,
-                                                                                ctx->centres, M, (size_t)batch * M);
-    // ---- opened area mask: foreground 8-connected; background 4-connected only in frames with holes --
-    if ((e = cudaMemsetAsync(ctx->rowcnt, 0, sizeof(int32_t) * nrows, st)) != cudaSuccess) return e;
-    ccl_init_kernel<true, false><<<wg, wb, 0, st>>>(ctx->open_bits, ctx->parent2, nullptr, H, W, WW);
-    ccl_merge_kernel<true, false, false><<<wg, wb, 0, st>>>(ctx->open_bits, ctx->parent2, nullptr, H, W, WW);
+    if ((e = cudaMemsetAsync(ctx->nroots, 0, sizeof(int32_t) * 2 * batch, st)) != cudaSuccess) return e;
+    FgImages im;
+    im.bits[0] = ctx->max_bits; im.bits[1] = ctx->open_bits; im.parent[0] = ctx->parent; im.parent[1] = ctx->parent2;
+    // segment starts were initialised by the morphology kernels that produced the two images
+    fg_merge_kernel<<<dim3((WW + 63) / 64, (H + 3) / 4, 2 * batch), wb, 0, st>>>(im, H, W, WW);
+    fg_roots_kernel<<<qg2, qb, 0, st>>>(im, ctx->nroots, ctx->rootlist, H, W, WW, M);
+    moments_kernel<<<qg1, qb, 0, st>>>(ctx->max_bits, ctx->parent, ctx->lab_cnt, ctx->lab_sx, ctx->lab_sy, H, W, WW, M);
     euler_kernel<<<eg, wb, 0, st>>>(ctx->open_bits, ctx->euler4, H, W, WW);
-    ccl_roots_kernel<<<wg, wb, 0, st>>>(ctx->open_bits, ctx->parent2, ctx->root_bits, ctx->rowcnt, H, W, WW);
-    row_scan_kernel<<<batch, 1024, 0, st>>>(ctx->rowcnt, ctx->rowoff, ctx->d_ncont, H);
-    rank_roots_kernel<1><<<gr, 256, 0, st>>>(ctx->root_bits, ctx->rowoff, ctx->d_ncont, nullptr, ctx->croot, H, W, WW, M, nrows, ctx->d_status);
-    holes_kernel<<<(batch + 127) / 128, 128, 0, st>>>(ctx->euler4, ctx->d_ncont, ctx->holes, batch);
-    // background pass: every thread of a hole-free frame returns at once
+    int P2 = 1;
+    while (P2 < M) P2 <<= 1;
+    rank_kernel<<<dim3(batch, 2), 1024, sizeof(int32_t) * P2, st>>>(ctx->nroots, ctx->rootlist, ctx->parent, ctx->lab_cnt, ctx->lab_sx, ctx->lab_sy,
+                                                                   ctx->euler4, ctx->slot2label, ctx->centres, ctx->d_nlabels, ctx->croot,
+                                                                   ctx->d_ncont, ctx->holes, H, W, M, P2, ctx->d_status);
+    // background pass of the opened image: every thread of a hole-free frame returns at once
     ccl_init_kernel<false, true><<<wg, wb, 0, st>>>(ctx->open_bits, ctx->parent2, ctx->holes, H, W, WW);
     ccl_merge_kernel<false, true, true><<<wg, wb, 0, st>>>(ctx->open_bits, ctx->parent2, ctx->holes, H, W, WW);
     ccl_flatten_bg_kernel<<<wg, wb, 0, st>>>(ctx->open_bits, ctx->parent2, ctx->holes, H, W, WW);
-    ctx->launches += 17;
+    ctx->launches += 8;
     return cudaGetLastError();
 }

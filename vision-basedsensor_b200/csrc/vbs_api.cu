@@ -31,15 +31,18 @@ int map_status(vbs_ctx *ctx, uint32_t st) {
 }
 
 void free_all(vbs_ctx *c) {
-    void *ptrs[] = {c->d_frames, c->area_bits, c->mask_bits, c->max_bits, c->open_bits, c->root_bits, c->area_count, c->thr_lut,
-                    c->d_n64, c->d_cn64, c->d_cnfix, c->recheck, c->recheck_n, c->parent, c->parent2, c->rowcnt, c->rowoff, c->d_nlabels,
+    void *ptrs[] = {c->d_frames, c->area_bits, c->mask_bits, c->max_bits, c->open_bits, c->area_count, c->thr_lut,
+                    c->d_n64, c->d_cn64, c->d_cnfix, c->recheck, c->recheck_n, c->parent, c->parent2, c->nroots, c->rootlist, c->slot2label, c->d_nlabels,
                     c->d_ncont, c->lab_cnt, c->lab_sx, c->lab_sy, c->centres, c->croot, c->cell, c->claim, c->cmatch, c->cpts, c->cpn, c->euler4, c->holes, c->d_nmarkers,
                     c->marker_xy, c->marker_axes, c->ref_row, c->ref_col, c->ref_xy, c->row_det, c->row_cxy, c->row_axes, c->obs,
                     c->pos3d, c->pos_flags, c->last_seen, c->pl_ref, c->pl_start, c->pl_dvert, c->pl_use, c->plane, c->plane_n,
                     c->d_status};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (c->h_status) cudaFreeHost(c->h_status);
-    for (cudaEvent_t e : c->ev) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->pev) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_a) if (e) cudaEventDestroy(e);
+    if (c->ev_b_done) cudaEventDestroy(c->ev_b_done);
+    if (c->stream_b) cudaStreamDestroy(c->stream_b);
     for (int i = 0; i < 2; ++i) { if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]); }
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -86,43 +89,162 @@ int plan_outputs(vbs_ctx *ctx, const vbs_outputs *out, int batch, CopyPlan *plan
     return n;
 }
 
+// ---- chunked two-stream pipeline -------------------------------------------------------------------
+// Stage A (blur + NCC: long, issue-bound kernels) of chunk c+1 runs on the caller's stream while stage B
+// (morphology, components, contours, tracking, 3D, plane, output copies: many short latency-bound
+// kernels) of chunk c runs on a second, higher-priority stream; chunks use disjoint frame ranges of the
+// context's scratch, so a "view" (pointer-offset copy of the context) is all a launcher needs.
+constexpr int VBS_MAX_CHUNKS = 8;
+constexpr int VBS_EV_PER_CHUNK = 9;       // A: blur start, ncc start, ncc end; B: morph, comp, contour, track, copies, end
+
 int prof_collect(vbs_ctx *ctx) {               // fold the previous batch's events into the totals
     if (!ctx->prof_pending) return VBS_OK;
-    VBS_CUDA(cudaEventSynchronize(ctx->ev[VBS_NSTAGES]));
-    for (int i = 0; i < VBS_NSTAGES; ++i) {
-        float ms = 0.f;
-        VBS_CUDA(cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]));
-        ctx->stage_ms[i] += ms;
+    for (int c = 0; c < ctx->prof_chunks; ++c) {
+        cudaEvent_t *e = ctx->pev + c * VBS_EV_PER_CHUNK;
+        VBS_CUDA(cudaEventSynchronize(e[8]));
+        const int lo[VBS_NSTAGES] = {0, 1, 3, 4, 5, 6, 7}, hi[VBS_NSTAGES] = {1, 2, 4, 5, 6, 7, 8};
+        for (int i = 0; i < VBS_NSTAGES; ++i) {
+            float ms = 0.f;
+            VBS_CUDA(cudaEventElapsedTime(&ms, e[lo[i]], e[hi[i]]));
+            ctx->stage_ms[i] += ms;
+        }
     }
     ctx->stage_calls += 1;
     ctx->prof_pending = 0;
     return VBS_OK;
 }
 
-#define VBS_MARK(i) do { if (ctx->profiling) VBS_CUDA(cudaEventRecord(ctx->ev[i], ctx->stream)); } while (0)
+#define VBS_MARKC(c, i, st) do { if (ctx->profiling) VBS_CUDA(cudaEventRecord(ctx->pev[(c) * VBS_EV_PER_CHUNK + (i)], st)); } while (0)
+
+// pointer-offset copy of the context for frames [off, off + n) on stream st
+vbs_ctx make_view(const vbs_ctx *c, int off, cudaStream_t st) {
+    vbs_ctx v = *c;
+    const size_t o = (size_t)off, HW = (size_t)c->H * c->W, HWW = (size_t)c->H * c->WW, M = c->M, R = c->Rcap;
+    v.stream = st;
+    v.area_bits += o * HWW; v.mask_bits += o * HWW; v.max_bits += o * HWW; v.open_bits += o * HWW;
+    v.area_count += o; v.recheck += o * c->recheck_cap; v.recheck_n += o;
+    v.parent += o * HW; v.parent2 += o * HW;
+    v.nroots += 2 * o; v.rootlist += 2 * o * M; v.slot2label += o * M;
+    v.d_nlabels += o; v.d_ncont += o;
+    v.lab_cnt += o * M; v.lab_sx += o * M; v.lab_sy += o * M; v.centres += o * M * 2;
+    v.croot += o * M; v.cell += o * M * 6; v.claim += o * M; v.cmatch += o * M; v.cpts += o * M * 128; v.cpn += o * M;
+    v.euler4 += o; v.holes += o;
+    v.d_nmarkers += o; v.marker_xy += o * M * 2; v.marker_axes += o * M * 3;
+    v.row_det += o * R; v.row_cxy += o * R * 2; v.row_axes += o * R * 3; v.obs += o * R * 3;
+    v.pos3d += o * R * 7; v.pos_flags += o * R; v.plane += o * 4; v.plane_n += o;
+    return v;
+}
+void fold_view(vbs_ctx *c, const vbs_ctx &v) {   // state a launcher may have changed
+    c->launches = v.launches; c->have_first = v.have_first; c->first_frame = v.first_frame;
+    if (!v.err.empty()) c->err = v.err;
+}
+
+vbs_outputs offset_outputs(const vbs_ctx *ctx, const vbs_outputs *out, int off) {
+    vbs_outputs o;
+    std::memset(&o, 0, sizeof(o));
+    if (!out) return o;
+    o = *out;
+    const size_t M = ctx->M, R = ctx->R, f = (size_t)off;
+    if (o.n_labels) o.n_labels += f;
+    if (o.centres) o.centres += f * M * 2;
+    if (o.n_markers) o.n_markers += f;
+    if (o.marker_xy) o.marker_xy += f * M * 2;
+    if (o.marker_axes) o.marker_axes += f * M * 3;
+    if (o.row_det) o.row_det += f * R;
+    if (o.row_cxy) o.row_cxy += f * R * 2;
+    if (o.row_axes) o.row_axes += f * R * 3;
+    if (o.pos3d) o.pos3d += f * R * 7;
+    if (o.pos_flags) o.pos_flags += f * R;
+    if (o.plane) o.plane += f * 4;
+    if (o.plane_n) o.plane_n += f;
+    return o;
+}
+
+// output copies of a view: the view's scratch pointers are already offset, the destination is not
+int copy_outputs(vbs_ctx *ctx, vbs_ctx &v, const vbs_outputs *out, int off, int n, cudaMemcpyKind kind) {
+    if (!out) return VBS_OK;
+    const vbs_outputs o = offset_outputs(ctx, out, off);
+    CopyPlan plan[16];
+    const int np = plan_outputs(&v, &o, n, plan);
+    for (int i = 0; i < np; ++i) VBS_CUDA(cudaMemcpyAsync(plan[i].dst, plan[i].src, plan[i].bytes, kind, v.stream));
+    return VBS_OK;
+}
+
+int ensure_pipeline(vbs_ctx *ctx) {
+    if (ctx->stream_b) return VBS_OK;
+    int lo = 0, hi = 0;
+    VBS_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    VBS_CUDA(cudaStreamCreateWithPriority(&ctx->stream_b, cudaStreamNonBlocking, hi));
+    for (int i = 0; i < VBS_MAX_CHUNKS; ++i) VBS_CUDA(cudaEventCreateWithFlags(&ctx->ev_a[i], cudaEventDisableTiming));
+    VBS_CUDA(cudaEventCreateWithFlags(&ctx->ev_b_done, cudaEventDisableTiming));
+    return VBS_OK;
+}
+
+// stage A of one chunk on the context's stream
+int stage_a(vbs_ctx *ctx, int c, int off, int n, const uint8_t *frames, int64_t frame_stride, int64_t row_pitch) {
+    vbs_ctx v = make_view(ctx, off, ctx->stream);
+    VBS_MARKC(c, 0, v.stream);
+    cudaError_t e = vbs_launch_blur(&v, frames, n, frame_stride, row_pitch);
+    VBS_MARKC(c, 1, v.stream);
+    if (e == cudaSuccess) e = vbs_launch_ncc(&v, n);
+    VBS_MARKC(c, 2, v.stream);
+    fold_view(ctx, v);
+    VBS_CUDA(e);
+    return VBS_OK;
+}
+// stage B of one chunk on stream st
+int stage_b(vbs_ctx *ctx, int c, int off, int n, int64_t frameno0, const vbs_outputs *out, cudaMemcpyKind kind, cudaStream_t st) {
+    vbs_ctx v = make_view(ctx, off, st);
+    VBS_MARKC(c, 3, st);
+    cudaError_t e = vbs_launch_morph(&v, n);
+    VBS_MARKC(c, 4, st);
+    if (e == cudaSuccess) e = vbs_launch_components(&v, n);
+    VBS_MARKC(c, 5, st);
+    if (e == cudaSuccess) e = vbs_launch_contours(&v, n);
+    VBS_MARKC(c, 6, st);
+    if (e == cudaSuccess) e = vbs_launch_track(&v, n, frameno0 + off);
+    VBS_MARKC(c, 7, st);
+    fold_view(ctx, v);
+    VBS_CUDA(e);
+    int rc = copy_outputs(ctx, v, out, off, n, kind);
+    VBS_MARKC(c, 8, st);
+    return rc;
+}
+
+// chunk plan of a batch: up to 4 chunks of >= 32 frames (smaller batches run as one chunk on one stream)
+int plan_chunks(int batch, int *chunk) {
+    int nch = batch / 32;
+    if (nch > 4) nch = 4;
+    if (nch < 1) nch = 1;
+    *chunk = (batch + nch - 1) / nch;
+    return (batch + *chunk - 1) / *chunk;
+}
 
 int process_common(vbs_ctx *ctx, const uint8_t *d_frames, int batch, int64_t frame_stride, int64_t row_pitch, int64_t frameno0,
                    const vbs_outputs *out, cudaMemcpyKind kind) {
     int rc;
     if (ctx->profiling && (rc = prof_collect(ctx)) != VBS_OK) return rc;
-    VBS_MARK(0);
-    VBS_CUDA(vbs_launch_blur(ctx, d_frames, batch, frame_stride, row_pitch));
-    VBS_MARK(1);
-    VBS_CUDA(vbs_launch_ncc(ctx, batch));
-    VBS_MARK(2);
-    VBS_CUDA(vbs_launch_morph(ctx, batch));
-    VBS_MARK(3);
-    VBS_CUDA(vbs_launch_components(ctx, batch));
-    VBS_MARK(4);
-    VBS_CUDA(vbs_launch_contours(ctx, batch));
-    VBS_MARK(5);
-    VBS_CUDA(vbs_launch_track(ctx, batch, frameno0));
-    VBS_MARK(6);
-    CopyPlan plan[16];
-    const int n = plan_outputs(ctx, out, batch, plan);
-    for (int i = 0; i < n; ++i) VBS_CUDA(cudaMemcpyAsync(plan[i].dst, plan[i].src, plan[i].bytes, kind, ctx->stream));
-    VBS_MARK(7);
-    if (ctx->profiling) ctx->prof_pending = 1;
+    int chunk = batch;
+    // measured on B200 (1080p, batch 256): chunking costs more (shorter column segments in the marching
+    // kernels, 4x the launches, SM contention) than the overlap wins - 12.3 vs 10.7 ms - so device-resident
+    // batches run unchunked unless asked; the host path below always pipelines (it is PCIe-bound)
+    const int nch = ctx->overlap_device ? plan_chunks(batch, &chunk) : 1;
+    if (nch <= 1) {                                     // everything in order on the caller's stream
+        if ((rc = stage_a(ctx, 0, 0, batch, d_frames, frame_stride, row_pitch)) != VBS_OK) return rc;
+        if ((rc = stage_b(ctx, 0, 0, batch, frameno0, out, kind, ctx->stream)) != VBS_OK) return rc;
+    } else {
+        if ((rc = ensure_pipeline(ctx)) != VBS_OK) return rc;
+        for (int c = 0; c < nch; ++c) {
+            const int off = c * chunk, n = batch - off < chunk ? batch - off : chunk;
+            if ((rc = stage_a(ctx, c, off, n, d_frames + (size_t)frame_stride * off, frame_stride, row_pitch)) != VBS_OK) return rc;
+            VBS_CUDA(cudaEventRecord(ctx->ev_a[c], ctx->stream));
+            VBS_CUDA(cudaStreamWaitEvent(ctx->stream_b, ctx->ev_a[c], 0));
+            if ((rc = stage_b(ctx, c, off, n, frameno0, out, kind, ctx->stream_b)) != VBS_OK) return rc;
+        }
+        VBS_CUDA(cudaEventRecord(ctx->ev_b_done, ctx->stream_b));
+        VBS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_b_done, 0));      // the caller's stream sees finished results
+    }
+    if (ctx->profiling) { ctx->prof_pending = 1; ctx->prof_chunks = nch; }
     ctx->last_batch = batch;
     return VBS_OK;
 }
@@ -144,12 +266,13 @@ int vbs_create(vbs_ctx **out, const vbs_config *cfg) {
     if (!out || !cfg) return VBS_ERR_BAD_ARG;
     *out = nullptr;
     if (cfg->height < 8 || cfg->width < 8 || (cfg->channels != 1 && cfg->channels != 3) || cfg->max_batch < 1 ||
-        cfg->max_markers < 1 || cfg->max_refs < 0)
+        cfg->max_markers < 1 || cfg->max_markers > 8192 || cfg->max_refs < 0)
         return VBS_ERR_BAD_ARG;
     vbs_ctx *ctx = new (std::nothrow) vbs_ctx();
     if (!ctx) return VBS_ERR_CUDA;
     ctx->cfg = *cfg;
-    ctx->H = cfg->height; ctx->W = cfg->width; ctx->WW = (cfg->width + 31) / 32; ctx->C = cfg->channels;
+    ctx->H = cfg->height; ctx->W = cfg->width; ctx->C = cfg->channels;
+    ctx->WW = ((cfg->width + 31) / 32 + 3) / 4 * 4;      // bit-image rows padded to whole 128-bit quads
     ctx->B = cfg->max_batch; ctx->M = cfg->max_markers; ctx->Rcap = cfg->max_refs;
     ctx->big = cfg->height > 480;                                             // MD:117
     ctx->br = ctx->big ? VbsBranch{39, 101, 80, 13.0, 20, 200, 14} : VbsBranch{21, 35, 33, 7.4, 35, 180, 8};
@@ -165,14 +288,14 @@ int vbs_create(vbs_ctx **out, const vbs_config *cfg) {
     const size_t B = ctx->B, H = ctx->H, W = ctx->W, WW = ctx->WW, M = ctx->M, R = ctx->Rcap;
     const size_t nbits = B * H * WW;
     VBS_CUDA(dalloc(&ctx->area_bits, nbits)); VBS_CUDA(dalloc(&ctx->mask_bits, nbits)); VBS_CUDA(dalloc(&ctx->max_bits, nbits));
-    VBS_CUDA(dalloc(&ctx->open_bits, nbits)); VBS_CUDA(dalloc(&ctx->root_bits, nbits));
+    VBS_CUDA(dalloc(&ctx->open_bits, nbits));
     VBS_CUDA(dalloc(&ctx->area_count, B));
     VBS_CUDA(dalloc(&ctx->thr_lut, (size_t)ctx->br.tl * ctx->br.tl + 1));
     VBS_CUDA(dalloc(&ctx->d_n64, 96)); VBS_CUDA(dalloc(&ctx->d_cn64, 160)); VBS_CUDA(dalloc(&ctx->d_cnfix, 4 * 112));
     ctx->recheck_cap = 16384;
     VBS_CUDA(dalloc(&ctx->recheck, B * ctx->recheck_cap)); VBS_CUDA(dalloc(&ctx->recheck_n, B));
     VBS_CUDA(dalloc(&ctx->parent, B * H * W)); VBS_CUDA(dalloc(&ctx->parent2, B * H * W));
-    VBS_CUDA(dalloc(&ctx->rowcnt, B * H)); VBS_CUDA(dalloc(&ctx->rowoff, B * H));
+    VBS_CUDA(dalloc(&ctx->nroots, 2 * B)); VBS_CUDA(dalloc(&ctx->rootlist, 2 * B * M)); VBS_CUDA(dalloc(&ctx->slot2label, B * M));
     VBS_CUDA(dalloc(&ctx->d_nlabels, B)); VBS_CUDA(dalloc(&ctx->d_ncont, B));
     VBS_CUDA(dalloc(&ctx->lab_cnt, B * M)); VBS_CUDA(dalloc(&ctx->lab_sx, B * M)); VBS_CUDA(dalloc(&ctx->lab_sy, B * M));
     VBS_CUDA(dalloc(&ctx->centres, B * M * 2));
@@ -350,9 +473,11 @@ int vbs_process_host(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int64_t
             VBS_CUDA(cudaEventCreateWithFlags(&ctx->ev_consumed[i], cudaEventDisableTiming));
         }
     }
-    const size_t M = ctx->M, R = ctx->R;
     const int nchunks = (batch + CH - 1) / CH;
-    // the copy stream runs one chunk ahead of the compute stream
+    if (nchunks > VBS_MAX_CHUNKS) return fail(ctx, VBS_ERR_BAD_ARG, "batch / host_chunk exceeds 8 chunks");
+    if (ctx->profiling && (rc = prof_collect(ctx)) != VBS_OK) return rc;
+    if ((rc = ensure_pipeline(ctx)) != VBS_OK) return rc;
+    // the copy stream runs one chunk ahead of stage A, stage B of the previous chunk runs beside stage A
     auto upload = [&](int c) -> int {
         const int off = c * CH, n = batch - off < CH ? batch - off : CH, buf = c & 1;
         uint8_t *dst = ctx->d_frames + (size_t)buf * fb * CH;
@@ -374,28 +499,24 @@ int vbs_process_host(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int64_t
         uint8_t *dst = ctx->d_frames + (size_t)buf * fb * CH;
         if (c + 1 < nchunks && (rc = upload(c + 1)) != VBS_OK) return rc;
         VBS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[buf], 0));
-        vbs_outputs o;
-        std::memset(&o, 0, sizeof(o));
-        if (out) {
-            o = *out;
-            if (o.n_labels) o.n_labels += off;
-            if (o.centres) o.centres += (size_t)off * M * 2;
-            if (o.n_markers) o.n_markers += off;
-            if (o.marker_xy) o.marker_xy += (size_t)off * M * 2;
-            if (o.marker_axes) o.marker_axes += (size_t)off * M * 3;
-            if (o.row_det) o.row_det += (size_t)off * R;
-            if (o.row_cxy) o.row_cxy += (size_t)off * R * 2;
-            if (o.row_axes) o.row_axes += (size_t)off * R * 3;
-            if (o.pos3d) o.pos3d += (size_t)off * R * 7;
-            if (o.pos_flags) o.pos_flags += (size_t)off * R;
-            if (o.plane) o.plane += (size_t)off * 4;
-            if (o.plane_n) o.plane_n += off;
-        }
-        rc = process_common(ctx, dst, n, (int64_t)fb, (int64_t)rowb, frameno0 + off, out ? &o : nullptr, cudaMemcpyDeviceToHost);
-        if (rc != VBS_OK) return rc;
-        VBS_CUDA(cudaEventRecord(ctx->ev_consumed[buf], ctx->stream));
+        if ((rc = stage_a(ctx, c, off, n, dst, (int64_t)fb, (int64_t)rowb)) != VBS_OK) return rc;
+        VBS_CUDA(cudaEventRecord(ctx->ev_consumed[buf], ctx->stream));          // frames are dead after the blur
+        VBS_CUDA(cudaEventRecord(ctx->ev_a[c], ctx->stream));
+        VBS_CUDA(cudaStreamWaitEvent(ctx->stream_b, ctx->ev_a[c], 0));
+        if ((rc = stage_b(ctx, c, off, n, frameno0, out, cudaMemcpyDeviceToHost, ctx->stream_b)) != VBS_OK) return rc;
     }
+    VBS_CUDA(cudaEventRecord(ctx->ev_b_done, ctx->stream_b));
+    VBS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_b_done, 0));
+    if (ctx->profiling) { ctx->prof_pending = 1; ctx->prof_chunks = nchunks; }
+    ctx->last_batch = batch;
     return vbs_sync(ctx);
+}
+
+int vbs_set_overlap(vbs_ctx *ctx, int32_t enable) {
+    if (!ctx) return VBS_ERR_BAD_ARG;
+    VBS_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->overlap_device = enable ? 1 : 0;
+    return VBS_OK;
 }
 
 int vbs_set_host_chunk(vbs_ctx *ctx, int32_t frames_per_chunk) {
@@ -528,8 +649,8 @@ int64_t vbs_kernel_launches(const vbs_ctx *ctx) { return ctx ? ctx->launches : 0
 
 int vbs_set_profiling(vbs_ctx *ctx, int32_t enable) {
     if (!ctx) return VBS_ERR_BAD_ARG;
-    if (enable && !ctx->ev[0])
-        for (int i = 0; i <= VBS_NSTAGES; ++i) VBS_CUDA(cudaEventCreate(&ctx->ev[i]));
+    if (enable && !ctx->pev[0])
+        for (int i = 0; i < VBS_MAX_CHUNKS * VBS_EV_PER_CHUNK; ++i) VBS_CUDA(cudaEventCreate(&ctx->pev[i]));
     if (!enable) { int rc = prof_collect(ctx); if (rc != VBS_OK) return rc; }
     ctx->profiling = enable ? 1 : 0;
     return VBS_OK;

@@ -36,7 +36,7 @@ struct vbs_ctx {
     uint8_t *d_frames; size_t frames_bytes;      // two staging buffers of host_chunk frames
     int host_chunk; cudaStream_t copy_stream; cudaEvent_t ev_copied[2], ev_consumed[2];
     // bit images [B][H][WW]
-    uint32_t *area_bits, *mask_bits, *max_bits, *open_bits, *root_bits;
+    uint32_t *area_bits, *mask_bits, *max_bits, *open_bits;
     uint32_t *area_count;            // [B] set pixels of area_mask
     // NCC tables
     float *thr_lut;                  // [tl*tl+1] interior threshold on G as a function of S
@@ -47,7 +47,7 @@ struct vbs_ctx {
     int2 *recheck; uint32_t *recheck_n; int recheck_cap;   // float64 recheck list [B][cap]
     // union-find scratch
     int32_t *parent, *parent2;       // [B][H*W] ring maxima / opened image (fg + bg)
-    int32_t *rowcnt, *rowoff;        // [B][H]
+    int32_t *nroots, *rootlist, *slot2label;   // [2B] roots per (frame, image), [2B][M] their pixel indices, [B][M] slot -> label
     int32_t *d_nlabels, *d_ncont;    // [B]
     // ring components
     uint32_t *lab_cnt; unsigned long long *lab_sx, *lab_sy;   // [B][M]
@@ -80,8 +80,10 @@ struct vbs_ctx {
     int32_t *d_nrecheck;                     // [B] recheck counts (debug)
     int last_batch;
     // optional per-stage timing (events on the context's stream)
-    int profiling, prof_pending;
-    cudaEvent_t ev[8];
+    int profiling, prof_pending, prof_chunks;
+    cudaEvent_t pev[72];                        // 8 chunks x 9 stage boundaries
+    // chunked two-stream pipeline
+    cudaStream_t stream_b; cudaEvent_t ev_a[8], ev_b_done; int overlap_device;
     double stage_ms[7]; int64_t stage_calls;
 };
 enum { VBS_NSTAGES = 7 };   // blur, ncc, morph, components, contours, track3d, output copies

@@ -143,6 +143,10 @@ class MarkerPipeline:
                                                      us.ctypes.data if us is not None else None, int(bool(shell)), float(scale)))
         self.have_plane = True
 
+    def set_overlap(self, on: bool):
+        """Two-stream chunk pipelining inside process() (on by default)."""
+        capi.check(self._ctx, capi.lib.vbs_set_overlap(self._ctx, int(bool(on))))
+
     def set_host_chunk(self, frames_per_chunk: int):
         """Frames per chunk of the copy/compute overlap in the host entry point (0 = default 64)."""
         capi.check(self._ctx, capi.lib.vbs_set_host_chunk(self._ctx, int(frames_per_chunk)))
@@ -233,6 +237,11 @@ class MarkerPipeline:
         """Launch on torch's current stream so later torch ops on the results are stream-ordered."""
         import torch
         ptr = torch.cuda.current_stream(self.device).cuda_stream
+        if ptr == 0:
+            # torch's default stream is the LEGACY default stream; 0 means "own stream" at the C ABI, so
+            # name it explicitly (cudaStreamLegacy).  Without this the kernels would run on the context's
+            # non-blocking stream and could read frames whose .cuda() copy is still in flight.
+            ptr = 1
         if getattr(self, "_stream_ptr", None) != ptr:
             self.use_stream(ptr)
             self._stream_ptr = ptr
