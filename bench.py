@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU-baseline budget (bounded sample)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-overlap", action="store_true", help="single-stream execution (no chunk pipelining)")
+    ap.add_argument("--overlap", action="store_true", help="two-stream chunk pipelining for device-resident batches (default off)")
     ap.add_argument("--host-chunk", type=int, default=0, help="frames per chunk of the host path copy/compute overlap (0 = library default)")
     return ap.parse_args()
 
@@ -222,8 +222,8 @@ def main():
     B = args.batch
     pipe = pipeline.MarkerPipeline(H, W, 1, max_batch=B, max_markers=max(512, 2 * n_markers), max_refs=max(64, n_markers), device=local)
     stream = torch.cuda.current_stream()
-    if args.no_overlap:
-        pipe.set_overlap(False)
+    if args.overlap:
+        pipe.set_overlap(True)
     # MarkerPipeline.process() launches on torch's current stream, so the events below bracket the work
 
     # reference state = detections of frame 0 (GPU path), camera, plane baseline
