@@ -28,7 +28,7 @@ UNIT = "frames/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="1080p_20x20")
@@ -61,36 +61,47 @@ def workload_setup(name, unique):
 # clocks sampler (nvidia-smi during the timed region)
 # ------------------------------------------------------------------------------------------
 class Clocks:
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """One `nvidia-smi -lms` process streaming clock / throttle samples; samples taken between
+    start() and stop() (the timed region) are summarised."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.samples, self.stop = index, [], False
-        self.t = threading.Thread(target=self.run, daemon=True)
+        self.lines, self.t0, self.t1 = [], None, None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+            time.sleep(0.5)                      # let the sampler come up before the timed region
+        except Exception:
+            self.p = None
 
-    def run(self):
-        while not self.stop:
-            try:
-                o = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                   capture_output=True, text=True, timeout=5).stdout.strip().split("\n")[0]
-                self.samples.append([s.strip() for s in o.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.05)
+    def _read(self):
+        for line in self.p.stdout:
+            self.lines.append((time.time(), line.strip()))
 
     def __enter__(self):
-        self.t.start()
+        self.t0 = time.time()
         return self
 
     def __exit__(self, *a):
-        self.stop = True
-        self.t.join(timeout=6)
+        self.t1 = time.time()
+        if self.p is not None:
+            time.sleep(0.05)
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=3)
+            except Exception:
+                self.p.kill()
 
     def summary(self):
-        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        rows = [l.split(",") for t, l in self.lines if self.t0 is not None and self.t0 <= t <= self.t1 + 0.05]
+        rows = [[c.strip() for c in r] for r in rows if len(r) >= 7]
+        sm = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        reasons = sorted({n for r in rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
                 "samples": len(sm)}
 
@@ -272,7 +283,9 @@ def main():
     l0 = pipe.kernel_launches
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with Clocks(local) as clk:
+    clk_sampler = Clocks(local)
+    barrier()
+    with clk_sampler as clk:
         e0.record(stream)
         for s in range(args.steps):
             res = step(s)

@@ -130,16 +130,28 @@ blur_area_kernel(const uint8_t *__restrict__ frames, int64_t frame_stride, int64
     const int nsteps = nk + G::LEAD;
     uint32_t count = 0;
 
+    // loader: the (row-in-step, word) slots a thread fills never change, so their column and the
+    // "plain 32-bit load" test are hoisted; per step only the source row moves (REFLECT_101 outside [0,H))
     uint32_t pre[G::PRE];
+    int lrow[G::PRE], lcol[G::PRE];
+    bool lfast[G::PRE];
+#pragma unroll
+    for (int i = 0; i < G::PRE; ++i) {
+        const int wi = tid + i * TW;
+        lrow[i] = wi / G::TWORDS;
+        lcol[i] = x0 - G::HL + 4 * (wi - lrow[i] * G::TWORDS);
+        lfast[i] = !BGR && aligned4 && lcol[i] >= 0 && lcol[i] + 3 < W;
+    }
     auto fetch = [&](int m) {
+        const int p0 = ys - G::PL + RB * m;
 #pragma unroll
         for (int i = 0; i < G::PRE; ++i) {
-            const int wi = tid + i * TW;
-            if (wi < RB * G::TWORDS) {
-                const int r = wi / G::TWORDS, wc = wi - r * G::TWORDS;
-                const int p = ys - G::PL + RB * m + r;
-                const uint8_t *row = fbase + (size_t)reflect101(p, H) * row_pitch;
-                pre[i] = load_word<BGR>(row, x0 - G::HL + 4 * wc, W, aligned4);
+            if (tid + i * TW < RB * G::TWORDS) {
+                const int p = p0 + lrow[i];
+                const int pr = (p >= 0 && p < H) ? p : reflect101(p, H);
+                const uint8_t *row = fbase + (size_t)pr * row_pitch;
+                if (lfast[i]) pre[i] = __ldg(reinterpret_cast<const uint32_t *>(row + lcol[i]));
+                else pre[i] = load_word<BGR>(row, lcol[i], W, false);
             }
         }
     };
@@ -184,17 +196,17 @@ blur_area_kernel(const uint8_t *__restrict__ frames, int64_t frame_stride, int64
                     else { outL[s] |= aL[s] << 16; outS[s] |= aS[s] << 16; }
                 }
             }
-            // ring element (group, column).e[warp]; rotate the column order per lane so the
-            // 32 lanes of one store hit 8 distinct banks instead of 2
+            // ring element (group, column ^ swz).e[warp]: the column index is XOR-swizzled with two bits of
+            // the quad number, so the 32 lanes of one store spread over 8 banks (4-way instead of 16-way
+            // conflict) while the vertical pass still reads one conflict-free LDS.128 per group
             uint32_t *dstL = reinterpret_cast<uint32_t *>(ringL + gl * TW) + warp;
             uint32_t *dstS = reinterpret_cast<uint32_t *>(ringS + gs * TW) + warp;
+            const int swz = (lane >> 1) & 3;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int s = (j + (lane >> 1)) & 3;
-                const uint32_t vl = s == 0 ? outL[0] : s == 1 ? outL[1] : s == 2 ? outL[2] : outL[3];
-                const uint32_t vs = s == 0 ? outS[0] : s == 1 ? outS[1] : s == 2 ? outS[2] : outS[3];
-                dstL[(4 * lane + s) * 4] = vl;
-                dstS[(4 * lane + s) * 4] = vs;
+            for (int sft = 0; sft < 4; ++sft) {
+                const int c = (4 * lane + sft) ^ swz;
+                dstL[c * 4] = outL[sft];
+                dstS[c * 4] = outS[sft];
             }
         }
         __syncthreads();
@@ -208,11 +220,13 @@ blur_area_kernel(const uint8_t *__restrict__ frames, int64_t frame_stride, int64
             for (int r = 0; r < RB; ++r) { accL[r] = 32768u; accS[r] = 32768u; }
             // oldest live group of the large ring is (gl + 1) % NGL (written at step m - LEAD = k)
             int g0 = gl + 1; if (g0 >= G::NGL) g0 -= G::NGL;
+            const int vcol = tid ^ ((tid >> 3) & 3);                  // same swizzle as the stores
+            const uint4 *bL0 = ringL + g0 * TW + vcol, *bL1 = bL0 - G::NGL * TW;
+            const int wrapL = G::NGL - g0;                            // first group index that wraps
             static_for<0, G::NGL>([&](auto G_) {
                 constexpr int g = decltype(G_)::value;
                 if constexpr (4 * g < G::NPL) {
-                    int gi = g0 + g; if (gi >= G::NGL) gi -= G::NGL;
-                    const uint4 v = ringL[gi * TW + tid];
+                    const uint4 v = (g < wrapL ? bL0 : bL1)[g * TW];
                     static_for<0, RB>([&](auto R_) {
                         constexpr int r = decltype(R_)::value;
                         constexpr uint32_t w01 = pack4<KL>(2 * (4 * g) - r - G::PL + G::RL);
@@ -226,10 +240,11 @@ blur_area_kernel(const uint8_t *__restrict__ frames, int64_t frame_stride, int64
             });
             // small ring holds groups k+GS0 .. m; group written at step j sits in slot j % NGS
             int s0 = gs + 1 + 0; if (s0 >= G::NGS) s0 -= G::NGS;       // slot of step m - NGS + 1 = k + GS0
+            const uint4 *bS0 = ringS + s0 * TW + vcol, *bS1 = bS0 - G::NGS * TW;
+            const int wrapS = G::NGS - s0;
             static_for<G::GS0, G::GS1 + 1>([&](auto G_) {
                 constexpr int g = decltype(G_)::value;                 // group index relative to step k
-                int gi = s0 + (g - G::GS0); if (gi >= G::NGS) gi -= G::NGS;
-                const uint4 v = ringS[gi * TW + tid];
+                const uint4 v = ((g - G::GS0) < wrapS ? bS0 : bS1)[(g - G::GS0) * TW];
                 static_for<0, RB>([&](auto R_) {
                     constexpr int r = decltype(R_)::value;
                     // pair index relative to the small pass start: i = 4g + e - OFFS; tap = 2i - r - PS + RS
