@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(NT, 3) ncc_mask_kernel(NccParams P) {
             for (int i = 0; i < 4; ++i) pw[i] = 0u;
         }
     };
-    int s_prev = 0; uint32_t hb_m1 = 0;         // half 0: S of the previous output row and the box row that left the window
+    int s_prev = 0; uint32_t hb_m1 = 0;         // S of the previous output row and the box row that left the window
 
     if (hrole) fetch(0);
     __syncthreads();
@@ -206,9 +206,11 @@ __global__ void __launch_bounds__(NT, 3) ncc_mask_kernel(NccParams P) {
             const int k = m - G::LEAD;
             const int yb = ys + RB * k;
             int g0 = gw + 1; if (g0 >= G::NR) g0 -= G::NR;           // slot of step k = m - LEAD (NR = LEAD + 1)
-            // box sums of the 8 rows: half 0 runs the chain and hands rows 4..7 to half 1
+            // box sums of the 8 rows (both halves run the same integer chain: each needs them to decide
+            // whether the window of its warp is empty, and it saves an exchange)
             int S[VR];
-            if (vhalf == 0) {
+            bool empty;
+            {
                 auto box_at = [&](auto I_) -> int {
                     constexpr int idx = decltype(I_)::value;
                     int gi = g0 + idx / 8; if (gi >= G::NR) gi -= G::NR;
@@ -233,8 +235,14 @@ __global__ void __launch_bounds__(NT, 3) ncc_mask_kernel(NccParams P) {
                     S8[r] = S8[r - 1] + box_at(std::integral_constant<int, r + TL - 1>{}) - box_at(std::integral_constant<int, r - 1>{});
                 });
                 s_prev = S8[RB - 1]; hb_m1 = (uint32_t)box_at(std::integral_constant<int, RB - 1>{});
+                int any = 0;
 #pragma unroll
-                for (int r = 0; r < VR; ++r) { S[r] = S8[r]; sbuf[r * TW + vcol] = S8[VR + r]; }
+                for (int r = 0; r < RB; ++r) any |= S8[r];
+#pragma unroll
+                for (int r = 0; r < VR; ++r) S[r] = vhalf ? S8[VR + r] : S8[r];
+                // S == 0 <=> no area pixel in the whole L x L window <=> G == 0 and mask == 0: when that holds
+                // for all 8 rows of all 32 columns of the warp, the L-tap column sums are skipped (exact)
+                empty = !__any_sync(0xffffffffu, any != 0);
             }
             // partial Gaussian column sums: taps [A0, A1) of all 8 rows; ring rows A0 .. A1+6
             float part[RB];
@@ -264,7 +272,7 @@ __global__ void __launch_bounds__(NT, 3) ncc_mask_kernel(NccParams P) {
                     });
                 });
             };
-            if (vhalf == 0) vpart(std::integral_constant<int, 0>{}); else vpart(std::integral_constant<int, 1>{});
+            if (!empty) { if (vhalf == 0) vpart(std::integral_constant<int, 0>{}); else vpart(std::integral_constant<int, 1>{}); }
             // swap: each half sends the partials of the 4 rows the other half decides
             {
                 float *dst = xbuf + (vhalf * VR) * TW + vcol;
@@ -280,10 +288,6 @@ __global__ void __launch_bounds__(NT, 3) ncc_mask_kernel(NccParams P) {
                     const float mine = vhalf ? part[VR + r] : part[r];
                     const float other = src[r * TW];
                     acc[r] = vhalf ? other + mine : mine + other;     // low taps first on both sides
-                }
-                if (vhalf) {
-#pragma unroll
-                    for (int r = 0; r < VR; ++r) S[r] = sbuf[r * TW + vcol];
                 }
             }
             // ---- D: decision --------------------------------------------------------------------------
