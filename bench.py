@@ -312,11 +312,17 @@ def main():
         blur_ms = stage["blur_dog_area"] / max(calls, 1)
         ach = B * b_alg / (blur_ms * 1e-3) / 1e9
         whole = B * b_alg / (ms / args.steps * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tp):
+            t = json.load(open(tp)).get(args.workload)
+            if t and t.get("batch") == B:
+                traffic = t.get("blur_area_kernel")
         line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8 (integer blur/labels) + f32/f64 (NCC, geometry)", "data": "synthetic", "config": config,
                 "roofline": {"bound": "hbm", "kernel": "blur_area_kernel<39,101> (gray -> DoG -> area mask)", "achieved": ach, "peak": peak,
-                             "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                             "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": B * b_alg, "kernel_ms": blur_ms,
                              "whole_path_achieved": whole, "whole_path_frac": whole / peak,
                              "note": "ALU-bound path (integer dot products + FMA chains), see DESIGN.md; HBM fraction reported as specified"},

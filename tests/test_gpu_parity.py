@@ -344,3 +344,32 @@ def test_sharded_run_is_byte_identical_to_single_run(world):
         assert np.array_equal(cat, getattr(single, k), equal_nan=True), k
     for p in pipes:
         p.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# 6. BASELINE.json config 4 geometry: 4K frame with the densest array the reference detects (40 x 72)
+# ---------------------------------------------------------------------------------------------
+def test_4k_dense_array_matches_oracle():
+    name = "4k_40x72"
+    H, W, rows, cols, _, _ = synth.WORKLOADS[name]
+    uniq = synth.workload_frames(name, 1, seed0=0, jitter=1.0)
+    ora0 = pu.oracle_frames(uniq)
+    assert len(ora0[0]["markers"]) == rows * cols          # 2880/2880 at this pitch
+    keys, xy = pu.grid_reference(ora0[0]["markers"], cols)
+    oracle = pu.oracle_frames(uniq, keys, xy, 20.0)
+    batch = torch_cuda(np.tile(uniq, (4, 1, 1)))
+    with pipeline.MarkerPipeline(H, W, 1, max_batch=4, max_markers=4096, max_refs=len(keys)) as pipe:
+        pipe.set_reference([k[0] for k in keys], [k[1] for k in keys], xy[:, 0], xy[:, 1], 20.0)
+        res = pipe.process(batch, 0)
+        pipe.sync()
+        h = res.to_host()
+        first = pipeline.BatchResult(0, *[getattr(h, k)[:1] if getattr(h, k) is not None else None for k in
+                                          ("n_labels", "centres", "n_markers", "marker_xy", "marker_axes", "row_det", "row_cxy", "row_axes", "pos3d", "pos_flags", "plane", "plane_n")])
+        got = pipe.debug_stage(capi.STAGE_AREA_MASK, 4).cpu().numpy()
+        assert np.array_equal(got[0], oracle[0]["taps"]["area_mask"]) and np.array_equal(got[3], oracle[0]["taps"]["area_mask"])
+        assert np.array_equal(pipe.debug_stage(capi.STAGE_MASK, 4).cpu().numpy()[2], oracle[0]["taps"]["mask"])
+        assert np.array_equal(pipe.debug_stage(capi.STAGE_LABELS, 4).cpu().numpy()[1], oracle[0]["taps"]["labeled"])
+        rep = pu.compare_detection(pipe, uniq, first, oracle, stages=False)
+        rep.update(pu.compare_rows(first, oracle, keys))
+        pu.assert_report(rep)
+        assert (h.n_markers == rows * cols).all() and np.array_equal(h.marker_xy[0], h.marker_xy[3])

@@ -30,7 +30,9 @@ while i < len(rows):
         tables.append((name, hdr, rows[i + 2:j])); i = j
     else:
         i += 1
-name, hdr, body = [t for t in tables if sub.split("IL")[0].replace("_Z", "")[:8] in t[0] or True][0]
+m_ = re.search(r"([a-z0-9_]+_kernel)", sub)
+short = m_.group(1) if m_ else sub
+name, hdr, body = ([t for t in tables if short in t[0]] or tables)[0]
 ie, ss = hdr.index("Instructions Executed"), hdr.index("# Samples")
 stall_cols = [(i, h[6:]) for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
 agg = collections.defaultdict(lambda: [0, 0])
