@@ -182,6 +182,9 @@ int vbs_get_stage_ms(vbs_ctx *ctx, double ms[7], int64_t *calls);
 
 /* launch accounting for bench.py ("gpu_launches"): kernels launched by this context so far */
 int64_t vbs_kernel_launches(const vbs_ctx *ctx);
+/* how many of the blur launches staged their input tiles with TMA (cp.async.bulk.tensor); the rest used
+ * the generic loader (BGR input, unaligned crop views, or VBS_NO_TMA=1 in the environment) */
+int64_t vbs_tma_launches(const vbs_ctx *ctx);
 
 #ifdef __cplusplus
 }

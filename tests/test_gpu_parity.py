@@ -373,3 +373,90 @@ def test_4k_dense_array_matches_oracle():
         rep.update(pu.compare_rows(first, oracle, keys))
         pu.assert_report(rep)
         assert (h.n_markers == rows * cols).all() and np.array_equal(h.marker_xy[0], h.marker_xy[3])
+
+
+# ---------------------------------------------------------------------------------------------
+# 7. stress: random blob masks (holes, frame contact, nesting, ragged borders) through the
+#    labelling / border following / ellipse / matching kernels against cv2 + scipy (oracle port)
+# ---------------------------------------------------------------------------------------------
+def random_blob_masks(seed, h=520, w=608):
+    import cv2
+    rng = np.random.default_rng(seed)
+    field = cv2.GaussianBlur(rng.normal(0, 1, (h, w)).astype(np.float32), (0, 0), 6.0 + 3.0 * rng.random())
+    area = (field > np.quantile(field, 0.62 + 0.2 * rng.random())).astype(np.uint8)
+    field2 = cv2.GaussianBlur(rng.normal(0, 1, (h, w)).astype(np.float32), (0, 0), 9.0)
+    mask = ((field2 > np.quantile(field2, 0.7)) | (area > 0) & (rng.random((h, w)) < 0.5)).astype(np.uint8)
+    mask = cv2.morphologyEx(mask, cv2.MORPH_OPEN, np.ones((3, 3), np.uint8))
+    return mask, area * 255
+
+
+def random_ellipse_masks(seed, h=600, w=720, n=60):
+    """Random filled ellipses (some overlapping, some cut by the frame); the mask holds the same
+    ellipses 1.7x larger, so the ring maxima surround the area blobs and most of them match."""
+    import cv2
+    rng = np.random.default_rng(seed)
+    area = np.zeros((h, w), np.uint8)
+    mask = np.zeros((h, w), np.uint8)
+    for _ in range(n):
+        c = (int(rng.uniform(-10, w + 10)), int(rng.uniform(-10, h + 10)))
+        ax = (int(rng.uniform(7, 24)), int(rng.uniform(7, 24)))
+        ang = float(rng.uniform(0, 180))
+        cv2.ellipse(area, c, ax, ang, 0, 360, 255, -1)
+        cv2.ellipse(mask, c, (int(ax[0] * 1.7) + 6, int(ax[1] * 1.7) + 6), ang, 0, 360, 1, -1)
+    return mask, area
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6, 101, 102, 103])
+def test_random_blob_masks_match_oracle(seed):
+    mask, area = random_blob_masks(seed) if seed < 100 else random_ellipse_masks(seed)
+    taps = {}
+    want = port.marker_center(mask, area, taps)
+    n_contours = len(taps.get("contours", ()))
+    with pipeline.MarkerPipeline(mask.shape[0], mask.shape[1], 1, max_batch=1, max_markers=2048, max_refs=1) as pipe:
+        res = pipe.marker_center(torch_cuda(mask[None]), torch_cuda(area[None]))
+        pipe.sync()
+        if "labeled" in taps:
+            assert np.array_equal(pipe.debug_stage(capi.STAGE_MAXIMA, 1).cpu().numpy()[0], taps["maxima"].astype(np.uint8))
+            assert np.array_equal(pipe.debug_stage(capi.STAGE_LABELS, 1).cpu().numpy()[0], taps["labeled"])
+            assert np.array_equal(pipe.debug_stage(capi.STAGE_OPENED, 1).cpu().numpy()[0], taps["opened"])
+            h = res.to_host()
+            assert int(h.n_labels[0]) == taps["n_labels"]
+            assert np.array_equal(h.centres[0, : taps["n_labels"]], taps["centres"])
+        got = res.markers(0)
+        assert len(got) == len(want), (len(got), len(want), n_contours)
+        for a, b in zip(got, want):
+            assert a["center"] == b["center"]
+            assert pu.f32_ulps(a["major_axis"], b["major_axis"]) <= 2 and pu.f32_ulps(a["minor_axis"], b["minor_axis"]) <= 2
+            da = abs(a["angle"] - b["angle"]) % 180.0
+            assert min(da, 180 - da) <= 1e-3
+
+
+# ---------------------------------------------------------------------------------------------
+# 8. the TMA tile path and the generic loader give the same bits
+# ---------------------------------------------------------------------------------------------
+def test_tma_path_is_used_and_equals_generic_loader(monkeypatch):
+    frames = synth.workload_frames("small_6x8", 3, seed0=31)
+    H, W = frames.shape[1:]
+    x = torch_cuda(frames)
+    with pipeline.MarkerPipeline(H, W, 1, max_batch=3, max_markers=256, max_refs=1) as pipe:
+        a = pipe.process(x, 0); pipe.sync()
+        assert pipe.tma_launches >= 1                      # aligned gray frames: tiles staged by cp.async.bulk.tensor
+        area_tma = pipe.debug_stage(capi.STAGE_AREA_MASK, 3).cpu().numpy()
+        a = a.to_host()
+    monkeypatch.setenv("VBS_NO_TMA", "1")
+    with pipeline.MarkerPipeline(H, W, 1, max_batch=3, max_markers=256, max_refs=1) as pipe:
+        b = pipe.process(x, 0); pipe.sync()
+        assert pipe.tma_launches == 0
+        assert np.array_equal(pipe.debug_stage(capi.STAGE_AREA_MASK, 3).cpu().numpy(), area_tma)
+        b = b.to_host()
+    assert np.array_equal(a.marker_xy, b.marker_xy) and np.array_equal(a.marker_axes, b.marker_axes)
+    # a view whose first pixel is not 16-byte aligned must fall back silently and still be right
+    import torch
+    big = torch.zeros((3, H, W + 16), dtype=torch.uint8, device="cuda")
+    big[:, :, 3:W + 3] = x
+    with pipeline.MarkerPipeline(H, W, 1, max_batch=3, max_markers=256, max_refs=1) as pipe:
+        outs = pipe.alloc_outputs(3, True)
+        capi.check(pipe._ctx, capi.lib.vbs_process_device(pipe._ctx, big.data_ptr() + 3, 3, H * (W + 16), W + 16, 0, __import__("ctypes").byref(outs[1])))
+        pipe.sync()
+        assert pipe.tma_launches == 0
+        assert np.array_equal(outs[0]["marker_xy"].cpu().numpy(), a.marker_xy)

@@ -11,6 +11,8 @@
 //      every ring word is loaded once per 8 outputs,
 //   5. rounds, forms uint8(b_large - b_small + 15), range-tests and ballots 32 pixels per word.
 // Nothing but the 1 bit/pixel result leaves the SM.  No tensor cores: integer dot products only.
+#include <cuda.h>
+#include <cstring>
 #include <type_traits>
 #include <utility>
 #include "vbs_ctx.h"
@@ -79,7 +81,13 @@ template <int KS, int KL> struct Geo {
     static constexpr int GS1 = (OFFS + NPS - 1) / 4;      // last group
     static constexpr int NGS = NGL - GS0;                 // ring groups kept for the small kernel
     static constexpr int PRE = cdiv(RB * TWORDS, TW);     // prefetch registers per thread
-    static constexpr size_t SMEM = (size_t)(NGL + NGS) * TW * 16 + (size_t)RB * TWORDS * 4;
+    static constexpr int HLA = rup(HL, 16);               // TMA tiles must START on a 16-byte boundary (measured: an unaligned
+                                                          // inner coordinate raises 'illegal instruction' on sm_100a)
+    static constexpr int OFFW = (HLA - HL) / 4;           // first word of a staged row the horizontal pass uses
+    static constexpr int BOXW = rup(HLA - HL + TWORDS * 4, 16);   // bytes per staged row (<= 256)
+    static constexpr int TSTRIDE = BOXW / 4;              // words per staged row
+    static constexpr int TILE_BYTES = RB * BOXW;          // one staged tile (multiple of 128 B)
+    static constexpr size_t SMEM = 2 * (size_t)TILE_BYTES + 128 + (size_t)(NGL + NGS) * TW * 16;
 };
 
 __device__ __forceinline__ int reflect101(int i, int n) {
@@ -109,15 +117,41 @@ __device__ __forceinline__ uint32_t load_word(const uint8_t *row, int col0, int 
     return v;
 }
 
+// ---- TMA (cp.async.bulk.tensor) + mbarrier helpers ---------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bounded wait: returns false if the phase never completed (a mis-programmed copy must not hang the GPU)
+__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity) {
+    for (int spin = 0; spin < (1 << 22); ++spin) {
+        uint32_t done;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) return true;
+    }
+    return false;
+}
+// 8 rows x BOXW bytes of frame z starting at column x, row y -> shared memory, completion on the mbarrier
+__device__ __forceinline__ void tma_load_tile(void *dst, const CUtensorMap *map, int x, int y, int z, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
+
 template <int KS, int KL, bool BGR>
 __global__ void __launch_bounds__(TW, 4)
-blur_area_kernel(const uint8_t *__restrict__ frames, int64_t frame_stride, int64_t row_pitch, int H, int W, int WW,
-                 int seg_rows, int lo, int hi, uint32_t *__restrict__ area_bits, uint32_t *__restrict__ area_count) {
+blur_area_kernel(const __grid_constant__ CUtensorMap tmap, int use_tma, const uint8_t *__restrict__ frames, int64_t frame_stride,
+                 int64_t row_pitch, int H, int W, int WW, int seg_rows, int lo, int hi, uint32_t *__restrict__ area_bits,
+                 uint32_t *__restrict__ area_count, uint32_t *__restrict__ status) {
     using G = Geo<KS, KL>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint4 *ringL = reinterpret_cast<uint4 *>(smem_raw);                       // [NGL][TW]
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint32_t *tiles = reinterpret_cast<uint32_t *>(smem_raw);                 // [2][RB][TSTRIDE] staged input rows (double buffer)
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + 2 * G::TILE_BYTES);   // [2] TMA completion barriers
+    uint4 *ringL = reinterpret_cast<uint4 *>(smem_raw + 2 * G::TILE_BYTES + 128);  // [NGL][TW]
     uint4 *ringS = ringL + G::NGL * TW;                                       // [NGS][TW]
-    uint32_t *tile = reinterpret_cast<uint32_t *>(ringS + G::NGS * TW);       // [RB][TWORDS]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int x0 = blockIdx.x * TW;
@@ -133,13 +167,14 @@ blur_area_kernel(const uint8_t *__restrict__ frames, int64_t frame_stride, int64
     // loader: the (row-in-step, word) slots a thread fills never change, so their column and the
     // "plain 32-bit load" test are hoisted; per step only the source row moves (REFLECT_101 outside [0,H))
     uint32_t pre[G::PRE];
-    int lrow[G::PRE], lcol[G::PRE];
+    int lrow[G::PRE], lcol[G::PRE], lslot[G::PRE];
     bool lfast[G::PRE];
 #pragma unroll
     for (int i = 0; i < G::PRE; ++i) {
         const int wi = tid + i * TW;
         lrow[i] = wi / G::TWORDS;
         lcol[i] = x0 - G::HL + 4 * (wi - lrow[i] * G::TWORDS);
+        lslot[i] = lrow[i] * G::TSTRIDE + G::OFFW + (wi - lrow[i] * G::TWORDS);
         lfast[i] = !BGR && aligned4 && lcol[i] >= 0 && lcol[i] + 3 < W;
     }
     auto fetch = [&](int m) {
@@ -155,27 +190,56 @@ blur_area_kernel(const uint8_t *__restrict__ frames, int64_t frame_stride, int64
             }
         }
     };
-    auto stash = [&]() {
+    auto stash = [&](uint32_t *tile) {
 #pragma unroll
-        for (int i = 0; i < G::PRE; ++i) {
-            const int wi = tid + i * TW;
-            if (wi < RB * G::TWORDS) tile[wi] = pre[i];
+        for (int i = 0; i < G::PRE; ++i)
+            if (tid + i * TW < RB * G::TWORDS) tile[lslot[i]] = pre[i];
+    };
+    // A step's tile comes through TMA when it lies wholly inside the image (the tensor map fills
+    // out-of-bounds bytes with zeros, the blur needs REFLECT_101), otherwise through the generic loader.
+    const bool x_inside = use_tma && !BGR && x0 - G::HL >= 0 && x0 - G::HL + G::TWORDS * 4 <= W;
+    auto by_tma = [&](int m) -> bool {
+        const int p0 = ys - G::PL + RB * m;
+        return x_inside && p0 >= 0 && p0 + RB <= H;
+    };
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t phase = 0;                              // bit b: parity of the next completion of barrier b
+    auto issue = [&](int m) {                        // start loading the tile of step m into buffer m & 1
+        if (by_tma(m)) {
+            if (tid == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of this buffer are done
+                mbar_expect_tx(&mbar[m & 1], G::TILE_BYTES);
+                tma_load_tile(tiles + (m & 1) * (G::TILE_BYTES / 4), &tmap, x0 - G::HLA, ys - G::PL + RB * m, f, &mbar[m & 1]);
+            }
+        } else {
+            fetch(m);
         }
     };
 
-    fetch(0);
+    issue(0);
     int gl = 0, gs = 0;          // ring group written by horizontal step m: m % NGL, m % NGS
     for (int m = 0; m < nsteps; ++m) {
-        stash();
-        __syncthreads();
-        if (m + 1 < nsteps) fetch(m + 1);          // global loads of the next step fly during the math
+        uint32_t *tile = tiles + (m & 1) * (G::TILE_BYTES / 4);
+        const bool tma_now = by_tma(m);
+        if (!tma_now) stash(tile);
+        __syncthreads();                                // tile visible; the vertical pass of the previous step is done
+        if (tma_now) {
+            if (!mbar_wait(&mbar[m & 1], (phase >> (m & 1)) & 1u) && tid == 0) atomicOr(status, VBS_DEV_TMA_TIMEOUT);
+            phase ^= 1u << (m & 1);
+        }
+        if (m + 1 < nsteps) issue(m + 1);               // the next tile flies during the math (its buffer was last read in step m-1)
 
         // ---- horizontal passes: warp = row pair, lane = pixel quad ------------------------------
         {
             uint32_t outL[4], outS[4];
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-                const uint32_t *trow = tile + (2 * warp + half) * G::TWORDS + lane;
+                const uint32_t *trow = tile + (2 * warp + half) * G::TSTRIDE + G::OFFW + lane;
                 uint32_t x[G::NW];
 #pragma unroll
                 for (int w = 0; w < G::NW; ++w) x[w] = trow[w];
@@ -282,6 +346,37 @@ blur_area_kernel(const uint8_t *__restrict__ frames, int64_t frame_stride, int64
     if (lane == 0 && count) atomicAdd(area_count + f, count);
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// 3-D uint8 tensor map {W, H, batch} with an {BOXW, 8, 1} box; returns false when the frames cannot be
+// described to the TMA unit (unaligned base / pitches: e.g. a crop view) - the kernel then loads generically
+bool make_frame_map(CUtensorMap *map, const uint8_t *frames, int W, int H, int batch, int64_t row_pitch, int64_t frame_stride, int boxw) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    if ((reinterpret_cast<uintptr_t>(frames) & 15) || (row_pitch & 15) || (frame_stride & 15) || W < boxw) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)batch};
+    const cuuint64_t strides[2] = {(cuuint64_t)row_pitch, (cuuint64_t)frame_stride};
+    const cuuint32_t box[3] = {(cuuint32_t)boxw, (cuuint32_t)RB, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t *>(frames), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int KS, int KL>
 cudaError_t launch(vbs_ctx *ctx, const uint8_t *frames, int batch, int64_t frame_stride, int64_t row_pitch) {
     using G = Geo<KS, KL>;
@@ -293,18 +388,22 @@ cudaError_t launch(vbs_ctx *ctx, const uint8_t *frames, int batch, int64_t frame
     vsegs = (ctx->H + seg_rows - 1) / seg_rows;
     dim3 grid(strips, vsegs, batch), block(TW);
     cudaError_t e;
+    CUtensorMap map;
+    std::memset(&map, 0, sizeof(map));
+    const int use_tma = (ctx->C == 1 && !ctx->no_tma && make_frame_map(&map, frames, ctx->W, ctx->H, batch, row_pitch, frame_stride, G::BOXW)) ? 1 : 0;
     if (ctx->C == 3) {
         auto kern = blur_area_kernel<KS, KL, true>;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM)) != cudaSuccess) return e;
-        kern<<<grid, block, G::SMEM, ctx->stream>>>(frames, frame_stride, row_pitch, ctx->H, ctx->W, ctx->WW, seg_rows,
-                                                    ctx->br.lo, ctx->br.hi, ctx->area_bits, ctx->area_count);
+        kern<<<grid, block, G::SMEM, ctx->stream>>>(map, 0, frames, frame_stride, row_pitch, ctx->H, ctx->W, ctx->WW, seg_rows,
+                                                    ctx->br.lo, ctx->br.hi, ctx->area_bits, ctx->area_count, ctx->d_status);
     } else {
         auto kern = blur_area_kernel<KS, KL, false>;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM)) != cudaSuccess) return e;
-        kern<<<grid, block, G::SMEM, ctx->stream>>>(frames, frame_stride, row_pitch, ctx->H, ctx->W, ctx->WW, seg_rows,
-                                                    ctx->br.lo, ctx->br.hi, ctx->area_bits, ctx->area_count);
+        kern<<<grid, block, G::SMEM, ctx->stream>>>(map, use_tma, frames, frame_stride, row_pitch, ctx->H, ctx->W, ctx->WW, seg_rows,
+                                                    ctx->br.lo, ctx->br.hi, ctx->area_bits, ctx->area_count, ctx->d_status);
     }
     ctx->launches += 1;
+    ctx->tma_launches += use_tma;
     return cudaGetLastError();
 }
 

@@ -2,6 +2,7 @@
 // entry points that chain the kernels on the context's stream.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include "vbs_ctx.h"
@@ -25,8 +26,9 @@ int map_status(vbs_ctx *ctx, uint32_t st) {
     if (st & VBS_DEV_RECHECK_OVERFLOW) m += " float64 recheck list overflow;";
     if (st & VBS_DEV_TRACE_GUARD) m += " border following did not close;";
     if (st & VBS_DEV_MATCH_CONFLICT) m += " a centroid was matched by two contours;";
+    if (st & VBS_DEV_TMA_TIMEOUT) m += " a TMA tile load timed out;";
     ctx->err = m;
-    if (st & (VBS_DEV_TRACE_GUARD | VBS_DEV_MATCH_CONFLICT)) return VBS_ERR_INTERNAL;
+    if (st & (VBS_DEV_TRACE_GUARD | VBS_DEV_MATCH_CONFLICT | VBS_DEV_TMA_TIMEOUT)) return VBS_ERR_INTERNAL;
     return VBS_ERR_CAPACITY;
 }
 
@@ -135,7 +137,7 @@ vbs_ctx make_view(const vbs_ctx *c, int off, cudaStream_t st) {
     return v;
 }
 void fold_view(vbs_ctx *c, const vbs_ctx &v) {   // state a launcher may have changed
-    c->launches = v.launches; c->have_first = v.have_first; c->first_frame = v.first_frame;
+    c->launches = v.launches; c->tma_launches = v.tma_launches; c->have_first = v.have_first; c->first_frame = v.first_frame;
     if (!v.err.empty()) c->err = v.err;
 }
 
@@ -277,6 +279,7 @@ int vbs_create(vbs_ctx **out, const vbs_config *cfg) {
     ctx->big = cfg->height > 480;                                             // MD:117
     ctx->br = ctx->big ? VbsBranch{39, 101, 80, 13.0, 20, 200, 14} : VbsBranch{21, 35, 33, 7.4, 35, 180, 8};
     ctx->min_dist = 20.0;
+    { const char *e = getenv("VBS_NO_TMA"); ctx->no_tma = (e && e[0] == '1') ? 1 : 0; }
     ctx->first_frame = 0; ctx->have_first = 0;
     *out = ctx;                                    // returned even on failure so vbs_last_error works; caller destroys
     if (vbs_check_taps(ctx->err) != 0) return VBS_ERR_INTERNAL;
@@ -646,6 +649,7 @@ int vbs_fit_plane(vbs_ctx *ctx, int32_t n, const double *X, const double *Y, con
 }
 
 int64_t vbs_kernel_launches(const vbs_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int64_t vbs_tma_launches(const vbs_ctx *ctx) { return ctx ? ctx->tma_launches : 0; }
 
 int vbs_set_profiling(vbs_ctx *ctx, int32_t enable) {
     if (!ctx) return VBS_ERR_BAD_ARG;

@@ -13,6 +13,7 @@ enum : uint32_t {
     VBS_DEV_RECHECK_OVERFLOW = 1u << 2,  // float64 recheck list full
     VBS_DEV_TRACE_GUARD = 1u << 3,       // border following did not close
     VBS_DEV_MATCH_CONFLICT = 1u << 4,    // one centroid claimed by two contours
+    VBS_DEV_TMA_TIMEOUT = 1u << 5,       // a TMA tile never arrived (bounded wait gave up)
 };
 
 struct VbsBranch {       // constants that switch on the frame height (MD:117-126,129,170)
@@ -31,6 +32,7 @@ struct vbs_ctx {
     cudaStream_t stream, own_stream;
     std::string err;
     int64_t launches;
+    int no_tma; int64_t tma_launches;      // VBS_NO_TMA=1 forces the generic loader; launches that used the TMA path
 
     // frame staging for the host entry point
     uint8_t *d_frames; size_t frames_bytes;      // two staging buffers of host_chunk frames

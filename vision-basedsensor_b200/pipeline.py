@@ -97,6 +97,10 @@ class MarkerPipeline:
     def kernel_launches(self) -> int:
         return int(capi.lib.vbs_kernel_launches(self._ctx))
 
+    @property
+    def tma_launches(self) -> int:
+        return int(capi.lib.vbs_tma_launches(self._ctx))
+
     STAGES = ("blur_dog_area", "ncc_mask", "morphology", "components", "contours_ellipse", "track_3d_plane", "output_copies")
 
     def set_profiling(self, on: bool):
