@@ -84,7 +84,7 @@ __device__ void unite(int32_t *par, int a, int b) {
 #define VBS_QUAD_COORDS                                          \
     const int q = blockIdx.x * 16 + threadIdx.x;                \
     const int y = blockIdx.y * 16 + threadIdx.y;                \
-    const int z = blockIdx.z, f = z >> 1, img = z & 1;          \
+    const int f = blockIdx.z / im.nimg, img = im.img0 + blockIdx.z % im.nimg, z = 2 * f + img; \
     if (4 * q >= WW || y >= H) return;
 
 // ---- 1. every segment start becomes its own root ------------------------------------------------
@@ -175,6 +175,7 @@ __global__ void __launch_bounds__(256) ccl_flatten_bg_kernel(const uint32_t *__r
 struct FgImages {
     const uint32_t *bits[2];     // max_bits, open_bits
     int32_t *parent[2];          // parent, parent2
+    int img0, nimg;              // images handled by this launch: img0 .. img0 + nimg - 1 (grid.z = batch * nimg)
 };
 
 template <bool CONN8>
@@ -206,7 +207,7 @@ __device__ __forceinline__ void merge_word(int32_t *par, uint32_t w, uint32_t pr
 __global__ void __launch_bounds__(256) fg_merge_kernel(FgImages im, int H, int W, int WW) {
     const int wx = blockIdx.x * 64 + threadIdx.x;
     const int y = blockIdx.y * 4 + threadIdx.y;
-    const int z = blockIdx.z, f = z >> 1, img = z & 1;
+    const int f = blockIdx.z / im.nimg, img = im.img0 + blockIdx.z % im.nimg;
     if (wx >= WW || y >= H) return;
     const uint32_t *img_bits = im.bits[img] + (size_t)f * H * WW;
     const uint32_t w = __ldg(img_bits + (size_t)y * WW + wx);
@@ -325,9 +326,9 @@ __global__ void __launch_bounds__(1024) rank_kernel(const int32_t *__restrict__ 
                                                      const int32_t *__restrict__ euler4, int32_t *__restrict__ slot2label,
                                                      double *__restrict__ centres, int32_t *__restrict__ nlabels, int32_t *__restrict__ croot,
                                                      int32_t *__restrict__ ncont, int32_t *__restrict__ holes, int H, int W, int M, int P2,
-                                                     uint32_t *status) {
+                                                     int img0, uint32_t *status) {
     extern __shared__ int32_t key[];
-    const int f = blockIdx.x, img = blockIdx.y, z = 2 * f + img, tid = threadIdx.x;
+    const int f = blockIdx.x, img = img0 + blockIdx.y, z = 2 * f + img, tid = threadIdx.x;
     const int total = nroots[z];
     const int n = min(total, M);
     if (total > M && tid == 0) atomicOr(status, img == 0 ? VBS_DEV_LABEL_OVERFLOW : VBS_DEV_CONTOUR_OVERFLOW);
@@ -365,36 +366,51 @@ __global__ void __launch_bounds__(1024) rank_kernel(const int32_t *__restrict__ 
 
 }  // namespace
 
-cudaError_t vbs_launch_components(vbs_ctx *ctx, int batch) {
+// zero the per-batch accumulators once, before the two branches fork
+cudaError_t vbs_launch_prepare(vbs_ctx *ctx, int batch) {
+    const size_t M = ctx->M;
+    cudaStream_t st = ctx->stream;
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(ctx->lab_cnt, 0, sizeof(uint32_t) * batch * M, st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(ctx->lab_sx, 0, sizeof(unsigned long long) * batch * M, st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(ctx->lab_sy, 0, sizeof(unsigned long long) * batch * M, st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(ctx->euler4, 0, sizeof(int32_t) * batch, st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(ctx->nroots, 0, sizeof(int32_t) * 2 * batch, st)) != cudaSuccess) return e;
+    return cudaMemsetAsync(ctx->claim, 0, sizeof(int32_t) * batch * M, st);
+}
+
+// which: bit 0 = ring-maxima image (labels, centroids), bit 1 = opened area mask (blobs, contour order, holes,
+// background pass).  The two are independent, so they may run on different streams after vbs_launch_prepare.
+cudaError_t vbs_launch_components(vbs_ctx *ctx, int batch, int which) {
     const int H = ctx->H, W = ctx->W, WW = ctx->WW, M = ctx->M;
     const dim3 wb(64, 4);
     const dim3 wg((WW + 63) / 64, (H + 3) / 4, batch);
     const dim3 eg((WW + 1 + 63) / 64, (H + 1 + 3) / 4, batch);
     const dim3 qb(16, 16);
-    const dim3 qg2((WW + 63) / 64, (H + 15) / 16, 2 * batch), qg1((WW + 63) / 64, (H + 15) / 16, batch);
     cudaStream_t st = ctx->stream;
-    cudaError_t e;
-    if ((e = cudaMemsetAsync(ctx->lab_cnt, 0, sizeof(uint32_t) * (size_t)batch * M, st)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(ctx->lab_sx, 0, sizeof(unsigned long long) * (size_t)batch * M, st)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(ctx->lab_sy, 0, sizeof(unsigned long long) * (size_t)batch * M, st)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(ctx->euler4, 0, sizeof(int32_t) * batch, st)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(ctx->nroots, 0, sizeof(int32_t) * 2 * batch, st)) != cudaSuccess) return e;
     FgImages im;
     im.bits[0] = ctx->max_bits; im.bits[1] = ctx->open_bits; im.parent[0] = ctx->parent; im.parent[1] = ctx->parent2;
-    // segment starts were initialised by the morphology kernels that produced the two images
-    fg_merge_kernel<<<dim3((WW + 63) / 64, (H + 3) / 4, 2 * batch), wb, 0, st>>>(im, H, W, WW);
-    fg_roots_kernel<<<qg2, qb, 0, st>>>(im, ctx->nroots, ctx->rootlist, H, W, WW, M);
-    moments_kernel<<<qg1, qb, 0, st>>>(ctx->max_bits, ctx->parent, ctx->lab_cnt, ctx->lab_sx, ctx->lab_sy, H, W, WW, M);
-    euler_kernel<<<eg, wb, 0, st>>>(ctx->open_bits, ctx->euler4, H, W, WW);
+    im.img0 = (which & 1) ? 0 : 1;
+    im.nimg = (which == 3) ? 2 : 1;
+    const dim3 qgn((WW + 63) / 64, (H + 15) / 16, im.nimg * batch), qg1((WW + 63) / 64, (H + 15) / 16, batch);
+    // segment starts were initialised by the morphology kernels that produced the images
+    fg_merge_kernel<<<dim3((WW + 63) / 64, (H + 3) / 4, im.nimg * batch), wb, 0, st>>>(im, H, W, WW);
+    fg_roots_kernel<<<qgn, qb, 0, st>>>(im, ctx->nroots, ctx->rootlist, H, W, WW, M);
+    ctx->launches += 2;
+    if (which & 1) { moments_kernel<<<qg1, qb, 0, st>>>(ctx->max_bits, ctx->parent, ctx->lab_cnt, ctx->lab_sx, ctx->lab_sy, H, W, WW, M); ctx->launches += 1; }
+    if (which & 2) { euler_kernel<<<eg, wb, 0, st>>>(ctx->open_bits, ctx->euler4, H, W, WW); ctx->launches += 1; }
     int P2 = 1;
     while (P2 < M) P2 <<= 1;
-    rank_kernel<<<dim3(batch, 2), 1024, sizeof(int32_t) * P2, st>>>(ctx->nroots, ctx->rootlist, ctx->parent, ctx->lab_cnt, ctx->lab_sx, ctx->lab_sy,
-                                                                   ctx->euler4, ctx->slot2label, ctx->centres, ctx->d_nlabels, ctx->croot,
-                                                                   ctx->d_ncont, ctx->holes, H, W, M, P2, ctx->d_status);
-    // background pass of the opened image: every thread of a hole-free frame returns at once
-    ccl_init_kernel<false, true><<<wg, wb, 0, st>>>(ctx->open_bits, ctx->parent2, ctx->holes, H, W, WW);
-    ccl_merge_kernel<false, true, true><<<wg, wb, 0, st>>>(ctx->open_bits, ctx->parent2, ctx->holes, H, W, WW);
-    ccl_flatten_bg_kernel<<<wg, wb, 0, st>>>(ctx->open_bits, ctx->parent2, ctx->holes, H, W, WW);
-    ctx->launches += 8;
+    rank_kernel<<<dim3(batch, im.nimg), 1024, sizeof(int32_t) * P2, st>>>(ctx->nroots, ctx->rootlist, ctx->parent, ctx->lab_cnt, ctx->lab_sx, ctx->lab_sy,
+                                                                         ctx->euler4, ctx->slot2label, ctx->centres, ctx->d_nlabels, ctx->croot,
+                                                                         ctx->d_ncont, ctx->holes, H, W, M, P2, im.img0, ctx->d_status);
+    ctx->launches += 1;
+    if (which & 2) {
+        // background pass of the opened image: every thread of a hole-free frame returns at once
+        ccl_init_kernel<false, true><<<wg, wb, 0, st>>>(ctx->open_bits, ctx->parent2, ctx->holes, H, W, WW);
+        ccl_merge_kernel<false, true, true><<<wg, wb, 0, st>>>(ctx->open_bits, ctx->parent2, ctx->holes, H, W, WW);
+        ccl_flatten_bg_kernel<<<wg, wb, 0, st>>>(ctx->open_bits, ctx->parent2, ctx->holes, H, W, WW);
+        ctx->launches += 3;
+    }
     return cudaGetLastError();
 }

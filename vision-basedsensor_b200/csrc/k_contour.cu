@@ -170,19 +170,23 @@ __global__ void compact_kernel(const double *__restrict__ cell, const int32_t *_
 
 }  // namespace
 
-cudaError_t vbs_launch_contours(vbs_ctx *ctx, int batch) {
-    const size_t total = (size_t)batch * ctx->M;
-    cudaError_t e = cudaMemsetAsync(ctx->claim, 0, sizeof(int32_t) * total, ctx->stream);
-    if (e != cudaSuccess) return e;
+// which: bit 1 = follow + fit the blobs of the opened mask (open branch), bit 2 = match centroids to
+// ellipses and compact the marker list (needs both branches)
+cudaError_t vbs_launch_contours(vbs_ctx *ctx, int batch, int which) {
     const dim3 grid((ctx->M + 63) / 64, batch);
-    contour_trace_kernel<<<grid, 64, 0, ctx->stream>>>(ctx->open_bits, ctx->parent2, ctx->croot, ctx->d_ncont, ctx->holes, ctx->cpts,
-                                                       ctx->cpn, ctx->H, ctx->W, ctx->WW, ctx->M, ctx->d_status);
-    contour_fit_kernel<<<grid, 64, 0, ctx->stream>>>(ctx->open_bits, ctx->croot, ctx->cpts, ctx->cpn, ctx->cell, ctx->H, ctx->W, ctx->WW,
-                                                     ctx->M);
-    match_kernel<<<grid, 64, 0, ctx->stream>>>(ctx->open_bits, ctx->croot, ctx->cpts, ctx->cpn, ctx->cell, ctx->centres, ctx->d_nlabels,
-                                               ctx->cmatch, ctx->claim, ctx->H, ctx->W, ctx->WW, ctx->M, ctx->d_status);
-    compact_kernel<<<(batch + 3) / 4, 128, 0, ctx->stream>>>(ctx->cell, ctx->cmatch, ctx->centres, ctx->d_ncont, ctx->d_nmarkers,
-                                                             ctx->marker_xy, ctx->marker_axes, ctx->M, batch);
-    ctx->launches += 4;
+    if (which & 2) {
+        contour_trace_kernel<<<grid, 64, 0, ctx->stream>>>(ctx->open_bits, ctx->parent2, ctx->croot, ctx->d_ncont, ctx->holes, ctx->cpts,
+                                                           ctx->cpn, ctx->H, ctx->W, ctx->WW, ctx->M, ctx->d_status);
+        contour_fit_kernel<<<grid, 64, 0, ctx->stream>>>(ctx->open_bits, ctx->croot, ctx->cpts, ctx->cpn, ctx->cell, ctx->H, ctx->W, ctx->WW,
+                                                         ctx->M);
+        ctx->launches += 2;
+    }
+    if (which & 4) {
+        match_kernel<<<grid, 64, 0, ctx->stream>>>(ctx->open_bits, ctx->croot, ctx->cpts, ctx->cpn, ctx->cell, ctx->centres, ctx->d_nlabels,
+                                                   ctx->cmatch, ctx->claim, ctx->H, ctx->W, ctx->WW, ctx->M, ctx->d_status);
+        compact_kernel<<<(batch + 3) / 4, 128, 0, ctx->stream>>>(ctx->cell, ctx->cmatch, ctx->centres, ctx->d_ncont, ctx->d_nmarkers,
+                                                                 ctx->marker_xy, ctx->marker_axes, ctx->M, batch);
+        ctx->launches += 2;
+    }
     return cudaGetLastError();
 }

@@ -169,14 +169,20 @@ __global__ void unpack_labels_kernel(const uint32_t *__restrict__ bits, const in
 
 }  // namespace
 
-cudaError_t vbs_launch_morph(vbs_ctx *ctx, int batch) {
+// which: bit 0 = ring maxima of the NCC mask (needs K2), bit 1 = 5x5 open of the area mask (needs K1 only)
+cudaError_t vbs_launch_morph(vbs_ctx *ctx, int batch, int which) {
     const dim3 block(32, TY);
-    const dim3 gm((ctx->WW + 31) / 32, (ctx->H + TH - 1) / TH, batch);
-    if (ctx->br.nb == 14) maxima_kernel<14><<<gm, block, 0, ctx->stream>>>(ctx->mask_bits, ctx->max_bits, ctx->parent, ctx->H, ctx->W, ctx->WW);
-    else maxima_kernel<8><<<gm, block, 0, ctx->stream>>>(ctx->mask_bits, ctx->max_bits, ctx->parent, ctx->H, ctx->W, ctx->WW);
-    const dim3 go((ctx->WW + 29) / 30, (ctx->H + TH - 1) / TH, batch);
-    open5_kernel<<<go, block, 0, ctx->stream>>>(ctx->area_bits, ctx->open_bits, ctx->parent2, ctx->H, ctx->W, ctx->WW);
-    ctx->launches += 2;
+    if (which & 1) {
+        const dim3 gm((ctx->WW + 31) / 32, (ctx->H + TH - 1) / TH, batch);
+        if (ctx->br.nb == 14) maxima_kernel<14><<<gm, block, 0, ctx->stream>>>(ctx->mask_bits, ctx->max_bits, ctx->parent, ctx->H, ctx->W, ctx->WW);
+        else maxima_kernel<8><<<gm, block, 0, ctx->stream>>>(ctx->mask_bits, ctx->max_bits, ctx->parent, ctx->H, ctx->W, ctx->WW);
+        ctx->launches += 1;
+    }
+    if (which & 2) {
+        const dim3 go((ctx->WW + 29) / 30, (ctx->H + TH - 1) / TH, batch);
+        open5_kernel<<<go, block, 0, ctx->stream>>>(ctx->area_bits, ctx->open_bits, ctx->parent2, ctx->H, ctx->W, ctx->WW);
+        ctx->launches += 1;
+    }
     return cudaGetLastError();
 }
 

@@ -57,9 +57,10 @@ int run_detection(vbs_ctx *ctx, const uint8_t *frames, int batch, int64_t frame_
     return VBS_OK;
 }
 int run_centres(vbs_ctx *ctx, int batch) {
-    VBS_CUDA(vbs_launch_morph(ctx, batch));
-    VBS_CUDA(vbs_launch_components(ctx, batch));
-    VBS_CUDA(vbs_launch_contours(ctx, batch));
+    VBS_CUDA(vbs_launch_prepare(ctx, batch));
+    VBS_CUDA(vbs_launch_morph(ctx, batch, 3));
+    VBS_CUDA(vbs_launch_components(ctx, batch, 3));
+    VBS_CUDA(vbs_launch_contours(ctx, batch, 6));
     return VBS_OK;
 }
 
@@ -198,11 +199,12 @@ int stage_a(vbs_ctx *ctx, int c, int off, int n, const uint8_t *frames, int64_t 
 int stage_b(vbs_ctx *ctx, int c, int off, int n, int64_t frameno0, const vbs_outputs *out, cudaMemcpyKind kind, cudaStream_t st) {
     vbs_ctx v = make_view(ctx, off, st);
     VBS_MARKC(c, 3, st);
-    cudaError_t e = vbs_launch_morph(&v, n);
+    cudaError_t e = vbs_launch_prepare(&v, n);
+    if (e == cudaSuccess) e = vbs_launch_morph(&v, n, 3);
     VBS_MARKC(c, 4, st);
-    if (e == cudaSuccess) e = vbs_launch_components(&v, n);
+    if (e == cudaSuccess) e = vbs_launch_components(&v, n, 3);
     VBS_MARKC(c, 5, st);
-    if (e == cudaSuccess) e = vbs_launch_contours(&v, n);
+    if (e == cudaSuccess) e = vbs_launch_contours(&v, n, 6);
     VBS_MARKC(c, 6, st);
     if (e == cudaSuccess) e = vbs_launch_track(&v, n, frameno0 + off);
     VBS_MARKC(c, 7, st);
@@ -231,7 +233,45 @@ int process_common(vbs_ctx *ctx, const uint8_t *d_frames, int batch, int64_t fra
     // kernels, 4x the launches, SM contention) than the overlap wins - 12.3 vs 10.7 ms - so device-resident
     // batches run unchunked unless asked; the host path below always pipelines (it is PCIe-bound)
     const int nch = ctx->overlap_device ? plan_chunks(batch, &chunk) : 1;
-    if (nch <= 1) {                                     // everything in order on the caller's stream
+    if (nch <= 1 && !ctx->no_branch_overlap && ensure_pipeline(ctx) == VBS_OK) {
+        // The blobs of the opened AREA mask (5x5 open, labelling, border following, ellipse fits) depend on
+        // K1 only, so that branch runs on the second stream beside the NCC; the branches join at the
+        // centroid <-> ellipse matching.  Stage marks stay on the caller's stream (their sum = the step).
+        vbs_ctx va = make_view(ctx, 0, ctx->stream);
+        VBS_MARKC(0, 0, ctx->stream);
+        cudaError_t e = vbs_launch_prepare(&va, batch);
+        if (e == cudaSuccess) e = vbs_launch_blur(&va, d_frames, batch, frame_stride, row_pitch);
+        VBS_MARKC(0, 1, ctx->stream);
+        fold_view(ctx, va);
+        VBS_CUDA(e);
+        VBS_CUDA(cudaEventRecord(ctx->ev_a[0], ctx->stream));
+        VBS_CUDA(cudaStreamWaitEvent(ctx->stream_b, ctx->ev_a[0], 0));
+        vbs_ctx vb = make_view(ctx, 0, ctx->stream_b);
+        e = vbs_launch_morph(&vb, batch, 2);
+        if (e == cudaSuccess) e = vbs_launch_components(&vb, batch, 2);
+        if (e == cudaSuccess) e = vbs_launch_contours(&vb, batch, 2);
+        fold_view(ctx, vb);
+        VBS_CUDA(e);
+        VBS_CUDA(cudaEventRecord(ctx->ev_b_done, ctx->stream_b));
+        va.launches = ctx->launches; va.tma_launches = ctx->tma_launches;
+        e = vbs_launch_ncc(&va, batch);
+        VBS_MARKC(0, 2, ctx->stream); VBS_MARKC(0, 3, ctx->stream);
+        if (e == cudaSuccess) e = vbs_launch_morph(&va, batch, 1);
+        VBS_MARKC(0, 4, ctx->stream);
+        if (e == cudaSuccess) e = vbs_launch_components(&va, batch, 1);
+        VBS_MARKC(0, 5, ctx->stream);
+        fold_view(ctx, va);
+        VBS_CUDA(e);
+        VBS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_b_done, 0));       // join: ellipses are ready
+        e = vbs_launch_contours(&va, batch, 4);
+        VBS_MARKC(0, 6, ctx->stream);
+        if (e == cudaSuccess) e = vbs_launch_track(&va, batch, frameno0);
+        VBS_MARKC(0, 7, ctx->stream);
+        fold_view(ctx, va);
+        VBS_CUDA(e);
+        if ((rc = copy_outputs(ctx, va, out, 0, batch, kind)) != VBS_OK) return rc;
+        VBS_MARKC(0, 8, ctx->stream);
+    } else if (nch <= 1) {                              // everything in order on the caller's stream
         if ((rc = stage_a(ctx, 0, 0, batch, d_frames, frame_stride, row_pitch)) != VBS_OK) return rc;
         if ((rc = stage_b(ctx, 0, 0, batch, frameno0, out, kind, ctx->stream)) != VBS_OK) return rc;
     } else {
@@ -280,6 +320,9 @@ int vbs_create(vbs_ctx **out, const vbs_config *cfg) {
     ctx->br = ctx->big ? VbsBranch{39, 101, 80, 13.0, 20, 200, 14} : VbsBranch{21, 35, 33, 7.4, 35, 180, 8};
     ctx->min_dist = 20.0;
     { const char *e = getenv("VBS_NO_TMA"); ctx->no_tma = (e && e[0] == '1') ? 1 : 0; }
+    // measured on B200: running the open-mask branch beside the NCC stretches the NCC from 3.4 to 4.9 ms and
+    // the step from 10.5 to 10.7 ms (same SM resources), so it is opt-in: VBS_BRANCH_OVERLAP=1
+    { const char *e = getenv("VBS_BRANCH_OVERLAP"); ctx->no_branch_overlap = (e && e[0] == '1') ? 0 : 1; }
     ctx->first_frame = 0; ctx->have_first = 0;
     *out = ctx;                                    // returned even on failure so vbs_last_error works; caller destroys
     if (vbs_check_taps(ctx->err) != 0) return VBS_ERR_INTERNAL;

@@ -86,6 +86,7 @@ struct vbs_ctx {
     cudaEvent_t pev[72];                        // 8 chunks x 9 stage boundaries
     // chunked two-stream pipeline
     cudaStream_t stream_b; cudaEvent_t ev_a[8], ev_b_done; int overlap_device;
+    int no_branch_overlap;                      // 1: run the open-mask branch after the NCC instead of beside it
     double stage_ms[7]; int64_t stage_calls;
 };
 enum { VBS_NSTAGES = 7 };   // blur, ncc, morph, components, contours, track3d, output copies
@@ -103,9 +104,10 @@ enum { VBS_NSTAGES = 7 };   // blur, ncc, morph, components, contours, track3d, 
 cudaError_t vbs_launch_blur(vbs_ctx *ctx, const uint8_t *frames, int batch, int64_t frame_stride, int64_t row_pitch);
 cudaError_t vbs_launch_ncc(vbs_ctx *ctx, int batch);
 cudaError_t vbs_ncc_setup(vbs_ctx *ctx);
-cudaError_t vbs_launch_morph(vbs_ctx *ctx, int batch);
-cudaError_t vbs_launch_components(vbs_ctx *ctx, int batch);
-cudaError_t vbs_launch_contours(vbs_ctx *ctx, int batch);
+cudaError_t vbs_launch_prepare(vbs_ctx *ctx, int batch);
+cudaError_t vbs_launch_morph(vbs_ctx *ctx, int batch, int which);
+cudaError_t vbs_launch_components(vbs_ctx *ctx, int batch, int which);
+cudaError_t vbs_launch_contours(vbs_ctx *ctx, int batch, int which);
 cudaError_t vbs_launch_track(vbs_ctx *ctx, int batch, int64_t frameno0);
 cudaError_t vbs_launch_reconstruct(vbs_ctx *ctx, int batch, int64_t frameno0);
 cudaError_t vbs_launch_fix_displacement(vbs_ctx *ctx, double *pos3d, uint8_t *flags, const double *incoming_dev, long long nframes);
