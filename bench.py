@@ -332,26 +332,43 @@ def main():
     # ---- e2e: host frames -> results on the host through the public API, copies in the timed region
     if not args.no_e2e:
         pin = torch.from_numpy(host_frames).pin_memory()
-        houts = pipe.alloc_outputs(B, False)
+        houts = [pipe.alloc_outputs(B, False), pipe.alloc_outputs(B, False)]
         pipe.reset_sequence()
         if args.host_chunk:
             pipe.set_host_chunk(args.host_chunk)
-        for s in range(2):
-            pipe.process_host_ptr(pin.data_ptr(), B, H * W, W, s * B, houts)
+        # streaming use of the public host API: submit batch s+1 (its H2D copy starts at once) before
+        # waiting for batch s; every step still moves its own frames host->device and results device->host
+        def run(nsteps, s0):
+            pipe.submit_host_ptr(pin.data_ptr(), B, H * W, W, s0 * B, houts[0])
+            for s in range(1, nsteps):
+                pipe.submit_host_ptr(pin.data_ptr(), B, H * W, W, (s0 + s) * B, houts[s & 1])
+                pipe.wait_host()
+            pipe.wait_host()
+        run(2, 0)
         barrier()
         t0 = time.perf_counter()
-        for s in range(args.steps):
-            r = pipe.process_host_ptr(pin.data_ptr(), B, H * W, W, s * B, houts)
+        run(args.steps, 2)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        # the synchronous call (one batch in, results out, nothing in flight afterwards) for comparison
+        for s in range(2):
+            pipe.process_host_ptr(pin.data_ptr(), B, H * W, W, s * B, houts[0])
+        t1 = time.perf_counter()
+        for s in range(min(args.steps, 10)):
+            r = pipe.process_host_ptr(pin.data_ptr(), B, H * W, W, s * B, houts[0])
+        dts = (time.perf_counter() - t1) / min(args.steps, 10)
         if world > 1:
             t = torch.tensor([dt], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         if rank == 0:
-            d2h = sum(a.nbytes for a in houts[0].values())
+            d2h = sum(a.nbytes for a in houts[0][0].values())
             line["e2e"] = {"value": world * B * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(B * H * W),
-                           "d2h_bytes_per_step": int(d2h), "api": "MarkerPipeline.process_host_ptr -> vbs_process_host (pinned host frames in, host arrays out)"}
+                           "d2h_bytes_per_step": int(d2h),
+                           "api": "MarkerPipeline.submit_host_ptr / wait_host -> vbs_submit_host / vbs_wait_host (pinned host frames in, pinned host "
+                                  "arrays out, two batches in flight)",
+                           "synchronous_call_value": world * B / dts,
+                           "synchronous_api": "MarkerPipeline.process_host_ptr -> vbs_process_host (chunked copy/compute overlap inside one call)"}
 
     # ---- cpu_baseline: oracle port on a bounded sample, rank 0, N=1 only
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -145,6 +145,15 @@ int vbs_set_overlap(vbs_ctx *ctx, int32_t enable);
 /* frames per chunk of vbs_process_host's copy/compute overlap (0 = default 64) */
 int vbs_set_host_chunk(vbs_ctx *ctx, int32_t frames_per_chunk);
 
+/* Asynchronous host entry point for streams of batches (config 5): vbs_submit_host enqueues the H2D copy of
+ * the whole batch on a copy stream, the pipeline and the D2H copies of the results, and returns at once; up
+ * to two batches may be in flight, so batch i+1 crosses PCIe while batch i is processed.  vbs_wait_host
+ * blocks until the oldest batch in flight has landed in its `out` arrays and returns its status.  Frames and
+ * outputs must be pinned host memory and stay untouched until the matching vbs_wait_host. */
+int vbs_submit_host(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int64_t frame_stride, int64_t row_pitch,
+                    int64_t frameno0, const vbs_outputs *out);
+int vbs_wait_host(vbs_ctx *ctx);
+
 /* stage-level entry points (same kernels, for the static-method mirrors) -----------------------
  * vbs_find_markers : MarkerTracker._find_markers (MD:111-135): frames -> area_mask, mask (kept in ctx)
  * vbs_marker_center: MarkerTracker._marker_center (MD:166-249) on masks supplied by the caller

@@ -460,3 +460,41 @@ def test_tma_path_is_used_and_equals_generic_loader(monkeypatch):
         pipe.sync()
         assert pipe.tma_launches == 0
         assert np.array_equal(outs[0]["marker_xy"].cpu().numpy(), a.marker_xy)
+
+
+# ---------------------------------------------------------------------------------------------
+# 9. asynchronous host entry point (two batches in flight) == synchronous calls, incl. the last-seen carry
+# ---------------------------------------------------------------------------------------------
+def test_async_host_api_equals_synchronous_calls():
+    import torch
+    h, w, rows, cols = 560, 640, 6, 8
+    centres = synth.grid_layout(h, w, rows, cols, 60.0)
+    seq = synth.compression_sequence(h, w, centres, 11.0, 12, tilt=0.4, depth=1.0, seed0=700)
+    keys, xy = pu.grid_reference(port.find_markers_frame(seq[0]), cols)
+    K, D, R, T = synth.synthetic_camera()
+    K = K.copy(); K[0, 2] = w / 2 + 3.1; K[1, 2] = h / 2 - 2.3
+    pin = torch.from_numpy(seq).pin_memory()
+    B = 4
+    with pipeline.MarkerPipeline(h, w, 1, max_batch=B, max_markers=256, max_refs=len(keys)) as pipe:
+        pipe.set_reference([k[0] for k in keys], [k[1] for k in keys], xy[:, 0], xy[:, 1], 20.0)
+        pipe.set_camera(K, D, R, T, 2.0, 5.0, 50.0, warmup_frames=0)
+        sync_res = []
+        for s in range(3):
+            o = pipe.alloc_outputs(B, False)
+            r = pipe.process_host_ptr(pin.data_ptr() + s * B * h * w, B, h * w, w, s * B, o)
+            sync_res.append({k: np.copy(v) for k, v in o[0].items()})
+        pipe.reset_sequence()
+        outs = [pipe.alloc_outputs(B, False) for _ in range(3)]
+        pipe.submit_host_ptr(pin.data_ptr(), B, h * w, w, 0, outs[0])
+        pipe.submit_host_ptr(pin.data_ptr() + B * h * w, B, h * w, w, B, outs[1])
+        with pytest.raises(capi.VbsError, match="two batches already in flight"):
+            pipe.submit_host_ptr(pin.data_ptr(), B, h * w, w, 0, outs[2])
+        pipe.wait_host()
+        pipe.submit_host_ptr(pin.data_ptr() + 2 * B * h * w, B, h * w, w, 2 * B, outs[2])
+        pipe.wait_host(); pipe.wait_host()
+        with pytest.raises(capi.VbsError, match="no batch in flight"):
+            pipe.wait_host()
+        for s in range(3):
+            for k, v in sync_res[s].items():
+                assert np.array_equal(outs[s][0][k], v, equal_nan=True), (s, k)
+        assert (sync_res[2]["pos_flags"] & 4).any()

@@ -47,6 +47,8 @@ SYMBOLS = {
     "vbs_process_host": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.POINTER(VbsOutputs)]),
     "vbs_set_host_chunk": (C.c_int, [_P, C.c_int32]),
     "vbs_set_overlap": (C.c_int, [_P, C.c_int32]),
+    "vbs_submit_host": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.POINTER(VbsOutputs)]),
+    "vbs_wait_host": (C.c_int, [_P]),
     "vbs_find_markers": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int64]),
     "vbs_marker_center": (C.c_int, [_P, _P, _P, C.c_int32, C.POINTER(VbsOutputs)]),
     "vbs_track_markers": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P]),

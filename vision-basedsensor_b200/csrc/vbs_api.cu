@@ -41,6 +41,9 @@ void free_all(vbs_ctx *c) {
                     c->d_status};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (c->h_status) cudaFreeHost(c->h_status);
+    if (c->h_slot_status) cudaFreeHost(c->h_slot_status);
+    if (c->d_slots) cudaFree(c->d_slots);
+    for (int i = 0; i < 2; ++i) { if (c->ev_slot_in[i]) cudaEventDestroy(c->ev_slot_in[i]); if (c->ev_slot_free[i]) cudaEventDestroy(c->ev_slot_free[i]); if (c->ev_slot_done[i]) cudaEventDestroy(c->ev_slot_done[i]); }
     for (cudaEvent_t e : c->pev) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ev_a) if (e) cudaEventDestroy(e);
     if (c->ev_b_done) cudaEventDestroy(c->ev_b_done);
@@ -556,6 +559,68 @@ int vbs_process_host(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int64_t
     if (ctx->profiling) { ctx->prof_pending = 1; ctx->prof_chunks = nchunks; }
     ctx->last_batch = batch;
     return vbs_sync(ctx);
+}
+
+// ---- asynchronous host entry point: batch i+1 crosses PCIe while batch i is being processed ------------
+// Two device staging slots of max_batch frames.  submit: H2D of the whole batch on the copy stream (waits
+// until the slot's previous frames were consumed), then the unchunked pipeline + D2H of the results on the
+// context's stream, then a per-slot "done" event.  wait: blocks on the oldest batch in flight.
+int vbs_submit_host(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int64_t frame_stride, int64_t row_pitch, int64_t frameno0,
+                    const vbs_outputs *out) {
+    int rc = check_batch(ctx, frames, batch);
+    if (rc != VBS_OK) return rc;
+    const size_t rowb = (size_t)ctx->W * ctx->C, fb = rowb * ctx->H;
+    if (row_pitch < (int64_t)rowb) return fail(ctx, VBS_ERR_BAD_ARG, "row_pitch smaller than a row");
+    if (ctx->inflight >= 2) return fail(ctx, VBS_ERR_STATE, "two batches already in flight: call vbs_wait_host first");
+    if (!ctx->d_slots) {
+        VBS_CUDA(cudaMalloc((void **)&ctx->d_slots, 2 * fb * ctx->B));
+        for (int i = 0; i < 2; ++i) {
+            VBS_CUDA(cudaEventCreateWithFlags(&ctx->ev_slot_in[i], cudaEventDisableTiming));
+            VBS_CUDA(cudaEventCreateWithFlags(&ctx->ev_slot_free[i], cudaEventDisableTiming));
+            VBS_CUDA(cudaEventCreateWithFlags(&ctx->ev_slot_done[i], cudaEventDisableTiming));
+        }
+        VBS_CUDA(cudaHostAlloc((void **)&ctx->h_slot_status, 2 * sizeof(uint32_t), cudaHostAllocDefault));
+        ctx->h_slot_status[0] = ctx->h_slot_status[1] = 0;
+    }
+    if (!ctx->copy_stream) {
+        VBS_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            VBS_CUDA(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
+            VBS_CUDA(cudaEventCreateWithFlags(&ctx->ev_consumed[i], cudaEventDisableTiming));
+        }
+    }
+    const int slot = (int)(ctx->submitted & 1);
+    uint8_t *dst = ctx->d_slots + (size_t)slot * fb * ctx->B;
+    if (ctx->submitted >= 2) VBS_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_slot_free[slot], 0));
+    if ((size_t)row_pitch == rowb && (size_t)frame_stride == fb) {
+        VBS_CUDA(cudaMemcpyAsync(dst, frames, fb * batch, cudaMemcpyHostToDevice, ctx->copy_stream));
+    } else {
+        for (int f = 0; f < batch; ++f)
+            VBS_CUDA(cudaMemcpy2DAsync(dst + fb * f, rowb, frames + (size_t)frame_stride * f, (size_t)row_pitch, rowb, ctx->H,
+                                       cudaMemcpyHostToDevice, ctx->copy_stream));
+    }
+    VBS_CUDA(cudaEventRecord(ctx->ev_slot_in[slot], ctx->copy_stream));
+    VBS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_slot_in[slot], 0));
+    rc = process_common(ctx, dst, batch, (int64_t)fb, (int64_t)rowb, frameno0, out, cudaMemcpyDeviceToHost);
+    if (rc != VBS_OK) return rc;
+    VBS_CUDA(cudaEventRecord(ctx->ev_slot_free[slot], ctx->stream));     // (frames are dead after the blur; the end of the batch is a safe bound)
+    VBS_CUDA(cudaMemcpyAsync(&ctx->h_slot_status[slot], ctx->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    VBS_CUDA(cudaMemsetAsync(ctx->d_status, 0, sizeof(uint32_t), ctx->stream));
+    VBS_CUDA(cudaEventRecord(ctx->ev_slot_done[slot], ctx->stream));
+    ctx->submitted += 1;
+    ctx->inflight += 1;
+    return VBS_OK;
+}
+
+int vbs_wait_host(vbs_ctx *ctx) {
+    if (!ctx) return VBS_ERR_BAD_ARG;
+    if (ctx->inflight <= 0) return fail(ctx, VBS_ERR_STATE, "no batch in flight");
+    const int slot = (int)((ctx->submitted - ctx->inflight) & 1);
+    VBS_CUDA(cudaEventSynchronize(ctx->ev_slot_done[slot]));
+    ctx->inflight -= 1;
+    const uint32_t st = ctx->h_slot_status[slot];
+    ctx->h_slot_status[slot] = 0;
+    return map_status(ctx, st);
 }
 
 int vbs_set_overlap(vbs_ctx *ctx, int32_t enable) {

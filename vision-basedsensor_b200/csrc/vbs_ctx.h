@@ -37,6 +37,9 @@ struct vbs_ctx {
     // frame staging for the host entry point
     uint8_t *d_frames; size_t frames_bytes;      // two staging buffers of host_chunk frames
     int host_chunk; cudaStream_t copy_stream; cudaEvent_t ev_copied[2], ev_consumed[2];
+    // asynchronous host path: two whole-batch staging slots
+    uint8_t *d_slots; cudaEvent_t ev_slot_in[2], ev_slot_free[2], ev_slot_done[2]; uint32_t *h_slot_status;
+    int64_t submitted; int inflight;
     // bit images [B][H][WW]
     uint32_t *area_bits, *mask_bits, *max_bits, *open_bits;
     uint32_t *area_count;            // [B] set pixels of area_mask

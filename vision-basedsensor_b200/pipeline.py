@@ -260,6 +260,17 @@ class MarkerPipeline:
                                                         C.byref(out[1])))
         return BatchResult(frameno0=int(frameno0), **out[0])
 
+    def submit_host_ptr(self, ptr: int, batch: int, frame_stride: int, row_pitch: int, frameno0: int, out):
+        """Asynchronous host path: enqueue one batch (pinned frames by pointer, pinned outputs from
+        ``alloc_outputs(batch, False)``) and return at once; at most two batches in flight."""
+        capi.check(self._ctx, capi.lib.vbs_submit_host(self._ctx, C.c_void_p(ptr), batch, frame_stride, row_pitch, int(frameno0),
+                                                       C.byref(out[1])))
+        return BatchResult(frameno0=int(frameno0), **out[0])
+
+    def wait_host(self):
+        """Block until the oldest submitted batch has landed in its output arrays."""
+        capi.check(self._ctx, capi.lib.vbs_wait_host(self._ctx))
+
     def find_markers(self, frames):
         """Device frames -> (mask, area_mask) uint8 device tensors, like ``_find_markers`` (MD:111-135)."""
         import torch
