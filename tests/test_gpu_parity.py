@@ -498,3 +498,56 @@ def test_async_host_api_equals_synchronous_calls():
             for k, v in sync_res[s].items():
                 assert np.array_equal(outs[s][0][k], v, equal_nan=True), (s, k)
         assert (sync_res[2]["pos_flags"] & 4).any()
+
+
+# ---------------------------------------------------------------------------------------------
+# 10. BASELINE.json config 3: vertical / tilted compression sequences on the sensor's 65-marker ring
+#     layout -> tracking -> 3D displacement -> deviation against the vertical baseline -> plane tilt
+# ---------------------------------------------------------------------------------------------
+def test_compression_sequences_full_pipeline_matches_oracle():
+    full_h, full_w, n = 480, 640, 96
+    left, right, top, bottom = port.crop_box(full_w, full_h, (1 / 8, 1 / 8, 1 / 16, 0))
+    H, W = bottom - top, right - left
+    centres = synth.ring_layout(full_h, full_w, px_per_mm=11.0, dy=15.0)
+    vert = synth.compression_sequence(full_h, full_w, centres, 6.0, n, tilt=0.0, depth=1.0, seed0=900, noise_sigma=1.0)
+    tilt = synth.compression_sequence(full_h, full_w, centres, 6.0, n, tilt=0.7, depth=1.0, seed0=2900, noise_sigma=1.0)
+    crop = lambda s: np.ascontiguousarray(s[:, top:bottom, left:right])
+    vert, tilt = crop(vert), crop(tilt)
+    K, D, R, T = synth.synthetic_camera()
+    K = K.copy(); K[0, 2] = W / 2 + 3.1; K[1, 2] = H / 2 - 2.3
+    cam = port.Camera(K, D, R, T)
+    m0 = port.find_markers_frame(vert[0])
+    assert len(m0) == 65
+    keys = [(0, i) for i in range(65)]
+    xy = np.array([m["center"] for m in m0])
+    ref_xyz = np.stack([(xy[:, 0] - W / 2) / 11.0, (xy[:, 1] - H / 2) / 11.0, np.zeros(65)], 1)
+
+    def oracle_positions(frames):
+        orc = pu.oracle_frames(frames, keys, xy, 20.0)
+        rows3d, pos = pu.oracle_3d(orc, cam, warmup=0)
+        return orc, rows3d, pos
+
+    ov, rv, pv = oracle_positions(vert)
+    ot, rt, pt = oracle_positions(tilt)
+    start_v = np.array([pv[(0, 0, i)] for i in range(65)])
+    end_v = np.array([pv[(n - 1, 0, i)] for i in range(65)])
+    d_vert = end_v - start_v                                                    # FD:197-198
+    start_t = np.array([pt[(0, 0, i)] for i in range(65)])
+    planes = pu.oracle_plane(pt, keys, range(n), ref_xyz, start_t, d_vert)
+    with pipeline.MarkerPipeline(H, W, 1, max_batch=n, max_markers=256, max_refs=65) as pipe:
+        pipe.set_reference([k[0] for k in keys], [k[1] for k in keys], xy[:, 0], xy[:, 1], 20.0)
+        pipe.set_camera(K, D, R, T, 2.0, 5.0, 50.0, warmup_frames=0)
+        rvg = pipe.process(torch_cuda(vert), 0); pipe.sync(); rvg = rvg.to_host()
+        rep = pu.compare_rows(rvg, ov, keys)
+        rep.update(pu.compare_3d(rvg, keys, rv, pv))
+        gs, ge = rvg.pos3d[0, :, :3], rvg.pos3d[n - 1, :, :3]
+        assert np.abs((ge - gs) - d_vert).max() <= 1e-9
+        pipe.reset_sequence()
+        pipe.set_plane(ref_xyz, start_t, d_vert)
+        rtg = pipe.process(torch_cuda(tilt), 0); pipe.sync()
+        rep2 = pu.compare_rows(rtg, ot, keys)
+        rep2.update(pu.compare_3d(rtg, keys, rt, pt))
+        rep2.update(pu.compare_plane(rtg, planes))
+        pu.assert_report(rep); pu.assert_report(rep2)
+        tilts = rtg.to_host().plane[:, 3]
+        assert tilts[-1] > tilts[1] and tilts[-1] > 1.0             # the tilted press really tilts the fitted plane
