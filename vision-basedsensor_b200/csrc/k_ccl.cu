@@ -78,15 +78,6 @@ __device__ void unite(int32_t *par, int a, int b) {
     const int f = blockIdx.z;                                   \
     if (wx >= WW || y >= H) return;
 
-// quad kernels (foreground passes): one thread = 4 consecutive words (one 128-bit load; rows are padded
-// to a multiple of 4 words); block (16, 16), grid (ceil(WW/64), ceil(H/16), 2 * batch); z = 2 f + image,
-// image 0 = ring maxima (4-connected, parent), image 1 = opened area mask (8-connected, parent2)
-#define VBS_QUAD_COORDS                                          \
-    const int q = blockIdx.x * 16 + threadIdx.x;                \
-    const int y = blockIdx.y * 16 + threadIdx.y;                \
-    const int f = blockIdx.z / im.nimg, img = im.img0 + blockIdx.z % im.nimg, z = 2 * f + img; \
-    if (4 * q >= WW || y >= H) return;
-
 // ---- 1. every segment start becomes its own root ------------------------------------------------
 // FG: set bits.  BG (conditional on holes[f] != 0): cleared bits inside the image.
 template <bool FG, bool BG>
@@ -172,21 +163,34 @@ __global__ void __launch_bounds__(256) ccl_flatten_bg_kernel(const uint32_t *__r
 
 
 // ---- foreground, both images in one launch ---------------------------------------------------------
+// Two levels.  (1) fg_tile_kernel: a CTA owns a tile of TLH rows x TLW words, runs the union-find of the
+// segments inside it in SHARED memory, sums the moments of every tile-local component there, and
+// only then touches global memory: parent[segment] = tile-local root (one write per segment) plus
+// one 16-byte record per tile-local root.  (2) fg_border_kernel: the links that cross a tile edge
+// are united in the global array.  Everything after that (root discovery, moments, ranking) walks
+// the few records instead of the many segments.
 struct FgImages {
     const uint32_t *bits[2];     // max_bits, open_bits
     int32_t *parent[2];          // parent, parent2
     int img0, nimg;              // images handled by this launch: img0 .. img0 + nimg - 1 (grid.z = batch * nimg)
 };
+constexpr int TLH = 64, TLW = 4;              // tile: 64 rows x 4 words (128 px)
+constexpr int TPX = 32 * TLW;                 // tile width in pixels
+constexpr int TN = TLH * TPX / 2;             // node slots: two segment starts are never adjacent, so (local pixel >> 1) is unique
 
-template <bool CONN8>
-__device__ __forceinline__ void merge_word(int32_t *par, uint32_t w, uint32_t prev, uint32_t up, uint32_t upl, uint32_t upr, int base, int W) {
-    if ((w & 1u) && (prev >> 31)) unite(par, base, base - 32 + seg_start(prev, 31));
+// links of one word to its left / upper neighbours.  Node id of the segment that starts at bit s of a
+// word whose first pixel has index `base` is (base + s) >> SHIFT; `stride` is the index distance of a row.
+// Neighbour words that must not be linked by this caller are passed as 0.
+template <bool CONN8, int SHIFT>
+__device__ __forceinline__ void merge_word(int32_t *par, uint32_t w, uint32_t prev, uint32_t up, uint32_t upl, uint32_t upr, int base, int stride) {
+    if ((w & 1u) && (prev >> 31)) unite(par, base >> SHIFT, (base - 32 + seg_start(prev, 31)) >> SHIFT);
+    if (!(up | upl | upr)) return;
     uint32_t rem = w;
     while (rem) {
         const int s = __ffs(rem) - 1;
         const uint32_t seg = run_mask(w, s);
         rem &= ~seg;
-        const int id = base + s;
+        const int id = (base + s) >> SHIFT;
         uint32_t nb = seg;
         if (CONN8) nb |= (seg << 1) | (seg >> 1);
         uint32_t ov = up & nb;
@@ -194,101 +198,147 @@ __device__ __forceinline__ void merge_word(int32_t *par, uint32_t w, uint32_t pr
             const int b = __ffs(ov) - 1;
             const int us = seg_start(up, b);
             ov &= ~run_mask(up, us);
-            unite(par, id, base - W + us);
+            unite(par, id, (base - stride + us) >> SHIFT);
         }
         if (CONN8) {
-            if ((seg & 1u) && (upl >> 31)) unite(par, id, base - W - 32 + seg_start(upl, 31));
-            if ((seg >> 31) && (upr & 1u)) unite(par, id, base - W + 32);
+            if ((seg & 1u) && (upl >> 31)) unite(par, id, (base - stride - 32 + seg_start(upl, 31)) >> SHIFT);
+            if ((seg >> 31) && (upr & 1u)) unite(par, id, (base - stride + 32) >> SHIFT);
         }
     }
 }
 
-// one thread per word (a quad-per-thread version was 1.8x slower: the few busy threads serialise)
-__global__ void __launch_bounds__(256) fg_merge_kernel(FgImages im, int H, int W, int WW) {
+// block (TLW, TLH); grid (ceil(WW / TLW), ceil(H / TLH), nimg * batch)
+__global__ void __launch_bounds__(TLW * TLH) fg_tile_kernel(FgImages im, int32_t *__restrict__ nrec, int4 *__restrict__ recs,
+                                                             int H, int W, int WW, int RCAP, uint32_t *status) {
+    extern __shared__ int32_t tile_smem[];
+    int32_t *lp = tile_smem;                                          // [TN] tile-local union-find
+    uint32_t *acc_cy = reinterpret_cast<uint32_t *>(tile_smem) + TN;  // [TN] per local root: pixel count (14 bits) | sum of local y << 14
+    uint32_t *acc_x = acc_cy + TN;                                    // [TN] per local root: sum of local x
+    uint32_t(*sw)[TLW + 2] = reinterpret_cast<uint32_t(*)[TLW + 2]>(acc_x + TN);   // [TLH + 1][TLW + 2] the tile's words, zero frame above / left / right
+    const int lx = threadIdx.x, ly = threadIdx.y;
+    const int wx = blockIdx.x * TLW + lx, y = blockIdx.y * TLH + ly;
+    const int f = blockIdx.z / im.nimg, img = im.img0 + blockIdx.z % im.nimg, z = 2 * f + img;
+    const bool in = wx < WW && y < H;
+    const uint32_t w = in ? __ldg(im.bits[img] + ((size_t)f * H + y) * WW + wx) : 0u;
+    sw[ly + 1][lx + 1] = w;
+    if (ly == 0) sw[0][lx + 1] = 0u;
+    if (lx == 0) { sw[ly + 1][0] = 0u; sw[ly + 1][TLW + 1] = 0u; if (ly == 0) { sw[0][0] = 0u; sw[0][TLW + 1] = 0u; } }
+    const int lbase = ly * TPX + 32 * lx;
+    {
+        uint32_t starts = w & ~(w << 1);
+        while (starts) {
+            const int n = (lbase + __ffs(starts) - 1) >> 1;
+            starts &= starts - 1;
+            lp[n] = n; acc_cy[n] = 0u; acc_x[n] = 0u;
+        }
+    }
+    __syncthreads();
+    if (w) {
+        const uint32_t prev = sw[ly + 1][lx], up = sw[ly][lx + 1];
+        if (img) merge_word<true, 1>(lp, w, prev, up, sw[ly][lx], sw[ly][lx + 2], lbase, TPX);
+        else merge_word<false, 1>(lp, w, prev, up, 0u, 0u, lbase, TPX);
+    }
+    __syncthreads();
+    {   // flatten, and add every segment's moments to its local root
+        uint32_t rem = w;
+        while (rem) {
+            const int s = __ffs(rem) - 1;
+            const uint32_t seg = run_mask(w, s);
+            rem &= ~seg;
+            const int n = (lbase + s) >> 1;
+            const int r = find_root(lp, n);
+            if (r != n) lp[n] = r;
+            const uint32_t len = __popc(seg);
+            atomicAdd(acc_cy + r, len | ((len * (uint32_t)ly) << 14));
+            atomicAdd(acc_x + r, len * (uint32_t)(32 * lx + s) + len * (len - 1) / 2);
+        }
+    }
+    __syncthreads();
+    if (!w) return;
+    int32_t *par = im.parent[img] + (size_t)f * H * W;
+    const int x0 = blockIdx.x * TPX, y0 = blockIdx.y * TLH;
+    uint32_t starts = w & ~(w << 1);
+    while (starts) {
+        const int s = __ffs(starts) - 1;
+        starts &= starts - 1;
+        const int n = (lbase + s) >> 1;
+        const int r = lp[n];
+        const int gid = y * W + 32 * wx + s;
+        if (r != n) {
+            // the root node covers local pixels 2r and 2r+1; its start is 2r if that bit is set, else 2r+1
+            const int rp = 2 * r, ry = rp / TPX, rx = rp % TPX;
+            const int rs = rx + (((sw[ry + 1][(rx >> 5) + 1] >> (rx & 31)) & 1u) ? 0 : 1);
+            par[gid] = (y0 + ry) * W + x0 + rs;
+            continue;
+        }
+        par[gid] = gid;
+        const uint32_t cy = acc_cy[n], cnt = cy & 0x3fffu, sy = cy >> 14;
+        const int slot = atomicAdd(nrec + z, 1);
+        if (slot < RCAP) recs[(size_t)z * RCAP + slot] = make_int4(gid, (int)cnt, (int)(acc_x[n] + cnt * (uint32_t)x0), (int)(sy + cnt * (uint32_t)y0));
+        else atomicOr(status, img == 0 ? VBS_DEV_LABEL_OVERFLOW : VBS_DEV_CONTOUR_OVERFLOW);
+    }
+}
+
+// links across tile edges, in the global array.  block (64, 4) like the word kernels.
+__global__ void __launch_bounds__(256) fg_border_kernel(FgImages im, int H, int W, int WW) {
     const int wx = blockIdx.x * 64 + threadIdx.x;
     const int y = blockIdx.y * 4 + threadIdx.y;
     const int f = blockIdx.z / im.nimg, img = im.img0 + blockIdx.z % im.nimg;
     if (wx >= WW || y >= H) return;
+    const bool top = y % TLH == 0, left = wx % TLW == 0, right = wx % TLW == TLW - 1;
+    if (!(top | left | right)) return;
     const uint32_t *img_bits = im.bits[img] + (size_t)f * H * WW;
     const uint32_t w = __ldg(img_bits + (size_t)y * WW + wx);
     if (!w) return;
-    int32_t *par = im.parent[img] + (size_t)f * H * W;
-    const uint32_t prev = ((w & 1u) && wx > 0) ? __ldg(img_bits + (size_t)y * WW + wx - 1) : 0u;
+    const uint32_t prev = (left && (w & 1u) && wx > 0) ? __ldg(img_bits + (size_t)y * WW + wx - 1) : 0u;
     uint32_t up = 0, upl = 0, upr = 0;
     if (y > 0) {
         const uint32_t *urow = img_bits + (size_t)(y - 1) * WW;
-        up = __ldg(urow + wx);
+        if (top) up = __ldg(urow + wx);
         if (img) {                               // diagonal neighbours (8-connectivity)
-            upl = wx > 0 ? __ldg(urow + wx - 1) : 0u;
-            upr = wx + 1 < WW ? __ldg(urow + wx + 1) : 0u;
+            if ((top | left) && wx > 0) upl = __ldg(urow + wx - 1);
+            if ((top | right) && wx + 1 < WW) upr = __ldg(urow + wx + 1);
         }
     }
-    const int base = y * W + 32 * wx;
-    if (img) merge_word<true>(par, w, prev, up, upl, upr, base, W);
-    else merge_word<false>(par, w, prev, up, 0u, 0u, base, W);
-}
-
-// flatten + root discovery: a root takes the next slot of its (frame, image) list and encodes it
-// in place (parent[root] = -2 - slot); everybody else points at its root (or already at the code)
-__global__ void __launch_bounds__(256) fg_roots_kernel(FgImages im, int32_t *__restrict__ nroots, int32_t *__restrict__ rootlist,
-                                                        int H, int W, int WW, int M) {
-    VBS_QUAD_COORDS
-    const uint32_t *img_bits = im.bits[img] + (size_t)f * H * WW;
-    const uint4 w4 = __ldg(reinterpret_cast<const uint4 *>(img_bits + (size_t)y * WW) + q);
-    if (!(w4.x | w4.y | w4.z | w4.w)) return;
+    if (!(prev | up | upl | upr)) return;
     int32_t *par = im.parent[img] + (size_t)f * H * W;
-    const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int base = y * W + 32 * (4 * q + k);
-        uint32_t starts = w[k] & ~(w[k] << 1);
-        while (starts) {
-            const int s = __ffs(starts) - 1;
-            starts &= starts - 1;
-            const int r = find_root(par, base + s);
-            if (r == base + s) {
-                const int slot = atomicAdd(nroots + z, 1);
-                if (slot < M) { rootlist[(size_t)z * M + slot] = r; par[r] = -2 - slot; }
-            } else {
-                par[base + s] = r;
-            }
-        }
-    }
+    const int base = y * W + 32 * wx;
+    if (img) merge_word<true, 0>(par, w, prev, up, upl, upr, base, W);
+    else merge_word<false, 0>(par, w, prev, up, 0u, 0u, base, W);
 }
 
-// ring components: integer moments per root slot (MD:181 center_of_mass on a 0/1 mask)
-__global__ void __launch_bounds__(256) moments_kernel(const uint32_t *__restrict__ bits, const int32_t *__restrict__ parent,
-                                                       uint32_t *__restrict__ cnt, unsigned long long *__restrict__ sx,
-                                                       unsigned long long *__restrict__ sy, int H, int W, int WW, int M) {
-    const int q = blockIdx.x * 16 + threadIdx.x;
-    const int y = blockIdx.y * 16 + threadIdx.y;
-    const int f = blockIdx.z;
-    if (4 * q >= WW || y >= H) return;
-    const uint4 w4 = __ldg(reinterpret_cast<const uint4 *>(bits + ((size_t)f * H + y) * WW) + q);
-    if (!(w4.x | w4.y | w4.z | w4.w)) return;
-    const int32_t *par = parent + (size_t)f * H * W;
-    const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int wx = 4 * q + k;
-        const int base = y * W + 32 * wx;
-        uint32_t rem = w[k];
-        while (rem) {
-            const int s = __ffs(rem) - 1;
-            const uint32_t seg = run_mask(w[k], s);
-            rem &= ~seg;
-            int p = par[base + s];
-            if (p >= 0) p = par[p];                 // non-root segments point at their root, which holds the code
-            if (p >= 0) continue;                   // root beyond capacity (flagged by the sort kernel)
-            const int slot = -2 - p;
-            if (slot < 0 || slot >= M) continue;
-            const unsigned len = __popc(seg);
-            const unsigned long long xs = (unsigned long long)len * (unsigned)(32 * wx + s) + (unsigned long long)len * (len - 1) / 2;
-            atomicAdd(cnt + (size_t)f * M + slot, len);
-            atomicAdd(sx + (size_t)f * M + slot, xs);
-            atomicAdd(sy + (size_t)f * M + slot, (unsigned long long)len * (unsigned)y);
-        }
-    }
+// root discovery over the records: a record whose pixel is still its own root is a component; it takes
+// the next slot of its (frame, image) list and encodes it in place (parent[root] = -2 - slot)
+__global__ void __launch_bounds__(256) fg_roots_kernel(FgImages im, const int32_t *__restrict__ nrec, const int4 *__restrict__ recs,
+                                                        int32_t *__restrict__ nroots, int32_t *__restrict__ rootlist,
+                                                        int H, int W, int M, int RCAP) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = blockIdx.y / im.nimg, img = im.img0 + blockIdx.y % im.nimg, z = 2 * f + img;
+    if (i >= min(nrec[z], RCAP)) return;
+    int32_t *par = im.parent[img] + (size_t)f * H * W;
+    const int pix = recs[(size_t)z * RCAP + i].x;
+    if (par[pix] != pix) return;
+    const int slot = atomicAdd(nroots + z, 1);
+    if (slot < M) { rootlist[(size_t)z * M + slot] = pix; par[pix] = -2 - slot; }
+}
+
+// ring components: integer moments per root slot (MD:181 center_of_mass on a 0/1 mask), one atomic
+// triple per record
+__global__ void __launch_bounds__(256) moments_kernel(const int32_t *__restrict__ parent, const int32_t *__restrict__ nrec,
+                                                       const int4 *__restrict__ recs, uint32_t *__restrict__ cnt,
+                                                       unsigned long long *__restrict__ sx, unsigned long long *__restrict__ sy,
+                                                       int H, int W, int M, int RCAP) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = blockIdx.y, z = 2 * f;
+    if (i >= min(nrec[z], RCAP)) return;
+    const int4 rec = recs[(size_t)z * RCAP + i];
+    const int p = find_root(parent + (size_t)f * H * W, rec.x);
+    if (p >= 0) return;                         // root beyond capacity (flagged by the sort kernel)
+    const int slot = -2 - p;
+    if (slot < 0 || slot >= M) return;
+    atomicAdd(cnt + (size_t)f * M + slot, (uint32_t)rec.y);
+    atomicAdd(sx + (size_t)f * M + slot, (unsigned long long)(uint32_t)rec.z);
+    atomicAdd(sy + (size_t)f * M + slot, (unsigned long long)(uint32_t)rec.w);
 }
 
 // ---- Euler number of the 8-connected foreground by bit quads ----------------------------------------
@@ -376,6 +426,7 @@ cudaError_t vbs_launch_prepare(vbs_ctx *ctx, int batch) {
     if ((e = cudaMemsetAsync(ctx->lab_sy, 0, sizeof(unsigned long long) * batch * M, st)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(ctx->euler4, 0, sizeof(int32_t) * batch, st)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(ctx->nroots, 0, sizeof(int32_t) * 2 * batch, st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(ctx->nrec, 0, sizeof(int32_t) * 2 * batch, st)) != cudaSuccess) return e;
     return cudaMemsetAsync(ctx->claim, 0, sizeof(int32_t) * batch * M, st);
 }
 
@@ -386,18 +437,20 @@ cudaError_t vbs_launch_components(vbs_ctx *ctx, int batch, int which) {
     const dim3 wb(64, 4);
     const dim3 wg((WW + 63) / 64, (H + 3) / 4, batch);
     const dim3 eg((WW + 1 + 63) / 64, (H + 1 + 3) / 4, batch);
-    const dim3 qb(16, 16);
     cudaStream_t st = ctx->stream;
     FgImages im;
     im.bits[0] = ctx->max_bits; im.bits[1] = ctx->open_bits; im.parent[0] = ctx->parent; im.parent[1] = ctx->parent2;
     im.img0 = (which & 1) ? 0 : 1;
     im.nimg = (which == 3) ? 2 : 1;
-    const dim3 qgn((WW + 63) / 64, (H + 15) / 16, im.nimg * batch), qg1((WW + 63) / 64, (H + 15) / 16, batch);
-    // segment starts were initialised by the morphology kernels that produced the images
-    fg_merge_kernel<<<dim3((WW + 63) / 64, (H + 3) / 4, im.nimg * batch), wb, 0, st>>>(im, H, W, WW);
-    fg_roots_kernel<<<qgn, qb, 0, st>>>(im, ctx->nroots, ctx->rootlist, H, W, WW, M);
-    ctx->launches += 2;
-    if (which & 1) { moments_kernel<<<qg1, qb, 0, st>>>(ctx->max_bits, ctx->parent, ctx->lab_cnt, ctx->lab_sx, ctx->lab_sy, H, W, WW, M); ctx->launches += 1; }
+    const int RCAP = ctx->rcap;
+    constexpr int TILE_SMEM = (3 * TN + (TLH + 1) * (TLW + 2)) * 4;
+    static const cudaError_t attr = cudaFuncSetAttribute(fg_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM);
+    if (attr != cudaSuccess) return attr;
+    fg_tile_kernel<<<dim3((WW + TLW - 1) / TLW, (H + TLH - 1) / TLH, im.nimg * batch), dim3(TLW, TLH), TILE_SMEM, st>>>(im, ctx->nrec, ctx->recs, H, W, WW, RCAP, ctx->d_status);
+    fg_border_kernel<<<dim3((WW + 63) / 64, (H + 3) / 4, im.nimg * batch), wb, 0, st>>>(im, H, W, WW);
+    fg_roots_kernel<<<dim3((RCAP + 255) / 256, im.nimg * batch), 256, 0, st>>>(im, ctx->nrec, ctx->recs, ctx->nroots, ctx->rootlist, H, W, M, RCAP);
+    ctx->launches += 3;
+    if (which & 1) { moments_kernel<<<dim3((RCAP + 255) / 256, batch), 256, 0, st>>>(ctx->parent, ctx->nrec, ctx->recs, ctx->lab_cnt, ctx->lab_sx, ctx->lab_sy, H, W, M, RCAP); ctx->launches += 1; }
     if (which & 2) { euler_kernel<<<eg, wb, 0, st>>>(ctx->open_bits, ctx->euler4, H, W, WW); ctx->launches += 1; }
     int P2 = 1;
     while (P2 < M) P2 <<= 1;

@@ -43,16 +43,9 @@ __device__ __forceinline__ uint32_t ld_ones(const uint32_t *img, int y, int wx, 
     return __ldg(img + (size_t)y * WW + wx) | ~valid_mask(wx, W);
 }
 
-// every segment (maximal run of set bits inside the word) of a freshly written word becomes its own
-// union-find root: parent[index of its first pixel] = itself (k_ccl.cu links them afterwards)
-__device__ __forceinline__ void init_segments(uint32_t w, int32_t *par, int base) {
-    uint32_t starts = w & ~(w << 1);
-    while (starts) { const int s = __ffs(starts) - 1; starts &= starts - 1; par[base + s] = base + s; }
-}
-
 template <int NB>
 __global__ void __launch_bounds__(32 * TY) maxima_kernel(const uint32_t *__restrict__ mask_bits, uint32_t *__restrict__ max_bits,
-                                                          int32_t *__restrict__ parent, int H, int W, int WW) {
+                                                          int H, int W, int WW) {
     constexpr int LO = -(NB / 2), HI = NB - 1 - NB / 2;
     constexpr int ROWS = TH + NB - 1;
     __shared__ uint32_t eh[ROWS][33];
@@ -75,13 +68,12 @@ __global__ void __launch_bounds__(32 * TY) maxima_kernel(const uint32_t *__restr
         for (int d = 0; d < NB; ++d) e &= eh[r + d][threadIdx.x];
         const uint32_t m = __ldg(img + (size_t)y * WW + wx);
         max_bits[((size_t)f * H + y) * WW + wx] = m & ~e;
-        init_segments(m & ~e, parent + (size_t)f * H * W, y * W + 32 * wx);
     }
 }
 
 // 30 output words per CTA row + one halo word on each side (lanes 0 and 31)
 __global__ void __launch_bounds__(32 * TY) open5_kernel(const uint32_t *__restrict__ area_bits, uint32_t *__restrict__ open_bits,
-                                                         int32_t *__restrict__ parent2, int H, int W, int WW) {
+                                                         int H, int W, int WW) {
     constexpr int RA = TH + 8, RE = TH + 4;
     __shared__ uint32_t a[RA][33];     // horizontal erode, rows y0-4 .. y0+TH+3
     __shared__ uint32_t e[RE][33];     // eroded image,     rows y0-2 .. y0+TH+1
@@ -117,7 +109,6 @@ __global__ void __launch_bounds__(32 * TY) open5_kernel(const uint32_t *__restri
         if (y >= H) break;
         const uint32_t v = dh[r][lane] | dh[r + 1][lane] | dh[r + 2][lane] | dh[r + 3][lane] | dh[r + 4][lane];
         open_bits[((size_t)f * H + y) * WW + wx] = v & valid_mask(wx, W);
-        init_segments(v & valid_mask(wx, W), parent2 + (size_t)f * H * W, y * W + 32 * wx);
     }
 }
 
@@ -160,7 +151,7 @@ __global__ void unpack_labels_kernel(const uint32_t *__restrict__ bits, const in
         const int32_t *par = parent + f * (size_t)H * W;
         const int idx = (int)((fy % H) * W) + (x - b + s);
         int32_t p = par[idx];
-        if (p >= 0 && p != idx) p = par[p];
+        for (int q = idx; p >= 0 && p != q; p = par[q]) q = p;     // segment -> tile root -> ... -> coded root
         const int slot = -2 - p;
         out = (p < 0 && slot < M) ? slot2label[f * M + slot] + 1 : 0;
     }
@@ -174,13 +165,13 @@ cudaError_t vbs_launch_morph(vbs_ctx *ctx, int batch, int which) {
     const dim3 block(32, TY);
     if (which & 1) {
         const dim3 gm((ctx->WW + 31) / 32, (ctx->H + TH - 1) / TH, batch);
-        if (ctx->br.nb == 14) maxima_kernel<14><<<gm, block, 0, ctx->stream>>>(ctx->mask_bits, ctx->max_bits, ctx->parent, ctx->H, ctx->W, ctx->WW);
-        else maxima_kernel<8><<<gm, block, 0, ctx->stream>>>(ctx->mask_bits, ctx->max_bits, ctx->parent, ctx->H, ctx->W, ctx->WW);
+        if (ctx->br.nb == 14) maxima_kernel<14><<<gm, block, 0, ctx->stream>>>(ctx->mask_bits, ctx->max_bits, ctx->H, ctx->W, ctx->WW);
+        else maxima_kernel<8><<<gm, block, 0, ctx->stream>>>(ctx->mask_bits, ctx->max_bits, ctx->H, ctx->W, ctx->WW);
         ctx->launches += 1;
     }
     if (which & 2) {
         const dim3 go((ctx->WW + 29) / 30, (ctx->H + TH - 1) / TH, batch);
-        open5_kernel<<<go, block, 0, ctx->stream>>>(ctx->area_bits, ctx->open_bits, ctx->parent2, ctx->H, ctx->W, ctx->WW);
+        open5_kernel<<<go, block, 0, ctx->stream>>>(ctx->area_bits, ctx->open_bits, ctx->H, ctx->W, ctx->WW);
         ctx->launches += 1;
     }
     return cudaGetLastError();
