@@ -551,3 +551,47 @@ def test_compression_sequences_full_pipeline_matches_oracle():
         pu.assert_report(rep); pu.assert_report(rep2)
         tilts = rtg.to_host().plane[:, 3]
         assert tilts[-1] > tilts[1] and tilts[-1] > 1.0             # the tilted press really tilts the fitted plane
+
+
+# ---------------------------------------------------------------------------------------------
+# 11. labelling tiles whose label table fills up (closed early, k_ccl.cu) and links across tile edges
+# ---------------------------------------------------------------------------------------------
+def dense_masks(h=300, w=1100):
+    """Thousands of one-pixel components inside one 64 x 1024 labelling tile, lines that cross the tile
+    edges (rows 64, 128, ...; column 1024) in 4- and 8-connected ways, and a dense array of small blobs."""
+    mask = np.zeros((h, w), np.uint8)
+    mask[20:110:2, 100:380:2] = 1                       # 45 x 140 isolated dots
+    mask[5:250, 301] = 1                                # vertical line through the dot field (joins its neighbours)
+    mask[150, 900:1090] = 1                             # horizontal line across the band edge at x = 1024
+    for i in range(120):                                # 4-connected staircase across rows 64 / 128 and x = 1024
+        mask[40 + i, 960 + i] = 1; mask[40 + i, 961 + i] = 1
+    area = np.zeros((h, w), np.uint8)
+    blob = np.ones((7, 7), np.uint8); blob[0, 0] = blob[0, 6] = blob[6, 0] = blob[6, 6] = 0
+    for y in range(20, 200, 9):
+        for x in range(50, 1085, 9):
+            area[y:y + 7, x:x + 7] = blob
+            mask[y + 3, x + 3] = 1
+    for i in range(150):                                # 8-connected diagonal band, 5 px thick so that it survives the open
+        area[210 + i // 3: 215 + i // 3, 940 + i: 945 + i] = 1
+    return mask, area * 255
+
+
+def test_dense_components_overflow_the_tile_label_table():
+    mask, area = dense_masks()
+    taps = {}
+    want = port.marker_center(mask, area, taps)
+    assert 5000 < taps["n_labels"] <= 8192 and len(taps["contours"]) > 2000 and len(want) > 100
+    with pipeline.MarkerPipeline(mask.shape[0], mask.shape[1], 1, max_batch=2, max_markers=8192, max_refs=1) as pipe:
+        res = pipe.marker_center(torch_cuda(np.stack([mask, mask])), torch_cuda(np.stack([area, area])))
+        pipe.sync()
+        assert np.array_equal(pipe.debug_stage(capi.STAGE_LABELS, 2).cpu().numpy()[1], taps["labeled"])
+        assert np.array_equal(pipe.debug_stage(capi.STAGE_OPENED, 2).cpu().numpy()[0], taps["opened"])
+        h = res.to_host()
+        for f in range(2):
+            assert int(h.n_labels[f]) == taps["n_labels"]
+            assert np.array_equal(h.centres[f, : taps["n_labels"]], taps["centres"])
+            got = res.markers(f)
+            assert len(got) == len(want)
+            for a, b in zip(got, want):
+                assert a["center"] == b["center"]
+                assert pu.f32_ulps(a["major_axis"], b["major_axis"]) <= 2 and pu.f32_ulps(a["minor_axis"], b["minor_axis"]) <= 2

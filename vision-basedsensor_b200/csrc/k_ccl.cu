@@ -163,34 +163,38 @@ __global__ void __launch_bounds__(256) ccl_flatten_bg_kernel(const uint32_t *__r
 
 
 // ---- foreground, both images in one launch ---------------------------------------------------------
-// Two levels.  (1) fg_tile_kernel: a CTA owns a tile of TLH rows x TLW words, runs the union-find of the
-// segments inside it in SHARED memory, sums the moments of every tile-local component there, and
-// only then touches global memory: parent[segment] = tile-local root (one write per segment) plus
-// one 16-byte record per tile-local root.  (2) fg_border_kernel: the links that cross a tile edge
-// are united in the global array.  Everything after that (root discovery, moments, ranking) walks
-// the few records instead of the many segments.
+// Two levels.  (1) fg_strip_kernel: ONE WARP marches down a tile of SH rows x 32 words (1024 px), lane =
+// word column, the classic row-scan labelling done warp-synchronously: a segment that touches
+// segments of the row above inherits their (united) provisional label, a segment that touches
+// nothing opens a new label.  Labels, their equivalences and their moments live in shared memory;
+// global memory sees one store per segment (parent[segment] = first pixel of its label), one
+// store per merged label and one 16-byte record per tile-local component.  (2) fg_border_kernel:
+// the links that cross a tile edge are united in the global array.  Everything after that (root
+// discovery, moments, ranking) walks the few records instead of the many segments.
+// A tile whose label table would overflow is closed early at that row and continued as a new tile;
+// rowflag marks such rows so that the border kernel links them like a regular tile edge.  One row
+// can open at most 512 labels (1024 px / 2), hence SP = 512 always makes progress.
 struct FgImages {
     const uint32_t *bits[2];     // max_bits, open_bits
     int32_t *parent[2];          // parent, parent2
     int img0, nimg;              // images handled by this launch: img0 .. img0 + nimg - 1 (grid.z = batch * nimg)
 };
-constexpr int TLH = 64, TLW = 4;              // tile: 64 rows x 4 words (128 px)
-constexpr int TPX = 32 * TLW;                 // tile width in pixels
-constexpr int TN = TLH * TPX / 2;             // node slots: two segment starts are never adjacent, so (local pixel >> 1) is unique
+constexpr int SH = 64;           // rows per tile
+constexpr int SPX = 1024;        // tile width in pixels (32 words, one per lane)
+constexpr int SP = 512;          // provisional labels per tile
 
-// links of one word to its left / upper neighbours.  Node id of the segment that starts at bit s of a
-// word whose first pixel has index `base` is (base + s) >> SHIFT; `stride` is the index distance of a row.
-// Neighbour words that must not be linked by this caller are passed as 0.
-template <bool CONN8, int SHIFT>
+// links of one word to its left / upper neighbours in the global array.  Neighbour words that must
+// not be linked by this caller are passed as 0.
+template <bool CONN8>
 __device__ __forceinline__ void merge_word(int32_t *par, uint32_t w, uint32_t prev, uint32_t up, uint32_t upl, uint32_t upr, int base, int stride) {
-    if ((w & 1u) && (prev >> 31)) unite(par, base >> SHIFT, (base - 32 + seg_start(prev, 31)) >> SHIFT);
+    if ((w & 1u) && (prev >> 31)) unite(par, base, base - 32 + seg_start(prev, 31));
     if (!(up | upl | upr)) return;
     uint32_t rem = w;
     while (rem) {
         const int s = __ffs(rem) - 1;
         const uint32_t seg = run_mask(w, s);
         rem &= ~seg;
-        const int id = (base + s) >> SHIFT;
+        const int id = base + s;
         uint32_t nb = seg;
         if (CONN8) nb |= (seg << 1) | (seg >> 1);
         uint32_t ov = up & nb;
@@ -198,113 +202,221 @@ __device__ __forceinline__ void merge_word(int32_t *par, uint32_t w, uint32_t pr
             const int b = __ffs(ov) - 1;
             const int us = seg_start(up, b);
             ov &= ~run_mask(up, us);
-            unite(par, id, (base - stride + us) >> SHIFT);
+            unite(par, id, base - stride + us);
         }
         if (CONN8) {
-            if ((seg & 1u) && (upl >> 31)) unite(par, id, (base - stride - 32 + seg_start(upl, 31)) >> SHIFT);
-            if ((seg >> 31) && (upr & 1u)) unite(par, id, (base - stride + 32) >> SHIFT);
+            if ((seg & 1u) && (upl >> 31)) unite(par, id, base - stride - 32 + seg_start(upl, 31));
+            if ((seg >> 31) && (upr & 1u)) unite(par, id, base - stride + 32);
         }
     }
 }
 
-// block (TLW, TLH); grid (ceil(WW / TLW), ceil(H / TLH), nimg * batch)
-__global__ void __launch_bounds__(TLW * TLH) fg_tile_kernel(FgImages im, int32_t *__restrict__ nrec, int4 *__restrict__ recs,
-                                                             int H, int W, int WW, int RCAP, uint32_t *status) {
-    extern __shared__ int32_t tile_smem[];
-    int32_t *lp = tile_smem;                                          // [TN] tile-local union-find
-    uint32_t *acc_cy = reinterpret_cast<uint32_t *>(tile_smem) + TN;  // [TN] per local root: pixel count (14 bits) | sum of local y << 14
-    uint32_t *acc_x = acc_cy + TN;                                    // [TN] per local root: sum of local x
-    uint32_t(*sw)[TLW + 2] = reinterpret_cast<uint32_t(*)[TLW + 2]>(acc_x + TN);   // [TLH + 1][TLW + 2] the tile's words, zero frame above / left / right
-    const int lx = threadIdx.x, ly = threadIdx.y;
-    const int wx = blockIdx.x * TLW + lx, y = blockIdx.y * TLH + ly;
+// unite two labels, return the surviving (smaller) root
+__device__ __forceinline__ int unite_root(int32_t *par, int a, int b) {
+    for (;;) {
+        a = find_root_halving(par, a);
+        b = find_root_halving(par, b);
+        if (a == b) return a;
+        if (a < b) { const int t = a; a = b; b = t; }
+        const int old = atomicMin(par + a, b);
+        if (old == a) return b;
+        a = old;
+    }
+}
+
+struct StripTables {
+    int32_t rl[2][SPX / 2];      // label of every segment of the current / previous row, index = (local x of its start) >> 1
+    int32_t lp[SP];              // label equivalences (union-find, root = smallest = earliest label)
+    int32_t pg[SP];              // first pixel of the label, local: ly * SPX + lx
+    uint32_t ac[SP], ax[SP], ay[SP];   // pixel count, sum of local x, sum of local y
+};
+
+// end of a (sub-)tile: fold merged labels into their roots, emit one record per root
+__device__ __forceinline__ void strip_close(StripTables &T, int next, int lane, int32_t *par, int x0, int y0, int W, int z,
+                                            int32_t *nrec, int4 *recs, int RCAP, uint32_t *status, uint32_t overflow_bit) {
+    auto G = [&](int p) { return (y0 + p / SPX) * W + x0 + p % SPX; };
+    __syncwarp();
+    for (int L = lane; L < next; L += 32) {
+        const int r = find_root(T.lp, L);
+        if (r != L) {
+            par[G(T.pg[L])] = G(T.pg[r]);
+            atomicAdd(&T.ac[r], T.ac[L]); atomicAdd(&T.ax[r], T.ax[L]); atomicAdd(&T.ay[r], T.ay[L]);
+        }
+    }
+    __syncwarp();
+    int total = 0;
+    for (int L0 = 0; L0 < next; L0 += 32) {
+        const int L = L0 + lane;
+        total += __popc(__ballot_sync(0xffffffffu, L < next && T.lp[L] == L));
+    }
+    int off = 0;
+    if (lane == 0 && total) off = atomicAdd(nrec + z, total);
+    off = __shfl_sync(0xffffffffu, off, 0);
+    for (int L0 = 0; L0 < next; L0 += 32) {
+        const int L = L0 + lane;
+        const bool root = L < next && T.lp[L] == L;
+        const uint32_t m = __ballot_sync(0xffffffffu, root);
+        if (root) {
+            const int slot = off + __popc(m & ((1u << lane) - 1u));
+            const uint32_t c = T.ac[L];
+            const int p = T.pg[L];
+            if (slot < RCAP) recs[(size_t)z * RCAP + slot] = make_int4(G(p), (int)c, (int)(T.ax[L] + c * (uint32_t)x0), (int)(T.ay[L] + c * (uint32_t)y0));
+            else atomicOr(status, overflow_bit);
+        }
+        off += __popc(m);
+    }
+    __syncwarp();
+}
+
+// block 32 (one warp); grid (ceil(WW / 32), ceil(H / SH), nimg * batch)
+__global__ void __launch_bounds__(32) fg_strip_kernel(FgImages im, int32_t *__restrict__ nrec, int4 *__restrict__ recs, uint8_t *__restrict__ rowflag,
+                                                       int H, int W, int WW, int RCAP, uint32_t *status) {
+    __shared__ StripTables T;
+    const int lane = threadIdx.x;
+    const int band = blockIdx.x, nbands = gridDim.x;
+    const int x0 = band * SPX, wx = band * 32 + lane, lx0 = 32 * lane;
+    const int y0 = blockIdx.y * SH, rows = min(SH, H - y0);
     const int f = blockIdx.z / im.nimg, img = im.img0 + blockIdx.z % im.nimg, z = 2 * f + img;
-    const bool in = wx < WW && y < H;
-    const uint32_t w = in ? __ldg(im.bits[img] + ((size_t)f * H + y) * WW + wx) : 0u;
-    sw[ly + 1][lx + 1] = w;
-    if (ly == 0) sw[0][lx + 1] = 0u;
-    if (lx == 0) { sw[ly + 1][0] = 0u; sw[ly + 1][TLW + 1] = 0u; if (ly == 0) { sw[0][0] = 0u; sw[0][TLW + 1] = 0u; } }
-    const int lbase = ly * TPX + 32 * lx;
-    {
-        uint32_t starts = w & ~(w << 1);
-        while (starts) {
-            const int n = (lbase + __ffs(starts) - 1) >> 1;
-            starts &= starts - 1;
-            lp[n] = n; acc_cy[n] = 0u; acc_x[n] = 0u;
-        }
-    }
-    __syncthreads();
-    if (w) {
-        const uint32_t prev = sw[ly + 1][lx], up = sw[ly][lx + 1];
-        if (img) merge_word<true, 1>(lp, w, prev, up, sw[ly][lx], sw[ly][lx + 2], lbase, TPX);
-        else merge_word<false, 1>(lp, w, prev, up, 0u, 0u, lbase, TPX);
-    }
-    __syncthreads();
-    {   // flatten, and add every segment's moments to its local root
-        uint32_t rem = w;
-        while (rem) {
-            const int s = __ffs(rem) - 1;
-            const uint32_t seg = run_mask(w, s);
-            rem &= ~seg;
-            const int n = (lbase + s) >> 1;
-            const int r = find_root(lp, n);
-            if (r != n) lp[n] = r;
-            const uint32_t len = __popc(seg);
-            atomicAdd(acc_cy + r, len | ((len * (uint32_t)ly) << 14));
-            atomicAdd(acc_x + r, len * (uint32_t)(32 * lx + s) + len * (len - 1) / 2);
-        }
-    }
-    __syncthreads();
-    if (!w) return;
+    const uint32_t overflow_bit = img == 0 ? VBS_DEV_LABEL_OVERFLOW : VBS_DEV_CONTOUR_OVERFLOW;
+    const uint32_t *src = im.bits[img] + ((size_t)f * H + y0) * WW + wx;
     int32_t *par = im.parent[img] + (size_t)f * H * W;
-    const int x0 = blockIdx.x * TPX, y0 = blockIdx.y * TLH;
-    uint32_t starts = w & ~(w << 1);
-    while (starts) {
-        const int s = __ffs(starts) - 1;
-        starts &= starts - 1;
-        const int n = (lbase + s) >> 1;
-        const int r = lp[n];
-        const int gid = y * W + 32 * wx + s;
-        if (r != n) {
-            // the root node covers local pixels 2r and 2r+1; its start is 2r if that bit is set, else 2r+1
-            const int rp = 2 * r, ry = rp / TPX, rx = rp % TPX;
-            const int rs = rx + (((sw[ry + 1][(rx >> 5) + 1] >> (rx & 31)) & 1u) ? 0 : 1);
-            par[gid] = (y0 + ry) * W + x0 + rs;
-            continue;
+    uint8_t *flag = rowflag + ((size_t)z * nbands + band) * H + y0;
+    const bool inw = wx < WW;
+    int next = 0;
+    uint32_t up = 0u;
+    uint32_t wnext = inw ? __ldg(src) : 0u;
+    for (int ly = 0; ly < rows; ++ly) {
+        const uint32_t w = wnext;
+        if (ly + 1 < rows) wnext = inw ? __ldg(src + (size_t)(ly + 1) * WW) : 0u;
+        uint32_t upl = __shfl_up_sync(0xffffffffu, up, 1), upr = __shfl_down_sync(0xffffffffu, up, 1);
+        uint32_t prevw = __shfl_up_sync(0xffffffffu, w, 1);
+        if (lane == 0) { upl = 0u; prevw = 0u; }
+        if (lane == 31) upr = 0u;
+        bool closed_here = false;
+        if (__any_sync(0xffffffffu, w != 0u)) {
+            int32_t *cur = T.rl[ly & 1];
+            const int32_t *prv = T.rl[(ly & 1) ^ 1];
+            uint32_t touch;
+            int my_base;
+            for (;;) {
+                // bits of this word that are adjacent to a pixel of the row above
+                touch = w & (img ? (up | (up << 1) | (up >> 1) | (upl >> 31) | ((upr & 1u) << 31)) : up);
+                int fresh = 0;
+                for (uint32_t rem = w; rem;) {
+                    const uint32_t seg = run_mask(w, __ffs(rem) - 1);
+                    rem &= ~seg;
+                    fresh += (seg & touch) ? 0 : 1;
+                }
+                int incl = fresh;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                my_base = next + incl - fresh;
+                if (next + total <= SP) { next += total; break; }
+                // label table full: close the tile above this row and start a new one here
+                strip_close(T, next, lane, par, x0, y0, W, z, nrec, recs, RCAP, status, overflow_bit);
+                next = 0; up = 0u; upl = 0u; upr = 0u; closed_here = true;
+            }
+            for (uint32_t rem = w; rem;) {
+                const int s = __ffs(rem) - 1;
+                const uint32_t seg = run_mask(w, s);
+                rem &= ~seg;
+                const uint32_t len = __popc(seg);
+                const uint32_t xs = len * (uint32_t)(lx0 + s) + len * (len - 1) / 2, ys = len * (uint32_t)ly;
+                const int gid = (y0 + ly) * W + x0 + lx0 + s;
+                int L;
+                if (!(seg & touch)) {
+                    L = my_base++;
+                    T.lp[L] = L; T.pg[L] = ly * SPX + lx0 + s; T.ac[L] = len; T.ax[L] = xs; T.ay[L] = ys;
+                    par[gid] = gid;
+                } else {
+                    L = -1;
+                    const uint32_t nb = img ? (seg | (seg << 1) | (seg >> 1)) : seg;
+                    uint32_t ov = up & nb;
+                    while (ov) {
+                        const int us = seg_start(up, __ffs(ov) - 1);
+                        ov &= ~run_mask(up, us);
+                        const int Lu = prv[(lx0 + us) >> 1];
+                        L = L < 0 ? find_root_halving(T.lp, Lu) : unite_root(T.lp, L, Lu);
+                    }
+                    if (img) {
+                        if ((seg & 1u) && (upl >> 31)) {
+                            const int Lu = prv[(lx0 - 32 + seg_start(upl, 31)) >> 1];
+                            L = L < 0 ? find_root_halving(T.lp, Lu) : unite_root(T.lp, L, Lu);
+                        }
+                        if ((seg >> 31) && (upr & 1u)) {
+                            const int Lu = prv[(lx0 + 32) >> 1];
+                            L = L < 0 ? find_root_halving(T.lp, Lu) : unite_root(T.lp, L, Lu);
+                        }
+                    }
+                    atomicAdd(&T.ac[L], len); atomicAdd(&T.ax[L], xs); atomicAdd(&T.ay[L], ys);
+                    const int p = T.pg[L];
+                    par[gid] = (y0 + p / SPX) * W + x0 + p % SPX;
+                }
+                cur[(lx0 + s) >> 1] = L;
+            }
+            __syncwarp();
+            if ((w & 1u) && (prevw >> 31)) unite(T.lp, cur[lx0 >> 1], cur[(lx0 - 32 + seg_start(prevw, 31)) >> 1]);
+            __syncwarp();
         }
-        par[gid] = gid;
-        const uint32_t cy = acc_cy[n], cnt = cy & 0x3fffu, sy = cy >> 14;
-        const int slot = atomicAdd(nrec + z, 1);
-        if (slot < RCAP) recs[(size_t)z * RCAP + slot] = make_int4(gid, (int)cnt, (int)(acc_x[n] + cnt * (uint32_t)x0), (int)(sy + cnt * (uint32_t)y0));
-        else atomicOr(status, img == 0 ? VBS_DEV_LABEL_OVERFLOW : VBS_DEV_CONTOUR_OVERFLOW);
+        if (lane == 0) flag[ly] = closed_here ? 1 : 0;
+        up = w;
     }
+    strip_close(T, next, lane, par, x0, y0, W, z, nrec, recs, RCAP, status, overflow_bit);
 }
 
-// links across tile edges, in the global array.  block (64, 4) like the word kernels.
-__global__ void __launch_bounds__(256) fg_border_kernel(FgImages im, int H, int W, int WW) {
-    const int wx = blockIdx.x * 64 + threadIdx.x;
-    const int y = blockIdx.y * 4 + threadIdx.y;
-    const int f = blockIdx.z / im.nimg, img = im.img0 + blockIdx.z % im.nimg;
-    if (wx >= WW || y >= H) return;
-    const bool top = y % TLH == 0, left = wx % TLW == 0, right = wx % TLW == TLW - 1;
-    if (!(top | left | right)) return;
-    const uint32_t *img_bits = im.bits[img] + (size_t)f * H * WW;
+// links across tile edges, in the global array.  One thread per candidate; grid (ceil(n / 256), nimg * batch) with
+// n = nA + nB + nC:  A = words of the fixed tile-top rows (y = SH, 2 SH, ...), B = the (row, band edge) pairs, all
+// links across a vertical tile edge, C = (row, band) pairs, the rows that fg_strip_kernel flagged as early tile tops.
+// A and C link across the horizontal edge inside one band only (up, and the diagonals that stay in the band).
+template <bool CONN8>
+__device__ __forceinline__ void link_tile_top(int32_t *par, const uint32_t *img_bits, int y, int wx, int W, int WW) {
     const uint32_t w = __ldg(img_bits + (size_t)y * WW + wx);
     if (!w) return;
-    const uint32_t prev = (left && (w & 1u) && wx > 0) ? __ldg(img_bits + (size_t)y * WW + wx - 1) : 0u;
-    uint32_t up = 0, upl = 0, upr = 0;
-    if (y > 0) {
-        const uint32_t *urow = img_bits + (size_t)(y - 1) * WW;
-        if (top) up = __ldg(urow + wx);
-        if (img) {                               // diagonal neighbours (8-connectivity)
-            if ((top | left) && wx > 0) upl = __ldg(urow + wx - 1);
-            if ((top | right) && wx + 1 < WW) upr = __ldg(urow + wx + 1);
+    const uint32_t *urow = img_bits + (size_t)(y - 1) * WW;
+    const uint32_t up = __ldg(urow + wx);
+    const uint32_t upl = (CONN8 && wx % 32 != 0) ? __ldg(urow + wx - 1) : 0u;
+    const uint32_t upr = (CONN8 && wx % 32 != 31 && wx + 1 < WW) ? __ldg(urow + wx + 1) : 0u;
+    merge_word<CONN8>(par, w, 0u, up, upl, upr, y * W + 32 * wx, W);
+}
+
+__global__ void __launch_bounds__(256) fg_border_kernel(FgImages im, const uint8_t *__restrict__ rowflag, int H, int W, int WW, int nbands) {
+    const int f = blockIdx.y / im.nimg, img = im.img0 + blockIdx.y % im.nimg, z = 2 * f + img;
+    const uint32_t *img_bits = im.bits[img] + (size_t)f * H * WW;
+    int32_t *par = im.parent[img] + (size_t)f * H * W;
+    const int nA = ((H - 1) / SH) * WW, nB = H * (nbands - 1), nC = H * nbands;
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nA) {
+        const int y = (t / WW + 1) * SH, wx = t % WW;
+        if (img) link_tile_top<true>(par, img_bits, y, wx, W, WW);
+        else link_tile_top<false>(par, img_bits, y, wx, W, WW);
+        return;
+    }
+    t -= nA;
+    if (t < nB) {
+        const int y = t % H, wx = 32 * (1 + t / H);
+        const uint32_t w = __ldg(img_bits + (size_t)y * WW + wx), prev = __ldg(img_bits + (size_t)y * WW + wx - 1);
+        const int base = y * W + 32 * wx;
+        if ((w & 1u) && (prev >> 31)) unite(par, base, base - 32 + seg_start(prev, 31));
+        if (img && y > 0) {
+            const uint32_t upl = __ldg(img_bits + (size_t)(y - 1) * WW + wx - 1), upw = __ldg(img_bits + (size_t)(y - 1) * WW + wx);
+            if ((w & 1u) && (upl >> 31)) unite(par, base, base - W - 32 + seg_start(upl, 31));
+            if ((prev >> 31) && (upw & 1u)) unite(par, base - 32 + seg_start(prev, 31), base - W);
+        }
+        return;
+    }
+    t -= nB;
+    if (t < nC) {
+        const int y = t % H, band = t / H;
+        if (y % SH == 0 || !rowflag[((size_t)z * nbands + band) * H + y]) return;
+        for (int wx = 32 * band; wx < min(32 * band + 32, WW); ++wx) {
+            if (img) link_tile_top<true>(par, img_bits, y, wx, W, WW);
+            else link_tile_top<false>(par, img_bits, y, wx, W, WW);
         }
     }
-    if (!(prev | up | upl | upr)) return;
-    int32_t *par = im.parent[img] + (size_t)f * H * W;
-    const int base = y * W + 32 * wx;
-    if (img) merge_word<true, 0>(par, w, prev, up, upl, upr, base, W);
-    else merge_word<false, 0>(par, w, prev, up, 0u, 0u, base, W);
 }
 
 // root discovery over the records: a record whose pixel is still its own root is a component; it takes
@@ -443,11 +555,10 @@ cudaError_t vbs_launch_components(vbs_ctx *ctx, int batch, int which) {
     im.img0 = (which & 1) ? 0 : 1;
     im.nimg = (which == 3) ? 2 : 1;
     const int RCAP = ctx->rcap;
-    constexpr int TILE_SMEM = (3 * TN + (TLH + 1) * (TLW + 2)) * 4;
-    static const cudaError_t attr = cudaFuncSetAttribute(fg_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM);
-    if (attr != cudaSuccess) return attr;
-    fg_tile_kernel<<<dim3((WW + TLW - 1) / TLW, (H + TLH - 1) / TLH, im.nimg * batch), dim3(TLW, TLH), TILE_SMEM, st>>>(im, ctx->nrec, ctx->recs, H, W, WW, RCAP, ctx->d_status);
-    fg_border_kernel<<<dim3((WW + 63) / 64, (H + 3) / 4, im.nimg * batch), wb, 0, st>>>(im, H, W, WW);
+    const int nbands = (WW + 31) / 32;
+    fg_strip_kernel<<<dim3(nbands, (H + SH - 1) / SH, im.nimg * batch), 32, 0, st>>>(im, ctx->nrec, ctx->recs, ctx->rowflag, H, W, WW, RCAP, ctx->d_status);
+    const int nborder = ((H - 1) / SH) * WW + H * (nbands - 1) + H * nbands;
+    fg_border_kernel<<<dim3((nborder + 255) / 256, im.nimg * batch), 256, 0, st>>>(im, ctx->rowflag, H, W, WW, nbands);
     fg_roots_kernel<<<dim3((RCAP + 255) / 256, im.nimg * batch), 256, 0, st>>>(im, ctx->nrec, ctx->recs, ctx->nroots, ctx->rootlist, H, W, M, RCAP);
     ctx->launches += 3;
     if (which & 1) { moments_kernel<<<dim3((RCAP + 255) / 256, batch), 256, 0, st>>>(ctx->parent, ctx->nrec, ctx->recs, ctx->lab_cnt, ctx->lab_sx, ctx->lab_sy, H, W, M, RCAP); ctx->launches += 1; }

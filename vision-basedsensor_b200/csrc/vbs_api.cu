@@ -34,7 +34,7 @@ int map_status(vbs_ctx *ctx, uint32_t st) {
 
 void free_all(vbs_ctx *c) {
     void *ptrs[] = {c->d_frames, c->area_bits, c->mask_bits, c->max_bits, c->open_bits, c->area_count, c->thr_lut,
-                    c->d_n64, c->d_cn64, c->d_cnfix, c->recheck, c->recheck_n, c->parent, c->parent2, c->nroots, c->rootlist, c->slot2label, c->nrec, c->recs, c->d_nlabels,
+                    c->d_n64, c->d_cn64, c->d_cnfix, c->recheck, c->recheck_n, c->parent, c->parent2, c->nroots, c->rootlist, c->slot2label, c->nrec, c->recs, c->rowflag, c->d_nlabels,
                     c->d_ncont, c->lab_cnt, c->lab_sx, c->lab_sy, c->centres, c->croot, c->cell, c->claim, c->cmatch, c->cpts, c->cpn, c->euler4, c->holes, c->d_nmarkers,
                     c->marker_xy, c->marker_axes, c->ref_row, c->ref_col, c->ref_xy, c->row_det, c->row_cxy, c->row_axes, c->obs,
                     c->pos3d, c->pos_flags, c->last_seen, c->pl_ref, c->pl_start, c->pl_dvert, c->pl_use, c->plane, c->plane_n,
@@ -131,7 +131,7 @@ vbs_ctx make_view(const vbs_ctx *c, int off, cudaStream_t st) {
     v.area_count += o; v.recheck += o * c->recheck_cap; v.recheck_n += o;
     v.parent += o * HW; v.parent2 += o * HW;
     v.nroots += 2 * o; v.rootlist += 2 * o * M; v.slot2label += o * M;
-    v.nrec += 2 * o; v.recs += 2 * o * (size_t)c->rcap;
+    v.nrec += 2 * o; v.recs += 2 * o * (size_t)c->rcap; v.rowflag += 2 * o * (size_t)((c->WW + 31) / 32) * c->H;
     v.d_nlabels += o; v.d_ncont += o;
     v.lab_cnt += o * M; v.lab_sx += o * M; v.lab_sy += o * M; v.centres += o * M * 2;
     v.croot += o * M; v.cell += o * M * 6; v.claim += o * M; v.cmatch += o * M; v.cpts += o * M * 128; v.cpn += o * M;
@@ -346,7 +346,8 @@ int vbs_create(vbs_ctx **out, const vbs_config *cfg) {
     VBS_CUDA(dalloc(&ctx->recheck, B * ctx->recheck_cap)); VBS_CUDA(dalloc(&ctx->recheck_n, B));
     VBS_CUDA(dalloc(&ctx->parent, B * H * W)); VBS_CUDA(dalloc(&ctx->parent2, B * H * W));
     VBS_CUDA(dalloc(&ctx->nroots, 2 * B)); VBS_CUDA(dalloc(&ctx->rootlist, 2 * B * M)); VBS_CUDA(dalloc(&ctx->slot2label, B * M));
-    ctx->rcap = (int)(8 * M + 8 * ((W + 127) / 128) * ((H + 63) / 64));      // tile-local components: 64 x 128 px tiles (k_ccl.cu)
+    ctx->rcap = (int)(8 * M + 64 * ((W + 1023) / 1024) * ((H + 63) / 64));      // tile-local components: 64 x 1024 px tiles (k_ccl.cu)
+    VBS_CUDA(dalloc(&ctx->rowflag, 2 * B * ((WW + 31) / 32) * H));
     VBS_CUDA(dalloc(&ctx->nrec, 2 * B)); VBS_CUDA(dalloc(&ctx->recs, 2 * B * (size_t)ctx->rcap));
     VBS_CUDA(dalloc(&ctx->d_nlabels, B)); VBS_CUDA(dalloc(&ctx->d_ncont, B));
     VBS_CUDA(dalloc(&ctx->lab_cnt, B * M)); VBS_CUDA(dalloc(&ctx->lab_sx, B * M)); VBS_CUDA(dalloc(&ctx->lab_sy, B * M));

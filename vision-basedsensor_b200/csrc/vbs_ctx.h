@@ -54,6 +54,7 @@ struct vbs_ctx {
     int32_t *parent, *parent2;       // [B][H*W] ring maxima / opened image (fg + bg)
     int32_t *nroots, *rootlist, *slot2label;   // [2B] roots per (frame, image), [2B][M] their pixel indices, [B][M] slot -> label
     int32_t *nrec; int4 *recs; int rcap;       // [2B] tile-local components per (frame, image), [2B][rcap] {start pixel, count, sum x, sum y}
+    uint8_t *rowflag;                // [2B][ceil(WW/32)][H] 1: the labelling tile of this 1024-px band was closed early above this row
     int32_t *d_nlabels, *d_ncont;    // [B]
     // ring components
     uint32_t *lab_cnt; unsigned long long *lab_sx, *lab_sy;   // [B][M]
