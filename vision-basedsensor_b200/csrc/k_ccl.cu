@@ -71,72 +71,55 @@ __device__ void unite(int32_t *par, int a, int b) {
     }
 }
 
-// word kernels (background pass): block (64, 4) = 64 words x 4 rows, grid (ceil(WW/64), ceil(H/4), batch)
-#define VBS_WORD_COORDS                                          \
-    const int wx = blockIdx.x * 64 + threadIdx.x;               \
-    const int y = blockIdx.y * 4 + threadIdx.y;                 \
-    const int f = blockIdx.z;                                   \
-    if (wx >= WW || y >= H) return;
+// word kernels (background pass, only frames with holes do anything): block (64, 4) = 64 words x 4 rows, looped
+// BG_ROWS / 4 times; grid (ceil(WW/64), ceil(H/BG_ROWS), batch)
+constexpr int BG_ROWS = 64;
+#define VBS_BG_LOOP                                                                  \
+    const int wx = blockIdx.x * 64 + threadIdx.x;                                   \
+    const int f = blockIdx.z;                                                       \
+    if (holes[f] == 0 || wx >= WW) return;                                          \
+    for (int y = blockIdx.y * BG_ROWS + threadIdx.y; y < min(H, (int)(blockIdx.y + 1) * BG_ROWS); y += 4)
 
-// ---- 1. every segment start becomes its own root ------------------------------------------------
-// FG: set bits.  BG (conditional on holes[f] != 0): cleared bits inside the image.
-template <bool FG, bool BG>
-__global__ void __launch_bounds__(256) ccl_init_kernel(const uint32_t *__restrict__ bits, int32_t *__restrict__ parent,
-                                                        const int32_t *__restrict__ holes, int H, int W, int WW) {
-    VBS_WORD_COORDS
-    const uint32_t raw = __ldg(bits + ((size_t)f * H + y) * WW + wx);
-    int32_t *par = parent + (size_t)f * H * W;
-    const int base = y * W + 32 * wx;
-    if (FG) {
-        uint32_t starts = raw & ~(raw << 1);
-        while (starts) { const int s = __ffs(starts) - 1; starts &= starts - 1; par[base + s] = base + s; }
-    }
-    if (BG && holes[f] != 0) {
-        const uint32_t w = ~raw & valid_mask(wx, W);
+// ---- background of the opened image (4-connected, frames with holes only) -----------------------------
+// 1. every background segment start becomes its own root
+__global__ void __launch_bounds__(256) bg_init_kernel(const uint32_t *__restrict__ bits, int32_t *__restrict__ parent,
+                                                       const int32_t *__restrict__ holes, int H, int W, int WW) {
+    VBS_BG_LOOP {
+        const uint32_t w = ~__ldg(bits + ((size_t)f * H + y) * WW + wx) & valid_mask(wx, W);
+        int32_t *par = parent + (size_t)f * H * W;
+        const int base = y * W + 32 * wx;
         uint32_t starts = w & ~(w << 1);
         while (starts) { const int s = __ffs(starts) - 1; starts &= starts - 1; par[base + s] = base + s; }
     }
 }
 
-// ---- 2. link segments that touch -----------------------------------------------------------------
-template <bool CONN8, bool INV, bool BORDER>
-__global__ void __launch_bounds__(256) ccl_merge_kernel(const uint32_t *__restrict__ bits, int32_t *__restrict__ parent,
-                                                         const int32_t *__restrict__ holes, int H, int W, int WW) {
-    VBS_WORD_COORDS
-    if (INV && holes[f] == 0) return;          // no hole anywhere in this frame: background labels are not needed
-    const uint32_t *img = bits + (size_t)f * H * WW;
-    const uint32_t w = get_bits<INV>(img, y, wx, W, WW);
-    if (!w) return;
-    int32_t *par = parent + (size_t)f * H * W;
-    const int base = y * W + 32 * wx;
-    if ((w & 1u) && wx > 0) {
-        const uint32_t pw = get_bits<INV>(img, y, wx - 1, W, WW);
-        if (pw >> 31) unite(par, base, base - 32 + seg_start(pw, 31));
-    }
-    const uint32_t up = y > 0 ? get_bits<INV>(img, y - 1, wx, W, WW) : 0u;
-    const uint32_t upl = (CONN8 && y > 0 && wx > 0) ? get_bits<INV>(img, y - 1, wx - 1, W, WW) : 0u;
-    const uint32_t upr = (CONN8 && y > 0 && wx + 1 < WW) ? get_bits<INV>(img, y - 1, wx + 1, W, WW) : 0u;
-    const int last_bit = (W - 1) - 32 * wx;         // position of pixel W-1 in this word (may be >= 32)
-    uint32_t rem = w;
-    while (rem) {
-        const int s = __ffs(rem) - 1;
-        const uint32_t seg = run_mask(w, s);
-        rem &= ~seg;
-        const int id = base + s;
-        uint32_t nb = seg;
-        if (CONN8) nb |= (seg << 1) | (seg >> 1);
-        uint32_t ov = up & nb;
-        while (ov) {
-            const int b = __ffs(ov) - 1;
-            const int us = seg_start(up, b);
-            ov &= ~run_mask(up, us);
-            unite(par, id, base - W + us);
+// 2. link background segments that touch; segments on the frame are united with OUTSIDE
+__global__ void __launch_bounds__(256) bg_merge_kernel(const uint32_t *__restrict__ bits, int32_t *__restrict__ parent,
+                                                        const int32_t *__restrict__ holes, int H, int W, int WW) {
+    VBS_BG_LOOP {
+        const uint32_t *img = bits + (size_t)f * H * WW;
+        const uint32_t w = get_bits<true>(img, y, wx, W, WW);
+        if (!w) continue;
+        int32_t *par = parent + (size_t)f * H * W;
+        const int base = y * W + 32 * wx;
+        if ((w & 1u) && wx > 0) {
+            const uint32_t pw = get_bits<true>(img, y, wx - 1, W, WW);
+            if (pw >> 31) unite(par, base, base - 32 + seg_start(pw, 31));
         }
-        if (CONN8) {
-            if ((seg & 1u) && (upl >> 31)) unite(par, id, base - W - 32 + seg_start(upl, 31));
-            if ((seg >> 31) && (upr & 1u)) unite(par, id, base - W + 32);
-        }
-        if (BORDER) {
+        const uint32_t up = y > 0 ? get_bits<true>(img, y - 1, wx, W, WW) : 0u;
+        const int last_bit = (W - 1) - 32 * wx;         // position of pixel W-1 in this word (may be >= 32)
+        uint32_t rem = w;
+        while (rem) {
+            const int s = __ffs(rem) - 1;
+            const uint32_t seg = run_mask(w, s);
+            rem &= ~seg;
+            const int id = base + s;
+            uint32_t ov = up & seg;
+            while (ov) {
+                const int us = seg_start(up, __ffs(ov) - 1);
+                ov &= ~run_mask(up, us);
+                unite(par, id, base - W + us);
+            }
             const bool touches = y == 0 || y == H - 1 || (wx == 0 && (seg & 1u)) ||
                                  (last_bit >= 0 && last_bit < 32 && ((seg >> last_bit) & 1u));
             if (touches) unite(par, id, OUTSIDE);
@@ -144,20 +127,20 @@ __global__ void __launch_bounds__(256) ccl_merge_kernel(const uint32_t *__restri
     }
 }
 
-// background segments of frames with holes: point straight at the root (or at OUTSIDE)
-__global__ void __launch_bounds__(256) ccl_flatten_bg_kernel(const uint32_t *__restrict__ bits, int32_t *__restrict__ parent,
-                                                              const int32_t *__restrict__ holes, int H, int W, int WW) {
-    VBS_WORD_COORDS
-    if (holes[f] == 0) return;
-    const uint32_t bg = ~__ldg(bits + ((size_t)f * H + y) * WW + wx) & valid_mask(wx, W);
-    int32_t *par = parent + (size_t)f * H * W;
-    const int base = y * W + 32 * wx;
-    uint32_t bs = bg & ~(bg << 1);
-    while (bs) {
-        const int s = __ffs(bs) - 1;
-        bs &= bs - 1;
-        const int r = find_root(par, base + s);
-        if (r != base + s) par[base + s] = r;
+// 3. point every background segment straight at its root (or at OUTSIDE)
+__global__ void __launch_bounds__(256) bg_flatten_kernel(const uint32_t *__restrict__ bits, int32_t *__restrict__ parent,
+                                                          const int32_t *__restrict__ holes, int H, int W, int WW) {
+    VBS_BG_LOOP {
+        const uint32_t bg = ~__ldg(bits + ((size_t)f * H + y) * WW + wx) & valid_mask(wx, W);
+        int32_t *par = parent + (size_t)f * H * W;
+        const int base = y * W + 32 * wx;
+        uint32_t bs = bg & ~(bg << 1);
+        while (bs) {
+            const int s = __ffs(bs) - 1;
+            bs &= bs - 1;
+            const int r = find_root(par, base + s);
+            if (r != base + s) par[base + s] = r;
+        }
     }
 }
 
@@ -227,20 +210,20 @@ __device__ __forceinline__ int unite_root(int32_t *par, int a, int b) {
 struct StripTables {
     int32_t rl[2][SPX / 2];      // label of every segment of the current / previous row, index = (local x of its start) >> 1
     int32_t lp[SP];              // label equivalences (union-find, root = smallest = earliest label)
-    int32_t pg[SP];              // first pixel of the label, local: ly * SPX + lx
-    uint32_t ac[SP], ax[SP], ay[SP];   // pixel count, sum of local x, sum of local y
+    int32_t pg[SP];              // first pixel of the label (global pixel index of the frame)
+    uint32_t ac[SP], ax[SP], ay[SP];   // ring image only: pixel count, sum of local x, sum of local y
 };
 
 // end of a (sub-)tile: fold merged labels into their roots, emit one record per root
-__device__ __forceinline__ void strip_close(StripTables &T, int next, int lane, int32_t *par, int x0, int y0, int W, int z,
+template <bool MOMENTS>
+__device__ __forceinline__ void strip_close(StripTables &T, int next, int lane, int32_t *par, int x0, int y0, int z,
                                             int32_t *nrec, int4 *recs, int RCAP, uint32_t *status, uint32_t overflow_bit) {
-    auto G = [&](int p) { return (y0 + p / SPX) * W + x0 + p % SPX; };
     __syncwarp();
     for (int L = lane; L < next; L += 32) {
         const int r = find_root(T.lp, L);
         if (r != L) {
-            par[G(T.pg[L])] = G(T.pg[r]);
-            atomicAdd(&T.ac[r], T.ac[L]); atomicAdd(&T.ax[r], T.ax[L]); atomicAdd(&T.ay[r], T.ay[L]);
+            par[T.pg[L]] = T.pg[r];
+            if (MOMENTS) { atomicAdd(&T.ac[r], T.ac[L]); atomicAdd(&T.ax[r], T.ax[L]); atomicAdd(&T.ay[r], T.ay[L]); }
         }
     }
     __syncwarp();
@@ -258,9 +241,9 @@ __device__ __forceinline__ void strip_close(StripTables &T, int next, int lane, 
         const uint32_t m = __ballot_sync(0xffffffffu, root);
         if (root) {
             const int slot = off + __popc(m & ((1u << lane) - 1u));
-            const uint32_t c = T.ac[L];
-            const int p = T.pg[L];
-            if (slot < RCAP) recs[(size_t)z * RCAP + slot] = make_int4(G(p), (int)c, (int)(T.ax[L] + c * (uint32_t)x0), (int)(T.ay[L] + c * (uint32_t)y0));
+            const uint32_t c = MOMENTS ? T.ac[L] : 0u;
+            if (slot < RCAP) recs[(size_t)z * RCAP + slot] = make_int4(T.pg[L], (int)c, MOMENTS ? (int)(T.ax[L] + c * (uint32_t)x0) : 0,
+                                                                       MOMENTS ? (int)(T.ay[L] + c * (uint32_t)y0) : 0);
             else atomicOr(status, overflow_bit);
         }
         off += __popc(m);
@@ -268,104 +251,118 @@ __device__ __forceinline__ void strip_close(StripTables &T, int next, int lane, 
     __syncwarp();
 }
 
-// block 32 (one warp); grid (ceil(WW / 32), ceil(H / SH), nimg * batch)
-__global__ void __launch_bounds__(32) fg_strip_kernel(FgImages im, int32_t *__restrict__ nrec, int4 *__restrict__ recs, uint8_t *__restrict__ rowflag,
-                                                       int H, int W, int WW, int RCAP, uint32_t *status) {
-    __shared__ StripTables T;
+// CONN8 = opened area mask (8-connected, no moments); !CONN8 = ring maxima (4-connected, moments)
+template <bool CONN8>
+__device__ __forceinline__ void strip_march(StripTables &T, const uint32_t *__restrict__ bits, int32_t *__restrict__ par, int32_t *nrec, int4 *recs,
+                                            uint8_t *__restrict__ rowflag, int f, int z, int H, int W, int WW, int RCAP, uint32_t *status, uint32_t overflow_bit) {
+    constexpr bool MOMENTS = !CONN8;
     const int lane = threadIdx.x;
     const int band = blockIdx.x, nbands = gridDim.x;
     const int x0 = band * SPX, wx = band * 32 + lane, lx0 = 32 * lane;
     const int y0 = blockIdx.y * SH, rows = min(SH, H - y0);
-    const int f = blockIdx.z / im.nimg, img = im.img0 + blockIdx.z % im.nimg, z = 2 * f + img;
-    const uint32_t overflow_bit = img == 0 ? VBS_DEV_LABEL_OVERFLOW : VBS_DEV_CONTOUR_OVERFLOW;
-    const uint32_t *src = im.bits[img] + ((size_t)f * H + y0) * WW + wx;
-    int32_t *par = im.parent[img] + (size_t)f * H * W;
-    uint8_t *flag = rowflag + ((size_t)z * nbands + band) * H + y0;
+    const uint32_t *src = bits + ((size_t)f * H + y0) * WW + wx;
     const bool inw = wx < WW;
     int next = 0;
+    unsigned long long closed_rows = 0ull;
     uint32_t up = 0u;
     uint32_t wnext = inw ? __ldg(src) : 0u;
-    for (int ly = 0; ly < rows; ++ly) {
+    int gbase = y0 * W + x0 + lx0;                           // pixel index of this lane's bit 0 in the current row
+    for (int ly = 0; ly < rows; ++ly, gbase += W) {
         const uint32_t w = wnext;
         if (ly + 1 < rows) wnext = inw ? __ldg(src + (size_t)(ly + 1) * WW) : 0u;
-        uint32_t upl = __shfl_up_sync(0xffffffffu, up, 1), upr = __shfl_down_sync(0xffffffffu, up, 1);
+        if (!__any_sync(0xffffffffu, w != 0u)) { up = 0u; continue; }
+        uint32_t upl = 0u, upr = 0u;
+        if (CONN8) {
+            upl = __shfl_up_sync(0xffffffffu, up, 1); upr = __shfl_down_sync(0xffffffffu, up, 1);
+            if (lane == 0) upl = 0u;
+            if (lane == 31) upr = 0u;
+        }
         uint32_t prevw = __shfl_up_sync(0xffffffffu, w, 1);
-        if (lane == 0) { upl = 0u; prevw = 0u; }
-        if (lane == 31) upr = 0u;
-        bool closed_here = false;
-        if (__any_sync(0xffffffffu, w != 0u)) {
-            int32_t *cur = T.rl[ly & 1];
-            const int32_t *prv = T.rl[(ly & 1) ^ 1];
-            uint32_t touch;
-            int my_base;
-            for (;;) {
-                // bits of this word that are adjacent to a pixel of the row above
-                touch = w & (img ? (up | (up << 1) | (up >> 1) | (upl >> 31) | ((upr & 1u) << 31)) : up);
-                int fresh = 0;
-                for (uint32_t rem = w; rem;) {
-                    const uint32_t seg = run_mask(w, __ffs(rem) - 1);
-                    rem &= ~seg;
-                    fresh += (seg & touch) ? 0 : 1;
-                }
-                int incl = fresh;
+        if (lane == 0) prevw = 0u;
+        int32_t *cur = T.rl[ly & 1];
+        const int32_t *prv = T.rl[(ly & 1) ^ 1];
+        const uint32_t starts = w & ~(w << 1);
+        uint32_t touch;
+        int my_base;
+        for (;;) {
+            // bits of this word that are adjacent to a pixel of the row above
+            touch = w & (CONN8 ? (up | (up << 1) | (up >> 1) | (upl >> 31) | ((upr & 1u) << 31)) : up);
+            // a carry started at the first bit of a run climbs out of the run iff no touch bit stops it
+            const int fresh = __popcll(((unsigned long long)(w & ~touch) + starts) & ~(unsigned long long)w);
+            my_base = next;
+            if (!__any_sync(0xffffffffu, fresh != 0)) break;
+            int incl = fresh;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += v;
-                }
-                const int total = __shfl_sync(0xffffffffu, incl, 31);
-                my_base = next + incl - fresh;
-                if (next + total <= SP) { next += total; break; }
-                // label table full: close the tile above this row and start a new one here
-                strip_close(T, next, lane, par, x0, y0, W, z, nrec, recs, RCAP, status, overflow_bit);
-                next = 0; up = 0u; upl = 0u; upr = 0u; closed_here = true;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
             }
-            for (uint32_t rem = w; rem;) {
-                const int s = __ffs(rem) - 1;
-                const uint32_t seg = run_mask(w, s);
-                rem &= ~seg;
-                const uint32_t len = __popc(seg);
-                const uint32_t xs = len * (uint32_t)(lx0 + s) + len * (len - 1) / 2, ys = len * (uint32_t)ly;
-                const int gid = (y0 + ly) * W + x0 + lx0 + s;
-                int L;
-                if (!(seg & touch)) {
-                    L = my_base++;
-                    T.lp[L] = L; T.pg[L] = ly * SPX + lx0 + s; T.ac[L] = len; T.ax[L] = xs; T.ay[L] = ys;
-                    par[gid] = gid;
-                } else {
-                    L = -1;
-                    const uint32_t nb = img ? (seg | (seg << 1) | (seg >> 1)) : seg;
-                    uint32_t ov = up & nb;
-                    while (ov) {
-                        const int us = seg_start(up, __ffs(ov) - 1);
-                        ov &= ~run_mask(up, us);
-                        const int Lu = prv[(lx0 + us) >> 1];
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            my_base = next + incl - fresh;
+            if (next + total <= SP) { next += total; break; }
+            // label table full: close the tile above this row and start a new one here
+            strip_close<MOMENTS>(T, next, lane, par, x0, y0, z, nrec, recs, RCAP, status, overflow_bit);
+            next = 0; up = 0u; upl = 0u; upr = 0u; closed_rows |= 1ull << ly;
+        }
+        for (uint32_t rem = w; rem;) {
+            const int s = __ffs(rem) - 1;
+            const uint32_t seg = run_mask(w, s);
+            rem &= ~seg;
+            const int gid = gbase + s;
+            uint32_t len = 0, xs = 0, ys = 0;
+            if (MOMENTS) { len = __popc(seg); xs = len * (uint32_t)(lx0 + s) + len * (len - 1) / 2; ys = len * (uint32_t)ly; }
+            int L;
+            if (!(seg & touch)) {
+                L = my_base++;
+                T.lp[L] = L; T.pg[L] = gid;
+                if (MOMENTS) { T.ac[L] = len; T.ax[L] = xs; T.ay[L] = ys; }
+                par[gid] = gid;
+            } else {
+                L = -1;
+                const uint32_t nb = CONN8 ? (seg | (seg << 1) | (seg >> 1)) : seg;
+                uint32_t ov = up & nb;
+                while (ov) {
+                    const int us = seg_start(up, __ffs(ov) - 1);
+                    ov &= ~run_mask(up, us);
+                    const int Lu = prv[(lx0 + us) >> 1];
+                    L = L < 0 ? find_root_halving(T.lp, Lu) : unite_root(T.lp, L, Lu);
+                }
+                if (CONN8) {
+                    if ((seg & 1u) && (upl >> 31)) {
+                        const int Lu = prv[(lx0 - 32 + seg_start(upl, 31)) >> 1];
                         L = L < 0 ? find_root_halving(T.lp, Lu) : unite_root(T.lp, L, Lu);
                     }
-                    if (img) {
-                        if ((seg & 1u) && (upl >> 31)) {
-                            const int Lu = prv[(lx0 - 32 + seg_start(upl, 31)) >> 1];
-                            L = L < 0 ? find_root_halving(T.lp, Lu) : unite_root(T.lp, L, Lu);
-                        }
-                        if ((seg >> 31) && (upr & 1u)) {
-                            const int Lu = prv[(lx0 + 32) >> 1];
-                            L = L < 0 ? find_root_halving(T.lp, Lu) : unite_root(T.lp, L, Lu);
-                        }
+                    if ((seg >> 31) && (upr & 1u)) {
+                        const int Lu = prv[(lx0 + 32) >> 1];
+                        L = L < 0 ? find_root_halving(T.lp, Lu) : unite_root(T.lp, L, Lu);
                     }
-                    atomicAdd(&T.ac[L], len); atomicAdd(&T.ax[L], xs); atomicAdd(&T.ay[L], ys);
-                    const int p = T.pg[L];
-                    par[gid] = (y0 + p / SPX) * W + x0 + p % SPX;
                 }
-                cur[(lx0 + s) >> 1] = L;
+                if (MOMENTS) { atomicAdd(&T.ac[L], len); atomicAdd(&T.ax[L], xs); atomicAdd(&T.ay[L], ys); }
+                par[gid] = T.pg[L];
             }
-            __syncwarp();
-            if ((w & 1u) && (prevw >> 31)) unite(T.lp, cur[lx0 >> 1], cur[(lx0 - 32 + seg_start(prevw, 31)) >> 1]);
-            __syncwarp();
+            cur[(lx0 + s) >> 1] = L;
         }
-        if (lane == 0) flag[ly] = closed_here ? 1 : 0;
+        __syncwarp();
+        if ((w & 1u) && (prevw >> 31)) {
+            const int a = cur[lx0 >> 1], b = cur[(lx0 - 32 + seg_start(prevw, 31)) >> 1];
+            if (a != b) unite(T.lp, a, b);       // usually both already hold the same root
+        }
+        __syncwarp();
         up = w;
     }
-    strip_close(T, next, lane, par, x0, y0, W, z, nrec, recs, RCAP, status, overflow_bit);
+    strip_close<MOMENTS>(T, next, lane, par, x0, y0, z, nrec, recs, RCAP, status, overflow_bit);
+    uint8_t *flag = rowflag + ((size_t)z * nbands + band) * H + y0;
+    for (int r = lane; r < rows; r += 32) flag[r] = (uint8_t)((closed_rows >> r) & 1ull);
+}
+
+// block 32 (one warp); grid (ceil(WW / 32), ceil(H / SH), nimg * batch)
+__global__ void __launch_bounds__(32) fg_strip_kernel(FgImages im, int32_t *__restrict__ nrec, int4 *__restrict__ recs, uint8_t *__restrict__ rowflag,
+                                                       int H, int W, int WW, int RCAP, uint32_t *status) {
+    __shared__ StripTables T;
+    const int f = blockIdx.z / im.nimg, img = im.img0 + blockIdx.z % im.nimg, z = 2 * f + img;
+    int32_t *par = im.parent[img] + (size_t)f * H * W;
+    if (img) strip_march<true>(T, im.bits[1], par, nrec, recs, rowflag, f, z, H, W, WW, RCAP, status, VBS_DEV_CONTOUR_OVERFLOW);
+    else strip_march<false>(T, im.bits[0], par, nrec, recs, rowflag, f, z, H, W, WW, RCAP, status, VBS_DEV_LABEL_OVERFLOW);
 }
 
 // links across tile edges, in the global array.  One thread per candidate; grid (ceil(n / 256), nimg * batch) with
@@ -457,22 +454,27 @@ __global__ void __launch_bounds__(256) moments_kernel(const int32_t *__restrict_
 // 4 E = #Q1 - #Q3 - 2 #QD over all 2x2 windows of the zero-padded image (Gray's formula).  The
 // number of holes of the whole image is (#blobs - E); when it is 0 no blob can lie inside
 // another one, so the background labelling that RETR_EXTERNAL would need is skipped for the frame.
+constexpr int EU_ROWS = 16;      // quad rows per thread (consecutive, so every image row is loaded once per thread)
 __global__ void __launch_bounds__(256) euler_kernel(const uint32_t *__restrict__ bits, int32_t *__restrict__ euler4, int H, int W, int WW) {
     const int wx = blockIdx.x * 64 + threadIdx.x;            // 0 .. WW (one extra all-zero column)
-    const int yy = (int)(blockIdx.y * 4 + threadIdx.y) - 1;  // top row of the quad: -1 .. H-1
     const int f = blockIdx.z;
     int v = 0;
-    if (wx <= WW && yy < H) {
+    if (wx <= WW) {
         const uint32_t *img = bits + (size_t)f * H * WW;
         auto ld = [&](int y, int w) -> uint32_t { return (y >= 0 && y < H && w >= 0 && w < WW) ? __ldg(img + (size_t)y * WW + w) : 0u; };
-        const uint32_t b = ld(yy, wx), d = ld(yy + 1, wx);
-        if (b | d | (wx > 0 ? 1u : 0u)) {
-            const uint32_t a = (b << 1) | (ld(yy, wx - 1) >> 31), c = (d << 1) | (ld(yy + 1, wx - 1) >> 31);
-            const uint32_t x1 = a ^ b, x2 = c ^ d, n1 = a & b, n2 = c & d;
-            const uint32_t q1 = (x1 & ~x2 & ~n2) | (x2 & ~x1 & ~n1);
-            const uint32_t q3 = (x1 & n2) | (x2 & n1);
-            const uint32_t qd = x1 & x2 & ~(a ^ d);
-            v = __popc(q1) - __popc(q3) - 2 * __popc(qd);
+        int yy = (int)(blockIdx.y * 4 + threadIdx.y) * EU_ROWS - 1;      // top row of the quad: -1 .. H-1
+        uint32_t b = ld(yy, wx), bl = ld(yy, wx - 1);
+        for (int i = 0; i < EU_ROWS && yy < H; ++i, ++yy) {
+            const uint32_t d = ld(yy + 1, wx), dl = ld(yy + 1, wx - 1);
+            if (b | d | ((bl | dl) >> 31)) {
+                const uint32_t a = (b << 1) | (bl >> 31), c = (d << 1) | (dl >> 31);
+                const uint32_t x1 = a ^ b, x2 = c ^ d, n1 = a & b, n2 = c & d;
+                const uint32_t q1 = (x1 & ~x2 & ~n2) | (x2 & ~x1 & ~n1);
+                const uint32_t q3 = (x1 & n2) | (x2 & n1);
+                const uint32_t qd = x1 & x2 & ~(a ^ d);
+                v += __popc(q1) - __popc(q3) - 2 * __popc(qd);
+            }
+            b = d; bl = dl;
         }
     }
 #pragma unroll
@@ -547,8 +549,7 @@ cudaError_t vbs_launch_prepare(vbs_ctx *ctx, int batch) {
 cudaError_t vbs_launch_components(vbs_ctx *ctx, int batch, int which) {
     const int H = ctx->H, W = ctx->W, WW = ctx->WW, M = ctx->M;
     const dim3 wb(64, 4);
-    const dim3 wg((WW + 63) / 64, (H + 3) / 4, batch);
-    const dim3 eg((WW + 1 + 63) / 64, (H + 1 + 3) / 4, batch);
+    const dim3 eg((WW + 1 + 63) / 64, (H + 1 + 4 * EU_ROWS - 1) / (4 * EU_ROWS), batch);
     cudaStream_t st = ctx->stream;
     FgImages im;
     im.bits[0] = ctx->max_bits; im.bits[1] = ctx->open_bits; im.parent[0] = ctx->parent; im.parent[1] = ctx->parent2;
@@ -571,9 +572,10 @@ cudaError_t vbs_launch_components(vbs_ctx *ctx, int batch, int which) {
     ctx->launches += 1;
     if (which & 2) {
         // background pass of the opened image: every thread of a hole-free frame returns at once
-        ccl_init_kernel<false, true><<<wg, wb, 0, st>>>(ctx->open_bits, ctx->parent2, ctx->holes, H, W, WW);
-        ccl_merge_kernel<false, true, true><<<wg, wb, 0, st>>>(ctx->open_bits, ctx->parent2, ctx->holes, H, W, WW);
-        ccl_flatten_bg_kernel<<<wg, wb, 0, st>>>(ctx->open_bits, ctx->parent2, ctx->holes, H, W, WW);
+        const dim3 bg((WW + 63) / 64, (H + BG_ROWS - 1) / BG_ROWS, batch);
+        bg_init_kernel<<<bg, wb, 0, st>>>(ctx->open_bits, ctx->parent2, ctx->holes, H, W, WW);
+        bg_merge_kernel<<<bg, wb, 0, st>>>(ctx->open_bits, ctx->parent2, ctx->holes, H, W, WW);
+        bg_flatten_kernel<<<bg, wb, 0, st>>>(ctx->open_bits, ctx->parent2, ctx->holes, H, W, WW);
         ctx->launches += 3;
     }
     return cudaGetLastError();

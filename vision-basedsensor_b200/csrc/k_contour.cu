@@ -98,44 +98,59 @@ __global__ void contour_fit_kernel(const uint32_t *__restrict__ open_bits, const
 }
 
 // ---- 3. nearest centroid inside the contour polygon and inside the (minor/10)^2 gate (MD:222-237) --
-__global__ void match_kernel(const uint32_t *__restrict__ open_bits, const int32_t *__restrict__ croot,
+// block = MATCH_T contour slots of one frame; the frame's centroids stream through shared memory
+constexpr int MATCH_T = 128, MATCH_CHUNK = 512;
+__global__ void __launch_bounds__(MATCH_T) match_kernel(const uint32_t *__restrict__ open_bits, const int32_t *__restrict__ croot,
                              const uint32_t *__restrict__ cpts, const int32_t *__restrict__ cpn,
                              const double *__restrict__ cell, const double *__restrict__ centres,
                              const int32_t *__restrict__ nlabels, int32_t *__restrict__ cmatch, int32_t *__restrict__ claim,
                              int H, int W, int WW, int M, uint32_t *status) {
+    __shared__ double2 sc[MATCH_CHUNK];               // (row, col) of MATCH_CHUNK centroids
     const int f = blockIdx.y;
-    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= M) return;
-    const size_t i = (size_t)f * M + slot;
-    cmatch[i] = -1;
+    const int slot = blockIdx.x * MATCH_T + threadIdx.x;
+    const size_t i = (size_t)f * M + min(slot, M - 1);
     const double *c = cell + i * 6;
-    if (c[5] == 0.0) return;
-    const double ecx = c[0], ecy = c[1];
-    const double tenth = c[3] / 10.0;
-    const double gate = mul_rn(tenth, tenth);
+    const bool live = slot < M && c[5] != 0.0;
+    if (slot < M) cmatch[i] = -1;
+    if (!__syncthreads_or(live)) return;
+    double ecx = 0.0, ecy = 0.0, gate = 0.0;
+    int np = 0;
+    if (live) {
+        ecx = c[0]; ecy = c[1];
+        const double tenth = c[3] / 10.0;
+        gate = mul_rn(tenth, tenth);
+        np = cpn[i];
+    }
     const int n = min(nlabels[f], M);
-    const int np = cpn[i];
     int best = -1;
     double best_d = INFINITY;
-    const double *cen = centres + (size_t)f * M * 2;
-    for (int j = 0; j < n; ++j) {
-        const double y = cen[2 * j], x = cen[2 * j + 1];
-        const double dx = x - ecx, dy = y - ecy;
-        const double d = add_rn(mul_rn(dx, dx), mul_rn(dy, dy));
-        if (d < gate && d < best_d) {
-            PointPolygon pp; pp.init(x, y);
-            if (np <= PCAP) {
-                StoredSource src{cpts + i * PCAP, np};
-                src(pp);
-            } else {
-                const int idx = croot[i];
-                const int y0 = idx / W, x0 = idx - y0 * W;
-                BitImage fg{open_bits + (size_t)f * H * WW, H, W, WW};
-                trace_external_simple(fg, x0, y0, 8LL * H * W + 16, pp);
+    const double2 *cen = reinterpret_cast<const double2 *>(centres + (size_t)f * M * 2);
+    for (int j0 = 0; j0 < n; j0 += MATCH_CHUNK) {
+        const int m = min(MATCH_CHUNK, n - j0);
+        __syncthreads();
+        for (int k = threadIdx.x; k < m; k += MATCH_T) sc[k] = cen[j0 + k];
+        __syncthreads();
+        if (!live) continue;
+        for (int k = 0; k < m; ++k) {
+            const double y = sc[k].x, x = sc[k].y;
+            const double dx = x - ecx, dy = y - ecy;
+            const double d = add_rn(mul_rn(dx, dx), mul_rn(dy, dy));
+            if (d < gate && d < best_d) {
+                PointPolygon pp; pp.init(x, y);
+                if (np <= PCAP) {
+                    StoredSource src{cpts + i * PCAP, np};
+                    src(pp);
+                } else {
+                    const int idx = croot[i];
+                    const int y0 = idx / W, x0 = idx - y0 * W;
+                    BitImage fg{open_bits + (size_t)f * H * WW, H, W, WW};
+                    trace_external_simple(fg, x0, y0, 8LL * H * W + 16, pp);
+                }
+                if (pp.result() >= 0) { best = j0 + k; best_d = d; }
             }
-            if (pp.result() >= 0) { best = j; best_d = d; }
         }
     }
+    if (!live) return;
     cmatch[i] = best;
     if (best >= 0 && atomicAdd(claim + (size_t)f * M + best, 1) > 0) atomicOr(status, VBS_DEV_MATCH_CONFLICT);
 }
@@ -182,7 +197,7 @@ cudaError_t vbs_launch_contours(vbs_ctx *ctx, int batch, int which) {
         ctx->launches += 2;
     }
     if (which & 4) {
-        match_kernel<<<grid, 64, 0, ctx->stream>>>(ctx->open_bits, ctx->croot, ctx->cpts, ctx->cpn, ctx->cell, ctx->centres, ctx->d_nlabels,
+        match_kernel<<<dim3((ctx->M + MATCH_T - 1) / MATCH_T, batch), MATCH_T, 0, ctx->stream>>>(ctx->open_bits, ctx->croot, ctx->cpts, ctx->cpn, ctx->cell, ctx->centres, ctx->d_nlabels,
                                                    ctx->cmatch, ctx->claim, ctx->H, ctx->W, ctx->WW, ctx->M, ctx->d_status);
         compact_kernel<<<(batch + 3) / 4, 128, 0, ctx->stream>>>(ctx->cell, ctx->cmatch, ctx->centres, ctx->d_ncont, ctx->d_nmarkers,
                                                                  ctx->marker_xy, ctx->marker_axes, ctx->M, batch);
