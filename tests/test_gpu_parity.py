@@ -573,6 +573,9 @@ def dense_masks(h=300, w=1100):
             mask[y + 3, x + 3] = 1
     for i in range(150):                                # 8-connected diagonal band, 5 px thick so that it survives the open
         area[210 + i // 3: 215 + i // 3, 940 + i: 945 + i] = 1
+    _disk(area, 300, 255, 38)                           # one large blob with seven centroids inside its distance gate
+    for y, x in ((252, 296), (252, 300), (254, 298), (256, 302), (256, 296), (258, 300), (254, 304)):
+        mask[y, x] = 1
     return mask, area * 255
 
 

@@ -207,16 +207,17 @@ __device__ __forceinline__ int unite_root(int32_t *par, int a, int b) {
     }
 }
 
+template <bool MOMENTS>
 struct StripTables {
-    int32_t rl[2][SPX / 2];      // label of every segment of the current / previous row, index = (local x of its start) >> 1
+    int16_t rl[2][SPX / 2];      // label of every segment of the current / previous row, index = (local x of its start) >> 1
     int32_t lp[SP];              // label equivalences (union-find, root = smallest = earliest label)
     int32_t pg[SP];              // first pixel of the label (global pixel index of the frame)
-    uint32_t ac[SP], ax[SP], ay[SP];   // ring image only: pixel count, sum of local x, sum of local y
+    uint32_t ac[MOMENTS ? SP : 1], ax[MOMENTS ? SP : 1], ay[MOMENTS ? SP : 1];   // ring image only: pixel count, sum of local x, sum of local y
 };
 
 // end of a (sub-)tile: fold merged labels into their roots, emit one record per root
 template <bool MOMENTS>
-__device__ __forceinline__ void strip_close(StripTables &T, int next, int lane, int32_t *par, int x0, int y0, int z,
+__device__ __forceinline__ void strip_close(StripTables<MOMENTS> &T, int next, int lane, int32_t *par, int x0, int y0, int z,
                                             int32_t *nrec, int4 *recs, int RCAP, uint32_t *status, uint32_t overflow_bit) {
     __syncwarp();
     for (int L = lane; L < next; L += 32) {
@@ -252,10 +253,15 @@ __device__ __forceinline__ void strip_close(StripTables &T, int next, int lane, 
 }
 
 // CONN8 = opened area mask (8-connected, no moments); !CONN8 = ring maxima (4-connected, moments)
+// block 32 (one warp); grid (ceil(WW / 32), ceil(H / SH), batch)
 template <bool CONN8>
-__device__ __forceinline__ void strip_march(StripTables &T, const uint32_t *__restrict__ bits, int32_t *__restrict__ par, int32_t *nrec, int4 *recs,
-                                            uint8_t *__restrict__ rowflag, int f, int z, int H, int W, int WW, int RCAP, uint32_t *status, uint32_t overflow_bit) {
+__global__ void __launch_bounds__(32) fg_strip_kernel(const uint32_t *__restrict__ bits, int32_t *__restrict__ parent, int32_t *__restrict__ nrec,
+                                                       int4 *__restrict__ recs, uint8_t *__restrict__ rowflag, int H, int W, int WW, int RCAP, uint32_t *status) {
     constexpr bool MOMENTS = !CONN8;
+    constexpr uint32_t overflow_bit = CONN8 ? VBS_DEV_CONTOUR_OVERFLOW : VBS_DEV_LABEL_OVERFLOW;
+    __shared__ StripTables<MOMENTS> T;
+    const int f = blockIdx.z, z = 2 * f + (CONN8 ? 1 : 0);
+    int32_t *par = parent + (size_t)f * H * W;
     const int lane = threadIdx.x;
     const int band = blockIdx.x, nbands = gridDim.x;
     const int x0 = band * SPX, wx = band * 32 + lane, lx0 = 32 * lane;
@@ -265,11 +271,13 @@ __device__ __forceinline__ void strip_march(StripTables &T, const uint32_t *__re
     int next = 0;
     unsigned long long closed_rows = 0ull;
     uint32_t up = 0u;
-    uint32_t wnext = inw ? __ldg(src) : 0u;
+    uint32_t wnext = inw ? __ldg(src) : 0u;                  // rows are fetched two steps ahead
+    uint32_t wnext2 = (inw && rows > 1) ? __ldg(src + WW) : 0u;
     int gbase = y0 * W + x0 + lx0;                           // pixel index of this lane's bit 0 in the current row
     for (int ly = 0; ly < rows; ++ly, gbase += W) {
         const uint32_t w = wnext;
-        if (ly + 1 < rows) wnext = inw ? __ldg(src + (size_t)(ly + 1) * WW) : 0u;
+        wnext = wnext2;
+        wnext2 = (inw && ly + 2 < rows) ? __ldg(src + (size_t)(ly + 2) * WW) : 0u;
         if (!__any_sync(0xffffffffu, w != 0u)) { up = 0u; continue; }
         uint32_t upl = 0u, upr = 0u;
         if (CONN8) {
@@ -279,8 +287,8 @@ __device__ __forceinline__ void strip_march(StripTables &T, const uint32_t *__re
         }
         uint32_t prevw = __shfl_up_sync(0xffffffffu, w, 1);
         if (lane == 0) prevw = 0u;
-        int32_t *cur = T.rl[ly & 1];
-        const int32_t *prv = T.rl[(ly & 1) ^ 1];
+        int16_t *cur = T.rl[ly & 1];
+        const int16_t *prv = T.rl[(ly & 1) ^ 1];
         const uint32_t starts = w & ~(w << 1);
         uint32_t touch;
         int my_base;
@@ -340,7 +348,7 @@ __device__ __forceinline__ void strip_march(StripTables &T, const uint32_t *__re
                 if (MOMENTS) { atomicAdd(&T.ac[L], len); atomicAdd(&T.ax[L], xs); atomicAdd(&T.ay[L], ys); }
                 par[gid] = T.pg[L];
             }
-            cur[(lx0 + s) >> 1] = L;
+            cur[(lx0 + s) >> 1] = (int16_t)L;
         }
         __syncwarp();
         if ((w & 1u) && (prevw >> 31)) {
@@ -353,16 +361,6 @@ __device__ __forceinline__ void strip_march(StripTables &T, const uint32_t *__re
     strip_close<MOMENTS>(T, next, lane, par, x0, y0, z, nrec, recs, RCAP, status, overflow_bit);
     uint8_t *flag = rowflag + ((size_t)z * nbands + band) * H + y0;
     for (int r = lane; r < rows; r += 32) flag[r] = (uint8_t)((closed_rows >> r) & 1ull);
-}
-
-// block 32 (one warp); grid (ceil(WW / 32), ceil(H / SH), nimg * batch)
-__global__ void __launch_bounds__(32) fg_strip_kernel(FgImages im, int32_t *__restrict__ nrec, int4 *__restrict__ recs, uint8_t *__restrict__ rowflag,
-                                                       int H, int W, int WW, int RCAP, uint32_t *status) {
-    __shared__ StripTables T;
-    const int f = blockIdx.z / im.nimg, img = im.img0 + blockIdx.z % im.nimg, z = 2 * f + img;
-    int32_t *par = im.parent[img] + (size_t)f * H * W;
-    if (img) strip_march<true>(T, im.bits[1], par, nrec, recs, rowflag, f, z, H, W, WW, RCAP, status, VBS_DEV_CONTOUR_OVERFLOW);
-    else strip_march<false>(T, im.bits[0], par, nrec, recs, rowflag, f, z, H, W, WW, RCAP, status, VBS_DEV_LABEL_OVERFLOW);
 }
 
 // links across tile edges, in the global array.  One thread per candidate; grid (ceil(n / 256), nimg * batch) with
@@ -557,11 +555,13 @@ cudaError_t vbs_launch_components(vbs_ctx *ctx, int batch, int which) {
     im.nimg = (which == 3) ? 2 : 1;
     const int RCAP = ctx->rcap;
     const int nbands = (WW + 31) / 32;
-    fg_strip_kernel<<<dim3(nbands, (H + SH - 1) / SH, im.nimg * batch), 32, 0, st>>>(im, ctx->nrec, ctx->recs, ctx->rowflag, H, W, WW, RCAP, ctx->d_status);
+    const dim3 sg(nbands, (H + SH - 1) / SH, batch);
+    if (which & 2) { fg_strip_kernel<true><<<sg, 32, 0, st>>>(ctx->open_bits, ctx->parent2, ctx->nrec, ctx->recs, ctx->rowflag, H, W, WW, RCAP, ctx->d_status); ctx->launches += 1; }
+    if (which & 1) { fg_strip_kernel<false><<<sg, 32, 0, st>>>(ctx->max_bits, ctx->parent, ctx->nrec, ctx->recs, ctx->rowflag, H, W, WW, RCAP, ctx->d_status); ctx->launches += 1; }
     const int nborder = ((H - 1) / SH) * WW + H * (nbands - 1) + H * nbands;
     fg_border_kernel<<<dim3((nborder + 255) / 256, im.nimg * batch), 256, 0, st>>>(im, ctx->rowflag, H, W, WW, nbands);
     fg_roots_kernel<<<dim3((RCAP + 255) / 256, im.nimg * batch), 256, 0, st>>>(im, ctx->nrec, ctx->recs, ctx->nroots, ctx->rootlist, H, W, M, RCAP);
-    ctx->launches += 3;
+    ctx->launches += 2;
     if (which & 1) { moments_kernel<<<dim3((RCAP + 255) / 256, batch), 256, 0, st>>>(ctx->parent, ctx->nrec, ctx->recs, ctx->lab_cnt, ctx->lab_sx, ctx->lab_sy, H, W, M, RCAP); ctx->launches += 1; }
     if (which & 2) { euler_kernel<<<eg, wb, 0, st>>>(ctx->open_bits, ctx->euler4, H, W, WW); ctx->launches += 1; }
     int P2 = 1;

@@ -122,8 +122,12 @@ __global__ void __launch_bounds__(MATCH_T) match_kernel(const uint32_t *__restri
         np = cpn[i];
     }
     const int n = min(nlabels[f], M);
-    int best = -1;
-    double best_d = INFINITY;
+    // Pass 1 keeps the centroids inside the distance gate (rarely more than one); pass 2 runs the
+    // polygon tests in index order with the reference's running minimum.  Testing inside the scan
+    // would serialise the 32 slots of a warp, whose hits sit at 32 different loop indices.
+    constexpr int NC = 4;
+    int ck[NC]; double cd[NC], cx[NC], cy[NC];
+    int ncand = 0;
     const double2 *cen = reinterpret_cast<const double2 *>(centres + (size_t)f * M * 2);
     for (int j0 = 0; j0 < n; j0 += MATCH_CHUNK) {
         const int m = min(MATCH_CHUNK, n - j0);
@@ -135,22 +139,42 @@ __global__ void __launch_bounds__(MATCH_T) match_kernel(const uint32_t *__restri
             const double y = sc[k].x, x = sc[k].y;
             const double dx = x - ecx, dy = y - ecy;
             const double d = add_rn(mul_rn(dx, dx), mul_rn(dy, dy));
-            if (d < gate && d < best_d) {
-                PointPolygon pp; pp.init(x, y);
-                if (np <= PCAP) {
-                    StoredSource src{cpts + i * PCAP, np};
-                    src(pp);
-                } else {
-                    const int idx = croot[i];
-                    const int y0 = idx / W, x0 = idx - y0 * W;
-                    BitImage fg{open_bits + (size_t)f * H * WW, H, W, WW};
-                    trace_external_simple(fg, x0, y0, 8LL * H * W + 16, pp);
-                }
-                if (pp.result() >= 0) { best = j0 + k; best_d = d; }
+            if (d < gate) {
+#pragma unroll
+                for (int q = 0; q < NC; ++q)
+                    if (q == ncand) { ck[q] = j0 + k; cd[q] = d; cx[q] = x; cy[q] = y; }
+                ++ncand;
             }
         }
     }
     if (!live) return;
+    auto inside = [&](double x, double y) {
+        PointPolygon pp; pp.init(x, y);
+        if (np <= PCAP) {
+            StoredSource src{cpts + i * PCAP, np};
+            src(pp);
+        } else {
+            const int idx = croot[i];
+            const int y0 = idx / W, x0 = idx - y0 * W;
+            BitImage fg{open_bits + (size_t)f * H * WW, H, W, WW};
+            trace_external_simple(fg, x0, y0, 8LL * H * W + 16, pp);
+        }
+        return pp.result() >= 0;
+    };
+    int best = -1;
+    double best_d = INFINITY;
+    if (ncand <= NC) {
+#pragma unroll
+        for (int q = 0; q < NC; ++q)
+            if (q < ncand && cd[q] < best_d && inside(cx[q], cy[q])) { best = ck[q]; best_d = cd[q]; }
+    } else {                                        // more candidates than registers: the literal loop
+        for (int j = 0; j < n; ++j) {
+            const double y = cen[j].x, x = cen[j].y;
+            const double dx = x - ecx, dy = y - ecy;
+            const double d = add_rn(mul_rn(dx, dx), mul_rn(dy, dy));
+            if (d < gate && d < best_d && inside(x, y)) { best = j; best_d = d; }
+        }
+    }
     cmatch[i] = best;
     if (best >= 0 && atomicAdd(claim + (size_t)f * M + best, 1) > 0) atomicOr(status, VBS_DEV_MATCH_CONFLICT);
 }
