@@ -154,6 +154,21 @@ int vbs_submit_host(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int64_t 
                     int64_t frameno0, const vbs_outputs *out);
 int vbs_wait_host(vbs_ctx *ctx);
 
+/* optional lens correction of the cropped frame, MarkerTracker._undistort_frame (MD:93-109), applied by
+ * _preprocess_frame (MD:88-89) when config['calibration_params'] is present:
+ *   new_K = cv2.getOptimalNewCameraMatrix(K, D, (w,h), 0, (w,h)); maps = cv2.initUndistortRectifyMap(K, D, None,
+ *   new_K, (w,h), CV_16SC2); frame = cv2.remap(frame, maps, INTER_LINEAR)            (bit-exact, BORDER_CONSTANT 0)
+ * K: 3x3 row-major float64, D: nd = 4, 5 or 8 float64 coefficients (k1 k2 p1 p2 [k3 [k4 k5 k6]]).  Once set, every
+ * vbs_process_* / vbs_find_markers call corrects its frames first; K == NULL switches it off.  The maps depend on
+ * (K, D, size) only and are built once here (the reference rebuilds them for every frame).
+ * vbs_get_undistort_maps: new_K (host, 9 doubles) and the maps in OpenCV's layout (device: map1 int16 [H][W][2],
+ *                         map2 uint16 [H][W]); any pointer may be NULL (maps: both or neither)
+ * vbs_undistort_frames  : the corrected frames themselves, [batch][H][W*C] uint8, device                         */
+int vbs_set_undistort(vbs_ctx *ctx, const double *K, const double *D, int32_t nd);
+int vbs_get_undistort_maps(vbs_ctx *ctx, double *new_camera_matrix, int16_t *map1_device, uint16_t *map2_device);
+int vbs_undistort_frames(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int64_t frame_stride, int64_t row_pitch,
+                         uint8_t *out_device);
+
 /* stage-level entry points (same kernels, for the static-method mirrors) -----------------------
  * vbs_find_markers : MarkerTracker._find_markers (MD:111-135): frames -> area_mask, mask (kept in ctx)
  * vbs_marker_center: MarkerTracker._marker_center (MD:166-249) on masks supplied by the caller

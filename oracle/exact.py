@@ -377,17 +377,89 @@ def undistort_exact(K, D, pts):
     k1, k2, p1, p2, k3 = (float(v) for v in np.asarray(D, dtype=np.float32).astype(np.float64)[:5])
     fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
     pts = np.asarray(pts, dtype=np.float64).reshape(-1, 2)
-    x0 = (pts[:, 0] - cx) / fx
-    y0 = (pts[:, 1] - cy) / fy
-    x, y = x0.copy(), y0.copy()
-    for _ in range(5):
-        r2 = x * x + y * y
-        icd = 1.0 / (1 + ((k3 * r2 + k2) * r2 + k1) * r2)
-        dx = 2 * p1 * x * y + p2 * (r2 + 2 * x * x)
-        dy = p1 * (r2 + 2 * y * y) + 2 * p2 * x * y
-        x = (x0 - dx) * icd
-        y = (y0 - dy) * icd
-    return np.stack([x * fx + cx, y * fy + cy], axis=1)
+    n = undistort_normalized_exact(K, [k1, k2, p1, p2, k3], pts)
+    return np.stack([n[:, 0] * fx + cx, n[:, 1] * fy + cy], axis=1)
+
+
+def _lens(K, D):
+    K = np.asarray(K, dtype=np.float64)
+    d = np.zeros(8)
+    D = np.asarray(D, dtype=np.float64).ravel()
+    d[: min(len(D), 8)] = D[:8]
+    return K[0, 0], K[1, 1], K[0, 2], K[1, 2], d
+
+
+def undistort_normalized_exact(K, D, pts):
+    """cv2.undistortPoints(pts, K, D) (normalised output), bit for bit: (u - cx) * (1 / fx), exactly 5
+    iterations, rational factor, and the bail-out to the start value when the factor turns negative."""
+    fx, fy, cx, cy, (k1, k2, p1, p2, k3, k4, k5, k6) = _lens(K, D)
+    ifx, ify = 1.0 / fx, 1.0 / fy
+    pts = np.asarray(pts, dtype=np.float64).reshape(-1, 2)
+    out = np.empty_like(pts)
+    for i, (u, v) in enumerate(pts):
+        x0, y0 = (u - cx) * ifx, (v - cy) * ify
+        x, y = x0, y0
+        for _ in range(5):
+            r2 = x * x + y * y
+            icd = (1 + ((k6 * r2 + k5) * r2 + k4) * r2) / (1 + ((k3 * r2 + k2) * r2 + k1) * r2)
+            if icd < 0:
+                x, y = x0, y0
+                break
+            dx = 2 * p1 * x * y + p2 * (r2 + 2 * x * x)
+            dy = p1 * (r2 + 2 * y * y) + 2 * p2 * x * y
+            x, y = (x0 - dx) * icd, (y0 - dy) * icd
+        out[i] = (x, y)
+    return out
+
+
+# ---- MarkerTracker._undistort_frame (MD:93-109) ------------------------------------------------------
+def optimal_new_camera_matrix_exact(K, D, w: int, h: int) -> np.ndarray:
+    """cv2.getOptimalNewCameraMatrix(K, D, (w, h), 0, (w, h))[0]: inner rectangle of a 9 x 9 undistorted grid
+    (normalised coordinates) stretched over the image."""
+    n = 9
+    grid = np.array([[x * (w - 1) / (n - 1), y * (h - 1) / (n - 1)] for y in range(n) for x in range(n)], dtype=np.float64)
+    g = undistort_normalized_exact(K, D, grid).reshape(n, n, 2)
+    ix0, ix1 = g[:, 0, 0].max(), g[:, n - 1, 0].min()
+    iy0, iy1 = g[0, :, 1].max(), g[n - 1, :, 1].min()
+    fx0, fy0 = (w - 1) / (ix1 - ix0), (h - 1) / (iy1 - iy0)
+    return np.array([[fx0, 0.0, -fx0 * ix0], [0.0, fy0, -fy0 * iy0], [0.0, 0.0, 1.0]])
+
+
+def rectify_maps_exact(K, D, new_k, w: int, h: int):
+    """cv2.initUndistortRectifyMap(K, D, None, new_k, (w, h), CV_16SC2): (map1 int16 [h,w,2], map2 uint16 [h,w])."""
+    fx, fy, u0, v0, (k1, k2, p1, p2, k3, k4, k5, k6) = _lens(K, D)
+    nk = np.asarray(new_k, dtype=np.float64)
+    irx, iry, ox, oy = 1.0 / nk[0, 0], 1.0 / nk[1, 1], -nk[0, 2] / nk[0, 0], -nk[1, 2] / nk[1, 1]
+    j = np.arange(w, dtype=np.float64)[None, :]
+    i = np.arange(h, dtype=np.float64)[:, None]
+    x = j * irx + ox + 0 * i
+    y = i * iry + oy + 0 * j
+    x2, y2 = x * x, y * y
+    r2, xy2 = x2 + y2, 2 * x * y
+    kr = (1 + ((k3 * r2 + k2) * r2 + k1) * r2) / (1 + ((k6 * r2 + k5) * r2 + k4) * r2)
+    xd = x * kr + p1 * xy2 + p2 * (r2 + 2 * x2)
+    yd = y * kr + p1 * (r2 + 2 * y2) + p2 * xy2
+    iu = np.rint((fx * xd + u0) * 32).astype(np.int64)
+    iv = np.rint((fy * yd + v0) * 32).astype(np.int64)
+    map1 = np.stack([(iu >> 5).astype(np.int16), (iv >> 5).astype(np.int16)], axis=2)
+    map2 = ((iv & 31) * 32 + (iu & 31)).astype(np.uint16)
+    return map1, map2
+
+
+def remap_linear_exact(img: np.ndarray, map1: np.ndarray, map2: np.ndarray) -> np.ndarray:
+    """cv2.remap(img, map1, map2, INTER_LINEAR) on uint8 (BORDER_CONSTANT 0): 2^15 fixed-point bilinear weights from the
+    5-bit fractions, (sum + 2^14) >> 15, samples outside the image count as 0."""
+    H, W = img.shape[:2]
+    src = img.reshape(H, W, -1).astype(np.int64)
+    sx, sy = map1[..., 0].astype(np.int64), map1[..., 1].astype(np.int64)
+    fx, fy = (map2 & 31).astype(np.int64), ((map2 >> 5) & 31).astype(np.int64)
+    acc = 0
+    for dy, dx, wgt in ((0, 0, (32 - fx) * (32 - fy)), (0, 1, fx * (32 - fy)), (1, 0, (32 - fx) * fy), (1, 1, fx * fy)):
+        yy, xx = sy + dy, sx + dx
+        ok = (xx >= 0) & (xx < W) & (yy >= 0) & (yy < H)
+        acc = acc + (src[np.clip(yy, 0, H - 1), np.clip(xx, 0, W - 1)] * ok[..., None]) * (wgt * 32)[..., None]
+    out = ((acc + (1 << 14)) >> 15).astype(np.uint8)
+    return out.reshape(map2.shape + img.shape[2:])
 
 
 def position_3d_exact(K, R, T, u, v, diameter_px, marker_diameter_mm=2.0):

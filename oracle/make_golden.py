@@ -207,6 +207,46 @@ def video_case():
           f"video {os.path.getsize(vpath) / 1e3:.0f} kB")
 
 
+UNDISTORT_LENS = {"camera_matrix": [[520.3, 0.0, 243.1], [0.0, 518.7, 222.7], [0.0, 0.0, 1.0]],
+                  "dist_coeffs": [-0.12, 0.03, 5e-4, -3e-4, 0.0]}
+
+
+def undistorted_video_case():
+    """The same video through the UNMODIFIED reference with ``calibration_params`` configured, i.e. with the optional
+    lens correction of MD:88-109 active: golden CSV + the corrected first frame as ``_preprocess_frame`` returns it."""
+    import cv2
+    import shutil
+    import tempfile
+    md = refload.marker_detection()
+    vpath = os.path.join(OUT, "ring_video.avi")
+    tmp = tempfile.mkdtemp(prefix="vbs_vid_u_")
+    cfg = {"video_path": vpath, "output_dir": tmp, "crop_ratios": (1 / 8, 1 / 8, 1 / 16, 0), "num_layers": 5, "min_marker_distance": 20,
+           "calibration_params": UNDISTORT_LENS}
+    orig = md.cv2.destroyAllWindows
+    md.cv2.destroyAllWindows = lambda: None
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            tr = md.MarkerTracker(cfg)
+            tr.process()
+            cap = cv2.VideoCapture(vpath)
+            ok, fr = cap.read()
+            cap.release()
+            first = tr._preprocess_frame(fr)                      # width/height were set by process()
+    finally:
+        md.cv2.destroyAllWindows = orig
+    assert np.array_equal(first, port.undistort_frame(fr[30:, 80:560], UNDISTORT_LENS["camera_matrix"], UNDISTORT_LENS["dist_coeffs"]))
+    shutil.copyfile(os.path.join(tmp, "ring_video_markers.csv"), os.path.join(OUT, "ring_video_undistorted_markers.csv"))
+    np.savez_compressed(os.path.join(OUT, "ring_undistort.npz"), K=np.array(UNDISTORT_LENS["camera_matrix"]),
+                        D=np.array(UNDISTORT_LENS["dist_coeffs"]), first_frame=first)
+    import pandas as pd
+    df = pd.read_csv(os.path.join(OUT, "ring_video_undistorted_markers.csv"), float_precision="round_trip")
+    print(f"ring_video (undistorted): {len(df)} CSV rows, keys {sorted(set(zip(df.row, df.col)))}, first frame {first.shape}")
+
+
 if __name__ == "__main__":
-    main()
-    video_case()
+    import sys
+    if "--undistort-only" not in sys.argv:
+        main()
+        video_case()
+    undistorted_video_case()

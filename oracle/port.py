@@ -47,6 +47,19 @@ def crop_box(width: int, height: int, ratios) -> tuple[int, int, int, int]:
     return left, right, top, bottom
 
 
+def undistort_frame(frame: np.ndarray, camera_matrix, dist_coeffs, taps: dict | None = None) -> np.ndarray:
+    """Optional lens correction of the cropped frame (MD:93-109): new camera matrix with alpha = 0, CV_16SC2 maps,
+    bilinear remap.  The reference recomputes the maps for every frame; they only depend on (K, D, size)."""
+    K = np.array(camera_matrix)
+    D = np.array(dist_coeffs)
+    h, w = frame.shape[:2]
+    new_k, _roi = cv2.getOptimalNewCameraMatrix(K, D, (w, h), 0, (w, h))
+    map1, map2 = cv2.initUndistortRectifyMap(K, D, None, new_k, (w, h), cv2.CV_16SC2)
+    if taps is not None:
+        taps.update(new_camera_matrix=new_k, map1=map1, map2=map2)
+    return cv2.remap(frame, map1, map2, cv2.INTER_LINEAR)
+
+
 def to_gray(frame: np.ndarray) -> np.ndarray:
     """BGR -> gray as MD:114; a 2-D frame is already gray (gray-replicated BGR maps to itself)."""
     if frame.ndim == 2:

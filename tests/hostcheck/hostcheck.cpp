@@ -76,3 +76,38 @@ int hc_plane(const double *X, const double *Y, const double *Z, int n, double ou
 }
 
 }  // extern "C"
+
+extern "C" {
+
+static LensF64 make_lens(const double *K, const double *D, int nd) {
+    LensF64 c;
+    c.fx = K[0]; c.fy = K[4]; c.cx = K[2]; c.cy = K[5];
+    double d[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < nd && i < 8; ++i) d[i] = D[i];
+    c.k1 = d[0]; c.k2 = d[1]; c.p1 = d[2]; c.p2 = d[3]; c.k3 = d[4]; c.k4 = d[5]; c.k5 = d[6]; c.k6 = d[7];
+    return c;
+}
+
+// MD:93-109 geometry: new camera matrix {fx', fy', cx', cy'} and the CV_16SC2 maps
+void hc_optimal_new_camera(const double *K, const double *D, int nd, int w, int h, double out[4]) {
+    optimal_new_camera_alpha0(make_lens(K, D, nd), w, h, out);
+}
+
+void hc_rectify_maps(const double *K, const double *D, int nd, const double nk[4], int w, int h, int16_t *map1, uint16_t *map2) {
+    const LensF64 c = make_lens(K, D, nd);
+    for (int i = 0; i < h; ++i)
+        for (int j = 0; j < w; ++j) {
+            int iu, iv;
+            rectify_source_q5(c, nk, i, j, iu, iv);
+            map1[2 * ((size_t)i * w + j)] = (int16_t)(iu >> 5);
+            map1[2 * ((size_t)i * w + j) + 1] = (int16_t)(iv >> 5);
+            map2[(size_t)i * w + j] = (uint16_t)((iv & 31) * 32 + (iu & 31));
+        }
+}
+
+void hc_undistort_normalized(const double *K, const double *D, int nd, const double *uv, int n, double *out) {
+    const LensF64 c = make_lens(K, D, nd);
+    for (int i = 0; i < n; ++i) undistort_normalized(c, uv[2 * i], uv[2 * i + 1], out[2 * i], out[2 * i + 1]);
+}
+
+}  // extern "C"

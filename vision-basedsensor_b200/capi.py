@@ -49,6 +49,9 @@ SYMBOLS = {
     "vbs_set_overlap": (C.c_int, [_P, C.c_int32]),
     "vbs_submit_host": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.POINTER(VbsOutputs)]),
     "vbs_wait_host": (C.c_int, [_P]),
+    "vbs_set_undistort": (C.c_int, [_P, _P, _P, C.c_int32]),
+    "vbs_get_undistort_maps": (C.c_int, [_P, _P, _P, _P]),
+    "vbs_undistort_frames": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int64, _P]),
     "vbs_find_markers": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int64]),
     "vbs_marker_center": (C.c_int, [_P, _P, _P, C.c_int32, C.POINTER(VbsOutputs)]),
     "vbs_track_markers": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P]),

@@ -448,6 +448,12 @@ int vbs_check_taps(std::string &err) {
 cudaError_t vbs_launch_blur(vbs_ctx *ctx, const uint8_t *frames, int batch, int64_t frame_stride, int64_t row_pitch) {
     cudaError_t e = cudaMemsetAsync(ctx->area_count, 0, sizeof(uint32_t) * batch, ctx->stream);
     if (e != cudaSuccess) return e;
+    if (ctx->undist_on) {                       // MD:88-89: lens correction of the (cropped) frame comes first
+        if ((e = vbs_launch_remap(ctx, frames, batch, frame_stride, row_pitch, ctx->d_undist)) != cudaSuccess) return e;
+        frames = ctx->d_undist;
+        row_pitch = (int64_t)ctx->W * ctx->C;
+        frame_stride = row_pitch * ctx->H;
+    }
     if (ctx->big) return launch<39, 101>(ctx, frames, batch, frame_stride, row_pitch);
     return launch<21, 35>(ctx, frames, batch, frame_stride, row_pitch);
 }

@@ -33,7 +33,7 @@ int map_status(vbs_ctx *ctx, uint32_t st) {
 }
 
 void free_all(vbs_ctx *c) {
-    void *ptrs[] = {c->d_frames, c->area_bits, c->mask_bits, c->max_bits, c->open_bits, c->area_count, c->thr_lut,
+    void *ptrs[] = {c->d_frames, c->undist_map, c->d_undist, c->area_bits, c->mask_bits, c->max_bits, c->open_bits, c->area_count, c->thr_lut,
                     c->d_n64, c->d_cn64, c->d_cnfix, c->recheck, c->recheck_n, c->parent, c->parent2, c->nroots, c->rootlist, c->slot2label, c->nrec, c->recs, c->rowflag, c->d_nlabels,
                     c->d_ncont, c->lab_cnt, c->lab_sx, c->lab_sy, c->centres, c->croot, c->cell, c->claim, c->cmatch, c->cpts, c->cpn, c->euler4, c->holes, c->d_nmarkers,
                     c->marker_xy, c->marker_axes, c->ref_row, c->ref_col, c->ref_xy, c->row_det, c->row_cxy, c->row_axes, c->obs,
@@ -130,6 +130,7 @@ vbs_ctx make_view(const vbs_ctx *c, int off, cudaStream_t st) {
     v.area_bits += o * HWW; v.mask_bits += o * HWW; v.max_bits += o * HWW; v.open_bits += o * HWW;
     v.area_count += o; v.recheck += o * c->recheck_cap; v.recheck_n += o;
     v.parent += o * HW; v.parent2 += o * HW;
+    if (v.d_undist) v.d_undist += o * HW * c->C;
     v.nroots += 2 * o; v.rootlist += 2 * o * M; v.slot2label += o * M;
     v.nrec += 2 * o; v.recs += 2 * o * (size_t)c->rcap; v.rowflag += 2 * o * (size_t)((c->WW + 31) / 32) * c->H;
     v.d_nlabels += o; v.d_ncont += o;
@@ -638,6 +639,45 @@ int vbs_set_host_chunk(vbs_ctx *ctx, int32_t frames_per_chunk) {
     if (!ctx || frames_per_chunk < 0) return VBS_ERR_BAD_ARG;
     VBS_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->host_chunk = frames_per_chunk;
+    return VBS_OK;
+}
+
+// MD:93-109.  K == NULL switches the correction off again.
+int vbs_set_undistort(vbs_ctx *ctx, const double *K, const double *D, int32_t nd) {
+    if (!ctx) return VBS_ERR_BAD_ARG;
+    if (!K) { ctx->undist_on = 0; return VBS_OK; }
+    if (!D || (nd != 4 && nd != 5 && nd != 8)) return fail(ctx, VBS_ERR_BAD_ARG, "dist_coeffs must hold 4, 5 or 8 values");
+    for (int i = 0; i < 9; ++i) if (!std::isfinite(K[i])) return fail(ctx, VBS_ERR_BAD_ARG, "camera_matrix is not finite");
+    for (int i = 0; i < nd; ++i) if (!std::isfinite(D[i])) return fail(ctx, VBS_ERR_BAD_ARG, "dist_coeffs are not finite");
+    if (K[0] == 0.0 || K[4] == 0.0) return fail(ctx, VBS_ERR_BAD_ARG, "focal lengths must not be zero");
+    const size_t HW = (size_t)ctx->H * ctx->W;
+    if (!ctx->undist_map) VBS_CUDA(dalloc(&ctx->undist_map, HW));
+    if (!ctx->d_undist) VBS_CUDA(dalloc(&ctx->d_undist, (size_t)ctx->B * HW * ctx->C));
+    VBS_CUDA(vbs_undistort_setup(ctx, K, D, nd));
+    ctx->undist_on = 1;
+    return VBS_OK;
+}
+
+// the maps in OpenCV's CV_16SC2 layout (device pointers, either may be NULL) and the new camera matrix (host, 3x3 row-major)
+int vbs_get_undistort_maps(vbs_ctx *ctx, double *new_camera_matrix, int16_t *map1_device, uint16_t *map2_device) {
+    if (!ctx) return VBS_ERR_BAD_ARG;
+    if (!ctx->undist_on) return fail(ctx, VBS_ERR_STATE, "vbs_set_undistort has not been called");
+    if (new_camera_matrix) {
+        const double m[9] = {ctx->new_k[0], 0.0, ctx->new_k[2], 0.0, ctx->new_k[1], ctx->new_k[3], 0.0, 0.0, 1.0};
+        for (int i = 0; i < 9; ++i) new_camera_matrix[i] = m[i];
+    }
+    if (map1_device && map2_device) VBS_CUDA(vbs_launch_export_maps(ctx, map1_device, map2_device));
+    else if (map1_device || map2_device) return fail(ctx, VBS_ERR_BAD_ARG, "pass both maps or neither");
+    return VBS_OK;
+}
+
+// stage entry: corrected frames [batch][H][W*C] into out_device (what _preprocess_frame returns, MD:88-91)
+int vbs_undistort_frames(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int64_t frame_stride, int64_t row_pitch, uint8_t *out_device) {
+    int rc = check_batch(ctx, frames, batch);
+    if (rc != VBS_OK) return rc;
+    if (!out_device) return fail(ctx, VBS_ERR_BAD_ARG, "out_device is NULL");
+    if (!ctx->undist_on) return fail(ctx, VBS_ERR_STATE, "vbs_set_undistort has not been called");
+    VBS_CUDA(vbs_launch_remap(ctx, frames, batch, frame_stride, row_pitch, out_device));
     return VBS_OK;
 }
 

@@ -34,6 +34,10 @@ struct vbs_ctx {
     int64_t launches;
     int no_tma; int64_t tma_launches;      // VBS_NO_TMA=1 forces the generic loader; launches that used the TMA path
 
+    // optional lens correction before K1 (MD:93-109)
+    int undist_on; double new_k[4];            // fx', fy', cx', cy' of getOptimalNewCameraMatrix(alpha = 0)
+    int2 *undist_map; uint8_t *d_undist;       // [H][W] source position in 1/32 px; [B][H][W*C] corrected frames
+
     // frame staging for the host entry point
     uint8_t *d_frames; size_t frames_bytes;      // two staging buffers of host_chunk frames
     int host_chunk; cudaStream_t copy_stream; cudaEvent_t ev_copied[2], ev_consumed[2];
@@ -107,6 +111,9 @@ enum { VBS_NSTAGES = 7 };   // blur, ncc, morph, components, contours, track3d, 
 
 // launchers (each returns a cudaError_t from cudaGetLastError after the launches)
 cudaError_t vbs_launch_blur(vbs_ctx *ctx, const uint8_t *frames, int batch, int64_t frame_stride, int64_t row_pitch);
+cudaError_t vbs_undistort_setup(vbs_ctx *ctx, const double *K, const double *D, int nd);
+cudaError_t vbs_launch_export_maps(vbs_ctx *ctx, int16_t *map1, uint16_t *map2);
+cudaError_t vbs_launch_remap(vbs_ctx *ctx, const uint8_t *frames, int batch, int64_t frame_stride, int64_t row_pitch, uint8_t *out);
 cudaError_t vbs_launch_ncc(vbs_ctx *ctx, int batch);
 cudaError_t vbs_ncc_setup(vbs_ctx *ctx);
 cudaError_t vbs_launch_prepare(vbs_ctx *ctx, int batch);

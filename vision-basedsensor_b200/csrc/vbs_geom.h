@@ -337,7 +337,7 @@ struct CameraF64 {
 };
 
 VBS_HD void undistort5(const CameraF64 &c, double u, double v, double &uo, double &vo) {
-    const double x0 = (u - c.cx) / c.fx, y0 = (v - c.cy) / c.fy;
+    const double x0 = mul_rn(u - c.cx, 1.0 / c.fx), y0 = mul_rn(v - c.cy, 1.0 / c.fy);   // cv2 multiplies by 1/f (bit-exact this way)
     double x = x0, y = y0;
     for (int it = 0; it < 5; ++it) {
         const double r2 = add_rn(mul_rn(x, x), mul_rn(y, y));
@@ -351,6 +351,79 @@ VBS_HD void undistort5(const CameraF64 &c, double u, double v, double &uo, doubl
     }
     uo = add_rn(mul_rn(x, c.fx), c.cx);
     vo = add_rn(mul_rn(y, c.fy), c.cy);
+}
+
+// ---- MarkerTracker._undistort_frame (MD:93-109): lens model of the frame remap ----------------
+// float64 throughout (MD:96-97 builds K and D with np.array on Python lists); rational model k4..k6 = 0
+// unless 8 coefficients are given.
+struct LensF64 {
+    double fx, fy, cx, cy;
+    double k1, k2, p1, p2, k3, k4, k5, k6;
+};
+
+// cv2.undistortPoints(pt, K, D): 5 fixed-point iterations, normalised coordinates out
+VBS_HD void undistort_normalized(const LensF64 &c, double u, double v, double &xo, double &yo) {
+    const double x0 = mul_rn(u - c.cx, 1.0 / c.fx), y0 = mul_rn(v - c.cy, 1.0 / c.fy);
+    double x = x0, y = y0;
+    for (int it = 0; it < 5; ++it) {
+        const double r2 = add_rn(mul_rn(x, x), mul_rn(y, y));
+        const double num = add_rn(1.0, mul_rn(add_rn(mul_rn(add_rn(mul_rn(c.k6, r2), c.k5), r2), c.k4), r2));
+        const double den = add_rn(1.0, mul_rn(add_rn(mul_rn(add_rn(mul_rn(c.k3, r2), c.k2), r2), c.k1), r2));
+        const double icd = num / den;
+        if (icd < 0) { x = x0; y = y0; break; }
+        const double dx = add_rn(mul_rn(mul_rn(mul_rn(2.0, c.p1), x), y), mul_rn(c.p2, add_rn(r2, mul_rn(mul_rn(2.0, x), x))));
+        const double dy = add_rn(mul_rn(c.p1, add_rn(r2, mul_rn(mul_rn(2.0, y), y))), mul_rn(mul_rn(mul_rn(2.0, c.p2), x), y));
+        x = mul_rn(sub_rn(x0, dx), icd);
+        y = mul_rn(sub_rn(y0, dy), icd);
+    }
+    xo = x; yo = y;
+}
+
+// cv2.getOptimalNewCameraMatrix(K, D, (w,h), alpha = 0, (w,h)): the largest axis-aligned rectangle of
+// normalised coordinates that a 9 x 9 grid of undistorted image points proves to be free of invalid
+// pixels is stretched over the full image.  out = {fx', fy', cx', cy'}
+inline void optimal_new_camera_alpha0(const LensF64 &c, int w, int h, double out[4]) {
+    const int N = 9;
+    double ix0 = -1e300, ix1 = 1e300, iy0 = -1e300, iy1 = 1e300;
+    for (int y = 0; y < N; ++y)
+        for (int x = 0; x < N; ++x) {
+            double px, py;
+            undistort_normalized(c, (double)x * (w - 1) / (N - 1), (double)y * (h - 1) / (N - 1), px, py);
+            if (x == 0 && px > ix0) ix0 = px;
+            if (x == N - 1 && px < ix1) ix1 = px;
+            if (y == 0 && py > iy0) iy0 = py;
+            if (y == N - 1 && py < iy1) iy1 = py;
+        }
+    const double fx0 = (w - 1) / (ix1 - ix0), fy0 = (h - 1) / (iy1 - iy0);
+    out[0] = fx0; out[1] = fy0; out[2] = -fx0 * ix0; out[3] = -fy0 * iy0;
+}
+
+// cv2.initUndistortRectifyMap(K, D, None, newK, size, CV_16SC2) for destination pixel (column j, row i):
+// source position in 1/32 px; nk = {fx', fy', cx', cy'}
+VBS_HD void rectify_source_q5(const LensF64 &c, const double nk[4], int i, int j, int &iu, int &iv) {
+    const double irx = 1.0 / nk[0], iry = 1.0 / nk[1];                     // inverse of [[fx',0,cx'],[0,fy',cy'],[0,0,1]]
+    const double x = add_rn(mul_rn((double)j, irx), -nk[2] / nk[0]);
+    const double y = add_rn(mul_rn((double)i, iry), -nk[3] / nk[1]);
+    const double x2 = mul_rn(x, x), y2 = mul_rn(y, y), r2 = add_rn(x2, y2), xy2 = mul_rn(mul_rn(2.0, x), y);
+    const double kr = add_rn(1.0, mul_rn(add_rn(mul_rn(add_rn(mul_rn(c.k3, r2), c.k2), r2), c.k1), r2)) /
+                      add_rn(1.0, mul_rn(add_rn(mul_rn(add_rn(mul_rn(c.k6, r2), c.k5), r2), c.k4), r2));
+    const double xd = add_rn(add_rn(mul_rn(x, kr), mul_rn(c.p1, xy2)), mul_rn(c.p2, add_rn(r2, mul_rn(2.0, x2))));
+    const double yd = add_rn(add_rn(mul_rn(y, kr), mul_rn(c.p1, add_rn(r2, mul_rn(2.0, y2)))), mul_rn(c.p2, xy2));
+    const double u = add_rn(mul_rn(c.fx, xd), c.cx), v = add_rn(mul_rn(c.fy, yd), c.cy);
+    const double su = mul_rn(u, 32.0), sv = mul_rn(v, 32.0);               // cvRound(u * INTER_TAB_SIZE), saturating
+    iu = su >= 2147483647.0 ? 2147483647 : su <= -2147483648.0 ? (int)(-2147483647 - 1) : (int)rint(su);
+    iv = sv >= 2147483647.0 ? 2147483647 : sv <= -2147483648.0 ? (int)(-2147483647 - 1) : (int)rint(sv);
+}
+
+// cv2.remap(INTER_LINEAR, BORDER_CONSTANT 0) on uint8 with CV_16SC2 maps: 5-bit fractions, weights scaled
+// to 2^15 (exact products of 1/32 steps, so no table fix-up ever applies), (sum + 2^14) >> 15
+struct RemapTap { int sx, sy; int w00, w01, w10, w11; };
+VBS_HD RemapTap remap_tap(int iu, int iv) {
+    RemapTap t;
+    t.sx = (int)(short)(iu >> 5); t.sy = (int)(short)(iv >> 5);           // map1 is int16: cv2 casts, it does not saturate
+    const int fx = iu & 31, fy = iv & 31;
+    t.w00 = (32 - fx) * (32 - fy) * 32; t.w01 = fx * (32 - fy) * 32; t.w10 = (32 - fx) * fy * 32; t.w11 = fx * fy * 32;
+    return t;
 }
 
 // ---- MarkerAnalysis._calculate_3d_position (R3:195-238) ---------------------------------------

@@ -21,6 +21,7 @@ from . import pipeline as _pl
 from . import reference_state as _rs
 
 _pipes: dict = {}
+_undistort_pipes: dict = {}
 
 
 def _pipe_for(h: int, w: int, c: int, max_markers: int = 4096) -> "_pl.MarkerPipeline":
@@ -68,7 +69,28 @@ class MarkerTracker:
 
     def _preprocess_frame(self, frame):
         left, right, top, bottom = self._crop_box()
-        return frame[top:bottom, left:right]
+        cropped = frame[top:bottom, left:right]
+        if "calibration_params" in self.config:                  # MD:88-89
+            cropped = self._undistort_frame(cropped)
+        return cropped
+
+    # -- MD:93-109: lens correction (new camera matrix with alpha = 0, CV_16SC2 maps, bilinear remap) ---
+    def _undistort_frame(self, frame):
+        import torch
+        frame = np.ascontiguousarray(frame)
+        h, w = frame.shape[:2]
+        c = 1 if frame.ndim == 2 else frame.shape[2]
+        cal = self.config["calibration_params"]
+        K = np.array(cal["camera_matrix"], dtype=np.float64); D = np.array(cal["dist_coeffs"], dtype=np.float64).ravel()
+        key = (h, w, c, K.tobytes(), D.tobytes())
+        if key not in _undistort_pipes:                          # the maps are built once per (K, D, size)
+            pipe = _pl.MarkerPipeline(h, w, c, max_batch=1, max_markers=1, max_refs=1)
+            pipe.set_undistort(K, D)
+            _undistort_pipes[key] = pipe
+        pipe = _undistort_pipes[key]
+        out = pipe.undistort_frames(torch.from_numpy(frame[None]).cuda(pipe.device))
+        pipe.sync()
+        return out[0].cpu().numpy()
 
     # -- MD:111-135 --------------------------------------------------------------------------------
     @staticmethod
@@ -170,12 +192,15 @@ class MarkerTracker:
             if n == 0:
                 break
             if pipe is None:                 # first chunk: establish identities from frame 0 (MD:445-446)
-                first = MarkerTracker._marker_center(*MarkerTracker._find_markers(stage_np[0, top:bottom, left:right]))
+                first = MarkerTracker._marker_center(*MarkerTracker._find_markers(self._preprocess_frame(stage_np[0])))
                 self._process_first_frame(first)
                 keys = list(self.first_frame_markers)
                 pipe = _pl.MarkerPipeline(self.crop_height, self.crop_width, 3, max_batch=B, max_markers=4096, max_refs=len(keys))
                 pipe.set_reference([k[0] for k in keys], [k[1] for k in keys], [self.first_frame_markers[k]["Ox"] for k in keys],
                                    [self.first_frame_markers[k]["Oy"] for k in keys], self.config.get("min_marker_distance", 20))
+                if "calibration_params" in self.config:          # MD:88-89, inside the batched path
+                    cal = self.config["calibration_params"]
+                    pipe.set_undistort(cal["camera_matrix"], cal["dist_coeffs"])
                 outs = pipe.alloc_outputs(B, False)
             fs, rp = self.height * self.width * 3, self.width * 3
             res = pipe.process_host_ptr(staging.data_ptr() + top * rp + left * 3, n, fs, rp, self.frame_count, outs)

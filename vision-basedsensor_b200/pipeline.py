@@ -147,6 +147,42 @@ class MarkerPipeline:
                                                      us.ctypes.data if us is not None else None, int(bool(shell)), float(scale)))
         self.have_plane = True
 
+    def set_undistort(self, camera_matrix=None, dist_coeffs=None):
+        """Lens correction of every frame before detection, like ``_undistort_frame`` (MD:93-109);
+        ``set_undistort(None)`` switches it off.  K 3x3 and 4/5/8 distortion coefficients, float64."""
+        if camera_matrix is None:
+            capi.check(self._ctx, capi.lib.vbs_set_undistort(self._ctx, None, None, 0))
+            return
+        K = np.ascontiguousarray(np.array(camera_matrix), dtype=np.float64)          # MD:96-97
+        D = np.ascontiguousarray(np.array(dist_coeffs), dtype=np.float64).ravel()
+        if K.shape != (3, 3):
+            raise ValueError("camera_matrix must be 3x3")
+        self._follow_torch_stream()
+        capi.check(self._ctx, capi.lib.vbs_set_undistort(self._ctx, K.ctypes.data, D.ctypes.data, len(D)))
+
+    def undistort_maps(self):
+        """(new_camera_matrix [3,3] float64 host, map1 int16 [H,W,2], map2 uint16 [H,W] device) in OpenCV's CV_16SC2 layout."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        nk = np.zeros((3, 3))
+        m1 = torch.empty((self.H, self.W, 2), dtype=torch.int16, device=dev)
+        m2 = torch.empty((self.H, self.W), dtype=torch.uint16, device=dev)
+        self._follow_torch_stream()
+        capi.check(self._ctx, capi.lib.vbs_get_undistort_maps(self._ctx, nk.ctypes.data, m1.data_ptr(), m2.data_ptr()))
+        self.sync()
+        return nk, m1, m2
+
+    def undistort_frames(self, frames):
+        """Device frames [B,H,W(,3)] uint8 -> corrected frames, like ``_preprocess_frame`` after the crop (MD:88-91)."""
+        import torch
+        batch = self._geometry(frames)
+        fr = frames.contiguous()
+        out = torch.empty_like(fr)
+        self._follow_torch_stream()
+        rowb = self.W * self.C
+        capi.check(self._ctx, capi.lib.vbs_undistort_frames(self._ctx, fr.data_ptr(), batch, rowb * self.H, rowb, out.data_ptr()))
+        return out
+
     def set_overlap(self, on: bool):
         """Two-stream chunk pipelining inside process() (on by default)."""
         capi.check(self._ctx, capi.lib.vbs_set_overlap(self._ctx, int(bool(on))))
