@@ -30,25 +30,52 @@ __global__ void __launch_bounds__(256) export_maps_kernel(const int2 *__restrict
     map2[i] = (uint16_t)((m.y & 31) * 32 + (m.x & 31));
 }
 
-// one thread per output pixel; grid (ceil(W / 256), H, batch)
+// One thread = RPX consecutive output pixels of one row, for RFR frames in turn: the map entries are read once
+// per RFR frames and stay in registers; the RPX * C result bytes leave as 32-bit words when the row allows it.
+// grid (ceil(W / (RPX * 128)), H, ceil(batch / RFR)), block 128
+constexpr int RPX = 4, RFR = 8;
 template <int C>
-__global__ void __launch_bounds__(256) remap_kernel(const uint8_t *__restrict__ frames, int64_t frame_stride, int64_t row_pitch,
-                                                     const int2 *__restrict__ map, uint8_t *__restrict__ out, int H, int W) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+__global__ void __launch_bounds__(128) remap_kernel(const uint8_t *__restrict__ frames, int64_t frame_stride, int64_t row_pitch,
+                                                     const int2 *__restrict__ map, uint8_t *__restrict__ out, int H, int W, int batch) {
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * RPX, y = blockIdx.y;
     if (x >= W) return;
-    const int2 m = __ldg(map + (size_t)y * W + x);
-    const vbs::RemapTap t = vbs::remap_tap(m.x, m.y);
-    const uint8_t *src = frames + (size_t)blockIdx.z * frame_stride;
-    uint8_t *dst = out + ((size_t)blockIdx.z * H + y) * W * C + (size_t)x * C;
-    const bool x0 = t.sx >= 0 && t.sx < W, x1 = t.sx + 1 >= 0 && t.sx + 1 < W;
-    const bool y0 = t.sy >= 0 && t.sy < H, y1 = t.sy + 1 >= 0 && t.sy + 1 < H;
-    const uint8_t *r0 = src + (int64_t)t.sy * row_pitch + (int64_t)t.sx * C;
-    const uint8_t *r1 = r0 + row_pitch;
+    const int npx = min(RPX, W - x);
+    vbs::RemapTap t[RPX];
+    uint32_t ok[RPX];                                    // bit 0..3: sample (0,0) (0,1) (1,0) (1,1) lies inside the image
+    int64_t off[RPX];
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-        const int p00 = (x0 && y0) ? r0[c] : 0, p01 = (x1 && y0) ? r0[C + c] : 0;
-        const int p10 = (x0 && y1) ? r1[c] : 0, p11 = (x1 && y1) ? r1[C + c] : 0;
-        dst[c] = (uint8_t)((p00 * t.w00 + p01 * t.w01 + p10 * t.w10 + p11 * t.w11 + (1 << 14)) >> 15);
+    for (int k = 0; k < RPX; ++k) {
+        const int2 m = __ldg(map + (size_t)y * W + min(x + k, W - 1));
+        t[k] = vbs::remap_tap(m.x, m.y);
+        const bool x0 = t[k].sx >= 0 && t[k].sx < W, x1 = t[k].sx + 1 >= 0 && t[k].sx + 1 < W;
+        const bool y0 = t[k].sy >= 0 && t[k].sy < H, y1 = t[k].sy + 1 >= 0 && t[k].sy + 1 < H;
+        ok[k] = (x0 && y0 ? 1u : 0u) | (x1 && y0 ? 2u : 0u) | (x0 && y1 ? 4u : 0u) | (x1 && y1 ? 8u : 0u);
+        off[k] = (int64_t)t[k].sy * row_pitch + (int64_t)t[k].sx * C;
+    }
+    const size_t row_bytes = (size_t)W * C;
+    const bool words = npx == RPX && (row_bytes & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0;   // x * C is a multiple of 4 already
+    const int f0 = blockIdx.z * RFR, f1 = min(batch, f0 + RFR);
+    for (int f = f0; f < f1; ++f) {
+        const uint8_t *src = frames + (size_t)f * frame_stride;
+        uint8_t res[RPX * C];
+#pragma unroll
+        for (int k = 0; k < RPX; ++k) {
+            const uint8_t *r0 = src + off[k], *r1 = r0 + row_pitch;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const int p00 = (ok[k] & 1u) ? r0[c] : 0, p01 = (ok[k] & 2u) ? r0[C + c] : 0;
+                const int p10 = (ok[k] & 4u) ? r1[c] : 0, p11 = (ok[k] & 8u) ? r1[C + c] : 0;
+                res[k * C + c] = (uint8_t)((p00 * t[k].w00 + p01 * t[k].w01 + p10 * t[k].w10 + p11 * t[k].w11 + (1 << 14)) >> 15);
+            }
+        }
+        uint8_t *dst = out + ((size_t)f * H + y) * row_bytes + (size_t)x * C;
+        if (words) {
+#pragma unroll
+            for (int q = 0; q < RPX * C / 4; ++q)
+                reinterpret_cast<uint32_t *>(dst)[q] = res[4 * q] | (res[4 * q + 1] << 8) | (res[4 * q + 2] << 16) | ((uint32_t)res[4 * q + 3] << 24);
+        } else {
+            for (int q = 0; q < npx * C; ++q) dst[q] = res[q];
+        }
     }
 }
 
@@ -76,9 +103,9 @@ cudaError_t vbs_launch_export_maps(vbs_ctx *ctx, int16_t *map1, uint16_t *map2) 
 }
 
 cudaError_t vbs_launch_remap(vbs_ctx *ctx, const uint8_t *frames, int batch, int64_t frame_stride, int64_t row_pitch, uint8_t *out) {
-    const dim3 grid((ctx->W + 255) / 256, ctx->H, batch);
-    if (ctx->C == 3) remap_kernel<3><<<grid, 256, 0, ctx->stream>>>(frames, frame_stride, row_pitch, ctx->undist_map, out, ctx->H, ctx->W);
-    else remap_kernel<1><<<grid, 256, 0, ctx->stream>>>(frames, frame_stride, row_pitch, ctx->undist_map, out, ctx->H, ctx->W);
+    const dim3 grid((ctx->W + RPX * 128 - 1) / (RPX * 128), ctx->H, (batch + RFR - 1) / RFR);
+    if (ctx->C == 3) remap_kernel<3><<<grid, 128, 0, ctx->stream>>>(frames, frame_stride, row_pitch, ctx->undist_map, out, ctx->H, ctx->W, batch);
+    else remap_kernel<1><<<grid, 128, 0, ctx->stream>>>(frames, frame_stride, row_pitch, ctx->undist_map, out, ctx->H, ctx->W, batch);
     ctx->launches += 1;
     return cudaGetLastError();
 }
