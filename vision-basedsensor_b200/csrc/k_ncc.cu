@@ -36,6 +36,14 @@ constexpr int TWP = TW + TW / 8;          // padded column index: c + c/8
 constexpr float BAND = 6e-6f;             // > 80 * 2^-24 (FMA chain) + input / table roundings
 
 __constant__ float c_n32[2][96];          // template factor n, float32 (vertical pass weights); [0]: L=33, [1]: L=80
+__constant__ float2 c_n32x2[2][96];       // the same weights duplicated (n[a], n[a]): operands of the packed FFMA2
+
+// two independent float32 FMAs in one instruction (sm_100 FFMA2): acc.x += a.x * b.x, acc.y += a.y * b.y, both IEEE rn
+__device__ __forceinline__ void ffma2(float2 &acc, const float2 a, const float2 b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;"
+        : "+l"(reinterpret_cast<unsigned long long &>(acc))
+        : "l"(reinterpret_cast<const unsigned long long &>(a)), "l"(reinterpret_cast<const unsigned long long &>(b)));
+}
 
 template <int TL> struct Geo {
     static constexpr int OFF = (TL - 1) - (TL - 1) / 2;   // 40 / 16
@@ -245,9 +253,17 @@ __global__ void __launch_bounds__(NT, 3) ncc_mask_kernel(NccParams P) {
                 empty = !__any_sync(0xffffffffu, any != 0);
             }
             // partial Gaussian column sums: taps [A0, A1) of all 8 rows; ring rows A0 .. A1+6
+            // Packed form: ring rows come as float4 = two aligned pairs (h_t, h_t+1), t even.  With the accumulators
+            // paired as (row r, row r+1) one FFMA2 does  part[r] += n[t-r] h_t  and  part[r+1] += n[t-r] h_t+1  (the same
+            // tap).  Pairs with r even (E) cover the even taps of even rows / odd rows; pairs with r odd (O) plus the two
+            // singles o0, o7 cover the rest.  9 instructions per pair of ring rows instead of 16 FFMAs.
             float part[RB];
+            float2 E[4], O[3];
+            float o0 = 0.f, o7 = 0.f;
 #pragma unroll
-            for (int r = 0; r < RB; ++r) part[r] = 0.f;
+            for (int q = 0; q < 4; ++q) E[q] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) O[q] = make_float2(0.f, 0.f);
             auto vpart = [&](auto H_) {
                 constexpr int hh = decltype(H_)::value;
                 constexpr int A0 = hh == 0 ? 0 : (TL + 1) / 2 / 4 * 4;          // tap split on a 4-row unit boundary
@@ -261,18 +277,25 @@ __global__ void __launch_bounds__(NT, 3) ncc_mask_kernel(NccParams P) {
                 static_for<U0_, U1_ + 1>([&](auto U_) {
                     constexpr int u = decltype(U_)::value;
                     const float4 v = (u < wrap_at ? b0 : b1)[u * TWP];
-                    const float hv[4] = {v.x, v.y, v.z, v.w};
-                    static_for<0, 4>([&](auto E_) {
-                        constexpr int t = 4 * u + decltype(E_)::value;
-                        static_for<0, RB>([&](auto R_) {
-                            constexpr int r = decltype(R_)::value;
-                            constexpr int a = t - r;
-                            if constexpr (a >= A0 && a < A1) part[r] = fmaf(c_n32[TL == 80][a], hv[t - 4 * u], part[r]);
+                    static_for<0, 2>([&](auto P_) {
+                        constexpr int t = 4 * u + 2 * decltype(P_)::value;      // even ring row of the pair
+                        const float2 hp = decltype(P_)::value ? make_float2(v.z, v.w) : make_float2(v.x, v.y);
+                        static_for<0, 4>([&](auto Q_) {
+                            constexpr int a = t - 2 * decltype(Q_)::value;
+                            if constexpr (a >= A0 && a < A1) ffma2(E[decltype(Q_)::value], hp, c_n32x2[TL == 80][a]);
                         });
+                        static_for<0, 3>([&](auto Q_) {
+                            constexpr int a = t - 2 * decltype(Q_)::value - 1;
+                            if constexpr (a >= A0 && a < A1) ffma2(O[decltype(Q_)::value], hp, c_n32x2[TL == 80][a]);
+                        });
+                        if constexpr (t + 1 >= A0 && t + 1 < A1) o0 = fmaf(c_n32[TL == 80][t + 1], hp.y, o0);
+                        if constexpr (t - 7 >= A0 && t - 7 < A1) o7 = fmaf(c_n32[TL == 80][t - 7], hp.x, o7);
                     });
                 });
             };
             if (!empty) { if (vhalf == 0) vpart(std::integral_constant<int, 0>{}); else vpart(std::integral_constant<int, 1>{}); }
+            part[0] = E[0].x + o0;     part[1] = E[0].y + O[0].x; part[2] = E[1].x + O[0].y; part[3] = E[1].y + O[1].x;
+            part[4] = E[2].x + O[1].y; part[5] = E[2].y + O[2].x; part[6] = E[3].x + O[2].y; part[7] = E[3].y + o7;
             // swap: each half sends the partials of the 4 rows the other half decides
             {
                 float *dst = xbuf + (vhalf * VR) * TW + vcol;
@@ -459,6 +482,9 @@ cudaError_t vbs_ncc_setup(vbs_ctx *ctx) {
     err = cudaMemcpy(ctx->thr_lut, lut, sizeof(float) * NL, cudaMemcpyHostToDevice);
     delete[] lut;
     if (err != cudaSuccess) return err;
+    float2 n32x2[96];
+    for (int i = 0; i < 96; ++i) n32x2[i] = make_float2(n32[i], n32[i]);
+    if ((err = cudaMemcpyToSymbol(c_n32x2, n32x2, sizeof(float2) * 96, sizeof(float2) * 96 * (TL == 80 ? 1 : 0))) != cudaSuccess) return err;
     return cudaMemcpyToSymbol(c_n32, n32, sizeof(float) * 96, sizeof(float) * 96 * (TL == 80 ? 1 : 0));
 }
 
