@@ -598,3 +598,31 @@ def test_dense_components_overflow_the_tile_label_table():
             for a, b in zip(got, want):
                 assert a["center"] == b["center"]
                 assert pu.f32_ulps(a["major_axis"], b["major_axis"]) <= 2 and pu.f32_ulps(a["minor_axis"], b["minor_axis"]) <= 2
+
+
+# ---------------------------------------------------------------------------------------------
+# 12. nearest-marker match (MD:369-372): exact ties and near-ties resolve like cdist + argmin
+# ---------------------------------------------------------------------------------------------
+def test_track_markers_ties_match_cdist_argmin():
+    from scipy.spatial.distance import cdist
+    rng = np.random.default_rng(9)
+    refs = np.array([[100.0, 100.0], [300.25, 200.5], [50.0, 400.0], [600.0, 20.0], [333.3, 333.3]])
+    mk = [[97.0, 100.0], [103.0, 100.0],                       # exact tie for ref 0: first wins
+          [300.25, 205.5], [305.25, 200.5], [300.25, 195.5],   # three-way exact tie for ref 1
+          [50.0 + 7.0 * (1 + 2e-16), 400.0], [50.0, 407.0],    # near-tie (one ulp apart) for ref 2
+          [640.0, 20.0],                                       # farther than min_marker_distance from ref 3
+          [333.3 + 3e-13, 336.3], [333.3, 336.3 + 1e-13]]      # near-tie for ref 4
+    mk += rng.uniform(700, 900, (300, 2)).tolist()
+    mk = np.array(mk)
+    markers = [{"center": (float(x), float(y)), "major_axis": 12.0 + i, "minor_axis": 11.0, "angle": 90.0} for i, (x, y) in enumerate(mk)]
+    with pipeline.MarkerPipeline(64, 64, 1, max_batch=1, max_markers=512, max_refs=8) as pipe:
+        pipe.set_reference(np.arange(5), np.zeros(5, int), refs[:, 0], refs[:, 1], 20.0)
+        det, cxy, axes = pipe.track_markers(markers)
+    d = cdist(refs, mk)
+    for r in range(5):
+        j = int(np.argmin(d[r]))
+        if d[r, j] > 20.0:
+            assert det[r] == -1
+        else:
+            assert det[r] == j and tuple(cxy[r]) == tuple(mk[j]) and axes[r, 0] == 12.0 + j
+    assert det[3] == -1 and det[0] == 0 and det[1] == 2

@@ -10,28 +10,54 @@ namespace {
 
 using namespace vbs;
 
-__global__ void track_kernel(const double *__restrict__ ref_xy, const double *__restrict__ marker_xy,
+// block = TRACK_T reference entries of one frame; the frame's markers stream through shared memory.
+// cdist + argmin (MD:369-371) compares float64 square roots and keeps the FIRST minimum.  The scan works on
+// squared distances (uniform, branch-free): beyond a relative margin of 2^-40 the correctly rounded roots are
+// strictly ordered like the squares, so argmin of the squares is the answer unless the runner-up lies
+// within that margin of the minimum - then (practically never) the literal loop with square roots decides.
+constexpr int TRACK_T = 128, TRACK_CHUNK = 512;
+__global__ void __launch_bounds__(TRACK_T) track_kernel(const double *__restrict__ ref_xy, const double *__restrict__ marker_xy,
                              const double *__restrict__ marker_axes, const int32_t *__restrict__ nmarkers, int32_t *__restrict__ row_det,
-                             double *__restrict__ row_cxy, double *__restrict__ row_axes, int R, int M, double min_dist, size_t total) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const size_t f = i / R;
-    const int r = (int)(i % R);
-    const double ox = ref_xy[2 * r], oy = ref_xy[2 * r + 1];
+                             double *__restrict__ row_cxy, double *__restrict__ row_axes, int R, int M, double min_dist) {
+    __shared__ double2 sm[TRACK_CHUNK];
+    const size_t f = blockIdx.y;
+    const int r = blockIdx.x * TRACK_T + threadIdx.x;
+    const bool live = r < R;
+    const double ox = live ? ref_xy[2 * r] : 0.0, oy = live ? ref_xy[2 * r + 1] : 0.0;
     const int n = min(nmarkers[f], M);
-    const double *mk = marker_xy + f * (size_t)M * 2;
-    int best = -1;
-    double best_d = INFINITY;
-    for (int k = 0; k < n; ++k) {                // cdist(..)[0] then argmin: first minimum wins
-        const double dx = ox - mk[2 * k], dy = oy - mk[2 * k + 1];
-        const double d = __dsqrt_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)));
-        if (best < 0 || d < best_d) { best_d = d; best = k; }
+    const double2 *mk = reinterpret_cast<const double2 *>(marker_xy + f * (size_t)M * 2);
+    int best = -1;                               // argmin of the squares (first index on exact ties)
+    double best_sq = INFINITY, second_sq = INFINITY;     // minimum and runner-up
+    for (int k0 = 0; k0 < n; k0 += TRACK_CHUNK) {
+        const int m = min(TRACK_CHUNK, n - k0);
+        __syncthreads();
+        for (int k = threadIdx.x; k < m; k += TRACK_T) sm[k] = mk[k0 + k];
+        __syncthreads();
+        if (!live) continue;
+        for (int k = 0; k < m; ++k) {
+            const double dx = ox - sm[k].x, dy = oy - sm[k].y;
+            const double sq = add_rn(mul_rn(dx, dx), mul_rn(dy, dy));
+            second_sq = fmin(second_sq, fmax(sq, best_sq));
+            if (sq < best_sq) { best = k0 + k; best_sq = sq; }
+        }
+    }
+    if (!live) return;
+    double best_d = __dsqrt_rn(best_sq);
+    if (second_sq <= mul_rn(best_sq, 1.0 + 0x1p-40)) {      // near-tie: the reference's loop, literally
+        best = -1; best_d = INFINITY;
+        for (int k = 0; k < n; ++k) {
+            const double dx = ox - mk[k].x, dy = oy - mk[k].y;
+            const double d = __dsqrt_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)));
+            if (best < 0 || d < best_d) { best_d = d; best = k; }
+        }
     }
     if (best >= 0 && best_d > min_dist) best = -1;              // MD:372
+    const size_t i = f * R + r;
     row_det[i] = best;
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
     if (best >= 0) {
-        row_cxy[2 * i] = mk[2 * best]; row_cxy[2 * i + 1] = mk[2 * best + 1];
+        const double2 c = mk[best];
+        row_cxy[2 * i] = c.x; row_cxy[2 * i + 1] = c.y;
         const double *ax = marker_axes + (f * (size_t)M + best) * 3;
         row_axes[3 * i] = ax[0]; row_axes[3 * i + 1] = ax[1]; row_axes[3 * i + 2] = ax[2];
     } else {
@@ -249,10 +275,8 @@ cudaError_t vbs_launch_plane_points(vbs_ctx *ctx, const double *X, const double 
 cudaError_t vbs_launch_track(vbs_ctx *ctx, int batch, int64_t frameno0) {
     const int R = ctx->R;
     if (R <= 0) return cudaSuccess;
-    const size_t total = (size_t)batch * R;
-    const unsigned g = (unsigned)((total + 127) / 128);
-    track_kernel<<<g, 128, 0, ctx->stream>>>(ctx->ref_xy, ctx->marker_xy, ctx->marker_axes, ctx->d_nmarkers, ctx->row_det, ctx->row_cxy,
-                                             ctx->row_axes, R, ctx->M, ctx->min_dist, total);
+    track_kernel<<<dim3((R + TRACK_T - 1) / TRACK_T, batch), TRACK_T, 0, ctx->stream>>>(ctx->ref_xy, ctx->marker_xy, ctx->marker_axes, ctx->d_nmarkers,
+                                                                                          ctx->row_det, ctx->row_cxy, ctx->row_axes, R, ctx->M, ctx->min_dist);
     ctx->launches += 1;
     return vbs_launch_reconstruct(ctx, batch, frameno0);
 }
