@@ -2,7 +2,9 @@
 //
 // A segment is a maximal run of set bits inside one 32-bit word; its id is the pixel index of
 // its first bit, so ids live in a dense [H*W] int32 array that is only ever touched at segment
-// starts (sparse traffic, no clearing pass).  Links always point to the smaller index, hence a
+// starts (sparse traffic, no clearing pass).  The foreground is labelled in two levels: per
+// 64 x 1024-px tile in shared memory by one warp (fg_strip_kernel), then across tile edges in the
+// global array (fg_border_kernel).  Links always point to the smaller index, hence a
 // component's root is its first pixel in raster order - exactly what the reference needs:
 //   * scipy.ndimage.label numbers 4-connected components by first pixel (MD:176)  -> rank roots
 //   * cv2.findContours(RETR_EXTERNAL) starts each outer border at the blob's topmost-leftmost
