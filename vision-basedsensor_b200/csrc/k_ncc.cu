@@ -36,13 +36,13 @@ constexpr int TWP = TW + TW / 8;          // padded column index: c + c/8
 constexpr float BAND = 6e-6f;             // > 80 * 2^-24 (FMA chain) + input / table roundings
 
 __constant__ float c_n32[2][96];          // template factor n, float32 (vertical pass weights); [0]: L=33, [1]: L=80
-__constant__ float2 c_n32x2[2][96];       // the same weights duplicated (n[a], n[a]): operands of the packed FFMA2
 
-// two independent float32 FMAs in one instruction (sm_100 FFMA2): acc.x += a.x * b.x, acc.y += a.y * b.y, both IEEE rn
-__device__ __forceinline__ void ffma2(float2 &acc, const float2 a, const float2 b) {
-    asm("fma.rn.f32x2 %0, %1, %2, %0;"
+// two independent float32 FMAs in one instruction (sm_100 FFMA2), both IEEE rn:
+// acc.x += a.x * w, acc.y += a.y * w: ptxas folds the {w, w} pack into a broadcast operand (SASS `UR.F32`)
+__device__ __forceinline__ void ffma2(float2 &acc, const float2 a, const float w) {
+    asm("{ .reg .b64 t; mov.b64 t, {%2, %2}; fma.rn.f32x2 %0, %1, t, %0; }"
         : "+l"(reinterpret_cast<unsigned long long &>(acc))
-        : "l"(reinterpret_cast<const unsigned long long &>(a)), "l"(reinterpret_cast<const unsigned long long &>(b)));
+        : "l"(reinterpret_cast<const unsigned long long &>(a)), "f"(w));
 }
 
 template <int TL> struct Geo {
@@ -282,11 +282,11 @@ __global__ void __launch_bounds__(NT, 3) ncc_mask_kernel(NccParams P) {
                         const float2 hp = decltype(P_)::value ? make_float2(v.z, v.w) : make_float2(v.x, v.y);
                         static_for<0, 4>([&](auto Q_) {
                             constexpr int a = t - 2 * decltype(Q_)::value;
-                            if constexpr (a >= A0 && a < A1) ffma2(E[decltype(Q_)::value], hp, c_n32x2[TL == 80][a]);
+                            if constexpr (a >= A0 && a < A1) ffma2(E[decltype(Q_)::value], hp, c_n32[TL == 80][a]);
                         });
                         static_for<0, 3>([&](auto Q_) {
                             constexpr int a = t - 2 * decltype(Q_)::value - 1;
-                            if constexpr (a >= A0 && a < A1) ffma2(O[decltype(Q_)::value], hp, c_n32x2[TL == 80][a]);
+                            if constexpr (a >= A0 && a < A1) ffma2(O[decltype(Q_)::value], hp, c_n32[TL == 80][a]);
                         });
                         if constexpr (t + 1 >= A0 && t + 1 < A1) o0 = fmaf(c_n32[TL == 80][t + 1], hp.y, o0);
                         if constexpr (t - 7 >= A0 && t - 7 < A1) o7 = fmaf(c_n32[TL == 80][t - 7], hp.x, o7);
@@ -482,9 +482,6 @@ cudaError_t vbs_ncc_setup(vbs_ctx *ctx) {
     err = cudaMemcpy(ctx->thr_lut, lut, sizeof(float) * NL, cudaMemcpyHostToDevice);
     delete[] lut;
     if (err != cudaSuccess) return err;
-    float2 n32x2[96];
-    for (int i = 0; i < 96; ++i) n32x2[i] = make_float2(n32[i], n32[i]);
-    if ((err = cudaMemcpyToSymbol(c_n32x2, n32x2, sizeof(float2) * 96, sizeof(float2) * 96 * (TL == 80 ? 1 : 0))) != cudaSuccess) return err;
     return cudaMemcpyToSymbol(c_n32, n32, sizeof(float) * 96, sizeof(float) * 96 * (TL == 80 ? 1 : 0));
 }
 
