@@ -108,9 +108,17 @@ struct GivensLsq {
             const double aj = a[j];
             if (aj != 0.0) {
                 const double rjj = R[j][j];
-                // explicit fma everywhere: host (-ffp-contract=off) and device round identically
-                const double h = sqrt(fma(aj, aj, rjj * rjj));
+                // explicit fma everywhere: host (-ffp-contract=off) and device round alike.  The device takes the
+                // reciprocal square root (1 ulp, a third of the instructions of sqrt + divide); the fit only has to
+                // agree with cv2's SVD to ~1e-13 before its float32 outputs are rounded.
+                const double q = fma(aj, aj, rjj * rjj);
+#if defined(__CUDA_ARCH__)
+                const double inv = rsqrt(q);
+                const double h = q * inv;
+#else
+                const double h = sqrt(q);
                 const double inv = 1.0 / h;
+#endif
                 const double c = rjj * inv, sn = aj * inv;
                 R[j][j] = h;
 #if defined(__CUDA_ARCH__)
