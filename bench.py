@@ -334,6 +334,15 @@ def main():
                              "note": "ALU-bound path (integer dot products + FMA chains), see DESIGN.md; HBM fraction reported as specified"},
                 "stage_ms_per_step": {k: v / max(calls, 1) for k, v in stage.items()},
                 "gpu_launches": int(launches), "clocks": clk.summary(), "markers_per_frame": found}
+        # the binding roofline of the dominant kernel: integer-dot-product issue rate
+        csum = line["clocks"]
+        if H > 480 and csum.get("sm_mhz"):
+            idp_per_px = (284 + 544) / 8.0          # IDP.4A + IDP.2A per pixel of blur_area_kernel<39,101> (k_blur.cu)
+            sms = torch.cuda.get_device_properties(local).multi_processor_count
+            rate = idp_per_px * B * H * W / (blur_ms * 1e-3 * sms * csum["sm_mhz"] * 1e6)
+            line["roofline"]["alu"] = {"pipe": "IDP.4A/IDP.2A (fma pipe, half rate)", "achieved": rate, "peak": 62.8, "unit": "lane-instr/clk/SM",
+                                       "frac": rate / 62.8, "peak_source": "measured, profiles/r01_ubench_pipe_rates.txt",
+                                       "instr_per_pixel": idp_per_px}
 
     # ---- e2e: host frames -> results on the host through the public API, copies in the timed region
     if not args.no_e2e:

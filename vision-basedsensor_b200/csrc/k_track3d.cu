@@ -10,45 +10,94 @@ namespace {
 
 using namespace vbs;
 
-// block = TRACK_T reference entries of one frame; the frame's markers stream through shared memory.
-// cdist + argmin (MD:369-371) compares float64 square roots and keeps the FIRST minimum.  The scan works on
-// squared distances (uniform, branch-free): beyond a relative margin of 2^-40 the correctly rounded roots are
-// strictly ordered like the squares, so argmin of the squares is the answer unless the runner-up lies
-// within that margin of the minimum - then (practically never) the literal loop with square roots decides.
-constexpr int TRACK_T = 128, TRACK_CHUNK = 512;
-__global__ void __launch_bounds__(TRACK_T) track_kernel(const double *__restrict__ ref_xy, const double *__restrict__ marker_xy,
-                             const double *__restrict__ marker_axes, const int32_t *__restrict__ nmarkers, int32_t *__restrict__ row_det,
-                             double *__restrict__ row_cxy, double *__restrict__ row_axes, int R, int M, double min_dist) {
-    __shared__ double2 sm[TRACK_CHUNK];
-    const size_t f = blockIdx.y;
-    const int r = blockIdx.x * TRACK_T + threadIdx.x;
-    const bool live = r < R;
-    const double ox = live ? ref_xy[2 * r] : 0.0, oy = live ? ref_xy[2 * r + 1] : 0.0;
+// ---- MarkerTracker._track_markers (MD:349-396): nearest marker per reference entry --------------------
+// cdist + argmin (MD:369-371) compares float64 square roots, keeps the FIRST minimum and then rejects it when it is
+// farther than min_marker_distance (MD:372).  Only markers within that distance can therefore be returned, so the
+// markers of a frame are binned into square cells of side >= min_marker_distance and a reference entry looks at
+// the 3 x 3 cells around its own (cell indices are clamped, which never separates two points by more than their
+// distance).  Inside the scan the comparison runs on squared distances: beyond a relative margin of 2^-40 the
+// correctly rounded roots are strictly ordered like the squares; when the runner-up is within that margin
+// (practically never) the candidates are compared again by their rounded roots, smallest index first.
+constexpr int BIN_MAX_CELLS = 8192;
+struct BinGrid { double inv_cell; int gx, gy; };
+
+__device__ __forceinline__ int bin_coord(double v, double inv_cell, int g) {
+    const double c = floor(v * inv_cell);
+    return c < 0.0 ? 0 : (c >= (double)g ? g - 1 : (int)c);       // NaN compares false twice -> (int)NaN is 0 on the GPU
+}
+
+// one CTA per frame: counting sort of the marker indices by cell
+__global__ void __launch_bounds__(256) bin_kernel(const double *__restrict__ marker_xy, const int32_t *__restrict__ nmarkers, BinGrid g,
+                                                   int32_t *__restrict__ cell_start, int32_t *__restrict__ cell_items, int M) {
+    __shared__ int32_t cnt[BIN_MAX_CELLS];
+    __shared__ int32_t part[256];
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const int nc = g.gx * g.gy;
     const int n = min(nmarkers[f], M);
+    const double2 *mk = reinterpret_cast<const double2 *>(marker_xy + (size_t)f * M * 2);
+    for (int c = tid; c < nc; c += 256) cnt[c] = 0;
+    __syncthreads();
+    for (int k = tid; k < n; k += 256) {
+        const double2 p = mk[k];
+        atomicAdd(&cnt[bin_coord(p.y, g.inv_cell, g.gy) * g.gx + bin_coord(p.x, g.inv_cell, g.gx)], 1);
+    }
+    __syncthreads();
+    // exclusive scan: every thread owns a contiguous slice of cells
+    const int per = (nc + 255) / 256, c0 = tid * per, c1 = min(nc, c0 + per);
+    int sum = 0;
+    for (int c = c0; c < c1; ++c) sum += cnt[c];
+    part[tid] = sum;
+    __syncthreads();
+    if (tid == 0) { int run = 0; for (int i = 0; i < 256; ++i) { const int v = part[i]; part[i] = run; run += v; } }
+    __syncthreads();
+    int32_t *start = cell_start + (size_t)f * (BIN_MAX_CELLS + 1);
+    int run = part[tid];
+    for (int c = c0; c < c1; ++c) { const int v = cnt[c]; start[c] = run; cnt[c] = run; run += v; }     // cnt becomes the fill cursor
+    if (tid == 255) start[nc] = n;
+    __syncthreads();
+    int32_t *items = cell_items + (size_t)f * M;
+    for (int k = tid; k < n; k += 256) {
+        const double2 p = mk[k];
+        items[atomicAdd(&cnt[bin_coord(p.y, g.inv_cell, g.gy) * g.gx + bin_coord(p.x, g.inv_cell, g.gx)], 1)] = k;
+    }
+}
+
+__global__ void __launch_bounds__(128) track_kernel(const double *__restrict__ ref_xy, const double *__restrict__ marker_xy,
+                             const double *__restrict__ marker_axes, const int32_t *__restrict__ cell_start, const int32_t *__restrict__ cell_items,
+                             BinGrid g, int32_t *__restrict__ row_det, double *__restrict__ row_cxy, double *__restrict__ row_axes,
+                             int R, int M, double min_dist) {
+    const size_t f = blockIdx.y;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const double ox = ref_xy[2 * r], oy = ref_xy[2 * r + 1];
     const double2 *mk = reinterpret_cast<const double2 *>(marker_xy + f * (size_t)M * 2);
-    int best = -1;                               // argmin of the squares (first index on exact ties)
-    double best_sq = INFINITY, second_sq = INFINITY;     // minimum and runner-up
-    for (int k0 = 0; k0 < n; k0 += TRACK_CHUNK) {
-        const int m = min(TRACK_CHUNK, n - k0);
-        __syncthreads();
-        for (int k = threadIdx.x; k < m; k += TRACK_T) sm[k] = mk[k0 + k];
-        __syncthreads();
-        if (!live) continue;
-        for (int k = 0; k < m; ++k) {
-            const double dx = ox - sm[k].x, dy = oy - sm[k].y;
+    const int32_t *start = cell_start + f * (BIN_MAX_CELLS + 1);
+    const int32_t *items = cell_items + f * M;
+    const int cx = bin_coord(ox, g.inv_cell, g.gx), cy = bin_coord(oy, g.inv_cell, g.gy);
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.gx - 1), y0 = max(cy - 1, 0), y1 = min(cy + 1, g.gy - 1);
+    int best = -1;
+    double best_sq = INFINITY, second_sq = INFINITY;
+    for (int y = y0; y <= y1; ++y) {
+        const int i0 = start[y * g.gx + x0], i1 = start[y * g.gx + x1 + 1];      // the cells of one row are contiguous
+        for (int i = i0; i < i1; ++i) {
+            const int k = items[i];
+            const double dx = ox - mk[k].x, dy = oy - mk[k].y;
             const double sq = add_rn(mul_rn(dx, dx), mul_rn(dy, dy));
-            second_sq = fmin(second_sq, fmax(sq, best_sq));
-            if (sq < best_sq) { best = k0 + k; best_sq = sq; }
+            if (sq < best_sq || (sq == best_sq && k < best)) { second_sq = best_sq; best_sq = sq; best = k; }
+            else second_sq = fmin(second_sq, sq);
         }
     }
-    if (!live) return;
     double best_d = __dsqrt_rn(best_sq);
-    if (second_sq <= mul_rn(best_sq, 1.0 + 0x1p-40)) {      // near-tie: the reference's loop, literally
+    if (best >= 0 && second_sq <= mul_rn(best_sq, 1.0 + 0x1p-40)) {       // near-tie: compare the rounded roots, first index wins
         best = -1; best_d = INFINITY;
-        for (int k = 0; k < n; ++k) {
-            const double dx = ox - mk[k].x, dy = oy - mk[k].y;
-            const double d = __dsqrt_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)));
-            if (best < 0 || d < best_d) { best_d = d; best = k; }
+        for (int y = y0; y <= y1; ++y) {
+            const int i0 = start[y * g.gx + x0], i1 = start[y * g.gx + x1 + 1];
+            for (int i = i0; i < i1; ++i) {
+                const int k = items[i];
+                const double dx = ox - mk[k].x, dy = oy - mk[k].y;
+                const double d = __dsqrt_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)));
+                if (best < 0 || d < best_d || (d == best_d && k < best)) { best_d = d; best = k; }
+            }
         }
     }
     if (best >= 0 && best_d > min_dist) best = -1;              // MD:372
@@ -275,8 +324,21 @@ cudaError_t vbs_launch_plane_points(vbs_ctx *ctx, const double *X, const double 
 cudaError_t vbs_launch_track(vbs_ctx *ctx, int batch, int64_t frameno0) {
     const int R = ctx->R;
     if (R <= 0) return cudaSuccess;
-    track_kernel<<<dim3((R + TRACK_T - 1) / TRACK_T, batch), TRACK_T, 0, ctx->stream>>>(ctx->ref_xy, ctx->marker_xy, ctx->marker_axes, ctx->d_nmarkers,
-                                                                                          ctx->row_det, ctx->row_cxy, ctx->row_axes, R, ctx->M, ctx->min_dist);
+    // cells of side >= min_marker_distance (and >= 32 px), few enough to fit the CTA's shared-memory histogram
+    double cell = ctx->min_dist > 32.0 ? ctx->min_dist : 32.0;
+    if (!(cell < 1e300)) cell = 1e300;
+    BinGrid g;
+    for (;;) {
+        const double gx = ceil(ctx->W / cell), gy = ceil(ctx->H / cell);
+        g.gx = gx < 1.0 ? 1 : (int)gx; g.gy = gy < 1.0 ? 1 : (int)gy;
+        if ((long long)g.gx * g.gy <= BIN_MAX_CELLS) break;
+        cell *= 2.0;
+    }
+    g.inv_cell = 1.0 / cell;
+    bin_kernel<<<batch, 256, 0, ctx->stream>>>(ctx->marker_xy, ctx->d_nmarkers, g, ctx->cell_start, ctx->cell_items, ctx->M);
+    track_kernel<<<dim3((R + 127) / 128, batch), 128, 0, ctx->stream>>>(ctx->ref_xy, ctx->marker_xy, ctx->marker_axes, ctx->cell_start, ctx->cell_items, g,
+                                                                          ctx->row_det, ctx->row_cxy, ctx->row_axes, R, ctx->M, ctx->min_dist);
+    ctx->launches += 1;
     ctx->launches += 1;
     return vbs_launch_reconstruct(ctx, batch, frameno0);
 }
