@@ -465,7 +465,10 @@ def test_tma_path_is_used_and_equals_generic_loader(monkeypatch):
         capi.check(pipe._ctx, capi.lib.vbs_process_device(pipe._ctx, big.data_ptr() + 3, 3, H * (W + 16), W + 16, 0, __import__("ctypes").byref(outs[1])))
         pipe.sync()
         assert pipe.tma_launches == 0
-        assert np.array_equal(outs[0]["marker_xy"].cpu().numpy(), a.marker_xy)
+        got_n, got_xy = outs[0]["n_markers"].cpu().numpy(), outs[0]["marker_xy"].cpu().numpy()
+        assert np.array_equal(got_n, a.n_markers)
+        for f in range(3):
+            assert np.array_equal(got_xy[f, : got_n[f]], a.marker_xy[f, : got_n[f]])
 
 
 # ---------------------------------------------------------------------------------------------

@@ -2,6 +2,7 @@
 // ellipse fit (four re-traces, nothing stored), then centre <-> ellipse matching and compaction
 // of the marker list in the reference's output order.  Replaces MD:196-243.
 #include "vbs_ctx.h"
+#include "vbs_bin.cuh"
 
 namespace {
 
@@ -98,58 +99,68 @@ __global__ void contour_fit_kernel(const uint32_t *__restrict__ open_bits, const
 }
 
 // ---- 3. nearest centroid inside the contour polygon and inside the (minor/10)^2 gate (MD:222-237) --
-// block = MATCH_T contour slots of one frame; the frame's centroids stream through shared memory
-constexpr int MATCH_T = 128, MATCH_CHUNK = 512;
+// One thread per contour slot.  The gate d^2 < (minor/10)^2 only admits centroids within minor/10 of the ellipse
+// centre, so the frame's centroids are binned into cells (vbs_bin.cuh) and a slot whose gate radius fits a cell
+// looks at the 3 x 3 cells around its centre; larger blobs scan all centroids.  Pass 1 keeps the centroids inside
+// the gate (rarely more than one), pass 2 runs the polygon tests on them in index order with the reference's
+// running minimum - testing inside the scan would serialise the 32 slots of a warp.
+constexpr int MATCH_T = 128;
 __global__ void __launch_bounds__(MATCH_T) match_kernel(const uint32_t *__restrict__ open_bits, const int32_t *__restrict__ croot,
                              const uint32_t *__restrict__ cpts, const int32_t *__restrict__ cpn,
                              const double *__restrict__ cell, const double *__restrict__ centres,
-                             const int32_t *__restrict__ nlabels, int32_t *__restrict__ cmatch, int32_t *__restrict__ claim,
+                             const int32_t *__restrict__ nlabels, const int32_t *__restrict__ bin_start, const int32_t *__restrict__ bin_items,
+                             BinGrid g, int32_t *__restrict__ cmatch, int32_t *__restrict__ claim,
                              int H, int W, int WW, int M, uint32_t *status) {
-    __shared__ double2 sc[MATCH_CHUNK];               // (row, col) of MATCH_CHUNK centroids
     const int f = blockIdx.y;
     const int slot = blockIdx.x * MATCH_T + threadIdx.x;
-    const size_t i = (size_t)f * M + min(slot, M - 1);
+    if (slot >= M) return;
+    const size_t i = (size_t)f * M + slot;
     const double *c = cell + i * 6;
-    const bool live = slot < M && c[5] != 0.0;
-    if (slot < M) cmatch[i] = -1;
-    if (!__syncthreads_or(live)) return;
-    double ecx = 0.0, ecy = 0.0, gate = 0.0;
-    int np = 0;
-    if (live) {
-        ecx = c[0]; ecy = c[1];
-        const double tenth = c[3] / 10.0;
-        gate = mul_rn(tenth, tenth);
-        np = cpn[i];
-    }
+    cmatch[i] = -1;
+    if (c[5] == 0.0) return;
+    const double ecx = c[0], ecy = c[1];
+    const double tenth = c[3] / 10.0;
+    const double gate = mul_rn(tenth, tenth);
+    const int np = cpn[i];
     const int n = min(nlabels[f], M);
-    // Pass 1 keeps the centroids inside the distance gate (rarely more than one); pass 2 runs the
-    // polygon tests in index order with the reference's running minimum.  Testing inside the scan
-    // would serialise the 32 slots of a warp, whose hits sit at 32 different loop indices.
+    const double2 *cen = reinterpret_cast<const double2 *>(centres + (size_t)f * M * 2);     // (row, col)
     constexpr int NC = 4;
-    int ck[NC]; double cd[NC], cx[NC], cy[NC];
+    int ck[NC]; double cd[NC];
     int ncand = 0;
-    const double2 *cen = reinterpret_cast<const double2 *>(centres + (size_t)f * M * 2);
-    for (int j0 = 0; j0 < n; j0 += MATCH_CHUNK) {
-        const int m = min(MATCH_CHUNK, n - j0);
-        __syncthreads();
-        for (int k = threadIdx.x; k < m; k += MATCH_T) sc[k] = cen[j0 + k];
-        __syncthreads();
-        if (!live) continue;
-        for (int k = 0; k < m; ++k) {
-            const double y = sc[k].x, x = sc[k].y;
-            const double dx = x - ecx, dy = y - ecy;
-            const double d = add_rn(mul_rn(dx, dx), mul_rn(dy, dy));
-            if (d < gate) {
+    auto consider = [&](int j) {
+        const double y = cen[j].x, x = cen[j].y;
+        const double dx = x - ecx, dy = y - ecy;
+        const double d = add_rn(mul_rn(dx, dx), mul_rn(dy, dy));
+        if (d < gate) {
 #pragma unroll
-                for (int q = 0; q < NC; ++q)
-                    if (q == ncand) { ck[q] = j0 + k; cd[q] = d; cx[q] = x; cy[q] = y; }
-                ++ncand;
-            }
+            for (int q = 0; q < NC; ++q)
+                if (q == ncand) { ck[q] = j; cd[q] = d; }
+            ++ncand;
         }
+    };
+    if (tenth <= g.cell) {
+        const int32_t *start = bin_start + (size_t)f * (BIN_MAX_CELLS + 1);
+        const int32_t *items = bin_items + (size_t)f * M;
+        const int cx = bin_coord(ecx, g.inv_cell, g.gx), cy = bin_coord(ecy, g.inv_cell, g.gy);
+        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.gx - 1), y0 = max(cy - 1, 0), y1 = min(cy + 1, g.gy - 1);
+        for (int y = y0; y <= y1; ++y) {
+            const int i0 = start[y * g.gx + x0], i1 = start[y * g.gx + x1 + 1];      // the cells of one grid row are contiguous
+            for (int k = i0; k < i1; ++k) consider(items[k]);
+        }
+        // bins hold the indices in arbitrary order: the reference visits the centroids by ascending index
+#pragma unroll
+        for (int a = 1; a < NC; ++a)
+#pragma unroll
+            for (int b = NC - 1; b >= a; --b)
+                if (b < ncand && ck[b] < ck[b - 1]) {
+                    const int tk = ck[b]; ck[b] = ck[b - 1]; ck[b - 1] = tk;
+                    const double td = cd[b]; cd[b] = cd[b - 1]; cd[b - 1] = td;
+                }
+    } else {
+        for (int j = 0; j < n; ++j) consider(j);
     }
-    if (!live) return;
-    auto inside = [&](double x, double y) {
-        PointPolygon pp; pp.init(x, y);
+    auto inside = [&](int j) {
+        PointPolygon pp; pp.init(cen[j].y, cen[j].x);
         if (np <= PCAP) {
             StoredSource src{cpts + i * PCAP, np};
             src(pp);
@@ -166,13 +177,13 @@ __global__ void __launch_bounds__(MATCH_T) match_kernel(const uint32_t *__restri
     if (ncand <= NC) {
 #pragma unroll
         for (int q = 0; q < NC; ++q)
-            if (q < ncand && cd[q] < best_d && inside(cx[q], cy[q])) { best = ck[q]; best_d = cd[q]; }
+            if (q < ncand && cd[q] < best_d && inside(ck[q])) { best = ck[q]; best_d = cd[q]; }
     } else {                                        // more candidates than registers: the literal loop
         for (int j = 0; j < n; ++j) {
             const double y = cen[j].x, x = cen[j].y;
             const double dx = x - ecx, dy = y - ecy;
             const double d = add_rn(mul_rn(dx, dx), mul_rn(dy, dy));
-            if (d < gate && d < best_d && inside(x, y)) { best = j; best_d = d; }
+            if (d < gate && d < best_d && inside(j)) { best = j; best_d = d; }
         }
     }
     cmatch[i] = best;
@@ -221,8 +232,12 @@ cudaError_t vbs_launch_contours(vbs_ctx *ctx, int batch, int which) {
         ctx->launches += 2;
     }
     if (which & 4) {
-        match_kernel<<<dim3((ctx->M + MATCH_T - 1) / MATCH_T, batch), MATCH_T, 0, ctx->stream>>>(ctx->open_bits, ctx->croot, ctx->cpts, ctx->cpn, ctx->cell, ctx->centres, ctx->d_nlabels,
-                                                   ctx->cmatch, ctx->claim, ctx->H, ctx->W, ctx->WW, ctx->M, ctx->d_status);
+        const BinGrid g = make_bin_grid(ctx->W, ctx->H, 32.0);
+        bin_kernel<true><<<batch, 256, 0, ctx->stream>>>(ctx->centres, ctx->d_nlabels, g, ctx->cbin_start, ctx->cbin_items, ctx->M);
+        match_kernel<<<dim3((ctx->M + MATCH_T - 1) / MATCH_T, batch), MATCH_T, 0, ctx->stream>>>(ctx->open_bits, ctx->croot, ctx->cpts, ctx->cpn, ctx->cell, ctx->centres,
+                                                   ctx->d_nlabels, ctx->cbin_start, ctx->cbin_items, g, ctx->cmatch, ctx->claim, ctx->H, ctx->W, ctx->WW, ctx->M,
+                                                   ctx->d_status);
+        ctx->launches += 1;
         compact_kernel<<<(batch + 3) / 4, 128, 0, ctx->stream>>>(ctx->cell, ctx->cmatch, ctx->centres, ctx->d_ncont, ctx->d_nmarkers,
                                                                  ctx->marker_xy, ctx->marker_axes, ctx->M, batch);
         ctx->launches += 2;

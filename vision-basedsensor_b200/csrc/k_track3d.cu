@@ -5,6 +5,7 @@
 //   disp_kernel   : last-seen displacement along the frame axis                              R3:262-314
 //   plane_kernel  : deviation end points + least-squares plane + tilt                        FD:196-204,219-232,141-159
 #include "vbs_ctx.h"
+#include "vbs_bin.cuh"
 
 namespace {
 
@@ -18,50 +19,6 @@ using namespace vbs;
 // distance).  Inside the scan the comparison runs on squared distances: beyond a relative margin of 2^-40 the
 // correctly rounded roots are strictly ordered like the squares; when the runner-up is within that margin
 // (practically never) the candidates are compared again by their rounded roots, smallest index first.
-constexpr int BIN_MAX_CELLS = 8192;
-struct BinGrid { double inv_cell; int gx, gy; };
-
-__device__ __forceinline__ int bin_coord(double v, double inv_cell, int g) {
-    const double c = floor(v * inv_cell);
-    return c < 0.0 ? 0 : (c >= (double)g ? g - 1 : (int)c);       // NaN compares false twice -> (int)NaN is 0 on the GPU
-}
-
-// one CTA per frame: counting sort of the marker indices by cell
-__global__ void __launch_bounds__(256) bin_kernel(const double *__restrict__ marker_xy, const int32_t *__restrict__ nmarkers, BinGrid g,
-                                                   int32_t *__restrict__ cell_start, int32_t *__restrict__ cell_items, int M) {
-    __shared__ int32_t cnt[BIN_MAX_CELLS];
-    __shared__ int32_t part[256];
-    const int f = blockIdx.x, tid = threadIdx.x;
-    const int nc = g.gx * g.gy;
-    const int n = min(nmarkers[f], M);
-    const double2 *mk = reinterpret_cast<const double2 *>(marker_xy + (size_t)f * M * 2);
-    for (int c = tid; c < nc; c += 256) cnt[c] = 0;
-    __syncthreads();
-    for (int k = tid; k < n; k += 256) {
-        const double2 p = mk[k];
-        atomicAdd(&cnt[bin_coord(p.y, g.inv_cell, g.gy) * g.gx + bin_coord(p.x, g.inv_cell, g.gx)], 1);
-    }
-    __syncthreads();
-    // exclusive scan: every thread owns a contiguous slice of cells
-    const int per = (nc + 255) / 256, c0 = tid * per, c1 = min(nc, c0 + per);
-    int sum = 0;
-    for (int c = c0; c < c1; ++c) sum += cnt[c];
-    part[tid] = sum;
-    __syncthreads();
-    if (tid == 0) { int run = 0; for (int i = 0; i < 256; ++i) { const int v = part[i]; part[i] = run; run += v; } }
-    __syncthreads();
-    int32_t *start = cell_start + (size_t)f * (BIN_MAX_CELLS + 1);
-    int run = part[tid];
-    for (int c = c0; c < c1; ++c) { const int v = cnt[c]; start[c] = run; cnt[c] = run; run += v; }     // cnt becomes the fill cursor
-    if (tid == 255) start[nc] = n;
-    __syncthreads();
-    int32_t *items = cell_items + (size_t)f * M;
-    for (int k = tid; k < n; k += 256) {
-        const double2 p = mk[k];
-        items[atomicAdd(&cnt[bin_coord(p.y, g.inv_cell, g.gy) * g.gx + bin_coord(p.x, g.inv_cell, g.gx)], 1)] = k;
-    }
-}
-
 __global__ void __launch_bounds__(128) track_kernel(const double *__restrict__ ref_xy, const double *__restrict__ marker_xy,
                              const double *__restrict__ marker_axes, const int32_t *__restrict__ cell_start, const int32_t *__restrict__ cell_items,
                              BinGrid g, int32_t *__restrict__ row_det, double *__restrict__ row_cxy, double *__restrict__ row_axes,
@@ -324,22 +281,12 @@ cudaError_t vbs_launch_plane_points(vbs_ctx *ctx, const double *X, const double 
 cudaError_t vbs_launch_track(vbs_ctx *ctx, int batch, int64_t frameno0) {
     const int R = ctx->R;
     if (R <= 0) return cudaSuccess;
-    // cells of side >= min_marker_distance (and >= 32 px), few enough to fit the CTA's shared-memory histogram
-    double cell = ctx->min_dist > 32.0 ? ctx->min_dist : 32.0;
-    if (!(cell < 1e300)) cell = 1e300;
-    BinGrid g;
-    for (;;) {
-        const double gx = ceil(ctx->W / cell), gy = ceil(ctx->H / cell);
-        g.gx = gx < 1.0 ? 1 : (int)gx; g.gy = gy < 1.0 ? 1 : (int)gy;
-        if ((long long)g.gx * g.gy <= BIN_MAX_CELLS) break;
-        cell *= 2.0;
-    }
-    g.inv_cell = 1.0 / cell;
-    bin_kernel<<<batch, 256, 0, ctx->stream>>>(ctx->marker_xy, ctx->d_nmarkers, g, ctx->cell_start, ctx->cell_items, ctx->M);
+    const BinGrid g = make_bin_grid(ctx->W, ctx->H, ctx->min_dist);      // cells of side >= min_marker_distance
+    bin_kernel<false><<<batch, 256, 0, ctx->stream>>>(ctx->marker_xy, ctx->d_nmarkers, g, ctx->cell_start, ctx->cell_items, ctx->M);
     track_kernel<<<dim3((R + 127) / 128, batch), 128, 0, ctx->stream>>>(ctx->ref_xy, ctx->marker_xy, ctx->marker_axes, ctx->cell_start, ctx->cell_items, g,
                                                                           ctx->row_det, ctx->row_cxy, ctx->row_axes, R, ctx->M, ctx->min_dist);
     ctx->launches += 1;
-    ctx->launches += 1;
+    ctx->launches += 2;
     return vbs_launch_reconstruct(ctx, batch, frameno0);
 }
 

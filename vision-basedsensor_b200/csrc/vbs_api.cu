@@ -9,7 +9,13 @@
 
 namespace {
 
-template <class T> cudaError_t dalloc(T **p, size_t n) { *p = nullptr; return cudaMalloc((void **)p, (n ? n : 1) * sizeof(T)); }
+// zero-filled device allocation: padding entries of the per-frame tables (beyond n_markers / n_labels) read as 0
+template <class T> cudaError_t dalloc(T **p, size_t n) {
+    *p = nullptr;
+    const size_t bytes = (n ? n : 1) * sizeof(T);
+    cudaError_t e = cudaMalloc((void **)p, bytes);
+    return e != cudaSuccess ? e : cudaMemset(*p, 0, bytes);
+}
 
 int fail(vbs_ctx *ctx, int code, const char *msg) { ctx->err = msg; return code; }
 
@@ -36,7 +42,7 @@ void free_all(vbs_ctx *c) {
     void *ptrs[] = {c->d_frames, c->undist_map, c->d_undist, c->area_bits, c->mask_bits, c->max_bits, c->open_bits, c->area_count, c->thr_lut,
                     c->d_n64, c->d_cn64, c->d_cnfix, c->recheck, c->recheck_n, c->parent, c->parent2, c->nroots, c->rootlist, c->slot2label, c->nrec, c->recs, c->rowflag, c->d_nlabels,
                     c->d_ncont, c->lab_cnt, c->lab_sx, c->lab_sy, c->centres, c->croot, c->cell, c->claim, c->cmatch, c->cpts, c->cpn, c->euler4, c->holes, c->d_nmarkers,
-                    c->marker_xy, c->marker_axes, c->ref_row, c->ref_col, c->ref_xy, c->row_det, c->row_cxy, c->row_axes, c->cell_start, c->cell_items, c->obs,
+                    c->marker_xy, c->marker_axes, c->ref_row, c->ref_col, c->ref_xy, c->row_det, c->row_cxy, c->row_axes, c->cell_start, c->cell_items, c->cbin_start, c->cbin_items, c->obs,
                     c->pos3d, c->pos_flags, c->last_seen, c->pl_ref, c->pl_start, c->pl_dvert, c->pl_use, c->plane, c->plane_n,
                     c->d_status};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -138,7 +144,7 @@ vbs_ctx make_view(const vbs_ctx *c, int off, cudaStream_t st) {
     v.croot += o * M; v.cell += o * M * 6; v.claim += o * M; v.cmatch += o * M; v.cpts += o * M * 128; v.cpn += o * M;
     v.euler4 += o; v.holes += o;
     v.d_nmarkers += o; v.marker_xy += o * M * 2; v.marker_axes += o * M * 3;
-    v.cell_start += o * 8193; v.cell_items += o * M;
+    v.cell_start += o * 8193; v.cell_items += o * M; v.cbin_start += o * 8193; v.cbin_items += o * M;
     v.row_det += o * R; v.row_cxy += o * R * 2; v.row_axes += o * R * 3; v.obs += o * R * 3;
     v.pos3d += o * R * 7; v.pos_flags += o * R; v.plane += o * 4; v.plane_n += o;
     return v;
@@ -362,6 +368,7 @@ int vbs_create(vbs_ctx **out, const vbs_config *cfg) {
     VBS_CUDA(dalloc(&ctx->ref_row, R)); VBS_CUDA(dalloc(&ctx->ref_col, R)); VBS_CUDA(dalloc(&ctx->ref_xy, R * 2));
     VBS_CUDA(dalloc(&ctx->row_det, B * R)); VBS_CUDA(dalloc(&ctx->row_cxy, B * R * 2)); VBS_CUDA(dalloc(&ctx->row_axes, B * R * 3));
     VBS_CUDA(dalloc(&ctx->cell_start, B * 8193)); VBS_CUDA(dalloc(&ctx->cell_items, B * M));
+    VBS_CUDA(dalloc(&ctx->cbin_start, B * 8193)); VBS_CUDA(dalloc(&ctx->cbin_items, B * M));
     VBS_CUDA(dalloc(&ctx->obs, B * R * 3)); VBS_CUDA(dalloc(&ctx->pos3d, B * R * 7)); VBS_CUDA(dalloc(&ctx->pos_flags, B * R));
     VBS_CUDA(dalloc(&ctx->last_seen, R * 4));
     VBS_CUDA(dalloc(&ctx->pl_ref, R * 3)); VBS_CUDA(dalloc(&ctx->pl_start, R * 3)); VBS_CUDA(dalloc(&ctx->pl_dvert, R * 3));

@@ -79,6 +79,7 @@ struct vbs_ctx {
     int32_t *ref_row, *ref_col; double *ref_xy;
     int32_t *row_det; double *row_cxy; double *row_axes;  // [B][R]...
     int32_t *cell_start, *cell_items;                     // [B][8193] first item of every cell, [B][M] marker indices sorted by cell (k_track3d.cu)
+    int32_t *cbin_start, *cbin_items;                     // the same for the ring centroids (centre <-> ellipse match, k_contour.cu)
     double *obs;                     // [B][R][3] undistorted u, v and diameter of each observation
     // camera / 3D
     int have_cam; vbs::CameraF64 cam; int warmup; int64_t first_frame; int have_first;
