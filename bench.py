@@ -229,9 +229,18 @@ def main():
 
     torch.cuda.set_device(local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # the version banner goes to stdout; rank 0 prints exactly one line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # rank 0 prints exactly one line: keep NCCL's version banner (written to fd 1 when the communicator comes up)
+        # and any debug output off stdout
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.all_reduce(torch.zeros(1, device=torch.device("cuda", local)))
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
     dev = torch.device("cuda", local)
     B = args.batch
     pipe = pipeline.MarkerPipeline(H, W, 1, max_batch=B, max_markers=max(512, 2 * n_markers), max_refs=max(64, n_markers), device=local)
