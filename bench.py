@@ -202,7 +202,10 @@ def main():
     config = {"workload": f"{args.workload}: {H}x{W} gray u8, {rows}x{cols} markers, batch {args.batch}/GPU, "
                           f"{args.unique} unique synthetic frames tiled; tracking+IDs -> 3D displacement -> plane tilt",
               "batch_per_gpu": args.batch, "l2_policy": "inputs larger than L2 (batch of frames = %.0f MB/GPU)" % (args.batch * H * W / 1e6),
-              "parallelism": f"frame-sharded x{world}"}
+              "parallelism": f"frame-sharded x{world}",
+              "schedule": "sequential stages" if os.environ.get("VBS_BRANCH_OVERLAP", "")[:1] == "0" else
+                          "open-mask branch (open, blobs, contours, ellipse fits) on a second stream beside the NCC; stage_ms_per_step "
+                          "attributes that time to ncc_mask"}
 
     if args.impl == "reference":
         if rank != 0:

@@ -635,3 +635,36 @@ def test_track_markers_ties_match_cdist_argmin():
         else:
             assert det[r] == j and tuple(cxy[r]) == tuple(mk[j]) and axes[r, 0] == 12.0 + j
     assert det[3] == -1 and det[0] == 0 and det[1] == 2
+
+
+# ---------------------------------------------------------------------------------------------
+# 13. the two-stream schedule (open-mask branch beside the NCC) and the sequential one give the same tables
+# ---------------------------------------------------------------------------------------------
+def test_branch_overlap_equals_sequential_schedule(monkeypatch):
+    frames = synth.workload_frames("small_6x8", 4, seed0=61)
+    H, W = frames.shape[1:]
+    x = torch_cuda(frames)
+    keys, xy = pu.grid_reference(port.find_markers_frame(frames[0]), 8)
+    K, D, R, T = synth.synthetic_camera()
+
+    def run():
+        with pipeline.MarkerPipeline(H, W, 1, max_batch=4, max_markers=256, max_refs=len(keys)) as pipe:
+            pipe.set_reference([k[0] for k in keys], [k[1] for k in keys], xy[:, 0], xy[:, 1], 20.0)
+            pipe.set_camera(K, D, R, T, 2.0, 5.0, 50.0, warmup_frames=0)
+            res = pipe.process(x, 0); pipe.sync()
+            opened = pipe.debug_stage(capi.STAGE_OPENED, 4).cpu().numpy()
+            labels = pipe.debug_stage(capi.STAGE_LABELS, 4).cpu().numpy()
+            return res.to_host(), opened, labels
+
+    a, a_open, a_lab = run()                                   # default: overlapped
+    monkeypatch.setenv("VBS_BRANCH_OVERLAP", "0")
+    b, b_open, b_lab = run()
+    assert np.array_equal(a_open, b_open) and np.array_equal(a_lab, b_lab)
+    for k in ("n_labels", "n_markers", "row_det", "pos_flags"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    for f in range(4):
+        n = int(a.n_markers[f])
+        assert n >= 40 and np.array_equal(a.marker_xy[f, :n], b.marker_xy[f, :n]) and np.array_equal(a.marker_axes[f, :n], b.marker_axes[f, :n])
+    assert np.array_equal(a.row_cxy, b.row_cxy, equal_nan=True) and np.array_equal(a.pos3d, b.pos3d, equal_nan=True)
+    want = [port.find_markers_frame(f) for f in frames]
+    assert [len(w) for w in want] == a.n_markers.tolist()

@@ -332,9 +332,10 @@ int vbs_create(vbs_ctx **out, const vbs_config *cfg) {
     ctx->br = ctx->big ? VbsBranch{39, 101, 80, 13.0, 20, 200, 14} : VbsBranch{21, 35, 33, 7.4, 35, 180, 8};
     ctx->min_dist = 20.0;
     { const char *e = getenv("VBS_NO_TMA"); ctx->no_tma = (e && e[0] == '1') ? 1 : 0; }
-    // measured on B200: running the open-mask branch beside the NCC stretches the NCC from 3.4 to 4.9 ms and
-    // the step from 10.5 to 10.7 ms (same SM resources), so it is opt-in: VBS_BRANCH_OVERLAP=1
-    { const char *e = getenv("VBS_BRANCH_OVERLAP"); ctx->no_branch_overlap = (e && e[0] == '1') ? 0 : 1; }
+    // The open-mask branch (5x5 open, blobs, border following, ellipse fits) needs K1 only and runs on a second,
+    // high-priority stream beside the NCC: the NCC stretches from 3.0 to 3.7 ms but the 0.9 ms of small latency-bound
+    // kernels disappear behind it (8.41 -> 8.26 ms per 256 frames on B200).  VBS_BRANCH_OVERLAP=0 runs them in sequence.
+    { const char *e = getenv("VBS_BRANCH_OVERLAP"); ctx->no_branch_overlap = (e && e[0] == '0') ? 1 : 0; }
     ctx->first_frame = 0; ctx->have_first = 0;
     *out = ctx;                                    // returned even on failure so vbs_last_error works; caller destroys
     if (vbs_check_taps(ctx->err) != 0) return VBS_ERR_INTERNAL;
