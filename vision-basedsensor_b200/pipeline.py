@@ -184,7 +184,8 @@ class MarkerPipeline:
         return out
 
     def set_overlap(self, on: bool):
-        """Two-stream chunk pipelining inside process() (on by default)."""
+        """Two-stream chunk pipelining of device-resident batches inside process() (off by default: measured slower on
+        B200; the branch-level overlap of the open-mask kernels with the NCC is always on unless VBS_BRANCH_OVERLAP=0)."""
         capi.check(self._ctx, capi.lib.vbs_set_overlap(self._ctx, int(bool(on))))
 
     def set_host_chunk(self, frames_per_chunk: int):
