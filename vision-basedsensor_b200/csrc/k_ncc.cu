@@ -117,7 +117,6 @@ __global__ void __launch_bounds__(NT, 3) ncc_mask_kernel(NccParams P) {
     double *cn = reinterpret_cast<double *>(ringB + G::NR * TWP);                // [CNX] float64 prefix sums (border formula)
     int4 *fx = reinterpret_cast<int4 *>(cn + G::CNX + (G::CNX & 1));             // [4][FXN/4] shifted fixed-point copies
     float *xbuf = reinterpret_cast<float *>(fx + FXN);                           // [2][VR][TW] partial sums in flight
-    int *sbuf = reinterpret_cast<int *>(xbuf + 2 * VR * TW);                     // [VR][TW] box sums for half 1
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int x0 = blockIdx.x * TW;
@@ -358,7 +357,9 @@ __global__ void __launch_bounds__(NT, 3) ncc_mask_kernel(NccParams P) {
             const int yw = y0 + lane;
             if (lane < VR && yw < ye && wx < WW) P.mask_bits[((size_t)f * H + yw) * WW + wx] = myword;
         }
-        __syncthreads();                         // the next horizontal step overwrites the oldest ring group
+        // No barrier here: the next horizontal step overwrites the oldest ring group, whose last readers (the
+        // vertical pass of this step) all finished before the barrier of the partial-sum swap; the swap buffer is
+        // rewritten only after the next step's post-H barrier.
         if (++gw == G::NR) gw = 0;
     }
 }
