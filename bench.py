@@ -385,9 +385,9 @@ def main():
             r = pipe.process_host_ptr(pin.data_ptr(), B, H * W, W, s * B, houts[0])
         dts = (time.perf_counter() - t1) / min(args.steps, 10)
         if world > 1:
-            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            t = torch.tensor([dt, dts], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+            dt, dts = float(t[0].item()), float(t[1].item())
         if rank == 0:
             d2h = sum(a.nbytes for a in houts[0][0].values())
             line["e2e"] = {"value": world * B * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(B * H * W),
