@@ -446,6 +446,7 @@ int vbs_check_taps(std::string &err) {
 }
 
 cudaError_t vbs_launch_blur(vbs_ctx *ctx, const uint8_t *frames, int batch, int64_t frame_stride, int64_t row_pitch) {
+    VbsRange range("vbs:blur");
     cudaError_t e = cudaMemsetAsync(ctx->area_count, 0, sizeof(uint32_t) * batch, ctx->stream);
     if (e != cudaSuccess) return e;
     if (ctx->undist_on) {                       // MD:88-89: lens correction of the (cropped) frame comes first

@@ -547,6 +547,7 @@ cudaError_t vbs_launch_prepare(vbs_ctx *ctx, int batch) {
 // which: bit 0 = ring-maxima image (labels, centroids), bit 1 = opened area mask (blobs, contour order, holes,
 // background pass).  The two are independent, so they may run on different streams after vbs_launch_prepare.
 cudaError_t vbs_launch_components(vbs_ctx *ctx, int batch, int which) {
+    VbsRange range("vbs:components");
     const int H = ctx->H, W = ctx->W, WW = ctx->WW, M = ctx->M;
     const dim3 wb(64, 4);
     const dim3 eg((WW + 1 + 63) / 64, (H + 1 + 4 * EU_ROWS - 1) / (4 * EU_ROWS), batch);

@@ -223,6 +223,7 @@ __global__ void compact_kernel(const double *__restrict__ cell, const int32_t *_
 // which: bit 1 = follow + fit the blobs of the opened mask (open branch), bit 2 = match centroids to
 // ellipses and compact the marker list (needs both branches)
 cudaError_t vbs_launch_contours(vbs_ctx *ctx, int batch, int which) {
+    VbsRange range("vbs:contours");
     const dim3 grid((ctx->M + 63) / 64, batch);
     if (which & 2) {
         contour_trace_kernel<<<grid, 64, 0, ctx->stream>>>(ctx->open_bits, ctx->parent2, ctx->croot, ctx->d_ncont, ctx->holes, ctx->cpts,

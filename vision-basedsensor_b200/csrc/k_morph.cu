@@ -162,6 +162,7 @@ __global__ void unpack_labels_kernel(const uint32_t *__restrict__ bits, const in
 
 // which: bit 0 = ring maxima of the NCC mask (needs K2), bit 1 = 5x5 open of the area mask (needs K1 only)
 cudaError_t vbs_launch_morph(vbs_ctx *ctx, int batch, int which) {
+    VbsRange range("vbs:morphology");
     const dim3 block(32, TY);
     if (which & 1) {
         const dim3 gm((ctx->WW + 31) / 32, (ctx->H + TH - 1) / TH, batch);

@@ -487,6 +487,7 @@ cudaError_t vbs_ncc_setup(vbs_ctx *ctx) {
 }
 
 cudaError_t vbs_launch_ncc(vbs_ctx *ctx, int batch) {
+    VbsRange range("vbs:ncc");
     if (ctx->big) return launch<80>(ctx, batch, ctx->st2);
     return launch<33>(ctx, batch, ctx->st2);
 }

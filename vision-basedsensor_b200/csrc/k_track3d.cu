@@ -279,6 +279,7 @@ cudaError_t vbs_launch_plane_points(vbs_ctx *ctx, const double *X, const double 
 }
 
 cudaError_t vbs_launch_track(vbs_ctx *ctx, int batch, int64_t frameno0) {
+    VbsRange range("vbs:track");
     const int R = ctx->R;
     if (R <= 0) return cudaSuccess;
     const BinGrid g = make_bin_grid(ctx->W, ctx->H, ctx->min_dist);      // cells of side >= min_marker_distance
@@ -292,6 +293,7 @@ cudaError_t vbs_launch_track(vbs_ctx *ctx, int batch, int64_t frameno0) {
 
 // R3:240-316 + FD:138-162 on the tracking rows currently in ctx->row_* (batch x R)
 cudaError_t vbs_launch_reconstruct(vbs_ctx *ctx, int batch, int64_t frameno0) {
+    VbsRange range("vbs:reconstruct");
     const int R = ctx->R;
     if (R <= 0) return cudaSuccess;
     const size_t total = (size_t)batch * R;

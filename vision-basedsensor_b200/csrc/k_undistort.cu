@@ -103,6 +103,7 @@ cudaError_t vbs_launch_export_maps(vbs_ctx *ctx, int16_t *map1, uint16_t *map2) 
 }
 
 cudaError_t vbs_launch_remap(vbs_ctx *ctx, const uint8_t *frames, int batch, int64_t frame_stride, int64_t row_pitch, uint8_t *out) {
+    VbsRange range("vbs:undistort");
     const dim3 grid((ctx->W + RPX * 128 - 1) / (RPX * 128), ctx->H, (batch + RFR - 1) / RFR);
     if (ctx->C == 3) remap_kernel<3><<<grid, 128, 0, ctx->stream>>>(frames, frame_stride, row_pitch, ctx->undist_map, out, ctx->H, ctx->W, batch);
     else remap_kernel<1><<<grid, 128, 0, ctx->stream>>>(frames, frame_stride, row_pitch, ctx->undist_map, out, ctx->H, ctx->W, batch);

@@ -5,6 +5,16 @@
 #include <string>
 #include "../../include/vbs.h"
 #include "vbs_geom.h"
+#include <nvtx3/nvToolsExt.h>
+
+// NVTX range around the launches of one stage (header-only NVTX 3: a no-op unless a profiler is attached;
+// `ncu --nvtx --nvtx-include "vbs:blur/"` or an nsys timeline then groups the kernels by stage)
+struct VbsRange {
+    explicit VbsRange(const char *name) { nvtxRangePushA(name); }
+    ~VbsRange() { nvtxRangePop(); }
+    VbsRange(const VbsRange &) = delete;
+    VbsRange &operator=(const VbsRange &) = delete;
+};
 
 // device-side status bits (OR-ed into ctx->d_status by kernels)
 enum : uint32_t {
