@@ -31,9 +31,12 @@ def parse():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="1080p_20x20")
+    ap.add_argument("--workload", default="1080p_20x20", help="1080p_20x20 (BASELINE config 2, the headline), 4k_40x72 (config 4), "
+                    "stream64k (config 5: a 65 536-frame 1080p sequence in contiguous shards, last-seen exchange, NCCL gather of records + tilt)")
     ap.add_argument("--batch", type=int, default=256)
-    ap.add_argument("--unique", type=int, default=16, help="distinct synthetic frames tiled to the batch")
+    ap.add_argument("--frames", type=int, default=65536, help="stream64k: frames of the whole job")
+    ap.add_argument("--unique", type=int, default=32, help="distinct synthetic frames tiled to the batch (the 32 frames of seed 0..31 are the "
+                    "ones tests/test_gpu_parity.py checks against the oracle, stage by stage)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU-baseline budget (bounded sample)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
@@ -165,8 +168,17 @@ def cpu_single_process(frames, keys, xy, cam_params, plane_params, budget_s):
     return n / dt, n, cv2.getNumThreads()
 
 
+def _cpu_tail_job(args):
+    rows, cam_params, plane_params, keys = args
+    cpu_tail(rows, cam_params, plane_params, keys)
+    return len(rows)
+
+
 def reference_arm(args, frames, keys, xy, cam_params, plane_params):
-    """--impl reference: every host core (spawn pool, one OpenCV thread each; fork deadlocks after cv2 ran)."""
+    """--impl reference: every host core (spawn pool, one OpenCV thread each; fork deadlocks after cv2 ran).
+    The 3D + plane tail of a step runs in the pool as well, one slice of the step's frames per worker (each
+    slice starts its last-seen table empty, so it emits one displacement row per marker fewer than a
+    sequential pass - 1/len(slice) of the tail's work, in the CPU arm's favour)."""
     import multiprocessing as mp
     ncpu = os.cpu_count() or 1
     per_step = 2 * ncpu
@@ -175,7 +187,8 @@ def reference_arm(args, frames, keys, xy, cam_params, plane_params):
         def step(s):
             jobs = [(frames[(s * per_step + i) % len(frames)], keys, xy, s * per_step + i, 1) for i in range(per_step)]
             rows = pool.map(_cpu_frame, jobs, chunksize=1)
-            cpu_tail(rows, cam_params, plane_params, keys)
+            k = max(1, len(rows) // ncpu)
+            pool.map(_cpu_tail_job, [(rows[i:i + k], cam_params, plane_params, keys) for i in range(0, len(rows), k)], chunksize=1)
         for s in range(max(args.warmup, 1)):
             step(s)
         t0 = time.perf_counter()
@@ -184,6 +197,156 @@ def reference_arm(args, frames, keys, xy, cam_params, plane_params):
         dt = time.perf_counter() - t0
     fps = per_step * args.steps / dt
     return fps, dt, per_step, ncpu
+
+
+def periodic_ok(t, period, start=0):
+    """Frames repeat with `period` (unique frames tiled): record rows of frame f and f + period must be
+    byte-identical (NaN-safe: compared as raw bytes).  Size-independent check over the whole batch / stream."""
+    import torch
+    if t is None or t.shape[0] <= start + period:
+        return True
+    a = t[start:-period].contiguous().view(torch.uint8)
+    b = t[start + period:].contiguous().view(torch.uint8)
+    return bool(torch.equal(a, b))
+
+
+def setup_pipe(args, frames_u, H, W, rows, cols, local, B, warmup_frames=0):
+    """Context + reference state (detections of frame 0, GPU path) + camera + plane baseline."""
+    import torch
+    from vbs_b200 import pipeline, reference_state, synth
+    dev = torch.device("cuda", local)
+    n_markers = rows * cols
+    pipe = pipeline.MarkerPipeline(H, W, 1, max_batch=B, max_markers=max(512, 2 * n_markers), max_refs=max(64, n_markers), device=local)
+    r0 = pipe.process(torch.from_numpy(frames_u[:1]).to(dev), 0)
+    pipe.sync()
+    h0 = r0.to_host()
+    keys, xy = reference_state.grid_ids(h0.marker_xy[0, : int(h0.n_markers[0])], cols)
+    pipe.set_reference([k[0] for k in keys], [k[1] for k in keys], xy[:, 0], xy[:, 1], 20.0)
+    cam_params = synth.synthetic_camera()
+    pipe.set_camera(*cam_params, 2.0, 5.0, 50.0, warmup_frames=0)
+    r0 = pipe.process(torch.from_numpy(frames_u[:1]).to(dev), 0)
+    pipe.sync()
+    start = np.nan_to_num(r0.to_host().pos3d[0, :, :3])
+    ref_xyz = np.stack([(xy[:, 0] - W / 2) / 11.0, (xy[:, 1] - H / 2) / 11.0, np.zeros(len(xy))], 1)
+    if warmup_frames:
+        pipe.set_camera(*cam_params, 2.0, 5.0, 50.0, warmup_frames=warmup_frames)
+    pipe.set_plane(ref_xyz, start, np.zeros_like(start))
+    return pipe, keys, xy, (ref_xyz, start, np.zeros_like(start))
+
+
+def init_dist(world, local):
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    if world > 1:
+        # rank 0 prints exactly one line: keep NCCL's version banner (written to fd 1 when the communicator comes up)
+        # and any debug output off stdout
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dev = torch.device("cuda", local)
+            dist.init_process_group("nccl", device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))
+            warm = torch.zeros(8, device=dev)
+            dist.gather(warm, [torch.empty_like(warm) for _ in range(world)] if dist.get_rank() == 0 else None, dst=0)
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
+
+
+def stream_main(args, rank, world, local):
+    """BASELINE config 5: `--frames` 1080p frames in contiguous shards (one per GPU), processed batch by batch,
+    last-seen state patched across shard boundaries, records + plane tilt gathered to rank 0 over NCCL - all
+    inside the timed region.  One step = one pass over the whole stream."""
+    import torch
+    import torch.distributed as dist
+    from vbs_b200 import sharding, streaming
+    geom = "1080p_20x20"
+    frames_u, (H, W, rows, cols) = workload_setup(geom, args.unique)
+    init_dist(world, local)
+    dev = torch.device("cuda", local)
+    B, U, N = args.batch, args.unique, args.frames
+    assert B % U == 0 and all((sharding.shard_bounds(N, r, world)[0] % B) == 0 for r in range(world)), "shards must start on a batch boundary"
+    pipe, keys, xy, plane_params = setup_pipe(args, frames_u, H, W, rows, cols, local, B, warmup_frames=100)   # R3:22 default warm-up
+    R = pipe.R
+    frames_d = torch.from_numpy(np.ascontiguousarray(np.tile(frames_u, (B // U, 1, 1)))).to(dev)      # frame g of the stream = unique frame g % U
+
+    def frames_of(lo, hi):
+        return frames_d[lo % B: lo % B + (hi - lo)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stream = torch.cuda.current_stream()
+    warm_frames = min(N, 2 * B * world)
+    for _ in range(max(args.warmup, 1)):               # short warm-up streams: kernels, NCCL gather and all_gather paths
+        streaming.run_stream(pipe, frames_of, warm_frames, B, rank, world)
+    pipe.sync()
+    pipe.set_profiling(True)
+    l0 = pipe.kernel_launches
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clk_sampler = Clocks(local)
+    steps = max(1, min(args.steps, 3))
+    barrier()
+    with clk_sampler as clk:
+        e0.record(stream)
+        for _ in range(steps):
+            got, rec = streaming.run_stream(pipe, frames_of, N, B, rank, world)
+        e1.record(stream)
+        barrier()
+    ms = e0.elapsed_time(e1)
+    pipe.sync()
+    stage, calls = pipe.stage_ms()
+    pipe.set_profiling(False)
+    launches = pipe.kernel_launches - l0
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    fps = N * steps / (ms * 1e-3)
+    if rank == 0:
+        # size-independent checks over the WHOLE gathered stream (shard boundaries included): past the warm-up window
+        # every record repeats with the period of the unique frames - also the displacement rows, whose first one per
+        # shard comes from the last-seen exchange (vbs_fix_displacement) rather than from the shard's own table
+        chk = {k: periodic_ok(got[k], U, start=100 + U + 1) for k in ("row_det", "row_cxy", "row_axes", "pos3d", "pos_flags", "plane", "n_markers")}
+        flags = got["pos_flags"]
+        rows3d = int(((flags & 4) != 0).sum().item())
+        tilt_ok = int(torch.isfinite(got["plane"][100:, 3]).sum().item())
+        found = (int(got["n_markers"].min().item()), int(got["n_markers"].max().item()))
+        peak, peak_src = peaks()
+        b_alg = H * W + 96 * rows * cols + 32
+        blur_ms = stage["blur_dog_area"] / max(calls, 1)
+        frames_per_launch = min(B, sharding.shard_bounds(N, 0, world)[1])
+        ach = frames_per_launch * b_alg / (blur_ms * 1e-3) / 1e9
+        rec_bytes = sum(int(v.numel() * v.element_size()) for v in got.values())
+        line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 1),
+                "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "u8 (integer blur/labels) + f32/f64 (NCC, geometry)", "data": "synthetic",
+                "config": {"workload": f"stream64k: {N} frames of {H}x{W} gray u8 ({rows}x{cols} markers, {U} unique oracle-checked frames tiled on the "
+                                       f"device), contiguous shards of {N // world} frames per GPU, batches of {B}; tracking+IDs -> 3D displacement "
+                                       f"(warm-up 100 frames, last-seen exchange across shards) -> plane tilt; NCCL gather of records + tilt to rank 0 in the timed region",
+                           "batch_per_gpu": B, "frames": N, "l2_policy": "inputs larger than L2 (batch of frames = %.0f MB/GPU)" % (B * H * W / 1e6),
+                           "parallelism": f"frame-sharded x{world}", "gathered_bytes": rec_bytes},
+                "roofline": {"bound": "hbm", "kernel": "blur_area_kernel<39,101> (gray -> DoG -> area mask)", "achieved": ach, "peak": peak, "unit": "GB/s",
+                             "frac": ach / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": frames_per_launch * b_alg,
+                             "kernel_ms": blur_ms, "note": "ALU-bound path, see DESIGN.md"},
+                "stage_ms_per_batch": {k: v / max(calls, 1) for k, v in stage.items()}, "gpu_launches": int(launches), "clocks": clk.summary(),
+                "markers_per_frame": found, "checks": {"periodic_records": chk, "displacement_rows": rows3d, "frames_with_tilt": tilt_ok,
+                                                        "frames_gathered": int(flags.shape[0])}}
+        ok = all(chk.values()) and rows3d > 0 and flags.shape[0] == N and found == (rows * cols, rows * cols)
+        line["checks"]["ok"] = bool(ok)
+        print(json.dumps(line))
+        if not ok:
+            sys.exit("stream check failed: " + json.dumps(line["checks"]))
+    pipe.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():
@@ -195,7 +358,10 @@ def main():
     import vbs_b200  # noqa: F401
     from vbs_b200 import synth, reference_state
 
-    frames_u, (H, W, rows, cols) = workload_setup(args.workload, args.unique)
+    if args.workload == "stream64k" and args.impl != "reference":
+        return stream_main(args, rank, world, local)
+    geom = "1080p_20x20" if args.workload == "stream64k" else args.workload
+    frames_u, (H, W, rows, cols) = workload_setup(geom, args.unique)
     n_markers = rows * cols
     b_alg = H * W * 1 + 96 * n_markers + 32             # SURVEY 8d algorithmic bytes per frame (gray input)
     cam_params = synth.synthetic_camera()
@@ -221,50 +387,24 @@ def main():
                 "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8/f64 (OpenCV, SciPy, NumPy)", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": fps, "unit": UNIT, "cores": ncpu, "kind": "port",
-                                 "sample": f"{per_step} frames per step x {args.steps} steps, spawn pool of {ncpu} processes, cv2.setNumThreads(1)"},
+                                 "sample": f"{per_step} frames per step x {args.steps} steps, spawn pool of {ncpu} processes, cv2.setNumThreads(1); "
+                                           "detection, ID match, 3D rows and plane fit all inside the pool"},
                 "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         print(json.dumps(line))
         return
 
     import torch
     import torch.distributed as dist
-    from vbs_b200 import pipeline
+    from vbs_b200 import sharding
 
-    torch.cuda.set_device(local)
-    if world > 1:
-        # rank 0 prints exactly one line: keep NCCL's version banner (written to fd 1 when the communicator comes up)
-        # and any debug output off stdout
-        sys.stdout.flush()
-        saved = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-            dist.all_reduce(torch.zeros(1, device=torch.device("cuda", local)))
-            torch.cuda.synchronize()
-        finally:
-            os.dup2(saved, 1)
-            os.close(saved)
+    init_dist(world, local)
     dev = torch.device("cuda", local)
     B = args.batch
-    pipe = pipeline.MarkerPipeline(H, W, 1, max_batch=B, max_markers=max(512, 2 * n_markers), max_refs=max(64, n_markers), device=local)
+    pipe, keys, xy, plane_params = setup_pipe(args, frames_u, H, W, rows, cols, local, B)
     stream = torch.cuda.current_stream()
     if args.overlap:
         pipe.set_overlap(True)
     # MarkerPipeline.process() launches on torch's current stream, so the events below bracket the work
-
-    # reference state = detections of frame 0 (GPU path), camera, plane baseline
-    r0 = pipe.process(torch.from_numpy(frames_u[:1]).to(dev), 0)
-    pipe.sync()
-    h0 = r0.to_host()
-    keys, xy = reference_state.grid_ids(h0.marker_xy[0, : int(h0.n_markers[0])], cols)
-    pipe.set_reference([k[0] for k in keys], [k[1] for k in keys], xy[:, 0], xy[:, 1], 20.0)
-    pipe.set_camera(*cam_params, 2.0, 5.0, 50.0, warmup_frames=0)
-    r0 = pipe.process(torch.from_numpy(frames_u[:1]).to(dev), 0)
-    pipe.sync()
-    start = np.nan_to_num(r0.to_host().pos3d[0, :, :3])
-    ref_xyz = np.stack([(xy[:, 0] - W / 2) / 11.0, (xy[:, 1] - H / 2) / 11.0, np.zeros(len(xy))], 1)
-    pipe.set_plane(ref_xyz, start, np.zeros_like(start))
-    plane_params = (ref_xyz, start, np.zeros_like(start))
     if args.undistort:                  # a nearly distortion-free lens: the frames stay detectable, the remap cost is the same
         pipe.set_undistort([[0.9 * W, 0, W / 2 + 0.3], [0, 0.9 * W, H / 2 - 0.2], [0, 0, 1]], [-2e-3, 1e-4, 1e-5, -1e-5, 0.0])
         config["workload"] += "; WITH optional lens correction (side measurement)"
@@ -273,20 +413,18 @@ def main():
     host_frames = np.ascontiguousarray(np.tile(frames_u, (reps, 1, 1))[:B])
     frames_d = torch.from_numpy(host_frames).to(dev)
     outs = pipe.alloc_outputs(B, True)
-    R = pipe.R
-    rec_bytes = B * (R * (7 * 8 + 1 + 4 + 2 * 8 + 3 * 8) + 4 * 8 + 4 + 4)
+    REC = ("pos3d", "pos_flags", "row_det", "row_cxy", "row_axes", "plane", "plane_n", "n_markers")
 
-    from vbs_b200 import sharding
-
-    def gather(res):
-        """NCCL gather of the per-frame records (3D field, flags, IDs, plane) to rank 0."""
+    def gather(arrays):
+        """NCCL gather of the per-frame records (3D field, flags, IDs, tracking rows, plane) to rank 0."""
         if world > 1:
-            sharding.gather_records({"pos3d": res.pos3d, "pos_flags": res.pos_flags, "row_det": res.row_det, "plane": res.plane}, rank, world)
+            return sharding.gather_records({k: arrays[k] for k in REC}, rank, world)
+        return arrays
 
     def step(s):
         pipe.reset_sequence() if s == 0 else None
         res = pipe.process(frames_d, frameno0=(rank * args.steps + s) * B, out=outs)
-        gather(res)
+        gather(outs[0])
         return res
 
     def barrier():
@@ -320,9 +458,14 @@ def main():
         ms = float(t.item())
     fps = world * B * args.steps / (ms * 1e-3)
 
-    # sanity inside the bench: every frame of the batch found the whole array
+    # sanity inside the bench: every frame of the batch found the whole array, and the records of the tiled batch
+    # repeat with the period of the unique frames (the unique frames themselves are checked against the oracle,
+    # stage by stage, in tests/test_gpu_parity.py::test_full_1080p_batch256_properties - same seeds)
     hres = res.to_host()
     found = int(hres.n_markers.min()), int(hres.n_markers.max())
+    U = len(frames_u)
+    periodic = {k: periodic_ok(outs[0][k][:, :found[0]] if k.startswith("marker_") else outs[0][k], U, start=1 if k in ("pos3d", "pos_flags") else 0)
+                for k in ("n_markers", "marker_xy", "marker_axes", "row_det", "row_cxy", "plane", "pos3d", "pos_flags")}
 
     line = None
     if rank == 0:
@@ -345,7 +488,8 @@ def main():
                              "whole_path_achieved": whole, "whole_path_frac": whole / peak,
                              "note": "ALU-bound path (integer dot products + FMA chains), see DESIGN.md; HBM fraction reported as specified"},
                 "stage_ms_per_step": {k: v / max(calls, 1) for k, v in stage.items()},
-                "gpu_launches": int(launches), "clocks": clk.summary(), "markers_per_frame": found}
+                "gpu_launches": int(launches), "clocks": clk.summary(), "markers_per_frame": found,
+                "checks": {"periodic_records": periodic, "ok": bool(all(periodic.values()) and found == (n_markers, n_markers))}}
         # the binding roofline of the dominant kernel: integer-dot-product issue rate
         csum = line["clocks"]
         if H > 480 and csum.get("sm_mhz"):
@@ -356,46 +500,77 @@ def main():
                                        "frac": rate / 62.8, "peak_source": "measured, profiles/r01_ubench_pipe_rates.txt",
                                        "instr_per_pixel": idp_per_px}
 
-    # ---- e2e: host frames -> results on the host through the public API, copies in the timed region
+    # ---- e2e: host frames -> records on the host (rank 0's host for N > 1) through the public API, all copies and the
+    #      NCCL gather in the timed region
     if not args.no_e2e:
         pin = torch.from_numpy(host_frames).pin_memory()
-        houts = [pipe.alloc_outputs(B, False), pipe.alloc_outputs(B, False)]
+        on_dev = world > 1                                  # N > 1: records land in device memory, are gathered over NCCL, then one D2H on rank 0
+        houts = [pipe.alloc_outputs(B, on_dev, compact=True) for _ in range(2)]
+        if on_dev and rank == 0:
+            hgath = {k: torch.empty((world * v.shape[0],) + tuple(v.shape[1:]), dtype=v.dtype).pin_memory() for k, v in houts[0][0].items() if k in REC}
         pipe.reset_sequence()
-        if args.host_chunk:
-            pipe.set_host_chunk(args.host_chunk)
+
+        def land(s):
+            """batch s is complete on this rank: gather it to rank 0 and bring it to rank 0's host"""
+            if not on_dev:
+                return
+            g = gather(houts[s & 1][0])
+            if rank == 0:
+                for k, v in g.items():
+                    hgath[k].copy_(v, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+
         # streaming use of the public host API: submit batch s+1 (its H2D copy starts at once) before
         # waiting for batch s; every step still moves its own frames host->device and results device->host
         def run(nsteps, s0):
-            pipe.submit_host_ptr(pin.data_ptr(), B, H * W, W, s0 * B, houts[0])
-            for s in range(1, nsteps):
-                pipe.submit_host_ptr(pin.data_ptr(), B, H * W, W, (s0 + s) * B, houts[s & 1])
+            pipe.submit_host_ptr(pin.data_ptr(), B, H * W, W, s0 * B, houts[s0 & 1])
+            for s in range(s0 + 1, s0 + nsteps):
+                pipe.submit_host_ptr(pin.data_ptr(), B, H * W, W, s * B, houts[s & 1])
                 pipe.wait_host()
+                land(s - 1)
             pipe.wait_host()
-        run(2, 0)
-        barrier()
-        t0 = time.perf_counter()
-        run(args.steps, 2)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
+            land(s0 + nsteps - 1)
+
+        def timed(chunk):
+            pipe.set_host_chunk(chunk)
+            run(2, 0)
+            barrier()
+            t0 = time.perf_counter()
+            run(args.steps, 2)
+            torch.cuda.synchronize()
+            d = time.perf_counter() - t0
+            if world > 1:
+                tt = torch.tensor([d], device=dev, dtype=torch.float64)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                d = float(tt.item())
+            return world * B * args.steps / d
+
+        chunk = args.host_chunk or 64
+        modes = {"whole_batch": timed(0), f"chunked_{chunk}": timed(chunk)}
+        pipe.set_host_chunk(args.host_chunk)
         # the synchronous call (one batch in, results out, nothing in flight afterwards) for comparison
+        souts = pipe.alloc_outputs(B, False, compact=True)
         for s in range(2):
-            pipe.process_host_ptr(pin.data_ptr(), B, H * W, W, s * B, houts[0])
+            pipe.process_host_ptr(pin.data_ptr(), B, H * W, W, s * B, souts)
+        barrier()
         t1 = time.perf_counter()
         for s in range(min(args.steps, 10)):
-            r = pipe.process_host_ptr(pin.data_ptr(), B, H * W, W, s * B, houts[0])
+            pipe.process_host_ptr(pin.data_ptr(), B, H * W, W, s * B, souts)
         dts = (time.perf_counter() - t1) / min(args.steps, 10)
         if world > 1:
-            t = torch.tensor([dt, dts], device=dev, dtype=torch.float64)
+            t = torch.tensor([dts], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt, dts = float(t[0].item()), float(t[1].item())
+            dts = float(t[0].item())
         if rank == 0:
-            d2h = sum(a.nbytes for a in houts[0][0].values())
-            line["e2e"] = {"value": world * B * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(B * H * W),
-                           "d2h_bytes_per_step": int(d2h),
-                           "api": "MarkerPipeline.submit_host_ptr / wait_host -> vbs_submit_host / vbs_wait_host (pinned host frames in, pinned host "
-                                  "arrays out, two batches in flight)",
+            best = max(modes, key=modes.get)
+            d2h = sum(int(a.numel() * a.element_size()) if hasattr(a, "numel") else a.nbytes for a in houts[0][0].values())
+            line["e2e"] = {"value": modes[best], "unit": UNIT, "h2d_bytes_per_step": int(B * H * W), "d2h_bytes_per_step": int(d2h),
+                           "mode": best, "modes": modes,
+                           "api": "MarkerPipeline.submit_host_ptr / wait_host -> vbs_submit_host / vbs_wait_host (pinned host frames in, compact record "
+                                  "block out, two batches in flight); the copy schedule (whole batch vs chunks, vbs_set_host_chunk) is picked by "
+                                  "measuring both" + ("; records gathered to rank 0 over NCCL and copied to its pinned host memory every step" if on_dev else ""),
                            "synchronous_call_value": world * B / dts,
-                           "synchronous_api": "MarkerPipeline.process_host_ptr -> vbs_process_host (chunked copy/compute overlap inside one call)"}
+                           "synchronous_api": "MarkerPipeline.process_host_ptr -> vbs_process_host (chunked copy/compute overlap inside one call, per-rank host results)"}
 
     # ---- cpu_baseline: oracle port on a bounded sample, rank 0, N=1 only
     if rank == 0 and world == 1 and not args.no_cpu:

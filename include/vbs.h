@@ -130,9 +130,9 @@ int vbs_set_first_frame(vbs_ctx *ctx, int64_t first_frame);
  *   row_pitch    bytes between consecutive rows
  *   frameno0     frame number of the first frame of the batch (CSV column 'frameno')
  * vbs_process_device: frames and outputs live in device memory, nothing is copied.
- * vbs_process_host  : frames and outputs live in host memory (pinned for full speed); the
- *                     H2D / D2H copies are part of the call, which returns after the results
- *                     have landed.                                                              */
+ * vbs_process_host  : frames live in host memory (pinned for full speed), outputs in host or device
+ *                     memory; the H2D / D2H copies are part of the call, which returns after the
+ *                     results have landed.                                                      */
 int vbs_process_device(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int64_t frame_stride,
                        int64_t row_pitch, int64_t frameno0, const vbs_outputs *out);
 int vbs_process_host(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int64_t frame_stride,
@@ -142,14 +142,20 @@ int vbs_process_host(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int64_t
  * frames into chunks and run the long detection kernels of chunk c+1 beside the short latency-bound
  * kernels of chunk c on a second stream */
 int vbs_set_overlap(vbs_ctx *ctx, int32_t enable);
-/* frames per chunk of vbs_process_host's copy/compute overlap (0 = default 64) */
+/* frames per chunk of the host entry points' copy/compute overlap.  vbs_process_host: 0 = default 64.
+ * vbs_submit_host: 0 = copy each batch in one piece into one of two max_batch-sized staging slots and run the
+ * unchunked pipeline (fastest on one GPU); > 0 = chunked like vbs_process_host, the chunk rotation continuing
+ * across batches (less host memory traffic in flight per rank: faster when several ranks share one host).
+ * A batch always fits: the chunk is raised to ceil(batch / 8) when needed.  Not while batches are in flight. */
 int vbs_set_host_chunk(vbs_ctx *ctx, int32_t frames_per_chunk);
 
-/* Asynchronous host entry point for streams of batches (config 5): vbs_submit_host enqueues the H2D copy of
- * the whole batch on a copy stream, the pipeline and the D2H copies of the results, and returns at once; up
- * to two batches may be in flight, so batch i+1 crosses PCIe while batch i is processed.  vbs_wait_host
- * blocks until the oldest batch in flight has landed in its `out` arrays and returns its status.  Frames and
- * outputs must be pinned host memory and stay untouched until the matching vbs_wait_host. */
+/* Asynchronous host entry point for streams of batches (config 5): vbs_submit_host enqueues the H2D copies of
+ * the batch on a copy stream, the pipeline and the copies of the results, and returns at once; up to two
+ * batches may be in flight, so batch i+1 crosses PCIe while batch i is processed.  vbs_wait_host blocks until
+ * the oldest batch in flight has landed in its `out` arrays and returns its status.  Frames must be pinned
+ * host memory; the `out` pointers of the host entry points may be pinned host memory OR device memory (e.g. to
+ * gather the records of several GPUs with NCCL before one copy to the host); both must stay untouched until the
+ * matching vbs_wait_host. */
 int vbs_submit_host(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int64_t frame_stride, int64_t row_pitch,
                     int64_t frameno0, const vbs_outputs *out);
 int vbs_wait_host(vbs_ctx *ctx);
@@ -176,6 +182,11 @@ int vbs_undistort_frames(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int
 int vbs_find_markers(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int64_t frame_stride, int64_t row_pitch);
 int vbs_marker_center(vbs_ctx *ctx, const uint8_t *mask, const uint8_t *area_mask, int32_t batch,
                       const vbs_outputs *out);
+/* vbs_ncc_mask     : the second half of _find_markers alone (MD:132-133 with MarkerTracker._normxcorr2, MD:146-164):
+ *                    mask = normxcorr2(gkern, area_mask) > 0.1 for area masks supplied by the caller (uint8, device,
+ *                    [B][H][W], nonzero = 255).  The mask stays in the context: read it with
+ *                    vbs_debug_stage(VBS_STAGE_MASK), the float64 re-decisions with VBS_STAGE_RECHECKS.            */
+int vbs_ncc_mask(vbs_ctx *ctx, const uint8_t *area_mask, int32_t batch);
 
 /* table-level entry points: host arrays in and out, synchronous.  They run the same kernels as
  * vbs_process_* on rows / points supplied by the caller, for the per-call mirrors of the reference:
@@ -195,7 +206,8 @@ int vbs_undistort_points(vbs_ctx *ctx, int32_t n, const double *uv, double *out)
 int vbs_position_3d(vbs_ctx *ctx, int32_t n, const double *uvd, double *P, uint8_t *ok);
 int vbs_fit_plane(vbs_ctx *ctx, int32_t n, const double *X, const double *Y, const double *Z, double out[4]);
 
-/* copy one stage image of the most recent batch into dst (device memory, `bytes` capacity) */
+/* copy the stage images of the most recent batch into dst (device memory): the first frames of the batch, as many as
+ * `bytes` holds (at least one whole frame) */
 int vbs_debug_stage(vbs_ctx *ctx, int32_t stage, void *dst_device, size_t bytes);
 
 /* per-stage device timing for bench.py's roofline: CUDA events on the context's stream around

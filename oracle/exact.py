@@ -463,18 +463,19 @@ def remap_linear_exact(img: np.ndarray, map1: np.ndarray, map2: np.ndarray) -> n
 
 
 def position_3d_exact(K, R, T, u, v, diameter_px, marker_diameter_mm=2.0):
-    """R3:209-228 with NumPy-2 promotion written out: f_avg and 2.0/f_avg are float32, the rest float64."""
+    """R3:209-228 with NumPy-2 promotion written out: f_avg, f_avg**2 and 2.0/f_avg are float32, the rest float64."""
     K32 = np.asarray(K, dtype=np.float32)
     fx32, fy32 = K32[0, 0], K32[1, 1]
     f_avg32 = np.float32(np.float32(fx32 + fy32) / np.float32(2))
     ratio32 = np.float32(np.float32(marker_diameter_mm) / f_avg32)
     fx, fy, cx, cy = float(fx32), float(fy32), float(K32[0, 2]), float(K32[1, 2])
     f_avg, ratio = float(f_avg32), float(ratio32)
+    f_avg_sq = float(np.float32(f_avg32 * f_avg32))          # `f_avg**2` on an np.float32 scalar is a float32 product
     du, dv = u - cx, v - cy
     rad = np.sqrt(du ** 2 + dv ** 2)
     if rad < 1e-6:
         return None
-    d_eff = ratio * np.sqrt(rad ** 2 + f_avg ** 2)
+    d_eff = ratio * np.sqrt(rad ** 2 + f_avg_sq)
     h = f_avg * (d_eff / diameter_px)
     pc = np.array([h * du / fx, h * dv / fy, h]) - np.asarray(T, dtype=np.float32).astype(np.float64).reshape(3)
     Rm = np.asarray(R, dtype=np.float32).astype(np.float64)

@@ -47,7 +47,8 @@ static CameraF64 make_cam(const float *K, const float *D, const float *R, const 
     for (int i = 0; i < 3; ++i) c.T[i] = T[i];
     volatile float favg = (K[0] + K[4]) / 2.0f;
     volatile float ratio = (float)diam / favg;
-    c.f_avg = favg; c.ratio = ratio; c.min_size = 5; c.max_disp = 50;
+    volatile float favg_sq = favg * favg;
+    c.f_avg = favg; c.ratio = ratio; c.f_avg_sq = favg_sq; c.min_size = 5; c.max_disp = 50;
     return c;
 }
 

@@ -55,7 +55,10 @@ def _worker(rank, world, port, q):
         # records: one row per frame holding its global frame number
         rec = {"frameno": torch.arange(lo, hi, dtype=torch.float64).reshape(-1, 1).repeat(1, 3)[: (n // world)]}
         got = sharding.gather_records(rec, rank, world, dst=0)
-        q.put((rank, inc, None if got is None else got["frameno"].numpy()))
+        # ragged shards (6 + 5 frames): padded for the collective, trimmed on the destination
+        full = {"frameno": torch.arange(lo, hi, dtype=torch.float64).reshape(-1, 1), "flag": torch.full((hi - lo, 2), rank, dtype=torch.uint8)}
+        rag = sharding.gather_records(full, rank, world, dst=0, counts=[b - a for a, b in (sharding.shard_bounds(n, r, world) for r in range(world))])
+        q.put((rank, inc, None if got is None else got["frameno"].numpy(), None if rag is None else (rag["frameno"].numpy(), rag["flag"].numpy())))
     finally:
         dist.destroy_process_group()
 
@@ -69,8 +72,8 @@ def test_two_rank_gloo_exchange_and_gather():
         p.start()
     out = {}
     for _ in range(world):
-        r, inc, rec = q.get(timeout=120)
-        out[r] = (inc, rec)
+        r, inc, rec, rag = q.get(timeout=120)
+        out[r] = (inc, rec, rag)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -81,3 +84,6 @@ def test_two_rank_gloo_exchange_and_gather():
     assert out[1][1] is None
     frames = out[0][1][:, 0]
     assert frames.tolist() == list(range(0, 5)) + list(range(6, 11))      # rank-major = frame order
+    assert out[1][2] is None
+    rf, rflag = out[0][2]
+    assert rf[:, 0].tolist() == list(range(11)) and rflag[:, 0].tolist() == [0] * 6 + [1] * 5

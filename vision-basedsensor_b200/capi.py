@@ -54,6 +54,7 @@ SYMBOLS = {
     "vbs_undistort_frames": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int64, _P]),
     "vbs_find_markers": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int64]),
     "vbs_marker_center": (C.c_int, [_P, _P, _P, C.c_int32, C.POINTER(VbsOutputs)]),
+    "vbs_ncc_mask": (C.c_int, [_P, _P, C.c_int32]),
     "vbs_track_markers": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P]),
     "vbs_reconstruct_rows": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P, _P, _P, _P, _P, _P]),
     "vbs_undistort_points": (C.c_int, [_P, C.c_int32, _P, _P]),

@@ -113,7 +113,8 @@ __global__ void __launch_bounds__(32 * TY) open5_kernel(const uint32_t *__restri
 }
 
 // uint8 image -> bits (nonzero = 1); one warp per output word
-__global__ void pack_kernel(const uint8_t *__restrict__ src, uint32_t *__restrict__ dst, int H, int W, int WW, size_t nwords) {
+__global__ void pack_kernel(const uint8_t *__restrict__ src, uint32_t *__restrict__ dst, int H, int W, int WW, size_t nwords,
+                            uint32_t *__restrict__ count = nullptr) {
     const size_t w = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w >= nwords) return;
     const int lane = threadIdx.x & 31;
@@ -122,7 +123,10 @@ __global__ void pack_kernel(const uint8_t *__restrict__ src, uint32_t *__restric
     const int x = 32 * wx + lane;
     const bool on = x < W && src[fy * W + x] != 0;
     const uint32_t word = __ballot_sync(0xffffffffu, on);
-    if (lane == 0) dst[w] = word;
+    if (lane == 0) {
+        dst[w] = word;
+        if (count && word) atomicAdd(count + fy / H, (uint32_t)__popc(word));   // per-frame set pixels (mean of area_mask, MD:153)
+    }
 }
 
 __global__ void unpack_kernel(const uint32_t *__restrict__ bits, uint8_t *__restrict__ dst, int W, int WW, size_t npx, uint8_t on_value) {
@@ -185,6 +189,18 @@ cudaError_t vbs_launch_pack_masks(vbs_ctx *ctx, const uint8_t *mask, const uint8
     pack_kernel<<<grid, wpb * 32, 0, ctx->stream>>>(mask, ctx->mask_bits, ctx->H, ctx->W, ctx->WW, nwords);
     pack_kernel<<<grid, wpb * 32, 0, ctx->stream>>>(area, ctx->area_bits, ctx->H, ctx->W, ctx->WW, nwords);
     ctx->launches += 2;
+    return cudaGetLastError();
+}
+
+// area mask supplied by the caller -> area_bits + per-frame popcount, i.e. the state K1 leaves behind for K2
+cudaError_t vbs_launch_pack_area(vbs_ctx *ctx, const uint8_t *area, int batch) {
+    const size_t nwords = (size_t)batch * ctx->H * ctx->WW;
+    const int wpb = 8;
+    const unsigned grid = (unsigned)((nwords + wpb - 1) / wpb);
+    cudaError_t e = cudaMemsetAsync(ctx->area_count, 0, sizeof(uint32_t) * batch, ctx->stream);
+    if (e != cudaSuccess) return e;
+    pack_kernel<<<grid, wpb * 32, 0, ctx->stream>>>(area, ctx->area_bits, ctx->H, ctx->W, ctx->WW, nwords, ctx->area_count);
+    ctx->launches += 1;
     return cudaGetLastError();
 }
 

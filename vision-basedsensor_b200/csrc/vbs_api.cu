@@ -19,6 +19,68 @@ template <class T> cudaError_t dalloc(T **p, size_t n) {
 
 int fail(vbs_ctx *ctx, int code, const char *msg) { ctx->err = msg; return code; }
 
+// Every exported call runs on the context's GPU, whatever device is current in the calling thread, and
+// leaves the caller's current device as it found it (two contexts on different GPUs in one process,
+// or a caller that switches devices between calls, must not allocate or launch on the wrong GPU).
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess) cur = -1;
+        if (cur != dev) {
+            ok = cudaSetDevice(dev) == cudaSuccess;
+            prev = cur;
+        }
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+#define VBS_ON_DEVICE(ctx)                                                  \
+    DeviceGuard guard_((ctx)->cfg.device);                                  \
+    if (!guard_.ok) return fail(ctx, VBS_ERR_CUDA, "cudaSetDevice failed for the context's device")
+
+// cell grids of the nearest-marker match (k_track3d.cu), sized for `frames` frames per call
+int ensure_track(vbs_ctx *ctx, int frames) {
+    if (ctx->track_cap >= frames) return VBS_OK;
+    VBS_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->cell_start) { cudaFree(ctx->cell_start); ctx->cell_start = nullptr; }
+    if (ctx->cell_items) { cudaFree(ctx->cell_items); ctx->cell_items = nullptr; }
+    ctx->track_cap = 0;
+    VBS_CUDA(dalloc(&ctx->cell_start, (size_t)frames * 8193)); VBS_CUDA(dalloc(&ctx->cell_items, (size_t)frames * ctx->M));
+    ctx->track_cap = frames;
+    return VBS_OK;
+}
+
+// Per-pixel scratch of the image pipeline.  Allocated on the first call that processes frames or masks, so a
+// context that only serves the table-level entry points (vbs_reconstruct_rows, vbs_undistort_points, ...)
+// with a large max_batch never pays for it (recheck lists alone are 128 KiB per frame).
+int ensure_image(vbs_ctx *ctx) {
+    if (ctx->image_ready) return VBS_OK;
+    const size_t B = ctx->B, H = ctx->H, W = ctx->W, WW = ctx->WW, M = ctx->M;
+    const size_t nbits = B * H * WW;
+    VBS_CUDA(dalloc(&ctx->area_bits, nbits)); VBS_CUDA(dalloc(&ctx->mask_bits, nbits)); VBS_CUDA(dalloc(&ctx->max_bits, nbits));
+    VBS_CUDA(dalloc(&ctx->open_bits, nbits));
+    VBS_CUDA(dalloc(&ctx->area_count, B));
+    VBS_CUDA(dalloc(&ctx->recheck, B * ctx->recheck_cap)); VBS_CUDA(dalloc(&ctx->recheck_n, B));
+    VBS_CUDA(dalloc(&ctx->parent, B * H * W)); VBS_CUDA(dalloc(&ctx->parent2, B * H * W));
+    VBS_CUDA(dalloc(&ctx->nroots, 2 * B)); VBS_CUDA(dalloc(&ctx->rootlist, 2 * B * M)); VBS_CUDA(dalloc(&ctx->slot2label, B * M));
+    VBS_CUDA(dalloc(&ctx->rowflag, 2 * B * ((WW + 31) / 32) * H));
+    VBS_CUDA(dalloc(&ctx->nrec, 2 * B)); VBS_CUDA(dalloc(&ctx->recs, 2 * B * (size_t)ctx->rcap));
+    VBS_CUDA(dalloc(&ctx->lab_cnt, B * M)); VBS_CUDA(dalloc(&ctx->lab_sx, B * M)); VBS_CUDA(dalloc(&ctx->lab_sy, B * M));
+    VBS_CUDA(dalloc(&ctx->centres, B * M * 2));
+    VBS_CUDA(dalloc(&ctx->croot, B * M)); VBS_CUDA(dalloc(&ctx->cell, B * M * 6)); VBS_CUDA(dalloc(&ctx->claim, B * M));
+    VBS_CUDA(dalloc(&ctx->cmatch, B * M));
+    VBS_CUDA(dalloc(&ctx->cpts, B * M * 128)); VBS_CUDA(dalloc(&ctx->cpn, B * M));
+    VBS_CUDA(dalloc(&ctx->euler4, B)); VBS_CUDA(dalloc(&ctx->holes, B));
+    VBS_CUDA(dalloc(&ctx->cbin_start, B * 8193)); VBS_CUDA(dalloc(&ctx->cbin_items, B * M));
+    int rc = ensure_track(ctx, ctx->B);
+    if (rc != VBS_OK) return rc;
+    ctx->image_ready = 1;
+    return VBS_OK;
+}
+
 struct Scratch {                       // small device staging buffer, freed on scope exit
     void *p = nullptr;
     ~Scratch() { if (p) cudaFree(p); }
@@ -52,6 +114,7 @@ void free_all(vbs_ctx *c) {
     for (int i = 0; i < 2; ++i) { if (c->ev_slot_in[i]) cudaEventDestroy(c->ev_slot_in[i]); if (c->ev_slot_free[i]) cudaEventDestroy(c->ev_slot_free[i]); if (c->ev_slot_done[i]) cudaEventDestroy(c->ev_slot_done[i]); }
     for (cudaEvent_t e : c->pev) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ev_a) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_bchunk) if (e) cudaEventDestroy(e);
     if (c->ev_b_done) cudaEventDestroy(c->ev_b_done);
     if (c->stream_b) cudaStreamDestroy(c->stream_b);
     for (int i = 0; i < 2; ++i) { if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]); }
@@ -341,41 +404,24 @@ int vbs_create(vbs_ctx **out, const vbs_config *cfg) {
     if (vbs_check_taps(ctx->err) != 0) return VBS_ERR_INTERNAL;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(ctx, VBS_ERR_CUDA, "no CUDA device (this library has no CPU path)");
-    VBS_CUDA(cudaSetDevice(cfg->device));
+    VBS_ON_DEVICE(ctx);                              // the caller's current device is restored on return
     VBS_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
-    const size_t B = ctx->B, H = ctx->H, W = ctx->W, WW = ctx->WW, M = ctx->M, R = ctx->Rcap;
-    const size_t nbits = B * H * WW;
-    VBS_CUDA(dalloc(&ctx->area_bits, nbits)); VBS_CUDA(dalloc(&ctx->mask_bits, nbits)); VBS_CUDA(dalloc(&ctx->max_bits, nbits));
-    VBS_CUDA(dalloc(&ctx->open_bits, nbits));
-    VBS_CUDA(dalloc(&ctx->area_count, B));
+    const size_t B = ctx->B, H = ctx->H, W = ctx->W, M = ctx->M, R = ctx->Rcap;
     VBS_CUDA(dalloc(&ctx->thr_lut, (size_t)ctx->br.tl * ctx->br.tl + 1));
     VBS_CUDA(dalloc(&ctx->d_n64, 96)); VBS_CUDA(dalloc(&ctx->d_cn64, 160)); VBS_CUDA(dalloc(&ctx->d_cnfix, 4 * 112));
     ctx->recheck_cap = 16384;
-    VBS_CUDA(dalloc(&ctx->recheck, B * ctx->recheck_cap)); VBS_CUDA(dalloc(&ctx->recheck_n, B));
-    VBS_CUDA(dalloc(&ctx->parent, B * H * W)); VBS_CUDA(dalloc(&ctx->parent2, B * H * W));
-    VBS_CUDA(dalloc(&ctx->nroots, 2 * B)); VBS_CUDA(dalloc(&ctx->rootlist, 2 * B * M)); VBS_CUDA(dalloc(&ctx->slot2label, B * M));
     ctx->rcap = (int)(8 * M + 64 * ((W + 1023) / 1024) * ((H + 63) / 64));      // tile-local components: 64 x 1024 px tiles (k_ccl.cu)
-    VBS_CUDA(dalloc(&ctx->rowflag, 2 * B * ((WW + 31) / 32) * H));
-    VBS_CUDA(dalloc(&ctx->nrec, 2 * B)); VBS_CUDA(dalloc(&ctx->recs, 2 * B * (size_t)ctx->rcap));
+    // per-pixel scratch and the cell grids come later (ensure_image / ensure_track): table-only contexts skip them
     VBS_CUDA(dalloc(&ctx->d_nlabels, B)); VBS_CUDA(dalloc(&ctx->d_ncont, B));
-    VBS_CUDA(dalloc(&ctx->lab_cnt, B * M)); VBS_CUDA(dalloc(&ctx->lab_sx, B * M)); VBS_CUDA(dalloc(&ctx->lab_sy, B * M));
-    VBS_CUDA(dalloc(&ctx->centres, B * M * 2));
-    VBS_CUDA(dalloc(&ctx->croot, B * M)); VBS_CUDA(dalloc(&ctx->cell, B * M * 6)); VBS_CUDA(dalloc(&ctx->claim, B * M));
-    VBS_CUDA(dalloc(&ctx->cmatch, B * M));
-    VBS_CUDA(dalloc(&ctx->cpts, B * M * 128)); VBS_CUDA(dalloc(&ctx->cpn, B * M));
-    VBS_CUDA(dalloc(&ctx->euler4, B)); VBS_CUDA(dalloc(&ctx->holes, B));
     VBS_CUDA(dalloc(&ctx->d_nmarkers, B)); VBS_CUDA(dalloc(&ctx->marker_xy, B * M * 2)); VBS_CUDA(dalloc(&ctx->marker_axes, B * M * 3));
     VBS_CUDA(dalloc(&ctx->ref_row, R)); VBS_CUDA(dalloc(&ctx->ref_col, R)); VBS_CUDA(dalloc(&ctx->ref_xy, R * 2));
     VBS_CUDA(dalloc(&ctx->row_det, B * R)); VBS_CUDA(dalloc(&ctx->row_cxy, B * R * 2)); VBS_CUDA(dalloc(&ctx->row_axes, B * R * 3));
-    VBS_CUDA(dalloc(&ctx->cell_start, B * 8193)); VBS_CUDA(dalloc(&ctx->cell_items, B * M));
-    VBS_CUDA(dalloc(&ctx->cbin_start, B * 8193)); VBS_CUDA(dalloc(&ctx->cbin_items, B * M));
     VBS_CUDA(dalloc(&ctx->obs, B * R * 3)); VBS_CUDA(dalloc(&ctx->pos3d, B * R * 7)); VBS_CUDA(dalloc(&ctx->pos_flags, B * R));
     VBS_CUDA(dalloc(&ctx->last_seen, R * 4));
     VBS_CUDA(dalloc(&ctx->pl_ref, R * 3)); VBS_CUDA(dalloc(&ctx->pl_start, R * 3)); VBS_CUDA(dalloc(&ctx->pl_dvert, R * 3));
     VBS_CUDA(dalloc(&ctx->pl_use, R)); VBS_CUDA(dalloc(&ctx->plane, B * 4)); VBS_CUDA(dalloc(&ctx->plane_n, B));
-    VBS_CUDA(dalloc(&ctx->d_status, 1));
-    VBS_CUDA(cudaMemset(ctx->d_status, 0, sizeof(uint32_t)));
+    VBS_CUDA(dalloc(&ctx->d_status, 4));             // [0]: synchronous calls, [1], [2]: the two batches vbs_submit_host keeps in flight
     VBS_CUDA(cudaHostAlloc((void **)&ctx->h_status, sizeof(uint32_t), cudaHostAllocDefault));
     *ctx->h_status = 0;
     VBS_CUDA(vbs_ncc_setup(ctx));
@@ -384,9 +430,11 @@ int vbs_create(vbs_ctx **out, const vbs_config *cfg) {
 
 void vbs_destroy(vbs_ctx *ctx) {
     if (!ctx) return;
-    cudaSetDevice(ctx->cfg.device);
-    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    free_all(ctx);
+    {
+        DeviceGuard guard(ctx->cfg.device);
+        if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+        free_all(ctx);
+    }
     delete ctx;
 }
 
@@ -394,6 +442,7 @@ const char *vbs_last_error(const vbs_ctx *ctx) { return ctx ? ctx->err.c_str() :
 
 int vbs_set_stream(vbs_ctx *ctx, void *cuda_stream) {
     if (!ctx) return VBS_ERR_BAD_ARG;
+    VBS_ON_DEVICE(ctx);
     VBS_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
     return VBS_OK;
@@ -401,6 +450,7 @@ int vbs_set_stream(vbs_ctx *ctx, void *cuda_stream) {
 
 int vbs_sync(vbs_ctx *ctx) {
     if (!ctx) return VBS_ERR_BAD_ARG;
+    VBS_ON_DEVICE(ctx);
     VBS_CUDA(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     VBS_CUDA(cudaMemsetAsync(ctx->d_status, 0, sizeof(uint32_t), ctx->stream));
     VBS_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -414,6 +464,7 @@ int vbs_set_reference(vbs_ctx *ctx, int32_t n, const int32_t *row, const int32_t
     if (!ctx) return VBS_ERR_BAD_ARG;
     if (n < 0 || n > ctx->Rcap) return fail(ctx, VBS_ERR_BAD_ARG, "reference count exceeds max_refs");
     if (n > 0 && (!row || !col || !ox || !oy)) return fail(ctx, VBS_ERR_BAD_ARG, "NULL reference array");
+    VBS_ON_DEVICE(ctx);
     VBS_CUDA(cudaStreamSynchronize(ctx->stream));
     double *xy = new double[2 * (size_t)(n ? n : 1)];
     for (int i = 0; i < n; ++i) { xy[2 * i] = ox[i]; xy[2 * i + 1] = oy[i]; }
@@ -440,7 +491,8 @@ int vbs_set_camera(vbs_ctx *ctx, const float K[9], const float D[5], const float
     // python float / float32 -> float32
     volatile float favg = (K[0] + K[4]) / 2.0f;
     volatile float ratio = (float)marker_diameter_mm / favg;
-    c.f_avg = favg; c.ratio = ratio;
+    volatile float favg_sq = favg * favg;                    // np.float32 ** 2 -> float32 (R3:219)
+    c.f_avg = favg; c.ratio = ratio; c.f_avg_sq = favg_sq;
     c.min_size = min_marker_size_px; c.max_disp = max_displacement;
     ctx->cam = c; ctx->have_cam = 1; ctx->warmup = warmup_frames;
     return vbs_reset_sequence(ctx);
@@ -451,6 +503,7 @@ int vbs_set_plane(vbs_ctx *ctx, int32_t n, const double *ref_xyz, const double *
     if (!ctx) return VBS_ERR_BAD_ARG;
     if (n != ctx->R || n <= 0) return fail(ctx, VBS_ERR_BAD_ARG, "plane arrays must match the reference array length");
     if (!ref_xyz || !start_xyz) return fail(ctx, VBS_ERR_BAD_ARG, "NULL plane array");
+    VBS_ON_DEVICE(ctx);
     VBS_CUDA(cudaStreamSynchronize(ctx->stream));
     VBS_CUDA(cudaMemcpy(ctx->pl_ref, ref_xyz, sizeof(double) * 3 * n, cudaMemcpyHostToDevice));
     VBS_CUDA(cudaMemcpy(ctx->pl_start, start_xyz, sizeof(double) * 3 * n, cudaMemcpyHostToDevice));
@@ -464,6 +517,7 @@ int vbs_set_plane(vbs_ctx *ctx, int32_t n, const double *ref_xyz, const double *
 
 int vbs_reset_sequence(vbs_ctx *ctx) {
     if (!ctx) return VBS_ERR_BAD_ARG;
+    VBS_ON_DEVICE(ctx);
     const int R = ctx->Rcap;
     VBS_CUDA(cudaStreamSynchronize(ctx->stream));
     if (R > 0) {
@@ -479,6 +533,7 @@ int vbs_reset_sequence(vbs_ctx *ctx) {
 
 int vbs_get_last_seen(vbs_ctx *ctx, double *host_table) {
     if (!ctx || !host_table) return VBS_ERR_BAD_ARG;
+    VBS_ON_DEVICE(ctx);
     VBS_CUDA(cudaStreamSynchronize(ctx->stream));
     VBS_CUDA(cudaMemcpy(host_table, ctx->last_seen, sizeof(double) * 4 * ctx->R, cudaMemcpyDeviceToHost));
     return VBS_OK;
@@ -486,6 +541,7 @@ int vbs_get_last_seen(vbs_ctx *ctx, double *host_table) {
 
 int vbs_set_last_seen(vbs_ctx *ctx, const double *host_table) {
     if (!ctx || !host_table) return VBS_ERR_BAD_ARG;
+    VBS_ON_DEVICE(ctx);
     VBS_CUDA(cudaStreamSynchronize(ctx->stream));
     VBS_CUDA(cudaMemcpy(ctx->last_seen, host_table, sizeof(double) * 4 * ctx->R, cudaMemcpyHostToDevice));
     return VBS_OK;
@@ -494,6 +550,7 @@ int vbs_set_last_seen(vbs_ctx *ctx, const double *host_table) {
 int vbs_fix_displacement(vbs_ctx *ctx, double *pos3d_device, uint8_t *pos_flags_device, int64_t nframes, const double *incoming_host) {
     if (!ctx || !pos3d_device || !pos_flags_device || !incoming_host || nframes < 0) return VBS_ERR_BAD_ARG;
     if (ctx->R <= 0 || !ctx->have_cam) return fail(ctx, VBS_ERR_STATE, "reference array and camera must be set first");
+    VBS_ON_DEVICE(ctx);
     Scratch s;
     VBS_CUDA(cudaMalloc(&s.p, sizeof(double) * 4 * ctx->R));
     VBS_CUDA(cudaMemcpyAsync(s.p, incoming_host, sizeof(double) * 4 * ctx->R, cudaMemcpyHostToDevice, ctx->stream));
@@ -512,83 +569,35 @@ int vbs_process_device(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int64
     int rc = check_batch(ctx, frames, batch);
     if (rc != VBS_OK) return rc;
     if (row_pitch < (int64_t)ctx->W * ctx->C) return fail(ctx, VBS_ERR_BAD_ARG, "row_pitch smaller than a row");
-    return process_common(ctx, frames, batch, frame_stride, row_pitch, frameno0, out, cudaMemcpyDeviceToDevice);
+    VBS_ON_DEVICE(ctx);
+    if ((rc = ensure_image(ctx)) != VBS_OK) return rc;
+    return process_common(ctx, frames, batch, frame_stride, row_pitch, frameno0, out, cudaMemcpyDefault);
 }
 
-// Host frames in, host results out.  The batch is cut into chunks; chunk c+1 crosses PCIe on a
-// copy stream while chunk c is being processed (two staging buffers, events both ways), so the
-// call costs max(copy, compute) instead of their sum.
-int vbs_process_host(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int64_t frame_stride, int64_t row_pitch, int64_t frameno0,
-                     const vbs_outputs *out) {
-    int rc = check_batch(ctx, frames, batch);
-    if (rc != VBS_OK) return rc;
-    const size_t rowb = (size_t)ctx->W * ctx->C, fb = rowb * ctx->H;
-    if (row_pitch < (int64_t)rowb) return fail(ctx, VBS_ERR_BAD_ARG, "row_pitch smaller than a row");
-    const int CH = ctx->host_chunk > 0 ? (ctx->host_chunk < ctx->B ? ctx->host_chunk : ctx->B) : (ctx->B < 64 ? ctx->B : 64);
-    if (!ctx->d_frames || ctx->frames_bytes < 2 * fb * CH) {
-        if (ctx->d_frames) { VBS_CUDA(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->d_frames); ctx->d_frames = nullptr; }
-        ctx->frames_bytes = 2 * fb * CH;
-        VBS_CUDA(cudaMalloc((void **)&ctx->d_frames, ctx->frames_bytes));
-    }
+}  // extern "C"
+
+namespace {
+
+// ---- host entry points -----------------------------------------------------------------------------------
+// Frames live in host memory (pinned for full speed); outputs may be host OR device pointers (the copies are
+// cudaMemcpyDefault, the driver tells them apart).  Two ways to overlap the PCIe copy with the kernels:
+//   chunked : the batch is cut into chunks; chunk c+1 crosses PCIe on a copy stream while chunk c is processed
+//             (two rotating staging buffers of one chunk each, events both ways).  The rotation continues
+//             ACROSS calls, so with vbs_submit_host the first chunk of batch i+1 flies beside the tail of batch i.
+//   whole   : two staging slots of max_batch frames; batch i+1 is copied in one piece beside the unchunked
+//             pipeline of batch i (fewer, longer kernels: faster on the device, but every rank of a multi-GPU
+//             job then pulls max_batch frames through the host at once).
+// vbs_process_host is always chunked; vbs_submit_host is whole-batch unless vbs_set_host_chunk(> 0) was called.
+int ensure_host_streams(vbs_ctx *ctx) {
     if (!ctx->copy_stream) {
         VBS_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         for (int i = 0; i < 2; ++i) {
             VBS_CUDA(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
             VBS_CUDA(cudaEventCreateWithFlags(&ctx->ev_consumed[i], cudaEventDisableTiming));
         }
+        for (int i = 0; i < VBS_MAX_CHUNKS; ++i) VBS_CUDA(cudaEventCreateWithFlags(&ctx->ev_bchunk[i], cudaEventDisableTiming));
     }
-    const int nchunks = (batch + CH - 1) / CH;
-    if (nchunks > VBS_MAX_CHUNKS) return fail(ctx, VBS_ERR_BAD_ARG, "batch / host_chunk exceeds 8 chunks");
-    if (ctx->profiling && (rc = prof_collect(ctx)) != VBS_OK) return rc;
-    if ((rc = ensure_pipeline(ctx)) != VBS_OK) return rc;
-    // the copy stream runs one chunk ahead of stage A, stage B of the previous chunk runs beside stage A
-    auto upload = [&](int c) -> int {
-        const int off = c * CH, n = batch - off < CH ? batch - off : CH, buf = c & 1;
-        uint8_t *dst = ctx->d_frames + (size_t)buf * fb * CH;
-        if (c >= 2) VBS_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[buf], 0));
-        const uint8_t *src = frames + (size_t)frame_stride * off;
-        if ((size_t)row_pitch == rowb && (size_t)frame_stride == fb) {
-            VBS_CUDA(cudaMemcpyAsync(dst, src, fb * n, cudaMemcpyHostToDevice, ctx->copy_stream));
-        } else {                                           // crop view (MD:85): one strided copy per frame
-            for (int f = 0; f < n; ++f)
-                VBS_CUDA(cudaMemcpy2DAsync(dst + fb * f, rowb, src + (size_t)frame_stride * f, (size_t)row_pitch, rowb, ctx->H,
-                                           cudaMemcpyHostToDevice, ctx->copy_stream));
-        }
-        VBS_CUDA(cudaEventRecord(ctx->ev_copied[buf], ctx->copy_stream));
-        return VBS_OK;
-    };
-    if ((rc = upload(0)) != VBS_OK) return rc;
-    for (int c = 0; c < nchunks; ++c) {
-        const int off = c * CH, n = batch - off < CH ? batch - off : CH, buf = c & 1;
-        uint8_t *dst = ctx->d_frames + (size_t)buf * fb * CH;
-        if (c + 1 < nchunks && (rc = upload(c + 1)) != VBS_OK) return rc;
-        VBS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[buf], 0));
-        if ((rc = stage_a(ctx, c, off, n, dst, (int64_t)fb, (int64_t)rowb)) != VBS_OK) return rc;
-        VBS_CUDA(cudaEventRecord(ctx->ev_consumed[buf], ctx->stream));          // frames are dead after the blur
-        VBS_CUDA(cudaEventRecord(ctx->ev_a[c], ctx->stream));
-        VBS_CUDA(cudaStreamWaitEvent(ctx->stream_b, ctx->ev_a[c], 0));
-        if ((rc = stage_b(ctx, c, off, n, frameno0, out, cudaMemcpyDeviceToHost, ctx->stream_b)) != VBS_OK) return rc;
-    }
-    VBS_CUDA(cudaEventRecord(ctx->ev_b_done, ctx->stream_b));
-    VBS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_b_done, 0));
-    if (ctx->profiling) { ctx->prof_pending = 1; ctx->prof_chunks = nchunks; }
-    ctx->last_batch = batch;
-    return vbs_sync(ctx);
-}
-
-// ---- asynchronous host entry point: batch i+1 crosses PCIe while batch i is being processed ------------
-// Two device staging slots of max_batch frames.  submit: H2D of the whole batch on the copy stream (waits
-// until the slot's previous frames were consumed), then the unchunked pipeline + D2H of the results on the
-// context's stream, then a per-slot "done" event.  wait: blocks on the oldest batch in flight.
-int vbs_submit_host(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int64_t frame_stride, int64_t row_pitch, int64_t frameno0,
-                    const vbs_outputs *out) {
-    int rc = check_batch(ctx, frames, batch);
-    if (rc != VBS_OK) return rc;
-    const size_t rowb = (size_t)ctx->W * ctx->C, fb = rowb * ctx->H;
-    if (row_pitch < (int64_t)rowb) return fail(ctx, VBS_ERR_BAD_ARG, "row_pitch smaller than a row");
-    if (ctx->inflight >= 2) return fail(ctx, VBS_ERR_STATE, "two batches already in flight: call vbs_wait_host first");
-    if (!ctx->d_slots) {
-        VBS_CUDA(cudaMalloc((void **)&ctx->d_slots, 2 * fb * ctx->B));
+    if (!ctx->h_slot_status) {
         for (int i = 0; i < 2; ++i) {
             VBS_CUDA(cudaEventCreateWithFlags(&ctx->ev_slot_in[i], cudaEventDisableTiming));
             VBS_CUDA(cudaEventCreateWithFlags(&ctx->ev_slot_free[i], cudaEventDisableTiming));
@@ -597,31 +606,147 @@ int vbs_submit_host(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int64_t 
         VBS_CUDA(cudaHostAlloc((void **)&ctx->h_slot_status, 2 * sizeof(uint32_t), cudaHostAllocDefault));
         ctx->h_slot_status[0] = ctx->h_slot_status[1] = 0;
     }
-    if (!ctx->copy_stream) {
-        VBS_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) {
-            VBS_CUDA(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
-            VBS_CUDA(cudaEventCreateWithFlags(&ctx->ev_consumed[i], cudaEventDisableTiming));
-        }
-    }
-    const int slot = (int)(ctx->submitted & 1);
-    uint8_t *dst = ctx->d_slots + (size_t)slot * fb * ctx->B;
-    if (ctx->submitted >= 2) VBS_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_slot_free[slot], 0));
+    return ensure_pipeline(ctx);
+}
+
+// frames per chunk of a chunked host call: the caller's setting (or 64), raised so that the batch needs at most
+// VBS_MAX_CHUNKS chunks (any batch <= max_batch is accepted)
+int host_chunk_frames(const vbs_ctx *ctx, int batch, int setting) {
+    int ch = setting > 0 ? setting : 64;
+    const int floor_ch = (batch + VBS_MAX_CHUNKS - 1) / VBS_MAX_CHUNKS;
+    if (ch < floor_ch) ch = floor_ch;
+    if (ch > ctx->B) ch = ctx->B;
+    return ch;
+}
+
+int upload_frames(vbs_ctx *ctx, uint8_t *dst, const uint8_t *src, int n, int64_t frame_stride, int64_t row_pitch) {
+    const size_t rowb = (size_t)ctx->W * ctx->C, fb = rowb * ctx->H;
     if ((size_t)row_pitch == rowb && (size_t)frame_stride == fb) {
-        VBS_CUDA(cudaMemcpyAsync(dst, frames, fb * batch, cudaMemcpyHostToDevice, ctx->copy_stream));
-    } else {
-        for (int f = 0; f < batch; ++f)
-            VBS_CUDA(cudaMemcpy2DAsync(dst + fb * f, rowb, frames + (size_t)frame_stride * f, (size_t)row_pitch, rowb, ctx->H,
+        VBS_CUDA(cudaMemcpyAsync(dst, src, fb * n, cudaMemcpyHostToDevice, ctx->copy_stream));
+    } else {                                           // crop view (MD:85): one strided copy per frame
+        for (int f = 0; f < n; ++f)
+            VBS_CUDA(cudaMemcpy2DAsync(dst + fb * f, rowb, src + (size_t)frame_stride * f, (size_t)row_pitch, rowb, ctx->H,
                                        cudaMemcpyHostToDevice, ctx->copy_stream));
     }
-    VBS_CUDA(cudaEventRecord(ctx->ev_slot_in[slot], ctx->copy_stream));
-    VBS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_slot_in[slot], 0));
-    rc = process_common(ctx, dst, batch, (int64_t)fb, (int64_t)rowb, frameno0, out, cudaMemcpyDeviceToHost);
+    return VBS_OK;
+}
+
+// Enqueue one batch on the chunked pipeline.  On return the last stage-B work (and the output copies) of the
+// batch sit on ctx->stream_b; nothing has been waited for.
+int enqueue_host_chunks(vbs_ctx *ctx, const uint8_t *frames, int batch, int64_t frame_stride, int64_t row_pitch, int64_t frameno0,
+                        const vbs_outputs *out, int CH) {
+    int rc;
+    const size_t fb = (size_t)ctx->W * ctx->C * ctx->H;
+    if (!ctx->d_frames || ctx->frames_bytes < 2 * fb * CH) {
+        if (ctx->d_frames) { VBS_CUDA(cudaDeviceSynchronize()); cudaFree(ctx->d_frames); ctx->d_frames = nullptr; }
+        ctx->frames_bytes = 2 * fb * CH;
+        ctx->chunk_seq = 0;                            // fresh buffers: no previous consumer to wait for
+        VBS_CUDA(cudaMalloc((void **)&ctx->d_frames, ctx->frames_bytes));
+    }
+    const size_t half = ctx->frames_bytes / 2;
+    const int nchunks = (batch + CH - 1) / CH;
+    if (ctx->profiling && (rc = prof_collect(ctx)) != VBS_OK) return rc;
+    // the copy stream runs one chunk ahead of stage A; stage B of the previous chunk runs beside stage A
+    auto upload = [&](int c) -> int {
+        const int off = c * CH, n = batch - off < CH ? batch - off : CH;
+        const int buf = (int)((ctx->chunk_seq + c) & 1);
+        if (ctx->chunk_seq + c >= 2) VBS_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[buf], 0));
+        int r = upload_frames(ctx, ctx->d_frames + (size_t)buf * half, frames + (size_t)frame_stride * off, n, frame_stride, row_pitch);
+        if (r != VBS_OK) return r;
+        VBS_CUDA(cudaEventRecord(ctx->ev_copied[buf], ctx->copy_stream));
+        return VBS_OK;
+    };
+    if ((rc = upload(0)) != VBS_OK) return rc;
+    for (int c = 0; c < nchunks; ++c) {
+        const int off = c * CH, n = batch - off < CH ? batch - off : CH;
+        const int buf = (int)((ctx->chunk_seq + c) & 1);
+        uint8_t *dst = ctx->d_frames + (size_t)buf * half;
+        if (c + 1 < nchunks && (rc = upload(c + 1)) != VBS_OK) return rc;
+        VBS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[buf], 0));
+        // the scratch range of chunk c was last read by stage B of chunk c of the previous batch (stream_b)
+        if (ctx->bchunk_live[c]) VBS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_bchunk[c], 0));
+        if ((rc = stage_a(ctx, c, off, n, dst, (int64_t)fb, (int64_t)ctx->W * ctx->C)) != VBS_OK) return rc;
+        VBS_CUDA(cudaEventRecord(ctx->ev_consumed[buf], ctx->stream));          // frames are dead after the blur
+        VBS_CUDA(cudaEventRecord(ctx->ev_a[c], ctx->stream));
+        VBS_CUDA(cudaStreamWaitEvent(ctx->stream_b, ctx->ev_a[c], 0));
+        if ((rc = stage_b(ctx, c, off, n, frameno0, out, cudaMemcpyDefault, ctx->stream_b)) != VBS_OK) return rc;
+        VBS_CUDA(cudaEventRecord(ctx->ev_bchunk[c], ctx->stream_b));
+        ctx->bchunk_live[c] = 1;
+    }
+    ctx->chunk_seq += nchunks;
+    if (ctx->profiling) { ctx->prof_pending = 1; ctx->prof_chunks = nchunks; }
+    ctx->last_batch = batch;
+    return VBS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vbs_process_host(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int64_t frame_stride, int64_t row_pitch, int64_t frameno0,
+                     const vbs_outputs *out) {
+    int rc = check_batch(ctx, frames, batch);
     if (rc != VBS_OK) return rc;
-    VBS_CUDA(cudaEventRecord(ctx->ev_slot_free[slot], ctx->stream));     // (frames are dead after the blur; the end of the batch is a safe bound)
-    VBS_CUDA(cudaMemcpyAsync(&ctx->h_slot_status[slot], ctx->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    VBS_CUDA(cudaMemsetAsync(ctx->d_status, 0, sizeof(uint32_t), ctx->stream));
-    VBS_CUDA(cudaEventRecord(ctx->ev_slot_done[slot], ctx->stream));
+    if (row_pitch < (int64_t)ctx->W * ctx->C) return fail(ctx, VBS_ERR_BAD_ARG, "row_pitch smaller than a row");
+    if (ctx->inflight > 0) return fail(ctx, VBS_ERR_STATE, "batches submitted with vbs_submit_host are still in flight: call vbs_wait_host first");
+    VBS_ON_DEVICE(ctx);
+    if ((rc = ensure_image(ctx)) != VBS_OK) return rc;
+    if ((rc = ensure_host_streams(ctx)) != VBS_OK) return rc;
+    if ((rc = enqueue_host_chunks(ctx, frames, batch, frame_stride, row_pitch, frameno0, out, host_chunk_frames(ctx, batch, ctx->host_chunk))) != VBS_OK)
+        return rc;
+    VBS_CUDA(cudaEventRecord(ctx->ev_b_done, ctx->stream_b));
+    VBS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_b_done, 0));
+    return vbs_sync(ctx);
+}
+
+// ---- asynchronous host entry point: batch i+1 crosses PCIe while batch i is being processed ------------
+// Up to two batches in flight.  submit: enqueue the copies, the pipeline and the output copies, then a per-slot
+// "done" event (device-side status travels in a per-slot word, so a batch never reports its neighbour's flags).
+// wait: blocks on the oldest batch in flight.
+int vbs_submit_host(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int64_t frame_stride, int64_t row_pitch, int64_t frameno0,
+                    const vbs_outputs *out) {
+    int rc = check_batch(ctx, frames, batch);
+    if (rc != VBS_OK) return rc;
+    const size_t rowb = (size_t)ctx->W * ctx->C, fb = rowb * ctx->H;
+    if (row_pitch < (int64_t)rowb) return fail(ctx, VBS_ERR_BAD_ARG, "row_pitch smaller than a row");
+    if (ctx->inflight >= 2) return fail(ctx, VBS_ERR_STATE, "two batches already in flight: call vbs_wait_host first");
+    VBS_ON_DEVICE(ctx);
+    if ((rc = ensure_image(ctx)) != VBS_OK) return rc;
+    if ((rc = ensure_host_streams(ctx)) != VBS_OK) return rc;
+    const int slot = (int)(ctx->submitted & 1);
+    uint32_t *const status_all = ctx->d_status;
+    uint32_t *const word = status_all + 1 + slot;
+    cudaStream_t tail;                                   // the stream the batch finishes on
+    ctx->d_status = word;                                // kernels of this batch flag into the slot's own word
+    if (ctx->host_chunk > 0) {
+        rc = enqueue_host_chunks(ctx, frames, batch, frame_stride, row_pitch, frameno0, out, host_chunk_frames(ctx, batch, ctx->host_chunk));
+        tail = ctx->stream_b;
+    } else {
+        rc = VBS_OK;
+        if (!ctx->d_slots) {
+            cudaError_t e = cudaMalloc((void **)&ctx->d_slots, 2 * fb * ctx->B);
+            if (e != cudaSuccess) { ctx->d_status = status_all; VBS_CUDA(e); }
+        }
+        uint8_t *dst = ctx->d_slots + (size_t)slot * fb * ctx->B;
+        cudaError_t e = cudaSuccess;
+        if (ctx->submitted >= 2 && ctx->slot_used[slot]) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_slot_free[slot], 0);
+        if (e == cudaSuccess) rc = upload_frames(ctx, dst, frames, batch, frame_stride, row_pitch);
+        if (e == cudaSuccess && rc == VBS_OK) e = cudaEventRecord(ctx->ev_slot_in[slot], ctx->copy_stream);
+        if (e == cudaSuccess && rc == VBS_OK) e = cudaStreamWaitEvent(ctx->stream, ctx->ev_slot_in[slot], 0);
+        // chunked batches of earlier calls may still be in stage B on stream_b and share the scratch
+        for (int c = 0; c < VBS_MAX_CHUNKS && e == cudaSuccess && rc == VBS_OK; ++c)
+            if (ctx->bchunk_live[c]) { e = cudaStreamWaitEvent(ctx->stream, ctx->ev_bchunk[c], 0); ctx->bchunk_live[c] = 0; }
+        if (e == cudaSuccess && rc == VBS_OK) rc = process_common(ctx, dst, batch, (int64_t)fb, (int64_t)rowb, frameno0, out, cudaMemcpyDefault);
+        if (e == cudaSuccess && rc == VBS_OK) e = cudaEventRecord(ctx->ev_slot_free[slot], ctx->stream);   // (frames are dead after the blur; the end of the batch is a safe bound)
+        if (e != cudaSuccess) { ctx->d_status = status_all; VBS_CUDA(e); }
+        ctx->slot_used[slot] = 1;
+        tail = ctx->stream;
+    }
+    ctx->d_status = status_all;
+    if (rc != VBS_OK) return rc;
+    VBS_CUDA(cudaMemcpyAsync(&ctx->h_slot_status[slot], word, sizeof(uint32_t), cudaMemcpyDeviceToHost, tail));
+    VBS_CUDA(cudaMemsetAsync(word, 0, sizeof(uint32_t), tail));
+    VBS_CUDA(cudaEventRecord(ctx->ev_slot_done[slot], tail));
     ctx->submitted += 1;
     ctx->inflight += 1;
     return VBS_OK;
@@ -630,9 +755,15 @@ int vbs_submit_host(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int64_t 
 int vbs_wait_host(vbs_ctx *ctx) {
     if (!ctx) return VBS_ERR_BAD_ARG;
     if (ctx->inflight <= 0) return fail(ctx, VBS_ERR_STATE, "no batch in flight");
+    VBS_ON_DEVICE(ctx);
     const int slot = (int)((ctx->submitted - ctx->inflight) & 1);
     VBS_CUDA(cudaEventSynchronize(ctx->ev_slot_done[slot]));
     ctx->inflight -= 1;
+    if (ctx->inflight == 0) {
+        // nothing in flight: later calls on the context's stream (vbs_process_device, setters) see finished work
+        VBS_CUDA(cudaEventRecord(ctx->ev_b_done, ctx->stream_b));
+        VBS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_b_done, 0));
+    }
     const uint32_t st = ctx->h_slot_status[slot];
     ctx->h_slot_status[slot] = 0;
     return map_status(ctx, st);
@@ -640,6 +771,7 @@ int vbs_wait_host(vbs_ctx *ctx) {
 
 int vbs_set_overlap(vbs_ctx *ctx, int32_t enable) {
     if (!ctx) return VBS_ERR_BAD_ARG;
+    VBS_ON_DEVICE(ctx);
     VBS_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->overlap_device = enable ? 1 : 0;
     return VBS_OK;
@@ -647,6 +779,8 @@ int vbs_set_overlap(vbs_ctx *ctx, int32_t enable) {
 
 int vbs_set_host_chunk(vbs_ctx *ctx, int32_t frames_per_chunk) {
     if (!ctx || frames_per_chunk < 0) return VBS_ERR_BAD_ARG;
+    if (ctx->inflight > 0) return fail(ctx, VBS_ERR_STATE, "batches are in flight: call vbs_wait_host first");
+    VBS_ON_DEVICE(ctx);
     VBS_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->host_chunk = frames_per_chunk;
     return VBS_OK;
@@ -660,6 +794,7 @@ int vbs_set_undistort(vbs_ctx *ctx, const double *K, const double *D, int32_t nd
     for (int i = 0; i < 9; ++i) if (!std::isfinite(K[i])) return fail(ctx, VBS_ERR_BAD_ARG, "camera_matrix is not finite");
     for (int i = 0; i < nd; ++i) if (!std::isfinite(D[i])) return fail(ctx, VBS_ERR_BAD_ARG, "dist_coeffs are not finite");
     if (K[0] == 0.0 || K[4] == 0.0) return fail(ctx, VBS_ERR_BAD_ARG, "focal lengths must not be zero");
+    VBS_ON_DEVICE(ctx);
     const size_t HW = (size_t)ctx->H * ctx->W;
     if (!ctx->undist_map) VBS_CUDA(dalloc(&ctx->undist_map, HW));
     if (!ctx->d_undist) VBS_CUDA(dalloc(&ctx->d_undist, (size_t)ctx->B * HW * ctx->C));
@@ -672,6 +807,7 @@ int vbs_set_undistort(vbs_ctx *ctx, const double *K, const double *D, int32_t nd
 int vbs_get_undistort_maps(vbs_ctx *ctx, double *new_camera_matrix, int16_t *map1_device, uint16_t *map2_device) {
     if (!ctx) return VBS_ERR_BAD_ARG;
     if (!ctx->undist_on) return fail(ctx, VBS_ERR_STATE, "vbs_set_undistort has not been called");
+    VBS_ON_DEVICE(ctx);
     if (new_camera_matrix) {
         const double m[9] = {ctx->new_k[0], 0.0, ctx->new_k[2], 0.0, ctx->new_k[1], ctx->new_k[3], 0.0, 0.0, 1.0};
         for (int i = 0; i < 9; ++i) new_camera_matrix[i] = m[i];
@@ -687,6 +823,7 @@ int vbs_undistort_frames(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int
     if (rc != VBS_OK) return rc;
     if (!out_device) return fail(ctx, VBS_ERR_BAD_ARG, "out_device is NULL");
     if (!ctx->undist_on) return fail(ctx, VBS_ERR_STATE, "vbs_set_undistort has not been called");
+    VBS_ON_DEVICE(ctx);
     VBS_CUDA(vbs_launch_remap(ctx, frames, batch, frame_stride, row_pitch, out_device));
     return VBS_OK;
 }
@@ -694,6 +831,8 @@ int vbs_undistort_frames(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int
 int vbs_find_markers(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int64_t frame_stride, int64_t row_pitch) {
     int rc = check_batch(ctx, frames, batch);
     if (rc != VBS_OK) return rc;
+    VBS_ON_DEVICE(ctx);
+    if ((rc = ensure_image(ctx)) != VBS_OK) return rc;
     ctx->last_batch = batch;
     return run_detection(ctx, frames, batch, frame_stride, row_pitch);
 }
@@ -702,10 +841,14 @@ int vbs_marker_center(vbs_ctx *ctx, const uint8_t *mask, const uint8_t *area_mas
     int rc = check_batch(ctx, mask, batch);
     if (rc != VBS_OK) return rc;
     if (!area_mask) return fail(ctx, VBS_ERR_BAD_ARG, "area_mask is NULL");
+    VBS_ON_DEVICE(ctx);
+    if ((rc = ensure_image(ctx)) != VBS_OK) return rc;
     VBS_CUDA(vbs_launch_pack_masks(ctx, mask, area_mask, batch));
     if ((rc = run_centres(ctx, batch)) != VBS_OK) return rc;
     CopyPlan plan[16];
-    vbs_outputs o = *out;
+    vbs_outputs o;
+    std::memset(&o, 0, sizeof(o));
+    if (out) o = *out;
     o.row_det = nullptr; o.row_cxy = nullptr; o.row_axes = nullptr; o.pos3d = nullptr; o.pos_flags = nullptr; o.plane = nullptr; o.plane_n = nullptr;
     const int n = plan_outputs(ctx, &o, batch, plan);
     for (int i = 0; i < n; ++i) VBS_CUDA(cudaMemcpyAsync(plan[i].dst, plan[i].src, plan[i].bytes, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -713,18 +856,31 @@ int vbs_marker_center(vbs_ctx *ctx, const uint8_t *mask, const uint8_t *area_mas
     return VBS_OK;
 }
 
+// K2 alone on area masks supplied by the caller: mask = normxcorr2(gkern, area_mask) > 0.1 (MD:132-133, 146-164)
+int vbs_ncc_mask(vbs_ctx *ctx, const uint8_t *area_mask, int32_t batch) {
+    int rc = check_batch(ctx, area_mask, batch);
+    if (rc != VBS_OK) return rc;
+    VBS_ON_DEVICE(ctx);
+    if ((rc = ensure_image(ctx)) != VBS_OK) return rc;
+    VBS_CUDA(vbs_launch_pack_area(ctx, area_mask, batch));
+    VBS_CUDA(vbs_launch_ncc(ctx, batch));
+    ctx->last_batch = batch;
+    return VBS_OK;
+}
+
 int vbs_debug_stage(vbs_ctx *ctx, int32_t stage, void *dst_device, size_t bytes) {
     if (!ctx || !dst_device) return VBS_ERR_BAD_ARG;
-    const int batch = ctx->last_batch;
-    if (batch <= 0) return fail(ctx, VBS_ERR_STATE, "no batch processed yet");
-    const size_t npx = (size_t)batch * ctx->H * ctx->W;
+    int batch = ctx->last_batch;
+    if (batch <= 0 || !ctx->image_ready) return fail(ctx, VBS_ERR_STATE, "no batch processed yet");
+    VBS_ON_DEVICE(ctx);
+    // the first frames of the most recent batch, as many as `bytes` holds (at least one)
+    const size_t per_frame = stage == VBS_STAGE_RECHECKS ? sizeof(int32_t) : (size_t)ctx->H * ctx->W * (stage == VBS_STAGE_LABELS ? 4 : 1);
+    if (bytes < per_frame) return fail(ctx, VBS_ERR_BAD_ARG, "destination too small");
+    if ((size_t)batch > bytes / per_frame) batch = (int)(bytes / per_frame);
     if (stage == VBS_STAGE_RECHECKS) {
-        if (bytes < sizeof(int32_t) * batch) return fail(ctx, VBS_ERR_BAD_ARG, "destination too small");
         VBS_CUDA(cudaMemcpyAsync(dst_device, ctx->recheck_n, sizeof(int32_t) * batch, cudaMemcpyDeviceToDevice, ctx->stream));
         return VBS_OK;
     }
-    const size_t need = npx * (stage == VBS_STAGE_LABELS ? 4 : 1);
-    if (bytes < need) return fail(ctx, VBS_ERR_BAD_ARG, "destination too small");
     VBS_CUDA(vbs_launch_unpack(ctx, stage, dst_device, batch));
     return VBS_OK;
 }
@@ -735,6 +891,8 @@ int vbs_track_markers(vbs_ctx *ctx, int32_t n, const double *marker_xy, const do
     if (!ctx || n < 0 || (n > 0 && (!marker_xy || !marker_axes))) return VBS_ERR_BAD_ARG;
     if (n > ctx->M) return fail(ctx, VBS_ERR_CAPACITY, "marker list exceeds max_markers");
     if (ctx->R <= 0) return fail(ctx, VBS_ERR_STATE, "no reference array set");
+    VBS_ON_DEVICE(ctx);
+    { int rc = ensure_track(ctx, 1); if (rc != VBS_OK) return rc; }
     VBS_CUDA(cudaMemcpyAsync(ctx->marker_xy, marker_xy, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
     VBS_CUDA(cudaMemcpyAsync(ctx->marker_axes, marker_axes, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
     VBS_CUDA(cudaMemcpyAsync(ctx->d_nmarkers, &n, sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -755,6 +913,7 @@ int vbs_reconstruct_rows(vbs_ctx *ctx, int32_t batch, int64_t frameno0, const in
     if (!ctx || !row_det || !row_cxy || !row_axes) return VBS_ERR_BAD_ARG;
     if (batch < 1 || batch > ctx->B) return fail(ctx, VBS_ERR_BAD_ARG, "batch must be in [1, max_batch]");
     if (ctx->R <= 0 || !ctx->have_cam) return fail(ctx, VBS_ERR_STATE, "reference array and camera must be set first");
+    VBS_ON_DEVICE(ctx);
     const size_t n = (size_t)batch * ctx->R;
     VBS_CUDA(cudaMemcpyAsync(ctx->row_det, row_det, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
     VBS_CUDA(cudaMemcpyAsync(ctx->row_cxy, row_cxy, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
@@ -773,6 +932,7 @@ int vbs_undistort_points(vbs_ctx *ctx, int32_t n, const double *uv, double *out)
     if (!ctx || n < 0 || (n > 0 && (!uv || !out))) return VBS_ERR_BAD_ARG;
     if (!ctx->have_cam) return fail(ctx, VBS_ERR_STATE, "camera not set");
     if (n == 0) return VBS_OK;
+    VBS_ON_DEVICE(ctx);
     Scratch s;
     VBS_CUDA(cudaMalloc(&s.p, sizeof(double) * 4 * n));
     double *d_in = (double *)s.p, *d_out = d_in + 2 * (size_t)n;
@@ -786,6 +946,7 @@ int vbs_position_3d(vbs_ctx *ctx, int32_t n, const double *uvd, double *P, uint8
     if (!ctx || n < 0 || (n > 0 && (!uvd || !P || !ok))) return VBS_ERR_BAD_ARG;
     if (!ctx->have_cam) return fail(ctx, VBS_ERR_STATE, "camera not set");
     if (n == 0) return VBS_OK;
+    VBS_ON_DEVICE(ctx);
     Scratch s;
     VBS_CUDA(cudaMalloc(&s.p, sizeof(double) * 6 * n + n));
     double *d_in = (double *)s.p, *d_P = d_in + 3 * (size_t)n;
@@ -799,6 +960,7 @@ int vbs_position_3d(vbs_ctx *ctx, int32_t n, const double *uvd, double *P, uint8
 
 int vbs_fit_plane(vbs_ctx *ctx, int32_t n, const double *X, const double *Y, const double *Z, double out[4]) {
     if (!ctx || n < 1 || !X || !Y || !Z || !out) return VBS_ERR_BAD_ARG;
+    VBS_ON_DEVICE(ctx);
     Scratch s;
     VBS_CUDA(cudaMalloc(&s.p, sizeof(double) * (3 * (size_t)n + 4)));
     double *dX = (double *)s.p, *dY = dX + n, *dZ = dY + n, *dO = dZ + n;
@@ -815,6 +977,7 @@ int64_t vbs_tma_launches(const vbs_ctx *ctx) { return ctx ? ctx->tma_launches : 
 
 int vbs_set_profiling(vbs_ctx *ctx, int32_t enable) {
     if (!ctx) return VBS_ERR_BAD_ARG;
+    VBS_ON_DEVICE(ctx);
     if (enable && !ctx->pev[0])
         for (int i = 0; i < VBS_MAX_CHUNKS * VBS_EV_PER_CHUNK; ++i) VBS_CUDA(cudaEventCreate(&ctx->pev[i]));
     if (!enable) { int rc = prof_collect(ctx); if (rc != VBS_OK) return rc; }
@@ -824,6 +987,7 @@ int vbs_set_profiling(vbs_ctx *ctx, int32_t enable) {
 
 int vbs_get_stage_ms(vbs_ctx *ctx, double ms[7], int64_t *calls) {
     if (!ctx || !ms) return VBS_ERR_BAD_ARG;
+    VBS_ON_DEVICE(ctx);
     int rc = prof_collect(ctx);
     if (rc != VBS_OK) return rc;
     for (int i = 0; i < VBS_NSTAGES; ++i) ms[i] = ctx->stage_ms[i];

@@ -53,7 +53,9 @@ struct vbs_ctx {
     int host_chunk; cudaStream_t copy_stream; cudaEvent_t ev_copied[2], ev_consumed[2];
     // asynchronous host path: two whole-batch staging slots
     uint8_t *d_slots; cudaEvent_t ev_slot_in[2], ev_slot_free[2], ev_slot_done[2]; uint32_t *h_slot_status;
-    int64_t submitted; int inflight;
+    int64_t submitted; int inflight; int slot_used[2];
+    int64_t chunk_seq;                           // chunks uploaded so far (staging buffer = chunk_seq & 1, across calls)
+    cudaEvent_t ev_bchunk[8]; int bchunk_live[8];    // end of stage B of chunk c of the latest chunked batch
     // bit images [B][H][WW]
     uint32_t *area_bits, *mask_bits, *max_bits, *open_bits;
     uint32_t *area_count;            // [B] set pixels of area_mask
@@ -102,6 +104,8 @@ struct vbs_ctx {
     uint32_t *d_status; uint32_t *h_status;  // device flag word, pinned host mirror
     int32_t *d_nrecheck;                     // [B] recheck counts (debug)
     int last_batch;
+    int image_ready;                         // per-pixel scratch allocated (lazily: table-only contexts never pay for it)
+    int track_cap;                           // frames the marker cell grids (cell_start / cell_items) are sized for
     // optional per-stage timing (events on the context's stream)
     int profiling, prof_pending, prof_chunks;
     cudaEvent_t pev[72];                        // 8 chunks x 9 stage boundaries
@@ -139,5 +143,6 @@ cudaError_t vbs_launch_undistort(vbs_ctx *ctx, const double *uv, double *out, in
 cudaError_t vbs_launch_position(vbs_ctx *ctx, const double *uvd, double *P, uint8_t *ok, int n);
 cudaError_t vbs_launch_plane_points(vbs_ctx *ctx, const double *X, const double *Y, const double *Z, int n, double *out);
 cudaError_t vbs_launch_pack_masks(vbs_ctx *ctx, const uint8_t *mask, const uint8_t *area, int batch);
+cudaError_t vbs_launch_pack_area(vbs_ctx *ctx, const uint8_t *area, int batch);
 cudaError_t vbs_launch_unpack(vbs_ctx *ctx, int stage, void *dst, int batch);
 int vbs_check_taps(std::string &err);       // baked integer taps == host recipe

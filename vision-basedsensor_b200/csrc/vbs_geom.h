@@ -340,6 +340,7 @@ struct CameraF64 {
     double k1, k2, p1, p2, k3;
     double R[9], T[3];              // world->cam, float32 values widened
     double f_avg;                   // float32((fx+fy)/2) widened        (R3:211)
+    double f_avg_sq;                // float32(f_avg * f_avg) widened: `f_avg**2` on an np.float32 scalar stays float32 (R3:219)
     double ratio;                   // float32(diam_mm / f_avg) widened  (R3:219)
     double min_size, max_disp;
 };
@@ -440,7 +441,7 @@ VBS_HD bool position3d(const CameraF64 &c, double u, double v, double diam, doub
     const double du = u - c.cx, dv = v - c.cy;
     const double rad = sqrt(add_rn(mul_rn(du, du), mul_rn(dv, dv)));
     if (rad < 1e-6) return false;
-    const double d_eff = mul_rn(c.ratio, sqrt(add_rn(mul_rn(rad, rad), mul_rn(c.f_avg, c.f_avg))));
+    const double d_eff = mul_rn(c.ratio, sqrt(add_rn(mul_rn(rad, rad), c.f_avg_sq)));
     const double h = mul_rn(c.f_avg, d_eff / diam);
     const double pc0 = sub_rn(mul_rn(h, du) / c.fx, c.T[0]);
     const double pc1 = sub_rn(mul_rn(h, dv) / c.fy, c.T[1]);

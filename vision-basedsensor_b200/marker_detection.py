@@ -7,9 +7,10 @@ exception types - every per-frame computation runs in the CUDA library (no CPU f
 ``find_marker`` / ``marker_center`` are the module-level names code/Marker_Tracking/tracking.py:7
 imports (they do not exist in the reference, so that script never ran).
 
-Out of scope here (host glue either side of the path): drawing on frames
-(MD:251-273,398-427), the XVID video writer (MD:69-76,453) and optional frame undistortion
-(MD:93-109).  ``frame=`` arguments are accepted and ignored.
+Optional frame undistortion (MD:93-109, ``config['calibration_params']``) runs on the GPU too, both in
+``_undistort_frame`` and inside the batched ``process()``.  Out of scope here (host glue
+either side of the path): drawing on frames (MD:251-273,398-427) and the XVID video writer (MD:69-76,453).
+``frame=`` arguments are accepted and ignored.
 """
 from __future__ import annotations
 
@@ -26,7 +27,7 @@ _undistort_pipes: dict = {}
 
 def _pipe_for(h: int, w: int, c: int, max_markers: int = 4096) -> "_pl.MarkerPipeline":
     """One small context per frame geometry for the static-method mirrors (created on first use)."""
-    key = (h, w, c)
+    key = (h, w, c, _pl._current_device())
     if key not in _pipes:
         _pipes[key] = _pl.MarkerPipeline(h, w, c, max_batch=1, max_markers=max_markers, max_refs=1)
     return _pipes[key]
@@ -82,7 +83,7 @@ class MarkerTracker:
         c = 1 if frame.ndim == 2 else frame.shape[2]
         cal = self.config["calibration_params"]
         K = np.array(cal["camera_matrix"], dtype=np.float64); D = np.array(cal["dist_coeffs"], dtype=np.float64).ravel()
-        key = (h, w, c, K.tobytes(), D.tobytes())
+        key = (h, w, c, K.tobytes(), D.tobytes(), _pl._current_device())
         if key not in _undistort_pipes:                          # the maps are built once per (K, D, size)
             pipe = _pl.MarkerPipeline(h, w, c, max_batch=1, max_markers=1, max_refs=1)
             pipe.set_undistort(K, D)
@@ -164,7 +165,9 @@ class MarkerTracker:
 
     # -- MD:429-474 --------------------------------------------------------------------------------
     def process(self):
-        """Decode the video in chunks, run every chunk through the batched CUDA path, write the CSV."""
+        """Decode the video in chunks, run every chunk through the batched CUDA path, write the CSV.
+        Chunk i+1 is decoded while chunk i is on the GPU (``vbs_submit_host`` / ``vbs_wait_host``, two pinned
+        staging buffers); only the per-frame tracking rows come back (compact output block)."""
         import cv2
         import torch
         cap = cv2.VideoCapture(self.config["video_path"])
@@ -179,9 +182,24 @@ class MarkerTracker:
         B = int(self.config.get("batch", 64))
         pipe = None
         data = []
-        staging = torch.empty((B, self.height, self.width, 3), dtype=torch.uint8).pin_memory()
-        stage_np = staging.numpy()
+        stagings = [torch.empty((B, self.height, self.width, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        fs, rp = self.height * self.width * 3, self.width * 3
+        keys, outs = [], None
+
+        def emit(n, frame0, res):
+            for f in range(n):
+                for r, k in enumerate(keys):
+                    if res.row_det[f, r] >= 0:
+                        ref = self.first_frame_markers[k]
+                        data.append({"frameno": frame0 + f, "row": k[0], "col": k[1], "Ox": ref["Ox"], "Oy": ref["Oy"],
+                                     "Cx": res.row_cxy[f, r, 0], "Cy": res.row_cxy[f, r, 1], "major_axis": float(res.row_axes[f, r, 0]),
+                                     "minor_axis": float(res.row_axes[f, r, 1]), "angle": float(res.row_axes[f, r, 2])})
+
+        pending = None                   # (frames, first frame number, result block) of the chunk on the GPU
+        chunk = 0
         while True:
+            slot = chunk & 1
+            stage_np = stagings[slot].numpy()
             n = 0
             while n < B:
                 ret, frame = cap.read()
@@ -201,20 +219,20 @@ class MarkerTracker:
                 if "calibration_params" in self.config:          # MD:88-89, inside the batched path
                     cal = self.config["calibration_params"]
                     pipe.set_undistort(cal["camera_matrix"], cal["dist_coeffs"])
-                outs = pipe.alloc_outputs(B, False)
-            fs, rp = self.height * self.width * 3, self.width * 3
-            res = pipe.process_host_ptr(staging.data_ptr() + top * rp + left * 3, n, fs, rp, self.frame_count, outs)
-            for f in range(n):
-                for r, k in enumerate(keys):
-                    if res.row_det[f, r] >= 0:
-                        ref = self.first_frame_markers[k]
-                        data.append({"frameno": self.frame_count + f, "row": k[0], "col": k[1], "Ox": ref["Ox"], "Oy": ref["Oy"],
-                                     "Cx": res.row_cxy[f, r, 0], "Cy": res.row_cxy[f, r, 1], "major_axis": float(res.row_axes[f, r, 0]),
-                                     "minor_axis": float(res.row_axes[f, r, 1]), "angle": float(res.row_axes[f, r, 2])})
+                outs = [pipe.alloc_outputs(B, False, compact=True) for _ in range(2)]
+            res = pipe.submit_host_ptr(stagings[slot].data_ptr() + top * rp + left * 3, n, fs, rp, self.frame_count, outs[slot])
+            if pending is not None:          # the previous chunk finishes while this one was being decoded
+                pipe.wait_host()
+                emit(*pending)
+            pending = (n, self.frame_count, res)
             before = self.frame_count
             self.frame_count += n
+            chunk += 1
             if self.frame_count // 100 != before // 100:
                 print(f"Processed frame {self.frame_count // 100 * 100}")
+        if pending is not None:
+            pipe.wait_host()
+            emit(*pending)
         self._save_results(data)
         self._cleanup()
         if pipe is not None:

@@ -20,11 +20,11 @@ from . import capi
 class BatchResult:
     """SoA outputs of one batch (device torch tensors or host numpy arrays)."""
     frameno0: int
-    n_labels: object      # [B] int32
-    centres: object       # [B, M, 2] float64 (row, col)
-    n_markers: object     # [B] int32
-    marker_xy: object     # [B, M, 2] float64 (x, y)
-    marker_axes: object   # [B, M, 3] float64 major, minor, angle
+    n_labels: object = None     # [B] int32
+    centres: object = None      # [B, M, 2] float64 (row, col)        (None in compact blocks)
+    n_markers: object = None    # [B] int32
+    marker_xy: object = None    # [B, M, 2] float64 (x, y)            (None in compact blocks)
+    marker_axes: object = None  # [B, M, 3] float64 major, minor, angle (None in compact blocks)
     row_det: object = None      # [B, R] int32
     row_cxy: object = None      # [B, R, 2]
     row_axes: object = None     # [B, R, 3]
@@ -35,7 +35,7 @@ class BatchResult:
 
     def to_host(self) -> "BatchResult":
         def cv(a):
-            return a.cpu().numpy() if hasattr(a, "cpu") else a
+            return a.cpu().numpy() if hasattr(a, "cpu") else a          # None stays None
         return BatchResult(self.frameno0, *[cv(getattr(self, k)) for k in
                                             ("n_labels", "centres", "n_markers", "marker_xy", "marker_axes", "row_det", "row_cxy",
                                              "row_axes", "pos3d", "pos_flags", "plane", "plane_n")])
@@ -48,12 +48,24 @@ class BatchResult:
                  "minor_axis": float(h.marker_axes[f, k, 1]), "angle": float(h.marker_axes[f, k, 2])} for k in range(n)]
 
 
+def _current_device() -> int:
+    """The GPU a context is created on when none is named: torch's current device (a rank of a sharded job has
+    called ``torch.cuda.set_device(local_rank)``), so helper contexts never pile up on GPU 0."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            return int(torch.cuda.current_device())
+    except ImportError:
+        pass
+    return 0
+
+
 class MarkerPipeline:
     def __init__(self, height: int, width: int, channels: int = 1, max_batch: int = 32, max_markers: int = 1024,
-                 max_refs: int = 1024, device: int = 0):
+                 max_refs: int = 1024, device: Optional[int] = None):
         self.H, self.W, self.C = int(height), int(width), int(channels)
         self.B, self.M, self.Rcap = int(max_batch), int(max_markers), int(max_refs)
-        self.device = int(device)
+        self.device = _current_device() if device is None else int(device)
         self.R = 0
         self.have_cam = False
         self.have_plane = False
@@ -209,10 +221,11 @@ class MarkerPipeline:
         capi.check(self._ctx, capi.lib.vbs_set_first_frame(self._ctx, int(frameno)))
 
     # -- output allocation --------------------------------------------------------------------
-    def _alloc(self, batch: int, on_device: bool):
+    def _alloc(self, batch: int, on_device: bool, compact: bool = False, pinned: bool = True):
         B, M, R = batch, self.M, self.R
-        shapes = {"n_labels": ((B,), "int32"), "centres": ((B, M, 2), "float64"), "n_markers": ((B,), "int32"),
-                  "marker_xy": ((B, M, 2), "float64"), "marker_axes": ((B, M, 3), "float64")}
+        shapes = {"n_labels": ((B,), "int32"), "n_markers": ((B,), "int32")}
+        if not compact:          # the padded per-frame marker lists: [B][M] arrays, 56 B per slot
+            shapes.update({"centres": ((B, M, 2), "float64"), "marker_xy": ((B, M, 2), "float64"), "marker_axes": ((B, M, 3), "float64")})
         if R > 0:
             shapes.update({"row_det": ((B, R), "int32"), "row_cxy": ((B, R, 2), "float64"), "row_axes": ((B, R, 3), "float64")})
             if self.have_cam:
@@ -228,12 +241,10 @@ class MarkerPipeline:
                 setattr(out, k, arrays[k].data_ptr())
         else:
             # pinned host memory: D2H copies into pageable memory would block the host per chunk and
-            # defeat the copy/compute overlap of vbs_process_host
+            # defeat the copy/compute overlap of vbs_process_host.  The numpy view keeps its tensor alive.
             import torch
-            self._pinned = getattr(self, "_pinned", [])
             for k, (shp, dt) in shapes.items():
-                t = torch.empty(shp, dtype=getattr(torch, dt), pin_memory=torch.cuda.is_available())
-                self._pinned.append(t)
+                t = torch.empty(shp, dtype=getattr(torch, dt), pin_memory=pinned and torch.cuda.is_available())
                 arrays[k] = t.numpy()
                 setattr(out, k, arrays[k].ctypes.data)
         return arrays, out
@@ -287,9 +298,12 @@ class MarkerPipeline:
             self.use_stream(ptr)
             self._stream_ptr = ptr
 
-    def alloc_outputs(self, batch: int, on_device: bool):
-        """Pre-allocate an output block to reuse across calls (pass as ``out=``)."""
-        return self._alloc(batch, on_device)
+    def alloc_outputs(self, batch: int, on_device: bool, compact: bool = False):
+        """Pre-allocate an output block to reuse across calls (pass as ``out=``).  ``compact=True`` leaves out
+        the padded marker lists (``centres``, ``marker_xy``, ``marker_axes``: 56 B x max_markers per frame) and keeps
+        the per-frame records the reference writes to its tables: tracking rows, 3D rows, plane, counts - the
+        algorithmic 96 B per reference entry + 32 B per frame (MD:380-391, R3:296-307, FD:141-159)."""
+        return self._alloc(batch, on_device, compact)
 
     def process_host_ptr(self, ptr: int, batch: int, frame_stride: int, row_pitch: int, frameno0: int, out):
         """Host frames by raw pointer (pinned staging buffers, crop views): MD:85 crop is a pointer + pitch."""
@@ -307,6 +321,18 @@ class MarkerPipeline:
     def wait_host(self):
         """Block until the oldest submitted batch has landed in its output arrays."""
         capi.check(self._ctx, capi.lib.vbs_wait_host(self._ctx))
+
+    def ncc_mask(self, area_mask):
+        """Device area masks [B,H,W] uint8 -> (mask uint8 {0,1} device tensor, float64 re-decisions per frame):
+        ``(normxcorr2(gkern, area_mask) > 0.1)`` alone (MD:132-133, 146-164)."""
+        import torch
+        batch = area_mask.shape[0]
+        if tuple(area_mask.shape[1:]) != (self.H, self.W) or batch > self.B:
+            raise ValueError(f"area_mask must be [B<={self.B},{self.H},{self.W}], got {tuple(area_mask.shape)}")
+        a = ((area_mask != 0).to(torch.uint8) * 255).contiguous()
+        self._follow_torch_stream()
+        capi.check(self._ctx, capi.lib.vbs_ncc_mask(self._ctx, a.data_ptr(), batch))
+        return self.debug_stage(capi.STAGE_MASK, batch), self.debug_stage(capi.STAGE_RECHECKS, batch)
 
     def find_markers(self, frames):
         """Device frames -> (mask, area_mask) uint8 device tensors, like ``_find_markers`` (MD:111-135)."""

@@ -54,7 +54,7 @@ class CameraParameters:
 
 
 class MarkerAnalysis:
-    def __init__(self, config: Config, max_frames_per_call: int = 4096):
+    def __init__(self, config: Config, max_frames_per_call: int = 1024):
         self.config = config
         self.camera = CameraParameters()
         self._max_frames = int(max_frames_per_call)
@@ -68,14 +68,13 @@ class MarkerAnalysis:
         K = np.asarray(c.matrix, dtype=np.float32)
         if K[0, 0] <= 0 or K[1, 1] <= 0:
             raise ValueError("Focal lengths must be positive")                      # R3:94-95
-        key = (K.tobytes(), np.asarray(c.dist_coeffs, np.float32).tobytes(), np.asarray(c.R_world_to_cam, np.float32).tobytes(),
-               np.asarray(c.T_world_to_cam, np.float32).tobytes(), self.config.marker_diameter_mm, self.config.min_marker_size_px,
-               self.config.max_displacement_px, self.config.warmup_frames, n_refs)
-        if self._pipe is None or self._pipe_key != key:
+        # One table-only context (the C library allocates per-pixel scratch lazily, so this one never does), kept
+        # while it is large enough: alternating per-point calls (n_refs = 1) and _track_markers (n_refs = R)
+        # only re-sets the reference array; it is rebuilt when a larger R arrives.
+        if self._pipe is None or self._pipe.Rcap < n_refs:
             if self._pipe is not None:
                 self._pipe.close()
-            self._pipe = _pl.MarkerPipeline(8, 8, 1, max_batch=self._max_frames, max_markers=1, max_refs=max(n_refs, 1))
-            self._pipe_key = key
+            self._pipe = _pl.MarkerPipeline(8, 8, 1, max_batch=self._max_frames, max_markers=1, max_refs=max(n_refs, 64))
             self._refs_set = 0
         if self._refs_set != n_refs:
             z = np.zeros(n_refs)

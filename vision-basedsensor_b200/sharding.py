@@ -50,18 +50,28 @@ def exchange_last_seen(table: np.ndarray, rank: int, world: int, device=None) ->
     return incoming_last_seen(np.stack([p.cpu().numpy() for p in parts]), rank)
 
 
-def gather_records(tensors: dict, rank: int, world: int, dst: int = 0):
-    """Gather per-frame record tensors (equal shapes on every rank) to ``dst``; returns a dict of
-    tensors concatenated in rank order (= global frame order for contiguous shards) on ``dst``, else None."""
+def gather_records(tensors: dict, rank: int, world: int, dst: int = 0, counts=None):
+    """Gather per-frame record tensors to ``dst``; returns a dict of tensors concatenated in rank order
+    (= global frame order for contiguous shards) on ``dst``, else None.  ``counts[r]`` = frames of rank r when
+    the shards are not all the same length (``shard_bounds`` blocks differ by at most one frame): the shorter
+    blocks are padded for the collective and trimmed on ``dst``."""
     import torch
     import torch.distributed as dist
     if world == 1:
         return dict(tensors)
+    ragged = counts is not None and len(set(counts)) > 1
+    nmax = max(counts) if ragged else None
     out = {}
     for name, t in tensors.items():
+        if ragged and t.shape[0] < nmax:
+            pad = torch.zeros((nmax - t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            t = torch.cat([t, pad], dim=0)
+        t = t.contiguous()
         parts = [torch.empty_like(t) for _ in range(world)] if rank == dst else None
         dist.gather(t, parts, dst=dst)
         if rank == dst:
+            if ragged:
+                parts = [p[:c] for p, c in zip(parts, counts)]
             out[name] = torch.cat(parts, dim=0)
     return out if rank == dst else None
 
