@@ -222,6 +222,14 @@ int64_t vbs_kernel_launches(const vbs_ctx *ctx);
  * the generic loader (BGR input, unaligned crop views, or VBS_NO_TMA=1 in the environment) */
 int64_t vbs_tma_launches(const vbs_ctx *ctx);
 
+/* OPT-IN experiment (off by default, also switched on by VBS_BLUR_TC=1 in the environment): run the
+ * two fixed-point Gaussian blurs of MD:117-126 as banded-Toeplitz int8 GEMMs on the tensor cores (tcgen05.mma kind::i8,
+ * accumulators in TMEM, TMA-staged operands) instead of the integer-dot-product kernel.  Same bits out (area_mask is
+ * tested equal); gray frames the TMA unit can describe only (16-byte aligned base and pitches, W >= 128, H >= 64) -
+ * anything else silently takes the default kernel.  vbs_tc_launches counts the blur launches that took this path. */
+int vbs_set_blur_tc(vbs_ctx *ctx, int32_t enable);
+int64_t vbs_tc_launches(const vbs_ctx *ctx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,6 +63,8 @@ SYMBOLS = {
     "vbs_debug_stage": (C.c_int, [_P, C.c_int32, _P, C.c_size_t]),
     "vbs_kernel_launches": (C.c_int64, [_P]),
     "vbs_tma_launches": (C.c_int64, [_P]),
+    "vbs_set_blur_tc": (C.c_int, [_P, C.c_int32]),
+    "vbs_tc_launches": (C.c_int64, [_P]),
     "vbs_set_profiling": (C.c_int, [_P, C.c_int32]),
     "vbs_get_stage_ms": (C.c_int, [_P, _P, _P]),
 }

@@ -436,6 +436,8 @@ void host_taps(int ksize, double sigma, int *out) {
 
 }  // namespace
 
+void vbs_host_taps(int ksize, double sigma, int *out) { host_taps(ksize, sigma, out); }
+
 int vbs_check_taps(std::string &err) {
     int t[128];
     host_taps(39, 8.0, t);    if (!taps_match<39>(t))  { err = "baked 39-tap kernel differs from the fixed-point recipe"; return -1; }
@@ -455,6 +457,10 @@ cudaError_t vbs_launch_blur(vbs_ctx *ctx, const uint8_t *frames, int batch, int6
         row_pitch = (int64_t)ctx->W * ctx->C;
         frame_stride = row_pitch * ctx->H;
     }
+    if (ctx->blur_tc) {                         // opt-in: both blurs as int8 GEMMs on the tensor cores (k_blur_tc.cu)
+        e = vbs_launch_blur_tc(ctx, frames, batch, frame_stride, row_pitch);
+        if (e != cudaErrorNotSupported) return e;
+    }                                           // BGR input / frames the TMA unit cannot describe: integer-dot-product kernel
     if (ctx->big) return launch<39, 101>(ctx, frames, batch, frame_stride, row_pitch);
     return launch<21, 35>(ctx, frames, batch, frame_stride, row_pitch);
 }

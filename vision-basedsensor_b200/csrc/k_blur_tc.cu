@@ -1,0 +1,435 @@
+// k_blur_tc.cu - K1 on the tensor cores (OPT-IN: VBS_BLUR_TC=1 or vbs_set_blur_tc, the default
+// stays the integer-dot-product kernel of k_blur.cu).  Same contract as k_blur.cu: gray frames -> two fixed-point
+// Gaussian blurs (cv2.GaussianBlur on CV_8U, MD:117-126) -> wrapping DoG -> inRange -> bit-packed area mask +
+// per-frame popcount, bit-exact.
+//
+// Both separable passes are banded-Toeplitz int8 GEMMs on tcgen05.mma kind::i8 (u8/s8 x u8/s8 -> s32, exact):
+//
+//   pass 1 (horizontal)  D1[m, y] = sum_x' A1[m, x'] * img[y, x']      M = 128 = 64 output columns x 2 blurs
+//        A1 = the two tap rows of every output column (REFLECT_101 at the left/right image edge FOLDED INTO the
+//        matrix: one variant per 64-px strip, built on the host), B = 64 image rows as they lie in memory (K-major),
+//        staged by TMA with 128-byte swizzle; out-of-image columns arrive as zeros, which is what the folded matrix wants.
+//   epilogue 1           D1 (<= 65280) leaves TMEM, is split into high / low bytes, both flipped to signed (^0x80),
+//        and stored K-major (y contiguous) as the B operand of pass 2 - no transposition: a thread owns one
+//        (blur, column) TMEM lane and writes its own 64-byte row.
+//   pass 2 (vertical)    D2_b[y, (x,hi|lo)] = sum_y' A2_b[y, y'] * Hb[(x,hi|lo), y']   per blur b, M = 128 rows
+//        A2 = plain Toeplitz.  REFLECT_101 at the top / bottom edge is handled by giving pass 1 MIRRORED image rows
+//        (single-row TMA loads) for the virtual rows above row 0 and below row H-1.
+//   epilogue 2           u_b = 256 * D2_b[hi] + D2_b[lo];  blur_b = (u_b >> 16) + const  (the rounding constant
+//        32768 and the sign flips cancel: sum(taps) = 256, so sum tap*(v-128) = sum tap*v - 32768, and the two
+//        constants are equal for both blurs)  ->  dog = uint8(b_large - b_small + 15), lo <= dog <= hi, 64 bits per row.
+//
+// One CTA = one 64-column strip of one frame, marching down in 64-row chunks: TMA warp, MMA warp (one thread
+// issues), 4 warps epilogue 1, 4 warps epilogue 2; accumulators in TMEM (D1 double-buffered), mbarrier hand-offs.
+#include <cuda.h>
+#include <cstring>
+#include <vector>
+#include "vbs_ctx.h"
+
+namespace {
+
+constexpr int SW = 64;             // output columns per CTA
+constexpr int CHR = 64;            // image rows per chunk (pass 1 step) = K bytes per ring slab
+constexpr int BLK = 128;           // output rows per pass-2 block
+constexpr int KEXT = 256;          // K extent of both passes in bytes (two 128-byte swizzle slabs)
+constexpr int NSLAB = 6;           // ring of pass-1 results (4 are read by a block, 2 are being produced)
+constexpr int NTHREADS = 384;      // warp 0: TMA, 1: MMA, 2: TMEM allocator, 3: idle, 4-7: epilogue 1, 8-11: epilogue 2
+
+constexpr uint32_t OFF_A1 = 0;                         // [2 K-slabs][128 rows][128 B]            32 KB
+constexpr uint32_t OFF_A2 = 32768;                     // [2 blurs][2 K-slabs][128 rows][128 B]   64 KB
+constexpr uint32_t OFF_B1 = 98304;                     // [2 stages][2 K-slabs][64 rows][128 B]   32 KB
+constexpr uint32_t OFF_H = 131072;                     // [NSLAB][2 blurs][128 rows][64 B]        96 KB
+constexpr uint32_t OFF_BAR = OFF_H + NSLAB * 16384;    // mbarriers + TMEM base + abort flag
+constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;  // + slack to align the base to 1024 B
+
+enum { BAR_A = 0, BAR_B1_FULL = 1, BAR_B1_EMPTY = 3, BAR_D1_FULL = 5, BAR_D1_EMPTY = 7, BAR_H_FULL = 9, BAR_BLK = 15, BAR_D2_FULL = 19,
+       BAR_D2_EMPTY = 20, NBARS = 21 };
+
+constexpr uint32_t TM_D1 = 0;      // TMEM columns: D1 stage s at 64 s
+constexpr uint32_t TM_D2 = 128;    // D2 of blur b at 128 + 128 b: columns [0,64) high bytes, [64,128) low bytes
+constexpr uint32_t TM_COLS = 512;
+
+struct TcParams {
+    int H, W, WW, lo, hi;
+    int nchunks, nblocks;          // chunks of 64 virtual rows starting at row -64; blocks of 128 output rows
+    int k1_lo, k1_hi;              // K steps (32 bytes each) of pass 1 with non-zero taps, [lo, hi)
+    int k2_lo[2], k2_hi[2];        // the same for pass 2, per blur (0 = large, 1 = small)
+    uint32_t *area_bits, *area_count, *status;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// bounded wait (a mis-programmed pipeline must not hang the GPU): false on time-out or when another role gave up
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile uint32_t *abort_flag) {
+    for (int spin = 0; spin < (1 << 20); ++spin) {
+        uint32_t done;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return true;
+        if ((spin & 63) == 63 && *abort_flag) return false;
+    }
+    *abort_flag = 1;
+    return false;
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int x, int y, int z, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int x, int y, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], 8-bit integer operands, int32 accumulators
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor, K-major, swizzled (cute::UMMA::SmemDescriptor): start address and stride between
+// 8-row groups in 16-byte units, version 1, layout 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)layout << 61);
+}
+// instruction descriptor for kind::i8 (cute::UMMA::InstrDescriptor): D = s32, A/B format 0 = u8, 1 = s8, both K-major
+__host__ __device__ constexpr uint32_t idesc_i8(int M, int N, uint32_t afmt, uint32_t bfmt) {
+    return (2u << 4) | (afmt << 7) | (bfmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = (i < 0) ? -i : 2 * (n - 1) - i;
+    return i;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+blur_area_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant__ CUtensorMap map_row,
+                    const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2, const TcParams P) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char *gen = smem_raw + (base - smem_u32(smem_raw));          // generic pointer to the aligned base
+    const uint32_t bars = base + OFF_BAR;
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen + OFF_BAR + 8 * NBARS);
+    volatile uint32_t *abort_flag = tmem_slot + 1;
+    auto bar = [&](int i) -> uint32_t { return bars + 8u * (uint32_t)i; };
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int strip = blockIdx.x, f = blockIdx.y;
+    const int x0 = strip * SW;
+    const int C = P.nchunks, NB = P.nblocks;
+
+    if (tid == 0) {
+        mbar_init(bar(BAR_A), 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar(BAR_B1_FULL + i), 1); mbar_init(bar(BAR_B1_EMPTY + i), 1);
+            mbar_init(bar(BAR_D1_FULL + i), 1); mbar_init(bar(BAR_D1_EMPTY + i), 128);
+        }
+        for (int i = 0; i < NSLAB; ++i) mbar_init(bar(BAR_H_FULL + i), 128);
+        for (int i = 0; i < 4; ++i) mbar_init(bar(BAR_BLK + i), 1);
+        mbar_init(bar(BAR_D2_FULL), 1); mbar_init(bar(BAR_D2_EMPTY), 128);
+        *abort_flag = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void *)tmem_slot)), "r"(TM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer (one thread) =================
+        if (lane == 0) {
+            mbar_expect_tx(bar(BAR_A), 32768u + 65536u);
+            for (int s = 0; s < 2; ++s) tma_load_2d(base + OFF_A1 + 16384u * s, &map_a1, 128 * s, 128 * strip, bar(BAR_A));
+            for (int b = 0; b < 2; ++b)
+                for (int s = 0; s < 2; ++s) tma_load_2d(base + OFF_A2 + 32768u * b + 16384u * s, &map_a2, 128 * s, 128 * b, bar(BAR_A));
+            for (int c = 0; c < C; ++c) {
+                const int st = c & 1;
+                if (c >= 2 && !mbar_wait(bar(BAR_B1_EMPTY + st), ((c >> 1) - 1) & 1, abort_flag)) break;
+                const uint32_t dst = base + OFF_B1 + 16384u * st;
+                mbar_expect_tx(bar(BAR_B1_FULL + st), 16384u);
+                const int v0 = CHR * (c - 1);                                   // first virtual row of the chunk
+                if (v0 >= 0 && v0 + CHR <= P.H) {
+                    tma_load_3d(dst, &map_img, x0 - 64, v0, f, bar(BAR_B1_FULL + st));
+                    tma_load_3d(dst + 8192u, &map_img, x0 + 64, v0, f, bar(BAR_B1_FULL + st));
+                } else {                                                        // rows mirrored at the top / bottom edge (REFLECT_101)
+                    for (int r = 0; r < CHR; ++r) {
+                        const int src = reflect101(v0 + r, P.H);
+                        tma_load_3d(dst + 128u * r, &map_row, x0 - 64, src, f, bar(BAR_B1_FULL + st));
+                        tma_load_3d(dst + 8192u + 128u * r, &map_row, x0 + 64, src, f, bar(BAR_B1_FULL + st));
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (one thread) =================
+        if (lane == 0) {
+            constexpr uint32_t ID1 = idesc_i8(128, 64, 0, 0);                   // taps (u8) x pixels (u8)
+            constexpr uint32_t ID2 = idesc_i8(128, 128, 1, 1);                  // taps (s8, <= 26) x sign-flipped bytes (s8)
+            bool ok = mbar_wait(bar(BAR_A), 0, abort_flag);
+            auto issue_block = [&](int b) -> bool {                             // pass 2 of output rows [128 b, 128 b + 128)
+                const int c_last = min(2 * b + 3, C - 1);
+                for (int cl = 2 * b; cl <= c_last; ++cl)                        // ring slabs of virtual rows [128 b - 64, 128 b + 192)
+                    if (!mbar_wait(bar(BAR_H_FULL + cl % NSLAB), (cl / NSLAB) & 1, abort_flag)) return false;
+                if (b >= 1 && !mbar_wait(bar(BAR_D2_EMPTY), (b - 1) & 1, abort_flag)) return false;
+                tc_fence_after();
+                for (int bl = 0; bl < 2; ++bl) {
+                    const int klo = P.k2_lo[bl], khi = P.k2_hi[bl];
+                    for (int j = klo; j < khi; ++j) {
+                        const int cl = min(2 * b + (j >> 1), C - 1);            // (clamped steps multiply rows that are never stored)
+                        const uint64_t ad = smem_desc(base + OFF_A2 + 32768u * bl + 16384u * (j >> 2) + 32u * (j & 3), 1024, 2);
+                        const uint64_t bd = smem_desc(base + OFF_H + 16384u * (cl % NSLAB) + 8192u * bl + 32u * (j & 1), 512, 4);
+                        tc_mma_i8(tmem + TM_D2 + 128u * bl, ad, bd, ID2, j > klo);
+                    }
+                }
+                tc_commit(bar(BAR_BLK + (b & 3)));
+                tc_commit(bar(BAR_D2_FULL));
+                return true;
+            };
+            int next_block = 0;
+            for (int c = 0; c < C && ok; ++c) {
+                const int st = c & 1;
+                ok = mbar_wait(bar(BAR_B1_FULL + st), (c >> 1) & 1, abort_flag);
+                if (ok && c >= 2) ok = mbar_wait(bar(BAR_D1_EMPTY + st), ((c >> 1) - 1) & 1, abort_flag);
+                if (!ok) break;
+                tc_fence_after();
+                for (int j = P.k1_lo; j < P.k1_hi; ++j) {
+                    const uint64_t ad = smem_desc(base + OFF_A1 + 16384u * (j >> 2) + 32u * (j & 3), 1024, 2);
+                    const uint64_t bd = smem_desc(base + OFF_B1 + 16384u * st + 8192u * (j >> 2) + 32u * (j & 3), 1024, 2);
+                    tc_mma_i8(tmem + TM_D1 + 64u * st, ad, bd, ID1, j > P.k1_lo);
+                }
+                tc_commit(bar(BAR_B1_EMPTY + st));
+                tc_commit(bar(BAR_D1_FULL + st));
+                // one chunk behind: the block whose last chunk is c - 1 (its epilogue 1 runs while the MMAs above execute)
+                while (ok && next_block < NB && min(2 * next_block + 3, C - 1) <= c - 1) ok = issue_block(next_block++);
+            }
+            while (ok && next_block < NB) ok = issue_block(next_block++);
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ================= epilogue 1: D1 -> signed high / low bytes, K-major, into the ring =================
+        const int q = warp & 3, row = 32 * q + lane;          // TMEM lane = (blur, column): blur = row / 64
+        const int bl = row >> 6, n = row & 63;
+        bool ok = true;
+        for (int c = 0; c < C && ok; ++c) {
+            const int st = c & 1;
+            ok = mbar_wait(bar(BAR_D1_FULL + st), (c >> 1) & 1, abort_flag);
+            if (!ok) break;
+            tc_fence_after();
+            uint32_t v[4][16];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) tmem_ld16(tmem + ((uint32_t)(32 * q) << 16) + TM_D1 + 64u * st + 16u * g, v[g]);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(bar(BAR_D1_EMPTY + st));                // the accumulator stage may be overwritten
+            // the slab this chunk goes to held chunk c - NSLAB, last read by block min(NB - 1, (c - NSLAB) / 2)
+            if (c >= NSLAB) {
+                const int bdone = min(NB - 1, (c - NSLAB) >> 1);
+                ok = mbar_wait(bar(BAR_BLK + (bdone & 3)), (bdone >> 2) & 1, abort_flag);
+                if (!ok) break;
+            }
+            unsigned char *tile = gen + OFF_H + 16384u * (c % NSLAB) + 8192u * bl;      // [128 rows][64 B]: rows 0..63 high bytes, 64..127 low bytes
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                uint32_t p[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) p[i] = __byte_perm(v[g][2 * i], v[g][2 * i + 1], 0x5140);   // {a.b0, b.b0, a.b1, b.b1}
+                uint4 lo4, hi4;
+                lo4.x = __byte_perm(p[0], p[1], 0x5410) ^ 0x80808080u; hi4.x = __byte_perm(p[0], p[1], 0x7632) ^ 0x80808080u;
+                lo4.y = __byte_perm(p[2], p[3], 0x5410) ^ 0x80808080u; hi4.y = __byte_perm(p[2], p[3], 0x7632) ^ 0x80808080u;
+                lo4.z = __byte_perm(p[4], p[5], 0x5410) ^ 0x80808080u; hi4.z = __byte_perm(p[4], p[5], 0x7632) ^ 0x80808080u;
+                lo4.w = __byte_perm(p[6], p[7], 0x5410) ^ 0x80808080u; hi4.w = __byte_perm(p[6], p[7], 0x7632) ^ 0x80808080u;
+                // SWIZZLE_64B: 16-byte chunk index ^= (row / 2) & 3
+                const uint32_t ch = (uint32_t)g ^ ((uint32_t)(n >> 1) & 3u);
+                *reinterpret_cast<uint4 *>(tile + 64u * n + 16u * ch) = hi4;
+                *reinterpret_cast<uint4 *>(tile + 64u * (64 + n) + 16u * ch) = lo4;      // (64 + n) / 2 & 3 == (n / 2) & 3
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                  // generic writes -> visible to the tensor core's reads
+            mbar_arrive(bar(BAR_H_FULL + c % NSLAB));
+        }
+    } else if (warp >= 8) {
+        // ================= epilogue 2: D2 -> rounding, wrapping DoG, inRange, 64 bits per row =================
+        const int q = warp & 3, r = 32 * q + lane;              // TMEM lane = output row within the block
+        const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
+        const uint32_t span = (uint32_t)(P.hi - P.lo), bias = (uint32_t)(15 - P.lo);
+        const int nvalid = min(SW, P.W - x0);                   // columns of this strip inside the image
+        const uint64_t colmask = nvalid >= 64 ? ~0ull : ((1ull << nvalid) - 1ull);
+        uint32_t count = 0;
+        bool ok = true;
+        for (int b = 0; b < NB && ok; ++b) {
+            ok = mbar_wait(bar(BAR_D2_FULL), b & 1, abort_flag);
+            if (!ok) break;
+            tc_fence_after();
+            uint64_t bits = 0;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                uint32_t hL[16], lL[16], hS[16], lS[16];
+                tmem_ld16(lane_addr + TM_D2 + 16u * g, hL);
+                tmem_ld16(lane_addr + TM_D2 + 64u + 16u * g, lL);
+                tmem_ld16(lane_addr + TM_D2 + 128u + 16u * g, hS);
+                tmem_ld16(lane_addr + TM_D2 + 192u + 16u * g, lS);
+                tmem_ld_wait();
+                if (g == 3) { tc_fence_before(); mbar_arrive(bar(BAR_D2_EMPTY)); }      // all of D2 is in registers
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int uL = (int)hL[i] * 256 + (int)lL[i];
+                    const int uS = (int)hS[i] * 256 + (int)lS[i];
+                    const uint32_t d = ((uint32_t)((uL >> 16) - (uS >> 16)) + bias) & 255u;       // uint8 wrap (MD:128), inRange (MD:129)
+                    bits |= (uint64_t)(d <= span) << (16 * g + i);
+                }
+            }
+            const int y = BLK * b + r;
+            if (y < P.H) {
+                bits &= colmask;
+                uint32_t *dst = P.area_bits + ((size_t)f * P.H + y) * P.WW + (x0 >> 5);
+                if ((x0 >> 5) < P.WW) dst[0] = (uint32_t)bits;
+                if ((x0 >> 5) + 1 < P.WW) dst[1] = (uint32_t)(bits >> 32);
+                count += __popcll(bits);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
+        if (lane == 0 && count) atomicAdd(P.area_count + f, count);              // mean of area_mask for the NCC (MD:153)
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0 && *abort_flag) atomicOr(P.status, VBS_DEV_TMA_TIMEOUT);
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TM_COLS) : "memory");
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+bool encode_u8(CUtensorMap *map, const void *ptr, int rank, const cuuint64_t *dims, const cuuint64_t *strides, const cuuint32_t *box) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return false;
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, (cuuint32_t)rank, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int host_reflect101(int i, int n) {
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = (i < 0) ? -i : 2 * (n - 1) - i;
+    return i;
+}
+
+}  // namespace
+
+// Operator matrices of both passes for the context's geometry (built once, kept on the device):
+//   A1 [nstrips][128][256]  rows 0..63 large blur, 64..127 small blur of output column x0 + (row & 63); K byte k = image column
+//                           x0 - 64 + k; taps that REFLECT_101 sends back into the image are added to the mirrored column
+//   A2 [2][128][256]        output row r of a block, K byte k = virtual row 128 b - 64 + k: tap index k - 64 - r + radius
+cudaError_t vbs_blur_tc_setup(vbs_ctx *ctx) {
+    if (ctx->tc_a1) return cudaSuccess;
+    const int W = ctx->W, KS = ctx->br.ks, KL = ctx->br.kl;
+    const int nstrips = (W + SW - 1) / SW;
+    int tapsL[128], tapsS[128];
+    vbs_host_taps(KL, ctx->big ? 20.0 : 11.4, tapsL);
+    vbs_host_taps(KS, ctx->big ? 8.0 : 4.56, tapsS);
+    const int RL = KL / 2, RS = KS / 2;
+    if (RL > 63 || RS > RL) return cudaErrorInvalidValue;
+    std::vector<uint8_t> a1((size_t)nstrips * 128 * KEXT, 0), a2((size_t)2 * 128 * KEXT, 0);
+    for (int s = 0; s < nstrips; ++s)
+        for (int row = 0; row < 128; ++row) {
+            const int bl = row >> 6, xo = s * SW + (row & 63);
+            if (xo >= W) continue;
+            const int R = bl ? RS : RL, *taps = bl ? tapsS : tapsL;
+            for (int t = 0; t <= 2 * R; ++t) {
+                const int k = host_reflect101(xo + t - R, W) - (s * SW - 64);
+                if (k < 0 || k >= KEXT) return cudaErrorInvalidValue;           // cannot happen: |reflected offset| <= radius <= 63
+                a1[((size_t)s * 128 + row) * KEXT + k] += (uint8_t)taps[t];
+            }
+        }
+    for (int bl = 0; bl < 2; ++bl) {
+        const int R = bl ? RS : RL, *taps = bl ? tapsS : tapsL;
+        for (int r = 0; r < 128; ++r)
+            for (int t = 0; t <= 2 * R; ++t) a2[((size_t)bl * 128 + r) * KEXT + (64 + r + t - R)] = (uint8_t)taps[t];
+    }
+    // K steps of 32 bytes that hold non-zero taps
+    ctx->tc_k1[0] = (64 - RL) / 32; ctx->tc_k1[1] = (64 + 63 + RL) / 32 + 1;
+    for (int bl = 0; bl < 2; ++bl) {
+        const int R = bl ? RS : RL;
+        ctx->tc_k2lo[bl] = (64 - R) / 32; ctx->tc_k2hi[bl] = (64 + 127 + R) / 32 + 1;
+    }
+    cudaError_t e;
+    if ((e = cudaMalloc((void **)&ctx->tc_a1, a1.size())) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void **)&ctx->tc_a2, a2.size())) != cudaSuccess) return e;
+    if ((e = cudaMemcpy(ctx->tc_a1, a1.data(), a1.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+    return cudaMemcpy(ctx->tc_a2, a2.data(), a2.size(), cudaMemcpyHostToDevice);
+}
+
+// returns cudaErrorNotSupported when this batch cannot take the tensor-core path (BGR input, frames the TMA unit cannot
+// describe): the caller then runs the integer-dot-product kernel
+cudaError_t vbs_launch_blur_tc(vbs_ctx *ctx, const uint8_t *frames, int batch, int64_t frame_stride, int64_t row_pitch) {
+    if (ctx->C != 1 || ctx->W < 128 || ctx->H < CHR || !encode_fn()) return cudaErrorNotSupported;
+    if ((reinterpret_cast<uintptr_t>(frames) & 15) || (row_pitch & 15) || (frame_stride & 15)) return cudaErrorNotSupported;
+    cudaError_t e = vbs_blur_tc_setup(ctx);
+    if (e != cudaSuccess) return e;
+    const int H = ctx->H, W = ctx->W, nstrips = (W + SW - 1) / SW;
+    CUtensorMap m_img, m_row, m_a1, m_a2;
+    {
+        const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)batch};
+        const cuuint64_t strides[2] = {(cuuint64_t)row_pitch, (cuuint64_t)frame_stride};
+        const cuuint32_t box[3] = {128, CHR, 1}, box1[3] = {128, 1, 1};
+        if (!encode_u8(&m_img, frames, 3, dims, strides, box) || !encode_u8(&m_row, frames, 3, dims, strides, box1)) return cudaErrorNotSupported;
+    }
+    {
+        const cuuint64_t d1[2] = {KEXT, (cuuint64_t)128 * nstrips}, d2[2] = {KEXT, 256}, st[1] = {KEXT};
+        const cuuint32_t box[2] = {128, 128};
+        if (!encode_u8(&m_a1, ctx->tc_a1, 2, d1, st, box) || !encode_u8(&m_a2, ctx->tc_a2, 2, d2, st, box)) return cudaErrorNotSupported;
+    }
+    TcParams P;
+    P.H = H; P.W = W; P.WW = ctx->WW; P.lo = ctx->br.lo; P.hi = ctx->br.hi;
+    P.nchunks = (H + ctx->br.kl / 2 + CHR - 1) / CHR + 1;        // virtual rows [-64, H + radius)
+    P.nblocks = (H + BLK - 1) / BLK;
+    P.k1_lo = ctx->tc_k1[0]; P.k1_hi = ctx->tc_k1[1];
+    for (int b = 0; b < 2; ++b) { P.k2_lo[b] = ctx->tc_k2lo[b]; P.k2_hi[b] = ctx->tc_k2hi[b]; }
+    P.area_bits = ctx->area_bits; P.area_count = ctx->area_count; P.status = ctx->d_status;
+    if ((e = cudaFuncSetAttribute(blur_area_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES)) != cudaSuccess) return e;
+    blur_area_tc_kernel<<<dim3(nstrips, batch), NTHREADS, SMEM_BYTES, ctx->stream>>>(m_img, m_row, m_a1, m_a2, P);
+    ctx->launches += 1;
+    ctx->tc_launches += 1;
+    return cudaGetLastError();
+}

@@ -71,21 +71,41 @@ __device__ __forceinline__ uint32_t ld_bits(const uint32_t *row, int wi, int WW)
     return (wi >= 0 && wi < WW) ? __ldg(row + wi) : 0u;
 }
 
-// threshold on G for a pixel whose window is clipped by the image border.  float32 is enough for the
-// filter: q <= L^4/4 ~ 1e7 is a sum of a few exactly representable integers times m, so thr carries
-// ~1e-6 relative error at worst; such pixels use the wider BAND_BORDER before the float64 re-decision.
+// Decision for a pixel whose window is clipped by the image border (A < L^2 window pixels inside the image).
+// Two window states make EVERY term of G - thr proportional to m or to 1 - m (m = mean(b)), so that an absolute
+// float32 band would queue the whole border of a nearly empty / nearly full frame; both have closed answers:
+//   S == 0 (no area pixel in the window): G = 0 and thr = m (g1 - A/L^2 + 0.1 sqrt(st2 A (L^2-A)) / L) > 0
+//           (a window that holds its own centre has g1 >= A/L^2)                       -> mask 0, for any m
+//   S == A (every in-image pixel set):    ncc = (g1 - A/L^2) / sqrt(st2 A (1 - A/L^2)), m cancels  -> float64, inline
+// Otherwise float32 is enough for the filter: q is evaluated as a sum of NON-NEGATIVE terms
+//   q = (L^2-A) (S (1-m)^2 + m^2 (A-S)) + S (A-S)        (= S(L^2-S) - 2 m S (L^2-A) + m^2 A (L^2-A), no cancellation)
+// so thr carries ~1e-6 relative error; such pixels use the wider BAND_BORDER before the float64 re-decision.
 constexpr float BAND_BORDER = 2e-5f;
+struct BorderGeo { int A; double g1; };
 template <int TL>
-__device__ __forceinline__ float border_threshold(int y, int x, int H, int W, float S, float m, float st2, const double *cn) {
+__device__ __forceinline__ BorderGeo border_geo(int y, int x, int H, int W, const double *cn) {
     using G = Geo<TL>;
     const int ylo = max(0, G::OFF - y), yhi = min(TL - 1, H - 1 - y + G::OFF);
     const int xlo = max(0, G::OFF - x), xhi = min(TL - 1, W - 1 - x + G::OFF);
-    const float A = (float)((yhi - ylo + 1) * (xhi - xlo + 1));
-    const float g1 = (float)(cn[yhi + 1 + 8] - cn[ylo + 8]) * (float)(cn[xhi + 1 + 8] - cn[xlo + 8]);
-    const float L2 = (float)(TL * TL);
-    const float q = S * (L2 - S) - 2.0f * m * S * (L2 - A) + m * m * A * (L2 - A);
+    BorderGeo g;
+    g.A = (yhi - ylo + 1) * (xhi - xlo + 1);
+    g.g1 = (cn[yhi + 1 + 8] - cn[ylo + 8]) * (cn[xhi + 1 + 8] - cn[xlo + 8]);
+    return g;
+}
+template <int TL>
+__device__ __forceinline__ bool border_full_window_on(const BorderGeo &g, double st2, float m) {
+    if (!(m < 1.0f)) return false;                         // the whole frame is set: the reference divides 0 by 0 -> 0
+    const double L2 = (double)(TL * TL), A = (double)g.A;
+    const double num = g.g1 - A / L2, den = sqrt((A - A * A / L2) * st2);
+    const double ncc = num / den;
+    return isfinite(ncc) && ncc > 0.1;
+}
+template <int TL>
+__device__ __forceinline__ float border_threshold(const BorderGeo &g, float S, float m, float mc, float st2) {
+    const float A = (float)g.A, L2 = (float)(TL * TL);
+    const float q = (L2 - A) * (S * mc * mc + m * m * (A - S)) + S * (A - S);
     if (!(q > 0.0f)) return INFINITY;
-    return m * g1 + (S - m * A) * (1.0f / L2) + (0.1f / (float)TL) * sqrtf(st2 * q);
+    return m * (float)g.g1 + (S - m * A) * (1.0f / L2) + (0.1f / (float)TL) * sqrtf(st2 * q);
 }
 
 // 256 threads per 128-pixel strip, three phases per 8-row step:
@@ -125,7 +145,8 @@ __global__ void __launch_bounds__(NT, 3) ncc_mask_kernel(NccParams P) {
     const int f = blockIdx.z;
     const int H = P.H, W = P.W, WW = P.WW;
     const uint32_t *abits = P.area_bits + (size_t)f * H * WW;
-    const float mfrac = (float)((double)P.area_count[f] / P.hw);  // mean(area_mask)/255
+    const double mfrac64 = (double)P.area_count[f] / P.hw;
+    const float mfrac = (float)mfrac64, mcomp = (float)(1.0 - mfrac64);   // mean(area_mask)/255 and its complement
     for (int i = tid; i < G::CNX; i += NT) cn[i] = P.cn64[i];
     for (int i = tid; i < 4 * FXN; i += NT) reinterpret_cast<int *>(fx)[i] = P.cnfix[i];
 
@@ -340,14 +361,21 @@ __global__ void __launch_bounds__(NT, 3) ncc_mask_kernel(NccParams P) {
                 for (int r = 0; r < VR; ++r) {
                     const int y = y0 + r;
                     bool on = false;
-                    if (x < W && y < ye) {
-                        float thr;
+                    if (x < W && y < ye && S[r] != 0) {                     // S == 0: G = 0 and thr > 0 (or infinite) -> 0
+                        float thr = INFINITY;
                         float band = BAND;
+                        bool decided = false;
                         if (xin && y >= G::OFF && y + G::HI < H) thr = __ldg(P.thr_lut + S[r]);
-                        else { thr = border_threshold<TL>(y, x, H, W, (float)S[r], mfrac, (float)P.st2, cn); band = BAND_BORDER; }
-                        const float d = acc[r] - thr;
-                        on = d > 0.f;
-                        if (fabsf(d) <= band) { on = false; queue(y); }
+                        else {
+                            const BorderGeo bg = border_geo<TL>(y, x, H, W, cn);
+                            if (S[r] == bg.A) { on = border_full_window_on<TL>(bg, P.st2, mfrac); decided = true; }
+                            else { thr = border_threshold<TL>(bg, (float)S[r], mfrac, mcomp, (float)P.st2); band = BAND_BORDER; }
+                        }
+                        if (!decided) {
+                            const float d = acc[r] - thr;
+                            on = d > 0.f;
+                            if (fabsf(d) <= band) { on = false; queue(y); }
+                        }
                     }
                     const uint32_t word = __ballot_sync(0xffffffffu, on);
                     if (lane == r) myword = word;

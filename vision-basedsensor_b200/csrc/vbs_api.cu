@@ -81,6 +81,12 @@ int ensure_image(vbs_ctx *ctx) {
     return VBS_OK;
 }
 
+// operator matrices of the opt-in tensor-core blur: built on the context itself (the launchers work on value copies)
+int ensure_blur_tc(vbs_ctx *ctx) {
+    if (ctx->blur_tc && !ctx->tc_a1) VBS_CUDA(vbs_blur_tc_setup(ctx));
+    return VBS_OK;
+}
+
 struct Scratch {                       // small device staging buffer, freed on scope exit
     void *p = nullptr;
     ~Scratch() { if (p) cudaFree(p); }
@@ -101,7 +107,7 @@ int map_status(vbs_ctx *ctx, uint32_t st) {
 }
 
 void free_all(vbs_ctx *c) {
-    void *ptrs[] = {c->d_frames, c->undist_map, c->d_undist, c->area_bits, c->mask_bits, c->max_bits, c->open_bits, c->area_count, c->thr_lut,
+    void *ptrs[] = {c->tc_a1, c->tc_a2, c->d_frames, c->undist_map, c->d_undist, c->area_bits, c->mask_bits, c->max_bits, c->open_bits, c->area_count, c->thr_lut,
                     c->d_n64, c->d_cn64, c->d_cnfix, c->recheck, c->recheck_n, c->parent, c->parent2, c->nroots, c->rootlist, c->slot2label, c->nrec, c->recs, c->rowflag, c->d_nlabels,
                     c->d_ncont, c->lab_cnt, c->lab_sx, c->lab_sy, c->centres, c->croot, c->cell, c->claim, c->cmatch, c->cpts, c->cpn, c->euler4, c->holes, c->d_nmarkers,
                     c->marker_xy, c->marker_axes, c->ref_row, c->ref_col, c->ref_xy, c->row_det, c->row_cxy, c->row_axes, c->cell_start, c->cell_items, c->cbin_start, c->cbin_items, c->obs,
@@ -213,7 +219,7 @@ vbs_ctx make_view(const vbs_ctx *c, int off, cudaStream_t st) {
     return v;
 }
 void fold_view(vbs_ctx *c, const vbs_ctx &v) {   // state a launcher may have changed
-    c->launches = v.launches; c->tma_launches = v.tma_launches; c->have_first = v.have_first; c->first_frame = v.first_frame;
+    c->launches = v.launches; c->tma_launches = v.tma_launches; c->tc_launches = v.tc_launches; c->have_first = v.have_first; c->first_frame = v.first_frame;
     if (!v.err.empty()) c->err = v.err;
 }
 
@@ -328,7 +334,7 @@ int process_common(vbs_ctx *ctx, const uint8_t *d_frames, int batch, int64_t fra
         fold_view(ctx, vb);
         VBS_CUDA(e);
         VBS_CUDA(cudaEventRecord(ctx->ev_b_done, ctx->stream_b));
-        va.launches = ctx->launches; va.tma_launches = ctx->tma_launches;
+        va.launches = ctx->launches; va.tma_launches = ctx->tma_launches; va.tc_launches = ctx->tc_launches;
         e = vbs_launch_ncc(&va, batch);
         VBS_MARKC(0, 2, ctx->stream); VBS_MARKC(0, 3, ctx->stream);
         if (e == cudaSuccess) e = vbs_launch_morph(&va, batch, 1);
@@ -395,6 +401,7 @@ int vbs_create(vbs_ctx **out, const vbs_config *cfg) {
     ctx->br = ctx->big ? VbsBranch{39, 101, 80, 13.0, 20, 200, 14} : VbsBranch{21, 35, 33, 7.4, 35, 180, 8};
     ctx->min_dist = 20.0;
     { const char *e = getenv("VBS_NO_TMA"); ctx->no_tma = (e && e[0] == '1') ? 1 : 0; }
+    { const char *e = getenv("VBS_BLUR_TC"); ctx->blur_tc = (e && e[0] == '1') ? 1 : 0; }      // opt-in tensor-core blur
     // The open-mask branch (5x5 open, blobs, border following, ellipse fits) needs K1 only and runs on a second,
     // high-priority stream beside the NCC: the NCC stretches from 3.0 to 3.7 ms but the 0.9 ms of small latency-bound
     // kernels disappear behind it (8.41 -> 8.26 ms per 256 frames on B200).  VBS_BRANCH_OVERLAP=0 runs them in sequence.
@@ -570,7 +577,7 @@ int vbs_process_device(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int64
     if (rc != VBS_OK) return rc;
     if (row_pitch < (int64_t)ctx->W * ctx->C) return fail(ctx, VBS_ERR_BAD_ARG, "row_pitch smaller than a row");
     VBS_ON_DEVICE(ctx);
-    if ((rc = ensure_image(ctx)) != VBS_OK) return rc;
+    if ((rc = ensure_image(ctx)) != VBS_OK || (rc = ensure_blur_tc(ctx)) != VBS_OK) return rc;
     return process_common(ctx, frames, batch, frame_stride, row_pitch, frameno0, out, cudaMemcpyDefault);
 }
 
@@ -690,7 +697,7 @@ int vbs_process_host(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int64_t
     if (row_pitch < (int64_t)ctx->W * ctx->C) return fail(ctx, VBS_ERR_BAD_ARG, "row_pitch smaller than a row");
     if (ctx->inflight > 0) return fail(ctx, VBS_ERR_STATE, "batches submitted with vbs_submit_host are still in flight: call vbs_wait_host first");
     VBS_ON_DEVICE(ctx);
-    if ((rc = ensure_image(ctx)) != VBS_OK) return rc;
+    if ((rc = ensure_image(ctx)) != VBS_OK || (rc = ensure_blur_tc(ctx)) != VBS_OK) return rc;
     if ((rc = ensure_host_streams(ctx)) != VBS_OK) return rc;
     if ((rc = enqueue_host_chunks(ctx, frames, batch, frame_stride, row_pitch, frameno0, out, host_chunk_frames(ctx, batch, ctx->host_chunk))) != VBS_OK)
         return rc;
@@ -711,7 +718,7 @@ int vbs_submit_host(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int64_t 
     if (row_pitch < (int64_t)rowb) return fail(ctx, VBS_ERR_BAD_ARG, "row_pitch smaller than a row");
     if (ctx->inflight >= 2) return fail(ctx, VBS_ERR_STATE, "two batches already in flight: call vbs_wait_host first");
     VBS_ON_DEVICE(ctx);
-    if ((rc = ensure_image(ctx)) != VBS_OK) return rc;
+    if ((rc = ensure_image(ctx)) != VBS_OK || (rc = ensure_blur_tc(ctx)) != VBS_OK) return rc;
     if ((rc = ensure_host_streams(ctx)) != VBS_OK) return rc;
     const int slot = (int)(ctx->submitted & 1);
     uint32_t *const status_all = ctx->d_status;
@@ -832,7 +839,7 @@ int vbs_find_markers(vbs_ctx *ctx, const uint8_t *frames, int32_t batch, int64_t
     int rc = check_batch(ctx, frames, batch);
     if (rc != VBS_OK) return rc;
     VBS_ON_DEVICE(ctx);
-    if ((rc = ensure_image(ctx)) != VBS_OK) return rc;
+    if ((rc = ensure_image(ctx)) != VBS_OK || (rc = ensure_blur_tc(ctx)) != VBS_OK) return rc;
     ctx->last_batch = batch;
     return run_detection(ctx, frames, batch, frame_stride, row_pitch);
 }
@@ -842,7 +849,7 @@ int vbs_marker_center(vbs_ctx *ctx, const uint8_t *mask, const uint8_t *area_mas
     if (rc != VBS_OK) return rc;
     if (!area_mask) return fail(ctx, VBS_ERR_BAD_ARG, "area_mask is NULL");
     VBS_ON_DEVICE(ctx);
-    if ((rc = ensure_image(ctx)) != VBS_OK) return rc;
+    if ((rc = ensure_image(ctx)) != VBS_OK || (rc = ensure_blur_tc(ctx)) != VBS_OK) return rc;
     VBS_CUDA(vbs_launch_pack_masks(ctx, mask, area_mask, batch));
     if ((rc = run_centres(ctx, batch)) != VBS_OK) return rc;
     CopyPlan plan[16];
@@ -861,7 +868,7 @@ int vbs_ncc_mask(vbs_ctx *ctx, const uint8_t *area_mask, int32_t batch) {
     int rc = check_batch(ctx, area_mask, batch);
     if (rc != VBS_OK) return rc;
     VBS_ON_DEVICE(ctx);
-    if ((rc = ensure_image(ctx)) != VBS_OK) return rc;
+    if ((rc = ensure_image(ctx)) != VBS_OK || (rc = ensure_blur_tc(ctx)) != VBS_OK) return rc;
     VBS_CUDA(vbs_launch_pack_area(ctx, area_mask, batch));
     VBS_CUDA(vbs_launch_ncc(ctx, batch));
     ctx->last_batch = batch;
@@ -974,6 +981,15 @@ int vbs_fit_plane(vbs_ctx *ctx, int32_t n, const double *X, const double *Y, con
 
 int64_t vbs_kernel_launches(const vbs_ctx *ctx) { return ctx ? ctx->launches : 0; }
 int64_t vbs_tma_launches(const vbs_ctx *ctx) { return ctx ? ctx->tma_launches : 0; }
+int64_t vbs_tc_launches(const vbs_ctx *ctx) { return ctx ? ctx->tc_launches : 0; }
+
+int vbs_set_blur_tc(vbs_ctx *ctx, int32_t enable) {
+    if (!ctx) return VBS_ERR_BAD_ARG;
+    VBS_ON_DEVICE(ctx);
+    VBS_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->blur_tc = enable ? 1 : 0;
+    return VBS_OK;
+}
 
 int vbs_set_profiling(vbs_ctx *ctx, int32_t enable) {
     if (!ctx) return VBS_ERR_BAD_ARG;

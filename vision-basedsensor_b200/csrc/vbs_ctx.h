@@ -43,6 +43,10 @@ struct vbs_ctx {
     std::string err;
     int64_t launches;
     int no_tma; int64_t tma_launches;      // VBS_NO_TMA=1 forces the generic loader; launches that used the TMA path
+    // opt-in tensor-core blur (k_blur_tc.cu): VBS_BLUR_TC=1 or vbs_set_blur_tc
+    int blur_tc; int64_t tc_launches;
+    uint8_t *tc_a1, *tc_a2;                // operator matrices [nstrips][128][256], [2][128][256]
+    int tc_k1[2], tc_k2lo[2], tc_k2hi[2];  // K-step ranges with non-zero taps
 
     // optional lens correction before K1 (MD:93-109)
     int undist_on; double new_k[4];            // fx', fy', cx', cy' of getOptimalNewCameraMatrix(alpha = 0)
@@ -146,3 +150,6 @@ cudaError_t vbs_launch_pack_masks(vbs_ctx *ctx, const uint8_t *mask, const uint8
 cudaError_t vbs_launch_pack_area(vbs_ctx *ctx, const uint8_t *area, int batch);
 cudaError_t vbs_launch_unpack(vbs_ctx *ctx, int stage, void *dst, int batch);
 int vbs_check_taps(std::string &err);       // baked integer taps == host recipe
+void vbs_host_taps(int ksize, double sigma, int *out);   // OpenCV's 8.8 fixed-point Gaussian kernel (k_blur.cu)
+cudaError_t vbs_blur_tc_setup(vbs_ctx *ctx);
+cudaError_t vbs_launch_blur_tc(vbs_ctx *ctx, const uint8_t *frames, int batch, int64_t frame_stride, int64_t row_pitch);

@@ -113,6 +113,15 @@ class MarkerPipeline:
     def tma_launches(self) -> int:
         return int(capi.lib.vbs_tma_launches(self._ctx))
 
+    @property
+    def tc_launches(self) -> int:
+        return int(capi.lib.vbs_tc_launches(self._ctx))
+
+    def set_blur_tc(self, on: bool):
+        """Opt-in experiment (SURVEY 8f f4): the two Gaussian blurs as int8 GEMMs on the tensor cores (tcgen05);
+        default off = the integer-dot-product kernel.  Same bits out."""
+        capi.check(self._ctx, capi.lib.vbs_set_blur_tc(self._ctx, int(bool(on))))
+
     STAGES = ("blur_dog_area", "ncc_mask", "morphology", "components", "contours_ellipse", "track_3d_plane", "output_copies")
 
     def set_profiling(self, on: bool):
