@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--overlap", action="store_true", help="two-stream chunk pipelining for device-resident batches (default off)")
     ap.add_argument("--undistort", action="store_true", help="side measurement: lens correction (MD:93-109) active on the CUDA arm; not the headline workload")
+    ap.add_argument("--no-tc", action="store_true", help="skip the opt-in tensor-core blur arm (reported beside the default arm as `tc_blur`)")
     ap.add_argument("--host-chunk", type=int, default=0, help="frames per chunk of the host path copy/compute overlap (0 = library default)")
     return ap.parse_args()
 
@@ -499,6 +500,45 @@ def main():
             line["roofline"]["alu"] = {"pipe": "IDP.4A/IDP.2A (fma pipe, half rate)", "achieved": rate, "peak": 62.8, "unit": "lane-instr/clk/SM",
                                        "frac": rate / 62.8, "peak_source": "measured, profiles/r01_ubench_pipe_rates.txt",
                                        "instr_per_pixel": idp_per_px}
+
+    # ---- opt-in arm: the same step with the two blurs on the tensor cores (vbs_set_blur_tc).  The default
+    #      arm above is the headline (north_star: no tensor cores); this one is reported beside it.
+    if not args.no_tc:
+        keep = {k: outs[0][k].clone() for k in ("n_markers", "marker_xy", "marker_axes", "row_det", "row_cxy", "pos3d", "pos_flags", "plane")}
+        pipe.set_blur_tc(True)
+        t0c = pipe.tc_launches
+        for s in range(max(args.warmup, 2)):
+            step(s)
+        pipe.sync()
+        pipe.set_profiling(True)
+        barrier()
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record(stream)
+        for s in range(args.steps):
+            step(s)
+        t1e.record(stream)
+        barrier()
+        ms_tc = t0e.elapsed_time(t1e)
+        pipe.sync()
+        stage_tc, calls_tc = pipe.stage_ms()
+        pipe.set_profiling(False)
+        used = pipe.tc_launches - t0c
+        same = all(bool(torch.equal(keep[k].contiguous().view(torch.uint8), outs[0][k].contiguous().view(torch.uint8))) for k in keep)
+        pipe.set_blur_tc(False)
+        if world > 1:
+            t = torch.tensor([ms_tc], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_tc = float(t.item())
+        if rank == 0:
+            bms = stage_tc["blur_dog_area"] / max(calls_tc, 1)
+            ach_tc = B * b_alg / (bms * 1e-3) / 1e9
+            line["tc_blur"] = {"value": world * B * args.steps / (ms_tc * 1e-3), "unit": UNIT, "ms_per_step": ms_tc / args.steps,
+                               "kernel": "blur_area_tc_kernel (tcgen05.mma kind::i8 banded-Toeplitz GEMMs, TMEM accumulators, TMA operands)",
+                               "kernel_ms": bms, "tc_launches": int(used), "records_equal_default_arm": bool(same),
+                               "stage_ms_per_step": {k: v / max(calls_tc, 1) for k, v in stage_tc.items()},
+                               "roofline": {"bound": "hbm", "achieved": ach_tc, "peak": peak, "unit": "GB/s", "frac": ach_tc / peak,
+                                            "algorithmic_bytes_per_launch": B * b_alg},
+                               "note": "opt-in (VBS_BLUR_TC=1 / vbs_set_blur_tc); not the default because the north_star rules tensor cores out"}
 
     # ---- e2e: host frames -> records on the host (rank 0's host for N > 1) through the public API, all copies and the
     #      NCCL gather in the timed region

@@ -33,7 +33,7 @@ constexpr int CHR = 64;            // image rows per chunk (pass 1 step) = K byt
 constexpr int BLK = 128;           // output rows per pass-2 block
 constexpr int KEXT = 256;          // K extent of both passes in bytes (two 128-byte swizzle slabs)
 constexpr int NSLAB = 6;           // ring of pass-1 results (4 are read by a block, 2 are being produced)
-constexpr int NTHREADS = 384;      // warp 0: TMA, 1: MMA, 2: TMEM allocator, 3: idle, 4-7: epilogue 1, 8-11: epilogue 2
+constexpr int NTHREADS = 512;      // warp 0: TMA, 1: MMA, 2: TMEM allocator, 3: idle, 4-7: epilogue 1, 8-15: epilogue 2
 
 constexpr uint32_t OFF_A1 = 0;                         // [2 K-slabs][128 rows][128 B]            32 KB
 constexpr uint32_t OFF_A2 = 32768;                     // [2 blurs][2 K-slabs][128 rows][128 B]   64 KB
@@ -42,8 +42,8 @@ constexpr uint32_t OFF_H = 131072;                     // [NSLAB][2 blurs][128 r
 constexpr uint32_t OFF_BAR = OFF_H + NSLAB * 16384;    // mbarriers + TMEM base + abort flag
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;  // + slack to align the base to 1024 B
 
-enum { BAR_A = 0, BAR_B1_FULL = 1, BAR_B1_EMPTY = 3, BAR_D1_FULL = 5, BAR_D1_EMPTY = 7, BAR_H_FULL = 9, BAR_BLK = 15, BAR_D2_FULL = 19,
-       BAR_D2_EMPTY = 20, NBARS = 21 };
+enum { BAR_A1 = 0, BAR_B1_FULL = 1, BAR_B1_EMPTY = 3, BAR_D1_FULL = 5, BAR_D1_EMPTY = 7, BAR_H_FULL = 9, BAR_BLK = 15, BAR_D2_FULL = 19,
+       BAR_D2_EMPTY = 20, BAR_A2 = 21, NBARS = 22 };
 
 constexpr uint32_t TM_D1 = 0;      // TMEM columns: D1 stage s at 64 s
 constexpr uint32_t TM_D2 = 128;    // D2 of blur b at 128 + 128 b: columns [0,64) high bytes, [64,128) low bytes
@@ -51,9 +51,8 @@ constexpr uint32_t TM_COLS = 512;
 
 struct TcParams {
     int H, W, WW, lo, hi;
-    int nchunks, nblocks;          // chunks of 64 virtual rows starting at row -64; blocks of 128 output rows
-    int k1_lo, k1_hi;              // K steps (32 bytes each) of pass 1 with non-zero taps, [lo, hi)
-    int k2_lo[2], k2_hi[2];        // the same for pass 2, per blur (0 = large, 1 = small)
+    int nreal, nchunks, nblocks;   // real chunks (image rows), chunk slots incl. the mirrored ones, blocks of 128 output rows
+    int radius;                    // rows mirrored above row 0 and below row H-1 (radius of the large blur)
     uint32_t *area_bits, *area_count, *status;
 };
 
@@ -66,6 +65,12 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {         // non-blocking
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done != 0;
 }
 // bounded wait (a mis-programmed pipeline must not hang the GPU): false on time-out or when another role gave up
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile uint32_t *abort_flag) {
@@ -107,7 +112,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptor, K-major, swizzled (cute::UMMA::SmemDescriptor): start address and stride between
-// 8-row groups in 16-byte units, version 1, layout 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
+// 8-row groups in 16-byte units, version 1, layout 2 = SWIZZLE_128B, 4 = SWIZZLE_64B.  Moving the start by n bytes
+// (a K step inside the swizzle row, another slab) is adding n / 16 to the descriptor.
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout) {
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46) |
            ((uint64_t)layout << 61);
@@ -116,16 +122,23 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t sbo_bytes
 __host__ __device__ constexpr uint32_t idesc_i8(int M, int N, uint32_t afmt, uint32_t bfmt) {
     return (2u << 4) | (afmt << 7) | (bfmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// K steps (32 bytes) that hold non-zero taps: pass 1 reads image columns x0 - 64 + k, pass 2 virtual rows 128 b - 64 + k
+__host__ __device__ constexpr int k1_lo(int R) { return (64 - R) / 32; }
+__host__ __device__ constexpr int k1_hi(int R) { return (64 + 63 + R) / 32 + 1; }
+__host__ __device__ constexpr int k2_lo(int R) { return (64 - R) / 32; }
+__host__ __device__ constexpr int k2_hi(int R) { return (64 + 127 + R) / 32 + 1; }
 
-__device__ __forceinline__ int reflect101(int i, int n) {
-    if (n == 1) return 0;
-    while (i < 0 || i >= n) i = (i < 0) ? -i : 2 * (n - 1) - i;
-    return i;
+// byte offset of (row, k) inside a [128 rows][64 B] K-major SWIZZLE_64B tile (tile base 1024-byte aligned)
+__device__ __forceinline__ uint32_t swz64(uint32_t row, uint32_t k) {
+    const uint32_t off = row * 64u + k;
+    return off ^ (((off >> 7) & 3u) << 4);
 }
 
+// RL / RS: radii of the large / small blur (50 / 19 above 480 rows, 17 / 10 below: MD:117-126)
+template <int RL, int RS>
 __global__ void __launch_bounds__(NTHREADS, 1)
-blur_area_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant__ CUtensorMap map_row,
-                    const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2, const TcParams P) {
+blur_area_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant__ CUtensorMap map_a1,
+                    const __grid_constant__ CUtensorMap map_a2, const TcParams P) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char *gen = smem_raw + (base - smem_u32(smem_raw));          // generic pointer to the aligned base
@@ -137,17 +150,17 @@ blur_area_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int strip = blockIdx.x, f = blockIdx.y;
     const int x0 = strip * SW;
-    const int C = P.nchunks, NB = P.nblocks;
+    const int CR = P.nreal, C = P.nchunks, NB = P.nblocks;    // chunk slot cc covers virtual rows [64 (cc - 1), 64 cc); real: 1 .. CR
 
     if (tid == 0) {
-        mbar_init(bar(BAR_A), 1);
+        mbar_init(bar(BAR_A1), 1); mbar_init(bar(BAR_A2), 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar(BAR_B1_FULL + i), 1); mbar_init(bar(BAR_B1_EMPTY + i), 1);
             mbar_init(bar(BAR_D1_FULL + i), 1); mbar_init(bar(BAR_D1_EMPTY + i), 128);
         }
         for (int i = 0; i < NSLAB; ++i) mbar_init(bar(BAR_H_FULL + i), 128);
         for (int i = 0; i < 4; ++i) mbar_init(bar(BAR_BLK + i), 1);
-        mbar_init(bar(BAR_D2_FULL), 1); mbar_init(bar(BAR_D2_EMPTY), 128);
+        mbar_init(bar(BAR_D2_FULL), 1); mbar_init(bar(BAR_D2_EMPTY), 256);
         *abort_flag = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -161,82 +174,105 @@ blur_area_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 0) {
-        // ================= TMA producer (one thread) =================
+        // ================= TMA producer (one thread): operator matrices, then 64 image rows per chunk =================
         if (lane == 0) {
-            mbar_expect_tx(bar(BAR_A), 32768u + 65536u);
-            for (int s = 0; s < 2; ++s) tma_load_2d(base + OFF_A1 + 16384u * s, &map_a1, 128 * s, 128 * strip, bar(BAR_A));
-            for (int b = 0; b < 2; ++b)
-                for (int s = 0; s < 2; ++s) tma_load_2d(base + OFF_A2 + 32768u * b + 16384u * s, &map_a2, 128 * s, 128 * b, bar(BAR_A));
-            for (int c = 0; c < C; ++c) {
-                const int st = c & 1;
-                if (c >= 2 && !mbar_wait(bar(BAR_B1_EMPTY + st), ((c >> 1) - 1) & 1, abort_flag)) break;
+            mbar_expect_tx(bar(BAR_A1), 32768u);
+            for (int s = 0; s < 2; ++s) tma_load_2d(base + OFF_A1 + 16384u * s, &map_a1, 128 * s, 128 * strip, bar(BAR_A1));
+            for (int i = 0; i < CR; ++i) {                                      // real chunk i + 1 = image rows [64 i, 64 i + 64)
+                const int st = i & 1;
+                if (i >= 2 && !mbar_wait(bar(BAR_B1_EMPTY + st), ((i >> 1) - 1) & 1, abort_flag)) break;
                 const uint32_t dst = base + OFF_B1 + 16384u * st;
-                mbar_expect_tx(bar(BAR_B1_FULL + st), 16384u);
-                const int v0 = CHR * (c - 1);                                   // first virtual row of the chunk
-                if (v0 >= 0 && v0 + CHR <= P.H) {
-                    tma_load_3d(dst, &map_img, x0 - 64, v0, f, bar(BAR_B1_FULL + st));
-                    tma_load_3d(dst + 8192u, &map_img, x0 + 64, v0, f, bar(BAR_B1_FULL + st));
-                } else {                                                        // rows mirrored at the top / bottom edge (REFLECT_101)
-                    for (int r = 0; r < CHR; ++r) {
-                        const int src = reflect101(v0 + r, P.H);
-                        tma_load_3d(dst + 128u * r, &map_row, x0 - 64, src, f, bar(BAR_B1_FULL + st));
-                        tma_load_3d(dst + 8192u + 128u * r, &map_row, x0 + 64, src, f, bar(BAR_B1_FULL + st));
-                    }
+                mbar_expect_tx(bar(BAR_B1_FULL + st), 16384u);                  // rows / columns outside the image arrive as zeros
+                tma_load_3d(dst, &map_img, x0 - 64, CHR * i, f, bar(BAR_B1_FULL + st));
+                tma_load_3d(dst + 8192u, &map_img, x0 + 64, CHR * i, f, bar(BAR_B1_FULL + st));
+                if (i == 1 || CR == 1) {                                        // pass 2 starts four chunks in: its matrices load behind the first rows
+                    mbar_expect_tx(bar(BAR_A2), 65536u);
+                    for (int b = 0; b < 2; ++b)
+                        for (int s = 0; s < 2; ++s) tma_load_2d(base + OFF_A2 + 32768u * b + 16384u * s, &map_a2, 128 * s, 128 * b, bar(BAR_A2));
                 }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer (one thread) =================
+        // ================= MMA issuer (one thread).  Everything between two MMAs is scalar code of ONE thread, so the
+        // descriptors are built once and moved by constants; the K loops are unrolled over compile-time ranges. ==========
         if (lane == 0) {
-            constexpr uint32_t ID1 = idesc_i8(128, 64, 0, 0);                   // taps (u8) x pixels (u8)
-            constexpr uint32_t ID2 = idesc_i8(128, 128, 1, 1);                  // taps (s8, <= 26) x sign-flipped bytes (s8)
-            bool ok = mbar_wait(bar(BAR_A), 0, abort_flag);
-            auto issue_block = [&](int b) -> bool {                             // pass 2 of output rows [128 b, 128 b + 128)
-                const int c_last = min(2 * b + 3, C - 1);
-                for (int cl = 2 * b; cl <= c_last; ++cl)                        // ring slabs of virtual rows [128 b - 64, 128 b + 192)
-                    if (!mbar_wait(bar(BAR_H_FULL + cl % NSLAB), (cl / NSLAB) & 1, abort_flag)) return false;
-                if (b >= 1 && !mbar_wait(bar(BAR_D2_EMPTY), (b - 1) & 1, abort_flag)) return false;
-                tc_fence_after();
-                for (int bl = 0; bl < 2; ++bl) {
-                    const int klo = P.k2_lo[bl], khi = P.k2_hi[bl];
-                    for (int j = klo; j < khi; ++j) {
-                        const int cl = min(2 * b + (j >> 1), C - 1);            // (clamped steps multiply rows that are never stored)
-                        const uint64_t ad = smem_desc(base + OFF_A2 + 32768u * bl + 16384u * (j >> 2) + 32u * (j & 3), 1024, 2);
-                        const uint64_t bd = smem_desc(base + OFF_H + 16384u * (cl % NSLAB) + 8192u * bl + 32u * (j & 1), 512, 4);
-                        tc_mma_i8(tmem + TM_D2 + 128u * bl, ad, bd, ID2, j > klo);
+            constexpr uint32_t ID1 = idesc_i8(128, 64, 0, 0);                   // taps (u8, <= 26) x pixels (u8)
+            constexpr uint32_t ID2 = idesc_i8(128, 128, 1, 1);                  // taps (s8, <= 13) x sign-flipped bytes (s8)
+            const uint64_t a1d = smem_desc(base + OFF_A1, 1024, 2), b1d = smem_desc(base + OFF_B1, 1024, 2);
+            const uint64_t a2d = smem_desc(base + OFF_A2, 1024, 2), hd = smem_desc(base + OFF_H, 512, 4);
+            int i1 = 0, b2 = 0, slab0 = 0;                                      // next real chunk, next block, ring slot of chunk 2 b2
+            bool a2_ready = false;
+            bool ok = mbar_wait(bar(BAR_A1), 0, abort_flag);
+            int idle = 0;
+            while (ok && (i1 < CR || b2 < NB)) {
+                bool progressed = false;
+                if (i1 < CR) {                                                  // pass 1 of real chunk i1 + 1
+                    const int st = i1 & 1;
+                    if (mbar_test(bar(BAR_B1_FULL + st), (i1 >> 1) & 1) && (i1 < 2 || mbar_test(bar(BAR_D1_EMPTY + st), ((i1 >> 1) - 1) & 1))) {
+                        tc_fence_after();
+                        const uint64_t bd = b1d + (uint64_t)(1024u * st);
+                        const uint32_t dd = tmem + TM_D1 + 64u * st;
+#pragma unroll
+                        for (int j = k1_lo(RL); j < k1_hi(RL); ++j)
+                            tc_mma_i8(dd, a1d + (uint64_t)(1024 * (j >> 2) + 2 * (j & 3)), bd + (uint64_t)(512 * (j >> 2) + 2 * (j & 3)), ID1, j > k1_lo(RL));
+                        tc_commit(bar(BAR_B1_EMPTY + st));
+                        tc_commit(bar(BAR_D1_FULL + st));
+                        ++i1;
+                        progressed = true;
                     }
                 }
-                tc_commit(bar(BAR_BLK + (b & 3)));
-                tc_commit(bar(BAR_D2_FULL));
-                return true;
-            };
-            int next_block = 0;
-            for (int c = 0; c < C && ok; ++c) {
-                const int st = c & 1;
-                ok = mbar_wait(bar(BAR_B1_FULL + st), (c >> 1) & 1, abort_flag);
-                if (ok && c >= 2) ok = mbar_wait(bar(BAR_D1_EMPTY + st), ((c >> 1) - 1) & 1, abort_flag);
-                if (!ok) break;
-                tc_fence_after();
-                for (int j = P.k1_lo; j < P.k1_hi; ++j) {
-                    const uint64_t ad = smem_desc(base + OFF_A1 + 16384u * (j >> 2) + 32u * (j & 3), 1024, 2);
-                    const uint64_t bd = smem_desc(base + OFF_B1 + 16384u * st + 8192u * (j >> 2) + 32u * (j & 3), 1024, 2);
-                    tc_mma_i8(tmem + TM_D1 + 64u * st, ad, bd, ID1, j > P.k1_lo);
+                if (b2 < NB) {                                                  // pass 2 of output rows [128 b2, 128 b2 + 128): chunk slots 2 b2 .. 2 b2 + 3
+                    bool ready = a2_ready || (a2_ready = mbar_test(bar(BAR_A2), 0));
+                    uint64_t hs[4];
+                    int sl = slab0, cc = 2 * b2;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (cc > C - 1) { hs[q] = hs[q - (q > 0)]; continue; }  // slots past the last one: taps there only feed rows that are never stored
+                        ready = ready && mbar_test(bar(BAR_H_FULL + sl), (uint32_t)(cc / NSLAB) & 1u);
+                        hs[q] = hd + (uint64_t)(1024u * sl);
+                        ++cc; if (++sl == NSLAB) sl = 0;
+                    }
+                    if (ready && (b2 == 0 || mbar_test(bar(BAR_D2_EMPTY), (b2 - 1) & 1))) {
+                        tc_fence_after();
+#pragma unroll
+                        for (int j = k2_lo(RL); j < k2_hi(RL); ++j)
+                            tc_mma_i8(tmem + TM_D2, a2d + (uint64_t)(1024 * (j >> 2) + 2 * (j & 3)), hs[j >> 1] + (uint64_t)(2 * (j & 1)), ID2, j > k2_lo(RL));
+#pragma unroll
+                        for (int j = k2_lo(RS); j < k2_hi(RS); ++j)
+                            tc_mma_i8(tmem + TM_D2 + 128u, a2d + (uint64_t)(2048 + 1024 * (j >> 2) + 2 * (j & 3)), hs[j >> 1] + (uint64_t)(512 + 2 * (j & 1)), ID2,
+                                      j > k2_lo(RS));
+                        tc_commit(bar(BAR_BLK + (b2 & 3)));
+                        tc_commit(bar(BAR_D2_FULL));
+                        ++b2;
+                        slab0 += 2; if (slab0 >= NSLAB) slab0 -= NSLAB;
+                        progressed = true;
+                    }
                 }
-                tc_commit(bar(BAR_B1_EMPTY + st));
-                tc_commit(bar(BAR_D1_FULL + st));
-                // one chunk behind: the block whose last chunk is c - 1 (its epilogue 1 runs while the MMAs above execute)
-                while (ok && next_block < NB && min(2 * next_block + 3, C - 1) <= c - 1) ok = issue_block(next_block++);
+                if (progressed) idle = 0;
+                else if (++idle > (1 << 22) || ((idle & 1023) == 0 && *abort_flag)) { *abort_flag = 1; ok = false; }
             }
-            while (ok && next_block < NB) ok = issue_block(next_block++);
         }
     } else if (warp >= 4 && warp < 8) {
         // ================= epilogue 1: D1 -> signed high / low bytes, K-major, into the ring =================
         const int q = warp & 3, row = 32 * q + lane;          // TMEM lane = (blur, column): blur = row / 64
         const int bl = row >> 6, n = row & 63;
+        auto tile_of = [&](int cc) -> unsigned char * { return gen + OFF_H + 16384u * (uint32_t)(cc % NSLAB) + 8192u * (uint32_t)bl; };
+        // one byte of both planes: (chunk slot, k) <- (chunk slot, k); a thread only ever touches its own two rows
+        auto copy_byte = [&](int cs, int ks, int ct, int kt) {
+            const unsigned char *src = tile_of(cs);
+            unsigned char *dst = tile_of(ct);
+            dst[swz64((uint32_t)n, (uint32_t)kt)] = src[swz64((uint32_t)n, (uint32_t)ks)];
+            dst[swz64((uint32_t)(64 + n), (uint32_t)kt)] = src[swz64((uint32_t)(64 + n), (uint32_t)ks)];
+        };
+        auto slot_free = [&](int cc) -> bool {                 // the slot of chunk cc held chunk cc - NSLAB, last read by block min(NB-1, (cc-NSLAB)/2)
+            if (cc < NSLAB) return true;
+            const int bdone = min(NB - 1, (cc - NSLAB) >> 1);
+            return mbar_wait(bar(BAR_BLK + (bdone & 3)), (bdone >> 2) & 1, abort_flag);
+        };
         bool ok = true;
-        for (int c = 0; c < C && ok; ++c) {
-            const int st = c & 1;
-            ok = mbar_wait(bar(BAR_D1_FULL + st), (c >> 1) & 1, abort_flag);
+        for (int i = 0; i < CR && ok; ++i) {
+            const int st = i & 1, cc = i + 1;
+            ok = mbar_wait(bar(BAR_D1_FULL + st), (i >> 1) & 1, abort_flag);
             if (!ok) break;
             tc_fence_after();
             uint32_t v[4][16];
@@ -245,69 +281,78 @@ blur_area_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(bar(BAR_D1_EMPTY + st));                // the accumulator stage may be overwritten
-            // the slab this chunk goes to held chunk c - NSLAB, last read by block min(NB - 1, (c - NSLAB) / 2)
-            if (c >= NSLAB) {
-                const int bdone = min(NB - 1, (c - NSLAB) >> 1);
-                ok = mbar_wait(bar(BAR_BLK + (bdone & 3)), (bdone >> 2) & 1, abort_flag);
-                if (!ok) break;
-            }
-            unsigned char *tile = gen + OFF_H + 16384u * (c % NSLAB) + 8192u * bl;      // [128 rows][64 B]: rows 0..63 high bytes, 64..127 low bytes
+            if (!(ok = slot_free(cc))) break;
+            unsigned char *tile = tile_of(cc);                  // [128 rows][64 B]: rows 0..63 high bytes, 64..127 low bytes
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
                 uint32_t p[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) p[i] = __byte_perm(v[g][2 * i], v[g][2 * i + 1], 0x5140);   // {a.b0, b.b0, a.b1, b.b1}
+                for (int t = 0; t < 8; ++t) p[t] = __byte_perm(v[g][2 * t], v[g][2 * t + 1], 0x5140);   // {a.b0, b.b0, a.b1, b.b1}
                 uint4 lo4, hi4;
                 lo4.x = __byte_perm(p[0], p[1], 0x5410) ^ 0x80808080u; hi4.x = __byte_perm(p[0], p[1], 0x7632) ^ 0x80808080u;
                 lo4.y = __byte_perm(p[2], p[3], 0x5410) ^ 0x80808080u; hi4.y = __byte_perm(p[2], p[3], 0x7632) ^ 0x80808080u;
                 lo4.z = __byte_perm(p[4], p[5], 0x5410) ^ 0x80808080u; hi4.z = __byte_perm(p[4], p[5], 0x7632) ^ 0x80808080u;
                 lo4.w = __byte_perm(p[6], p[7], 0x5410) ^ 0x80808080u; hi4.w = __byte_perm(p[6], p[7], 0x7632) ^ 0x80808080u;
-                // SWIZZLE_64B: 16-byte chunk index ^= (row / 2) & 3
-                const uint32_t ch = (uint32_t)g ^ ((uint32_t)(n >> 1) & 3u);
+                const uint32_t ch = (uint32_t)g ^ ((uint32_t)(n >> 1) & 3u);            // SWIZZLE_64B: 16-byte chunk index ^= (row / 2) & 3
                 *reinterpret_cast<uint4 *>(tile + 64u * n + 16u * ch) = hi4;
-                *reinterpret_cast<uint4 *>(tile + 64u * (64 + n) + 16u * ch) = lo4;      // (64 + n) / 2 & 3 == (n / 2) & 3
+                *reinterpret_cast<uint4 *>(tile + 64u * (64 + n) + 16u * ch) = lo4;      // ((64 + n) / 2) & 3 == (n / 2) & 3
+            }
+            // REFLECT_101 in y: the horizontal pass commutes with it, so the virtual rows above row 0 and below row H-1 are
+            // COPIES of rows this thread has already written (its own two ring rows: no cross-thread hazard)
+            if (cc == 1) {                                      // rows -j <- rows j, j = 1 .. radius: chunk slot 0, k = 64 - j
+                for (int j = 1; j <= P.radius; ++j) copy_byte(1, j, 0, 64 - j);
+            }
+            if (cc == CR) {                                     // rows H + t <- rows H - 2 - t (the last ones may sit in the previous chunk)
+                for (int ct = CR + 1; ct < C && ok; ++ct) ok = slot_free(ct);
+                if (!ok) break;
+                for (int t = 0; t < P.radius; ++t) {
+                    const int vt = P.H + t, vs = P.H - 2 - t;
+                    copy_byte((vs >> 6) + 1, vs & 63, (vt >> 6) + 1, vt & 63);
+                }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                  // generic writes -> visible to the tensor core's reads
-            mbar_arrive(bar(BAR_H_FULL + c % NSLAB));
+            if (cc == 1) mbar_arrive(bar(BAR_H_FULL + 0));
+            mbar_arrive(bar(BAR_H_FULL + cc % NSLAB));
+            if (cc == CR)
+                for (int ct = CR + 1; ct < C; ++ct) mbar_arrive(bar(BAR_H_FULL + ct % NSLAB));
         }
     } else if (warp >= 8) {
-        // ================= epilogue 2: D2 -> rounding, wrapping DoG, inRange, 64 bits per row =================
-        const int q = warp & 3, r = 32 * q + lane;              // TMEM lane = output row within the block
-        const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
+        // ================= epilogue 2: D2 -> rounding, wrapping DoG, inRange, 32 bits per thread and row =================
+        const int q = warp & 3, half = (warp - 8) >> 2, r = 32 * q + lane;     // TMEM lane = output row within the block; columns 32 half ..
+        const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16) + TM_D2 + 32u * half;
         const uint32_t span = (uint32_t)(P.hi - P.lo), bias = (uint32_t)(15 - P.lo);
-        const int nvalid = min(SW, P.W - x0);                   // columns of this strip inside the image
-        const uint64_t colmask = nvalid >= 64 ? ~0ull : ((1ull << nvalid) - 1ull);
+        const int nvalid = min(32, P.W - x0 - 32 * half);       // columns of this half strip inside the image
+        const uint32_t colmask = nvalid >= 32 ? ~0u : nvalid > 0 ? ((1u << nvalid) - 1u) : 0u;
+        const int wx = (x0 >> 5) + half;
         uint32_t count = 0;
         bool ok = true;
         for (int b = 0; b < NB && ok; ++b) {
             ok = mbar_wait(bar(BAR_D2_FULL), b & 1, abort_flag);
             if (!ok) break;
             tc_fence_after();
-            uint64_t bits = 0;
+            uint32_t bits = 0;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
+            for (int g = 0; g < 2; ++g) {
                 uint32_t hL[16], lL[16], hS[16], lS[16];
-                tmem_ld16(lane_addr + TM_D2 + 16u * g, hL);
-                tmem_ld16(lane_addr + TM_D2 + 64u + 16u * g, lL);
-                tmem_ld16(lane_addr + TM_D2 + 128u + 16u * g, hS);
-                tmem_ld16(lane_addr + TM_D2 + 192u + 16u * g, lS);
+                tmem_ld16(lane_addr + 16u * g, hL);
+                tmem_ld16(lane_addr + 64u + 16u * g, lL);
+                tmem_ld16(lane_addr + 128u + 16u * g, hS);
+                tmem_ld16(lane_addr + 192u + 16u * g, lS);
                 tmem_ld_wait();
-                if (g == 3) { tc_fence_before(); mbar_arrive(bar(BAR_D2_EMPTY)); }      // all of D2 is in registers
+                if (g == 1) { tc_fence_before(); mbar_arrive(bar(BAR_D2_EMPTY)); }      // this thread's part of D2 is in registers
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const int uL = (int)hL[i] * 256 + (int)lL[i];
                     const int uS = (int)hS[i] * 256 + (int)lS[i];
                     const uint32_t d = ((uint32_t)((uL >> 16) - (uS >> 16)) + bias) & 255u;       // uint8 wrap (MD:128), inRange (MD:129)
-                    bits |= (uint64_t)(d <= span) << (16 * g + i);
+                    bits |= (uint32_t)(d <= span) << (16 * g + i);
                 }
             }
             const int y = BLK * b + r;
-            if (y < P.H) {
+            if (y < P.H && wx < P.WW) {
                 bits &= colmask;
-                uint32_t *dst = P.area_bits + ((size_t)f * P.H + y) * P.WW + (x0 >> 5);
-                if ((x0 >> 5) < P.WW) dst[0] = (uint32_t)bits;
-                if ((x0 >> 5) + 1 < P.WW) dst[1] = (uint32_t)(bits >> 32);
-                count += __popcll(bits);
+                P.area_bits[((size_t)f * P.H + y) * P.WW + wx] = bits;
+                count += __popc(bits);
             }
         }
 #pragma unroll
@@ -369,7 +414,7 @@ cudaError_t vbs_blur_tc_setup(vbs_ctx *ctx) {
     vbs_host_taps(KL, ctx->big ? 20.0 : 11.4, tapsL);
     vbs_host_taps(KS, ctx->big ? 8.0 : 4.56, tapsS);
     const int RL = KL / 2, RS = KS / 2;
-    if (RL > 63 || RS > RL) return cudaErrorInvalidValue;
+    if (!((RL == 50 && RS == 19) || (RL == 17 && RS == 10))) return cudaErrorInvalidValue;     // the kernel's two instantiations
     std::vector<uint8_t> a1((size_t)nstrips * 128 * KEXT, 0), a2((size_t)2 * 128 * KEXT, 0);
     for (int s = 0; s < nstrips; ++s)
         for (int row = 0; row < 128; ++row) {
@@ -387,12 +432,6 @@ cudaError_t vbs_blur_tc_setup(vbs_ctx *ctx) {
         for (int r = 0; r < 128; ++r)
             for (int t = 0; t <= 2 * R; ++t) a2[((size_t)bl * 128 + r) * KEXT + (64 + r + t - R)] = (uint8_t)taps[t];
     }
-    // K steps of 32 bytes that hold non-zero taps
-    ctx->tc_k1[0] = (64 - RL) / 32; ctx->tc_k1[1] = (64 + 63 + RL) / 32 + 1;
-    for (int bl = 0; bl < 2; ++bl) {
-        const int R = bl ? RS : RL;
-        ctx->tc_k2lo[bl] = (64 - R) / 32; ctx->tc_k2hi[bl] = (64 + 127 + R) / 32 + 1;
-    }
     cudaError_t e;
     if ((e = cudaMalloc((void **)&ctx->tc_a1, a1.size())) != cudaSuccess) return e;
     if ((e = cudaMalloc((void **)&ctx->tc_a2, a2.size())) != cudaSuccess) return e;
@@ -408,27 +447,29 @@ cudaError_t vbs_launch_blur_tc(vbs_ctx *ctx, const uint8_t *frames, int batch, i
     cudaError_t e = vbs_blur_tc_setup(ctx);
     if (e != cudaSuccess) return e;
     const int H = ctx->H, W = ctx->W, nstrips = (W + SW - 1) / SW;
-    CUtensorMap m_img, m_row, m_a1, m_a2;
+    CUtensorMap m_img, m_a1, m_a2;
     {
         const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)batch};
         const cuuint64_t strides[2] = {(cuuint64_t)row_pitch, (cuuint64_t)frame_stride};
-        const cuuint32_t box[3] = {128, CHR, 1}, box1[3] = {128, 1, 1};
-        if (!encode_u8(&m_img, frames, 3, dims, strides, box) || !encode_u8(&m_row, frames, 3, dims, strides, box1)) return cudaErrorNotSupported;
+        const cuuint32_t box[3] = {128, CHR, 1};
+        if (!encode_u8(&m_img, frames, 3, dims, strides, box)) return cudaErrorNotSupported;
     }
     {
         const cuuint64_t d1[2] = {KEXT, (cuuint64_t)128 * nstrips}, d2[2] = {KEXT, 256}, st[1] = {KEXT};
         const cuuint32_t box[2] = {128, 128};
         if (!encode_u8(&m_a1, ctx->tc_a1, 2, d1, st, box) || !encode_u8(&m_a2, ctx->tc_a2, 2, d2, st, box)) return cudaErrorNotSupported;
     }
+    const int R = ctx->br.kl / 2;
     TcParams P;
     P.H = H; P.W = W; P.WW = ctx->WW; P.lo = ctx->br.lo; P.hi = ctx->br.hi;
-    P.nchunks = (H + ctx->br.kl / 2 + CHR - 1) / CHR + 1;        // virtual rows [-64, H + radius)
+    P.nreal = (H + CHR - 1) / CHR;
+    P.nchunks = (H - 1 + R) / CHR + 2;                           // slots for virtual rows [-64, H + radius)
     P.nblocks = (H + BLK - 1) / BLK;
-    P.k1_lo = ctx->tc_k1[0]; P.k1_hi = ctx->tc_k1[1];
-    for (int b = 0; b < 2; ++b) { P.k2_lo[b] = ctx->tc_k2lo[b]; P.k2_hi[b] = ctx->tc_k2hi[b]; }
+    P.radius = R;
     P.area_bits = ctx->area_bits; P.area_count = ctx->area_count; P.status = ctx->d_status;
-    if ((e = cudaFuncSetAttribute(blur_area_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES)) != cudaSuccess) return e;
-    blur_area_tc_kernel<<<dim3(nstrips, batch), NTHREADS, SMEM_BYTES, ctx->stream>>>(m_img, m_row, m_a1, m_a2, P);
+    auto kern = ctx->big ? blur_area_tc_kernel<50, 19> : blur_area_tc_kernel<17, 10>;
+    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES)) != cudaSuccess) return e;
+    kern<<<dim3(nstrips, batch), NTHREADS, SMEM_BYTES, ctx->stream>>>(m_img, m_a1, m_a2, P);
     ctx->launches += 1;
     ctx->tc_launches += 1;
     return cudaGetLastError();

@@ -46,7 +46,7 @@ struct vbs_ctx {
     // opt-in tensor-core blur (k_blur_tc.cu): VBS_BLUR_TC=1 or vbs_set_blur_tc
     int blur_tc; int64_t tc_launches;
     uint8_t *tc_a1, *tc_a2;                // operator matrices [nstrips][128][256], [2][128][256]
-    int tc_k1[2], tc_k2lo[2], tc_k2hi[2];  // K-step ranges with non-zero taps
+
 
     // optional lens correction before K1 (MD:93-109)
     int undist_on; double new_k[4];            // fx', fy', cx', cy' of getOptimalNewCameraMatrix(alpha = 0)
