@@ -25,7 +25,7 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-@pytest.mark.parametrize("world,n_frames,batch", [(2, 37, 8), (2, 24, 5), (4, 41, 4)])
+@pytest.mark.parametrize("world,n_frames,batch", [(2, 37, 8), (2, 24, 5), (2, 40, 8), (4, 41, 4), (4, 48, 5)])
 def test_streamed_shards_under_nccl_equal_one_sequential_run(world, n_frames, batch):
     if _gpus() < world:
         pytest.skip(f"needs {world} GPUs")

@@ -76,6 +76,32 @@ def gather_records(tensors: dict, rank: int, world: int, dst: int = 0, counts=No
     return out if rank == dst else None
 
 
+class RecordSink:
+    """Destination of the gathered records on ``dst``: one preallocated tensor per record, ``[n_frames, ...]`` in global
+    frame order (allocated once, reused across streams: no allocation or concatenation inside a timed region).
+    ``slices(name, r, s, e)`` = the rows of rank r's frames [s, e) of its shard."""
+
+    def __init__(self, like: dict, n_frames: int, world: int, device):
+        import torch
+        self.bounds = [shard_bounds(n_frames, r, world) for r in range(world)]
+        self.n_frames, self.world = n_frames, world
+        self.data = {k: torch.empty((n_frames,) + tuple(t.shape[1:]), dtype=t.dtype, device=device) for k, t in like.items()}
+
+    def parts(self, name: str, s: int, e: int):
+        return [self.data[name][lo + s: lo + e] for lo, _ in self.bounds]
+
+
+def gather_rows_async(tensors: dict, s: int, e: int, rank: int, world: int, sink, dst: int = 0):
+    """Start the gather of rows [s, e) of every record tensor (equal-length shards) into ``sink`` on ``dst``; returns the
+    work handles.  NCCL runs it on its own stream behind the work already queued on the current stream, so the next
+    batch's kernels run beside it."""
+    import torch.distributed as dist
+    works = []
+    for name, t in tensors.items():
+        works.append(dist.gather(t[s:e], sink.parts(name, s, e) if rank == dst else None, dst=dst, async_op=True))
+    return works
+
+
 def finish_shard(pipe, result, rank: int, world: int, device=None):
     """After ``pipe`` processed this rank's shard from an empty table: exchange tails and patch the
     missing displacement rows in ``result`` (device tensors pos3d / pos_flags) in place."""
@@ -85,3 +111,17 @@ def finish_shard(pipe, result, rank: int, world: int, device=None):
     capi.check(pipe._ctx, capi.lib.vbs_fix_displacement(pipe._ctx, result.pos3d.data_ptr(), result.pos_flags.data_ptr(), n,
                                                         incoming.ctypes.data))
     return incoming
+
+
+def all_tail_tables(table: np.ndarray, rank: int, world: int, device=None) -> np.ndarray:
+    """[world, R, 4]: the last-seen tables every shard ended with (one small all_gather)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.from_numpy(np.ascontiguousarray(table, dtype=np.float64))
+    if world == 1:
+        return t.numpy()[None]
+    if device is not None:
+        t = t.to(device)
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t)
+    return np.stack([p.cpu().numpy() for p in parts])

@@ -35,18 +35,21 @@ class ShardRecords:
     plane: object
     plane_n: object
     n_markers: object
+    works: object = ()                   # NCCL work handles of the per-batch gathers in flight
 
     def tensors(self) -> dict:
         return {k: getattr(self, k) for k in RECORD_KEYS if getattr(self, k) is not None}
 
 
 def process_shard(pipe, frames_of: Callable[[int, int], object], n_frames: int, batch: int, rank: int, world: int,
-                  first_frame: int = 0) -> ShardRecords:
+                  first_frame: int = 0, sink=None) -> ShardRecords:
     """Run this rank's contiguous shard of an ``n_frames`` sequence through ``pipe`` batch by batch.
 
     ``frames_of(lo, hi)`` returns the device tensor ``[hi-lo, H, W(,3)]`` uint8 of global frames lo..hi-1
     (``hi - lo <= batch``).  The reference array, camera and (optionally) plane inputs of ``pipe`` must be set.
-    Records accumulate in device memory (96 B per reference entry + 32 B per frame)."""
+    Records accumulate in device memory (96 B per reference entry + 32 B per frame).  With a ``sink``
+    (equal-length shards) the records of every batch start travelling to rank 0 as soon as the batch is queued:
+    the NCCL gather of batch k runs beside the kernels of batch k + 1."""
     import torch
     lo, hi = sharding.shard_bounds(n_frames, rank, world)
     n, R = hi - lo, pipe.R
@@ -61,6 +64,7 @@ def process_shard(pipe, frames_of: Callable[[int, int], object], n_frames: int, 
                        torch.empty((n,), dtype=i32, device=dev))
     pipe.reset_sequence()
     pipe.set_first_frame(first_frame)            # the warm-up window (R3:255-256) counts from the GLOBAL first frame
+    works = []
     for s in range(0, n, batch):                 # every batch writes straight into its slice of the shard's record block
         e = min(n, s + batch)
         arrays, o = {}, capi.VbsOutputs()
@@ -70,20 +74,64 @@ def process_shard(pipe, frames_of: Callable[[int, int], object], n_frames: int, 
                 arrays[k] = t[s:e]
                 setattr(o, k, arrays[k].data_ptr())
         pipe.process(frames_of(lo + s, lo + e), lo + s, out=(arrays, o))
+        if sink is not None and world > 1:
+            works += sharding.gather_rows_async(rec.tensors(), s, e, rank, world, sink)
+    rec.works = works
     return rec
 
 
-def finish_and_gather(pipe, rec: ShardRecords, n_frames: int, rank: int, world: int, dst: int = 0) -> Optional[dict]:
+def finish_and_gather(pipe, rec: ShardRecords, n_frames: int, rank: int, world: int, dst: int = 0, sink=None) -> Optional[dict]:
     """Patch the shard's first observation of every marker with the last-seen table arriving from the
-    preceding shards, then gather the records to ``dst`` (concatenated in global frame order)."""
+    preceding shards, and deliver the records to ``dst`` (concatenated in global frame order).
+
+    Without a sink: patch, then one gather of the whole shard.  With a sink the records are already on their way
+    (``process_shard``): only the R x 4 tail tables are exchanged, and ``dst`` applies every shard's patch to the
+    gathered block itself (``vbs_fix_displacement`` needs nothing but the block, the camera and the incoming table)."""
     import torch
+    dev = torch.device("cuda", pipe.device)
     pipe.sync()
-    sharding.finish_shard(pipe, rec, rank, world, torch.device("cuda", pipe.device))
-    counts = [hi - lo for lo, hi in (sharding.shard_bounds(n_frames, r, world) for r in range(world))]
-    return sharding.gather_records(rec.tensors(), rank, world, dst, counts)
+    if sink is None or world == 1:
+        sharding.finish_shard(pipe, rec, rank, world, dev)
+        counts = [hi - lo for lo, hi in (sharding.shard_bounds(n_frames, r, world) for r in range(world))]
+        return sharding.gather_records(rec.tensors(), rank, world, dst, counts)
+    tails = sharding.all_tail_tables(pipe.get_last_seen(), rank, world, dev)
+    for w in getattr(rec, "works", ()):
+        w.wait()                                 # the current stream now waits for the gathers
+    if rank != dst:
+        return None
+    for r in range(1, world):
+        lo, hi = sink.bounds[r]
+        inc = sharding.incoming_last_seen(tails, r)
+        capi.check(pipe._ctx, capi.lib.vbs_fix_displacement(pipe._ctx, sink.data["pos3d"][lo:hi].data_ptr(), sink.data["pos_flags"][lo:hi].data_ptr(),
+                                                            hi - lo, inc.ctypes.data))
+    return sink.data
 
 
-def run_stream(pipe, frames_of, n_frames: int, batch: int, rank: int, world: int, first_frame: int = 0):
-    """process_shard + finish_and_gather; returns (records dict on rank 0 / None elsewhere, ShardRecords)."""
-    rec = process_shard(pipe, frames_of, n_frames, batch, rank, world, first_frame)
-    return finish_and_gather(pipe, rec, n_frames, rank, world), rec
+def make_sink(pipe, n_frames: int, rank: int, world: int, dst: int = 0):
+    """Preallocated destination of the gathered records on ``dst`` (None elsewhere, and None when the shards are not all
+    the same length: the collective then pads instead, see ``sharding.gather_records``)."""
+    import torch
+    counts = {hi - lo for lo, hi in (sharding.shard_bounds(n_frames, r, world) for r in range(world))}
+    if world == 1 or len(counts) != 1:
+        return None
+    dev = torch.device("cuda", pipe.device)
+    R = pipe.R
+    like = {"row_det": torch.empty((0, R), dtype=torch.int32), "row_cxy": torch.empty((0, R, 2), dtype=torch.float64),
+            "row_axes": torch.empty((0, R, 3), dtype=torch.float64), "pos3d": torch.empty((0, R, 7), dtype=torch.float64),
+            "pos_flags": torch.empty((0, R), dtype=torch.uint8), "n_markers": torch.empty((0,), dtype=torch.int32)}
+    if pipe.have_plane:
+        like.update({"plane": torch.empty((0, 4), dtype=torch.float64), "plane_n": torch.empty((0,), dtype=torch.int32)})
+    return sharding.RecordSink(like, n_frames if rank == dst else 0, world, dev) if rank == dst else _RemoteSink()
+
+
+class _RemoteSink:
+    """Placeholder on the ranks that only send."""
+    def parts(self, name, s, e):
+        return None
+
+
+def run_stream(pipe, frames_of, n_frames: int, batch: int, rank: int, world: int, first_frame: int = 0, sink=None):
+    """process_shard + finish_and_gather; returns (records dict on rank 0 / None elsewhere, ShardRecords).
+    ``sink`` = ``make_sink(...)`` (reusable across calls) overlaps the gather with the kernels."""
+    rec = process_shard(pipe, frames_of, n_frames, batch, rank, world, first_frame, sink)
+    return finish_and_gather(pipe, rec, n_frames, rank, world, sink=sink), rec
