@@ -288,7 +288,7 @@ def stream_main(args, rank, world, local):
     for _ in range(max(args.warmup, 1)):               # short warm-up streams: kernels, NCCL gather and all_gather paths
         streaming.run_stream(pipe, frames_of, warm_frames, B, rank, world, sink=wsink)
     del wsink
-    sink = streaming.make_sink(pipe, N, rank, world)   # rank 0: preallocated [N, ...] record block the per-batch gathers land in
+    sink = streaming.make_sink(pipe, N, rank, world)   # rank 0: preallocated landing area of the gathered record blobs
     pipe.sync()
     pipe.set_profiling(True)
     l0 = pipe.kernel_launches
@@ -333,7 +333,7 @@ def stream_main(args, rank, world, local):
                 "dtype": "u8 (integer blur/labels) + f32/f64 (NCC, geometry)", "data": "synthetic",
                 "config": {"workload": f"stream64k: {N} frames of {H}x{W} gray u8 ({rows}x{cols} markers, {U} unique oracle-checked frames tiled on the "
                                        f"device), contiguous shards of {N // world} frames per GPU, batches of {B}; tracking+IDs -> 3D displacement "
-                                       f"(warm-up 100 frames, last-seen exchange across shards) -> plane tilt; per-batch NCCL gather of records + tilt to rank 0 beside the kernels of the next batch, all in the timed region",
+                                       f"(warm-up 100 frames, last-seen exchange across shards) -> plane tilt; one NCCL gather of the record blobs + tilt to rank 0, shard boundaries patched there, all in the timed region",
                            "batch_per_gpu": B, "frames": N, "l2_policy": "inputs larger than L2 (batch of frames = %.0f MB/GPU)" % (B * H * W / 1e6),
                            "parallelism": f"frame-sharded x{world}", "gathered_bytes": rec_bytes},
                 "roofline": {"bound": "hbm", "kernel": "blur_area_kernel<39,101> (gray -> DoG -> area mask)", "achieved": ach, "peak": peak, "unit": "GB/s",
@@ -557,11 +557,10 @@ def main():
             """batch s is complete on this rank: gather it to rank 0 and bring it to rank 0's host"""
             if not on_dev:
                 return
-            g = gather(houts[s & 1][0])
+            g = gather(houts[s & 1][0])              # stream-ordered: the host does not wait, the H2D copies of the next batches keep flowing
             if rank == 0:
                 for k, v in g.items():
                     hgath[k].copy_(v, non_blocking=True)
-                torch.cuda.current_stream().synchronize()
 
         # streaming use of the public host API: submit batch s+1 (its H2D copy starts at once) before
         # waiting for batch s; every step still moves its own frames host->device and results device->host
@@ -573,6 +572,7 @@ def main():
                 land(s - 1)
             pipe.wait_host()
             land(s0 + nsteps - 1)
+            torch.cuda.current_stream().synchronize()          # the last records are on rank 0's host
 
         def timed(chunk):
             pipe.set_host_chunk(chunk)

@@ -76,32 +76,6 @@ def gather_records(tensors: dict, rank: int, world: int, dst: int = 0, counts=No
     return out if rank == dst else None
 
 
-class RecordSink:
-    """Destination of the gathered records on ``dst``: one preallocated tensor per record, ``[n_frames, ...]`` in global
-    frame order (allocated once, reused across streams: no allocation or concatenation inside a timed region).
-    ``slices(name, r, s, e)`` = the rows of rank r's frames [s, e) of its shard."""
-
-    def __init__(self, like: dict, n_frames: int, world: int, device):
-        import torch
-        self.bounds = [shard_bounds(n_frames, r, world) for r in range(world)]
-        self.n_frames, self.world = n_frames, world
-        self.data = {k: torch.empty((n_frames,) + tuple(t.shape[1:]), dtype=t.dtype, device=device) for k, t in like.items()}
-
-    def parts(self, name: str, s: int, e: int):
-        return [self.data[name][lo + s: lo + e] for lo, _ in self.bounds]
-
-
-def gather_rows_async(tensors: dict, s: int, e: int, rank: int, world: int, sink, dst: int = 0):
-    """Start the gather of rows [s, e) of every record tensor (equal-length shards) into ``sink`` on ``dst``; returns the
-    work handles.  NCCL runs it on its own stream behind the work already queued on the current stream, so the next
-    batch's kernels run beside it."""
-    import torch.distributed as dist
-    works = []
-    for name, t in tensors.items():
-        works.append(dist.gather(t[s:e], sink.parts(name, s, e) if rank == dst else None, dst=dst, async_op=True))
-    return works
-
-
 def finish_shard(pipe, result, rank: int, world: int, device=None):
     """After ``pipe`` processed this rank's shard from an empty table: exchange tails and patch the
     missing displacement rows in ``result`` (device tensors pos3d / pos_flags) in place."""

@@ -17,121 +17,151 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import Callable, Optional
 
+import numpy as np
+
 from . import capi, sharding
 
 RECORD_KEYS = ("row_det", "row_cxy", "row_axes", "pos3d", "pos_flags", "plane", "plane_n", "n_markers")
 
 
+def record_layout(n: int, R: int, have_plane: bool):
+    """Sections of one shard's record blob: [(key, shape, torch dtype name, byte offset)], total bytes.  Every rank's
+    records live in ONE contiguous allocation so that the whole shard travels to rank 0 in one collective."""
+    spec = [("row_det", (n, R), "int32", 4), ("row_cxy", (n, R, 2), "float64", 8), ("row_axes", (n, R, 3), "float64", 8),
+            ("pos3d", (n, R, 7), "float64", 8), ("pos_flags", (n, R), "uint8", 1)]
+    if have_plane:
+        spec += [("plane", (n, 4), "float64", 8), ("plane_n", (n,), "int32", 4)]
+    spec += [("n_markers", (n,), "int32", 4)]
+    out, off = [], 0
+    for key, shape, dt, isz in spec:
+        nbytes = isz * int(np.prod(shape))
+        out.append((key, shape, dt, off))
+        off = (off + nbytes + 255) // 256 * 256
+    return out, off
+
+
+def blob_views(blob, n: int, R: int, have_plane: bool) -> dict:
+    """Typed views of the sections of a record blob (no copies)."""
+    import torch
+    views = {}
+    for key, shape, dt, off in record_layout(n, R, have_plane)[0]:
+        dtype = getattr(torch, dt)
+        nbytes = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        views[key] = blob[off: off + nbytes].view(dtype).view(shape)
+    return views
+
+
 @dataclass
 class ShardRecords:
-    """Per-frame records of one shard (device tensors, first axis = frame)."""
+    """Per-frame records of one shard (device tensors, first axis = frame), all views of ``blob``."""
     lo: int
     hi: int
-    row_det: object
-    row_cxy: object
-    row_axes: object
-    pos3d: object
-    pos_flags: object
-    plane: object
-    plane_n: object
-    n_markers: object
-    works: object = ()                   # NCCL work handles of the per-batch gathers in flight
+    blob: object
+    views: dict
+
+    def __getattr__(self, key):
+        views = object.__getattribute__(self, "views")
+        if key in RECORD_KEYS:
+            return views.get(key)
+        raise AttributeError(key)
 
     def tensors(self) -> dict:
-        return {k: getattr(self, k) for k in RECORD_KEYS if getattr(self, k) is not None}
+        return dict(self.views)
+
+
+class RecordSink:
+    """Rank 0's landing area: ``[world, blob_bytes]`` (allocated once, reused across streams) plus the assembled
+    ``[n_frames, ...]`` arrays in global frame order."""
+
+    def __init__(self, n_frames: int, R: int, have_plane: bool, world: int, device):
+        import torch
+        self.n_frames, self.R, self.have_plane, self.world = n_frames, R, have_plane, world
+        self.bounds = [sharding.shard_bounds(n_frames, r, world) for r in range(world)]
+        self.blob_bytes = max(record_layout(hi - lo, R, have_plane)[1] for lo, hi in self.bounds)
+        self.blobs = torch.empty((world, self.blob_bytes), dtype=torch.uint8, device=device)
+        self.data = {}
+        for key, shape, dt, _ in record_layout(n_frames, R, have_plane)[0]:
+            self.data[key] = torch.empty(shape, dtype=getattr(torch, dt), device=device)
+
+    def shard_views(self, r: int) -> dict:
+        lo, hi = self.bounds[r]
+        return blob_views(self.blobs[r], hi - lo, self.R, self.have_plane)
+
+    def assemble(self) -> dict:
+        for r, (lo, hi) in enumerate(self.bounds):
+            for key, v in self.shard_views(r).items():
+                self.data[key][lo:hi].copy_(v)
+        return self.data
+
+
+def blob_bytes_for(n_frames: int, R: int, have_plane: bool, world: int) -> int:
+    return max(record_layout(hi - lo, R, have_plane)[1] for lo, hi in (sharding.shard_bounds(n_frames, r, world) for r in range(world)))
 
 
 def process_shard(pipe, frames_of: Callable[[int, int], object], n_frames: int, batch: int, rank: int, world: int,
-                  first_frame: int = 0, sink=None) -> ShardRecords:
+                  first_frame: int = 0) -> ShardRecords:
     """Run this rank's contiguous shard of an ``n_frames`` sequence through ``pipe`` batch by batch.
 
     ``frames_of(lo, hi)`` returns the device tensor ``[hi-lo, H, W(,3)]`` uint8 of global frames lo..hi-1
     (``hi - lo <= batch``).  The reference array, camera and (optionally) plane inputs of ``pipe`` must be set.
-    Records accumulate in device memory (96 B per reference entry + 32 B per frame).  With a ``sink``
-    (equal-length shards) the records of every batch start travelling to rank 0 as soon as the batch is queued:
-    the NCCL gather of batch k runs beside the kernels of batch k + 1."""
+    Records accumulate in one device blob (96 B per reference entry + 32 B per frame); every batch writes
+    straight into its rows of it."""
     import torch
     lo, hi = sharding.shard_bounds(n_frames, rank, world)
     n, R = hi - lo, pipe.R
     dev = torch.device("cuda", pipe.device)
-    f64, i32, u8 = torch.float64, torch.int32, torch.uint8
-    rec = ShardRecords(lo, hi,
-                       torch.empty((n, R), dtype=i32, device=dev), torch.empty((n, R, 2), dtype=f64, device=dev),
-                       torch.empty((n, R, 3), dtype=f64, device=dev), torch.empty((n, R, 7), dtype=f64, device=dev),
-                       torch.empty((n, R), dtype=u8, device=dev),
-                       torch.empty((n, 4), dtype=f64, device=dev) if pipe.have_plane else None,
-                       torch.empty((n,), dtype=i32, device=dev) if pipe.have_plane else None,
-                       torch.empty((n,), dtype=i32, device=dev))
+    key = (n_frames, world, R, pipe.have_plane)
+    if getattr(pipe, "_stream_blob_key", None) != key:           # one allocation per stream geometry, reused across streams
+        pipe._stream_blob = torch.empty((blob_bytes_for(n_frames, R, pipe.have_plane, world),), dtype=torch.uint8, device=dev)
+        pipe._stream_blob_key = key
+    rec = ShardRecords(lo, hi, pipe._stream_blob, blob_views(pipe._stream_blob, n, R, pipe.have_plane))
     pipe.reset_sequence()
     pipe.set_first_frame(first_frame)            # the warm-up window (R3:255-256) counts from the GLOBAL first frame
-    works = []
-    for s in range(0, n, batch):                 # every batch writes straight into its slice of the shard's record block
+    for s in range(0, n, batch):
         e = min(n, s + batch)
         arrays, o = {}, capi.VbsOutputs()
-        for k in RECORD_KEYS:
-            t = getattr(rec, k)
-            if t is not None:
-                arrays[k] = t[s:e]
-                setattr(o, k, arrays[k].data_ptr())
+        for k, t in rec.views.items():
+            arrays[k] = t[s:e]
+            setattr(o, k, arrays[k].data_ptr())
         pipe.process(frames_of(lo + s, lo + e), lo + s, out=(arrays, o))
-        if sink is not None and world > 1:
-            works += sharding.gather_rows_async(rec.tensors(), s, e, rank, world, sink)
-    rec.works = works
     return rec
 
 
 def finish_and_gather(pipe, rec: ShardRecords, n_frames: int, rank: int, world: int, dst: int = 0, sink=None) -> Optional[dict]:
-    """Patch the shard's first observation of every marker with the last-seen table arriving from the
-    preceding shards, and deliver the records to ``dst`` (concatenated in global frame order).
-
-    Without a sink: patch, then one gather of the whole shard.  With a sink the records are already on their way
-    (``process_shard``): only the R x 4 tail tables are exchanged, and ``dst`` applies every shard's patch to the
-    gathered block itself (``vbs_fix_displacement`` needs nothing but the block, the camera and the incoming table)."""
+    """Deliver the records to ``dst`` in global frame order with the shard boundaries patched: ONE gather of the
+    record blobs, one small all_gather of the R x 4 last-seen tables, and on ``dst`` one ``vbs_fix_displacement``
+    per later shard (it needs nothing but the gathered block, the camera and the table arriving from the
+    preceding shards) - results byte-identical to one sequential run."""
     import torch
+    import torch.distributed as dist
     dev = torch.device("cuda", pipe.device)
     pipe.sync()
-    if sink is None or world == 1:
-        sharding.finish_shard(pipe, rec, rank, world, dev)
-        counts = [hi - lo for lo, hi in (sharding.shard_bounds(n_frames, r, world) for r in range(world))]
-        return sharding.gather_records(rec.tensors(), rank, world, dst, counts)
+    if world == 1:
+        return rec.tensors()
     tails = sharding.all_tail_tables(pipe.get_last_seen(), rank, world, dev)
-    for w in getattr(rec, "works", ()):
-        w.wait()                                 # the current stream now waits for the gathers
+    if rank == dst and sink is None:
+        sink = RecordSink(n_frames, pipe.R, pipe.have_plane, world, dev)
+    dist.gather(rec.blob, [sink.blobs[r] for r in range(world)] if rank == dst else None, dst=dst)
     if rank != dst:
         return None
     for r in range(1, world):
         lo, hi = sink.bounds[r]
+        v = sink.shard_views(r)
         inc = sharding.incoming_last_seen(tails, r)
-        capi.check(pipe._ctx, capi.lib.vbs_fix_displacement(pipe._ctx, sink.data["pos3d"][lo:hi].data_ptr(), sink.data["pos_flags"][lo:hi].data_ptr(),
-                                                            hi - lo, inc.ctypes.data))
-    return sink.data
+        capi.check(pipe._ctx, capi.lib.vbs_fix_displacement(pipe._ctx, v["pos3d"].data_ptr(), v["pos_flags"].data_ptr(), hi - lo, inc.ctypes.data))
+    return sink.assemble()
 
 
 def make_sink(pipe, n_frames: int, rank: int, world: int, dst: int = 0):
-    """Preallocated destination of the gathered records on ``dst`` (None elsewhere, and None when the shards are not all
-    the same length: the collective then pads instead, see ``sharding.gather_records``)."""
+    """Preallocated landing area on ``dst`` (None elsewhere / for one rank): pass it to ``run_stream`` so that no
+    allocation happens inside a timed region."""
     import torch
-    counts = {hi - lo for lo, hi in (sharding.shard_bounds(n_frames, r, world) for r in range(world))}
-    if world == 1 or len(counts) != 1:
+    if world == 1 or rank != dst:
         return None
-    dev = torch.device("cuda", pipe.device)
-    R = pipe.R
-    like = {"row_det": torch.empty((0, R), dtype=torch.int32), "row_cxy": torch.empty((0, R, 2), dtype=torch.float64),
-            "row_axes": torch.empty((0, R, 3), dtype=torch.float64), "pos3d": torch.empty((0, R, 7), dtype=torch.float64),
-            "pos_flags": torch.empty((0, R), dtype=torch.uint8), "n_markers": torch.empty((0,), dtype=torch.int32)}
-    if pipe.have_plane:
-        like.update({"plane": torch.empty((0, 4), dtype=torch.float64), "plane_n": torch.empty((0,), dtype=torch.int32)})
-    return sharding.RecordSink(like, n_frames if rank == dst else 0, world, dev) if rank == dst else _RemoteSink()
-
-
-class _RemoteSink:
-    """Placeholder on the ranks that only send."""
-    def parts(self, name, s, e):
-        return None
+    return RecordSink(n_frames, pipe.R, pipe.have_plane, world, torch.device("cuda", pipe.device))
 
 
 def run_stream(pipe, frames_of, n_frames: int, batch: int, rank: int, world: int, first_frame: int = 0, sink=None):
-    """process_shard + finish_and_gather; returns (records dict on rank 0 / None elsewhere, ShardRecords).
-    ``sink`` = ``make_sink(...)`` (reusable across calls) overlaps the gather with the kernels."""
-    rec = process_shard(pipe, frames_of, n_frames, batch, rank, world, first_frame, sink)
+    """process_shard + finish_and_gather; returns (records dict on rank 0 / None elsewhere, ShardRecords)."""
+    rec = process_shard(pipe, frames_of, n_frames, batch, rank, world, first_frame)
     return finish_and_gather(pipe, rec, n_frames, rank, world, sink=sink), rec
