@@ -392,6 +392,246 @@ __global__ void __launch_bounds__(NT, 3) ncc_mask_kernel(NccParams P) {
     }
 }
 
+// ---- column-per-thread variant (default) -------------------------------------------------------------------------
+// The kernel above keeps half of its 256 threads idle in the horizontal pass (8 rows x 16 octets = 128 items) and pays
+// two block barriers per 8-row step (ring hand-over, partial-sum swap).  Here a CTA has as many threads as its strip
+// has columns (TW2 = 128 or 192):
+//   H  8 rows x TW2/8 octets = TW2 items: every thread works
+//   V  thread = column, all L taps of its 8 rows: nothing to swap, the box-sum chain is computed once per column
+//   one barrier per step: the ring has a spare group, so the horizontal pass of step m+1 never writes a group the
+//   vertical pass of step m may still be reading.
+template <int TL, int TW2> struct GeoW : Geo<TL> {
+    static constexpr int TWP2 = TW2 + TW2 / 8;
+    static constexpr int NR = Geo<TL>::NG + 1;
+    static constexpr size_t SMEM = (size_t)NR * 2 * TWP2 * 16 + (size_t)NR * TWP2 * 8 + (size_t)(Geo<TL>::CNX + (Geo<TL>::CNX & 1)) * 8 + 4 * 112 * 4;
+};
+
+template <int TL, int TW2>
+__global__ void __launch_bounds__(TW2, TW2 == 128 ? 3 : 2) ncc_mask_wide_kernel(NccParams P) {
+    using G = GeoW<TL, TW2>;
+    constexpr int NT = TW2, TWP2 = G::TWP2, OCT = TW2 / 8;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4 *ringH = reinterpret_cast<float4 *>(smem_raw);                        // [NR*2][TWP2]
+    uint2 *ringB = reinterpret_cast<uint2 *>(ringH + G::NR * 2 * TWP2);          // [NR][TWP2]
+    double *cn = reinterpret_cast<double *>(ringB + G::NR * TWP2);               // [CNX] float64 prefix sums (border formula)
+    int4 *fx = reinterpret_cast<int4 *>(cn + G::CNX + (G::CNX & 1));             // [4][FXN/4] shifted fixed-point copies
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int x0 = blockIdx.x * TW2;
+    const int ys = blockIdx.y * P.seg_rows;
+    const int ye = min(P.H, ys + P.seg_rows);
+    const int f = blockIdx.z;
+    const int H = P.H, W = P.W, WW = P.WW;
+    const uint32_t *abits = P.area_bits + (size_t)f * H * WW;
+    const double mfrac64 = (double)P.area_count[f] / P.hw;
+    const float mfrac = (float)mfrac64, mcomp = (float)(1.0 - mfrac64);   // mean(area_mask)/255 and its complement
+    for (int i = tid; i < G::CNX; i += NT) cn[i] = P.cn64[i];
+    for (int i = tid; i < 4 * FXN; i += NT) reinterpret_cast<int *>(fx)[i] = P.cnfix[i];
+
+    const int nk = (ye - ys + RB - 1) / RB;
+    const int nsteps = nk + G::LEAD;
+    const int hr = tid / OCT, ho = tid - hr * OCT;                  // horizontal role: row hr of the step, pixel octet ho
+    const int sb = x0 + 8 * ho - G::OFF;                            // first bit of the union window
+    const int wi0 = sb >> 5, bo = sb & 31;                          // arithmetic shift: floor
+    const int vcol = tid;                                           // vertical role: one column
+    const int cp = vcol + (vcol >> 3);
+    const bool strip_interior = x0 >= G::OFF && x0 + TW2 - 1 + G::HI < W;
+    const bool warp_outside = x0 + (tid & ~31) >= W;                // this warp's 32 columns lie right of the image
+
+    uint32_t pw[4] = {0, 0, 0, 0};
+    auto fetch = [&](int m) {
+        const int p = ys - G::OFF + RB * m + hr;
+        if (p >= 0 && p < H) {
+            const uint32_t *row = abits + (size_t)p * WW;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pw[i] = ld_bits(row, wi0 + i, WW);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pw[i] = 0u;
+        }
+    };
+    int s_prev = 0; uint32_t hb_m1 = 0;         // S of the previous output row and the box row that left the window
+
+    fetch(0);
+    __syncthreads();
+    int gw = 0;                                  // ring slot written by step m (m % NR)
+    for (int m = 0; m < nsteps; ++m) {
+        // ---- H: horizontal pass on bits ------------------------------------------------------------
+        {
+            uint32_t U0 = __funnelshift_r(pw[0], pw[1], bo);
+            uint32_t U1 = __funnelshift_r(pw[1], pw[2], bo);
+            uint32_t U2 = __funnelshift_r(pw[2], pw[3], bo);
+            if (m + 1 < nsteps) fetch(m + 1);
+            if constexpr (G::UL <= 64) { U2 = 0; U1 &= (G::UL == 64) ? 0xffffffffu : ((1u << (G::UL - 32)) - 1u); }
+            else { U2 &= (1u << (G::UL - 64)) - 1u; }
+            const uint32_t T0 = U0 ^ (U0 << 1);
+            const uint32_t T1 = U1 ^ __funnelshift_l(U0, U1, 1);
+            const uint32_t T2 = U2 ^ __funnelshift_l(U1, U2, 1);
+            int acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0;
+            auto consume = [&](uint32_t T, uint32_t Uw, int base) {
+                while (T) {
+                    const int b = __ffs(T) - 1;
+                    T &= T - 1;
+                    const int sgn = ((Uw >> b) & 1u) ? -1 : 1;       // run start: -Cn, run end: +Cn
+                    const int i0 = base + b + 1;                     // table index of d = t - 7 (pixel j = 7)
+                    const int4 *src = fx + (i0 & 3) * (FXN / 4) + (i0 >> 2);
+                    const int4 lo = src[0], hi = src[1];
+                    acc[7] += sgn * lo.x; acc[6] += sgn * lo.y; acc[5] += sgn * lo.z; acc[4] += sgn * lo.w;
+                    acc[3] += sgn * hi.x; acc[2] += sgn * hi.y; acc[1] += sgn * hi.z; acc[0] += sgn * hi.w;
+                }
+            };
+            consume(T0, U0, 0);
+            consume(T1, U1, 32);
+            if constexpr (G::UL > 64) consume(T2, U2, 64);
+            auto bit = [&](int t) -> uint32_t {
+                return t < 32 ? (U0 >> t) & 1u : t < 64 ? (U1 >> (t - 32)) & 1u : (U2 >> (t - 64)) & 1u;
+            };
+            uint32_t hb[8];
+            if constexpr (TL >= 64) hb[0] = __popc(U0) + __popc(U1) + __popc(U2 & ((1u << (TL - 64)) - 1u));
+            else hb[0] = __popc(U0) + __popc(U1 & ((1u << (TL - 32)) - 1u));
+#pragma unroll
+            for (int j = 1; j < 8; ++j) hb[j] = hb[j - 1] + bit(j - 1 + TL) - bit(j - 1);
+            float *dstH = reinterpret_cast<float *>(ringH + (gw * 2 + (hr >> 2)) * TWP2) + (hr & 3);
+            unsigned char *dstB = reinterpret_cast<unsigned char *>(ringB + gw * TWP2) + hr;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = 9 * ho + j;                            // (8 ho + j) + (8 ho + j) / 8
+                dstH[c * 4] = (float)acc[j];                         // 2^30 h; the scale lives in the vertical weights
+                dstB[c * 8] = (unsigned char)hb[j];
+            }
+        }
+        __syncthreads();                                             // the only barrier of the step
+
+        // ---- V + D: vertical pass and decision, thread = column ------------------------------------
+        if (m >= G::LEAD) {
+            const int k = m - G::LEAD;
+            const int yb = ys + RB * k;
+            int g0 = gw - G::LEAD; if (g0 < 0) g0 += G::NR;          // slot of step k
+            int S8[RB];
+            bool empty;
+            {
+                auto box_at = [&](auto I_) -> int {
+                    constexpr int idx = decltype(I_)::value;
+                    int gi = g0 + idx / 8; if (gi >= G::NR) gi -= G::NR;
+                    const uint2 b = ringB[gi * TWP2 + cp];
+                    const uint32_t w = (idx % 8) < 4 ? b.x : b.y;
+                    return (int)((w >> (8 * (idx % 4))) & 255u);
+                };
+                if (k == 0) {                   // first step of the segment: sum the whole window once (rolled: code size)
+                    int s = 0;
+#pragma unroll 1
+                    for (int t = 0; t < TL; ++t) {
+                        int gi = g0 + (t >> 3); if (gi >= G::NR) gi -= G::NR;
+                        s += reinterpret_cast<const unsigned char *>(ringB + gi * TWP2 + cp)[t & 7];
+                    }
+                    S8[0] = s;
+                } else {
+                    S8[0] = s_prev + box_at(std::integral_constant<int, TL - 1>{}) - (int)hb_m1;
+                }
+                static_for<1, RB>([&](auto R_) {
+                    constexpr int r = decltype(R_)::value;
+                    S8[r] = S8[r - 1] + box_at(std::integral_constant<int, r + TL - 1>{}) - box_at(std::integral_constant<int, r - 1>{});
+                });
+                s_prev = S8[RB - 1]; hb_m1 = (uint32_t)box_at(std::integral_constant<int, RB - 1>{});
+                int any = 0;
+#pragma unroll
+                for (int r = 0; r < RB; ++r) any |= S8[r];
+                // S == 0 <=> no area pixel in the whole L x L window <=> G == 0 and mask == 0: when that holds
+                // for all 8 rows of all 32 columns of the warp, the L-tap column sums are skipped (exact)
+                empty = warp_outside || !__any_sync(0xffffffffu, any != 0);
+            }
+            // Gaussian column sums of the 8 rows, packed: ring rows come as float4 = two aligned pairs (h_t, h_t+1),
+            // accumulators are paired as (row r, row r+1), one FFMA2 applies one tap to two rows
+            float2 E[4], O[3];
+            float o0 = 0.f, o7 = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) E[q] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) O[q] = make_float2(0.f, 0.f);
+            if (!empty) {
+                constexpr int U1_ = (TL - 1 + RB - 1) / 4;                       // last ring unit touched
+                const int ub = 2 * g0;
+                const float4 *b0 = ringH + ub * TWP2 + cp;
+                const float4 *b1 = b0 - 2 * G::NR * TWP2;
+                const int wrap_at = 2 * G::NR - ub;                             // first unit index that wraps
+                static_for<0, U1_ + 1>([&](auto U_) {
+                    constexpr int u = decltype(U_)::value;
+                    const float4 v = (u < wrap_at ? b0 : b1)[u * TWP2];
+                    static_for<0, 2>([&](auto P_) {
+                        constexpr int t = 4 * u + 2 * decltype(P_)::value;      // even ring row of the pair
+                        const float2 hp = decltype(P_)::value ? make_float2(v.z, v.w) : make_float2(v.x, v.y);
+                        static_for<0, 4>([&](auto Q_) {
+                            constexpr int a = t - 2 * decltype(Q_)::value;
+                            if constexpr (a >= 0 && a < TL) ffma2(E[decltype(Q_)::value], hp, c_n32[TL == 80][a]);
+                        });
+                        static_for<0, 3>([&](auto Q_) {
+                            constexpr int a = t - 2 * decltype(Q_)::value - 1;
+                            if constexpr (a >= 0 && a < TL) ffma2(O[decltype(Q_)::value], hp, c_n32[TL == 80][a]);
+                        });
+                        if constexpr (t + 1 >= 0 && t + 1 < TL) o0 = fmaf(c_n32[TL == 80][t + 1], hp.y, o0);
+                        if constexpr (t - 7 >= 0 && t - 7 < TL) o7 = fmaf(c_n32[TL == 80][t - 7], hp.x, o7);
+                    });
+                });
+            }
+            float acc[RB];
+            acc[0] = E[0].x + o0;     acc[1] = E[0].y + O[0].x; acc[2] = E[1].x + O[0].y; acc[3] = E[1].y + O[1].x;
+            acc[4] = E[2].x + O[1].y; acc[5] = E[2].y + O[2].x; acc[6] = E[3].x + O[2].y; acc[7] = E[3].y + o7;
+            // ---- D: decision --------------------------------------------------------------------------
+            const int x = x0 + vcol;
+            uint32_t myword = 0;
+            auto queue = [&](int y) {                 // float32 cannot decide: queue for the float64 pass
+                const uint32_t slot = atomicAdd(P.recheck_n + f, 1u);
+                if (slot < (uint32_t)P.recheck_cap) P.recheck[(size_t)f * P.recheck_cap + slot] = make_int2(x, y);
+                else atomicOr(P.status, VBS_DEV_RECHECK_OVERFLOW);
+            };
+            if (strip_interior && yb >= G::OFF && yb + RB - 1 + G::HI < H && yb + RB <= ye) {
+                float thr[RB];                        // whole step inside the image: threshold is the table entry of the box sum
+#pragma unroll
+                for (int r = 0; r < RB; ++r) thr[r] = __ldg(P.thr_lut + S8[r]);
+#pragma unroll
+                for (int r = 0; r < RB; ++r) {
+                    const float d = acc[r] - thr[r];
+                    bool on = d > 0.f;
+                    if (fabsf(d) <= BAND) { on = false; queue(yb + r); }
+                    const uint32_t word = __ballot_sync(0xffffffffu, on);
+                    if (lane == r) myword = word;
+                }
+            } else {
+                const bool xin = x >= G::OFF && x + G::HI < W;
+#pragma unroll
+                for (int r = 0; r < RB; ++r) {
+                    const int y = yb + r;
+                    bool on = false;
+                    if (x < W && y < ye && S8[r] != 0) {                    // S == 0: G = 0 and thr > 0 (or infinite) -> 0
+                        float thr = INFINITY;
+                        float band = BAND;
+                        bool decided = false;
+                        if (xin && y >= G::OFF && y + G::HI < H) thr = __ldg(P.thr_lut + S8[r]);
+                        else {
+                            const BorderGeo bg = border_geo<TL>(y, x, H, W, cn);
+                            if (S8[r] == bg.A) { on = border_full_window_on<TL>(bg, P.st2, mfrac); decided = true; }
+                            else { thr = border_threshold<TL>(bg, (float)S8[r], mfrac, mcomp, (float)P.st2); band = BAND_BORDER; }
+                        }
+                        if (!decided) {
+                            const float d = acc[r] - thr;
+                            on = d > 0.f;
+                            if (fabsf(d) <= band) { on = false; queue(y); }
+                        }
+                    }
+                    const uint32_t word = __ballot_sync(0xffffffffu, on);
+                    if (lane == r) myword = word;
+                }
+            }
+            const int wx = (x0 >> 5) + (vcol >> 5);
+            const int yw = yb + lane;
+            if (lane < RB && yw < ye && wx < WW) P.mask_bits[((size_t)f * H + yw) * WW + wx] = myword;
+        }
+        if (++gw == G::NR) gw = 0;
+    }
+}
+
 // float64 re-decision of queued pixels with the reference's literal formula (MD:152-163).
 // One warp per pixel: lanes split the window rows; fixed-order butterfly keeps it deterministic.
 template <int TL>
@@ -444,12 +684,16 @@ __global__ void ncc_recheck_kernel(NccParams P, const double *__restrict__ n64, 
 }
 
 template <int TL> cudaError_t launch(vbs_ctx *ctx, int batch, double st2) {
-    using G = GeoR<TL>;
     NccParams P;
     P.H = ctx->H; P.W = ctx->W; P.WW = ctx->WW;
-    const int strips = (ctx->W + TW - 1) / TW;
+    const int variant = ctx->ncc_variant;          // 0: 128-px strips, 256 threads (two halves per column); 1: 128-px strips, thread = column; 2: 192-px
+    const bool wide = variant != 0;
+    const int tw = variant == 2 ? 192 : TW;
+    const int strips = (ctx->W + tw - 1) / tw;
+    // vertical segments cost LEAD halo steps each: split only while the grid is short of ~8 waves (296 or 444 CTA slots)
+    const long long want = 4096;
     int vsegs = 1;
-    while ((long long)strips * batch * vsegs < 4096 && (ctx->H + vsegs) / (vsegs + 1) >= 64) ++vsegs;
+    while ((long long)strips * batch * vsegs < want && (ctx->H + vsegs) / (vsegs + 1) >= 64) ++vsegs;
     P.seg_rows = ((ctx->H + vsegs - 1) / vsegs + RB - 1) / RB * RB;
     vsegs = (ctx->H + P.seg_rows - 1) / P.seg_rows;
     P.st2 = st2; P.hw = (double)ctx->H * (double)ctx->W;
@@ -459,9 +703,19 @@ template <int TL> cudaError_t launch(vbs_ctx *ctx, int batch, double st2) {
     P.status = ctx->d_status;
     cudaError_t e = cudaMemsetAsync(ctx->recheck_n, 0, sizeof(uint32_t) * batch, ctx->stream);
     if (e != cudaSuccess) return e;
-    auto kern = ncc_mask_kernel<TL>;
-    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM)) != cudaSuccess) return e;
-    kern<<<dim3(strips, vsegs, batch), NT, G::SMEM, ctx->stream>>>(P);
+    if (variant == 1) {
+        auto kern = ncc_mask_wide_kernel<TL, 128>;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GeoW<TL, 128>::SMEM)) != cudaSuccess) return e;
+        kern<<<dim3(strips, vsegs, batch), 128, GeoW<TL, 128>::SMEM, ctx->stream>>>(P);
+    } else if (variant == 2) {
+        auto kern = ncc_mask_wide_kernel<TL, 192>;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GeoW<TL, 192>::SMEM)) != cudaSuccess) return e;
+        kern<<<dim3(strips, vsegs, batch), 192, GeoW<TL, 192>::SMEM, ctx->stream>>>(P);
+    } else {
+        auto kern = ncc_mask_kernel<TL>;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GeoR<TL>::SMEM)) != cudaSuccess) return e;
+        kern<<<dim3(strips, vsegs, batch), NT, GeoR<TL>::SMEM, ctx->stream>>>(P);
+    }
     ncc_recheck_kernel<TL><<<dim3(16, batch), 256, 0, ctx->stream>>>(P, ctx->d_n64, batch);
     ctx->launches += 2;
     return cudaGetLastError();
