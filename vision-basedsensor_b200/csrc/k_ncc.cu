@@ -392,6 +392,27 @@ __global__ void __launch_bounds__(NT, 3) ncc_mask_kernel(NccParams P) {
     }
 }
 
+// One pixel of a step that touches the image border (or of a strip that does): 0 = off, 1 = on, 2 = float32 cannot
+// decide.  Kept out of line: it runs in a small minority of the steps and would otherwise be unrolled 8 times into
+// the hot loop's instruction footprint.
+template <int TL>
+__device__ __noinline__ int border_decide(int y, int x, int H, int W, int S, float acc, float mfrac, float mcomp, double st2, const float *thr_lut,
+                                          const double *cn) {
+    using G = Geo<TL>;
+    if (S == 0) return 0;                                   // G = 0 and thr > 0 (or infinite)
+    float thr, band = BAND;
+    if (x >= G::OFF && x + G::HI < W && y >= G::OFF && y + G::HI < H) thr = __ldg(thr_lut + S);
+    else {
+        const BorderGeo bg = border_geo<TL>(y, x, H, W, cn);
+        if (S == bg.A) return border_full_window_on<TL>(bg, st2, mfrac) ? 1 : 0;
+        thr = border_threshold<TL>(bg, (float)S, mfrac, mcomp, (float)st2);
+        band = BAND_BORDER;
+    }
+    const float d = acc - thr;
+    if (fabsf(d) <= band) return 2;
+    return d > 0.f ? 1 : 0;
+}
+
 // ---- column-per-thread variant (default) -------------------------------------------------------------------------
 // The kernel above keeps half of its 256 threads idle in the horizontal pass (8 rows x 16 octets = 128 items) and pays
 // two block barriers per 8-row step (ring hand-over, partial-sum swap).  Here a CTA has as many threads as its strip
@@ -580,12 +601,7 @@ __global__ void __launch_bounds__(TW2, TW2 == 128 ? 3 : 2) ncc_mask_wide_kernel(
             acc[4] = E[2].x + O[1].y; acc[5] = E[2].y + O[2].x; acc[6] = E[3].x + O[2].y; acc[7] = E[3].y + o7;
             // ---- D: decision --------------------------------------------------------------------------
             const int x = x0 + vcol;
-            uint32_t myword = 0;
-            auto queue = [&](int y) {                 // float32 cannot decide: queue for the float64 pass
-                const uint32_t slot = atomicAdd(P.recheck_n + f, 1u);
-                if (slot < (uint32_t)P.recheck_cap) P.recheck[(size_t)f * P.recheck_cap + slot] = make_int2(x, y);
-                else atomicOr(P.status, VBS_DEV_RECHECK_OVERFLOW);
-            };
+            uint32_t onmask = 0, needmask = 0;        // bit r: row r of this column is on / needs the float64 pass
             if (strip_interior && yb >= G::OFF && yb + RB - 1 + G::HI < H && yb + RB <= ye) {
                 float thr[RB];                        // whole step inside the image: threshold is the table entry of the box sum
 #pragma unroll
@@ -593,36 +609,33 @@ __global__ void __launch_bounds__(TW2, TW2 == 128 ? 3 : 2) ncc_mask_wide_kernel(
 #pragma unroll
                 for (int r = 0; r < RB; ++r) {
                     const float d = acc[r] - thr[r];
-                    bool on = d > 0.f;
-                    if (fabsf(d) <= BAND) { on = false; queue(yb + r); }
-                    const uint32_t word = __ballot_sync(0xffffffffu, on);
-                    if (lane == r) myword = word;
+                    const bool need = fabsf(d) <= BAND;
+                    onmask |= (uint32_t)(d > 0.f && !need) << r;
+                    needmask |= (uint32_t)need << r;
                 }
             } else {
-                const bool xin = x >= G::OFF && x + G::HI < W;
 #pragma unroll
                 for (int r = 0; r < RB; ++r) {
                     const int y = yb + r;
-                    bool on = false;
-                    if (x < W && y < ye && S8[r] != 0) {                    // S == 0: G = 0 and thr > 0 (or infinite) -> 0
-                        float thr = INFINITY;
-                        float band = BAND;
-                        bool decided = false;
-                        if (xin && y >= G::OFF && y + G::HI < H) thr = __ldg(P.thr_lut + S8[r]);
-                        else {
-                            const BorderGeo bg = border_geo<TL>(y, x, H, W, cn);
-                            if (S8[r] == bg.A) { on = border_full_window_on<TL>(bg, P.st2, mfrac); decided = true; }
-                            else { thr = border_threshold<TL>(bg, (float)S8[r], mfrac, mcomp, (float)P.st2); band = BAND_BORDER; }
-                        }
-                        if (!decided) {
-                            const float d = acc[r] - thr;
-                            on = d > 0.f;
-                            if (fabsf(d) <= band) { on = false; queue(y); }
-                        }
+                    if (x < W && y < ye) {
+                        const int dec = border_decide<TL>(y, x, H, W, S8[r], acc[r], mfrac, mcomp, P.st2, P.thr_lut, cn);
+                        onmask |= (uint32_t)(dec == 1) << r;
+                        needmask |= (uint32_t)(dec == 2) << r;
                     }
-                    const uint32_t word = __ballot_sync(0xffffffffu, on);
-                    if (lane == r) myword = word;
                 }
+            }
+            uint32_t myword = 0;
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                const uint32_t word = __ballot_sync(0xffffffffu, (onmask >> r) & 1u);
+                if (lane == r) myword = word;
+            }
+            while (needmask) {                        // float32 cannot decide: queue for the float64 pass (rare)
+                const int r = __ffs(needmask) - 1;
+                needmask &= needmask - 1;
+                const uint32_t slot = atomicAdd(P.recheck_n + f, 1u);
+                if (slot < (uint32_t)P.recheck_cap) P.recheck[(size_t)f * P.recheck_cap + slot] = make_int2(x, yb + r);
+                else atomicOr(P.status, VBS_DEV_RECHECK_OVERFLOW);
             }
             const int wx = (x0 >> 5) + (vcol >> 5);
             const int yw = yb + lane;
@@ -686,9 +699,8 @@ __global__ void ncc_recheck_kernel(NccParams P, const double *__restrict__ n64, 
 template <int TL> cudaError_t launch(vbs_ctx *ctx, int batch, double st2) {
     NccParams P;
     P.H = ctx->H; P.W = ctx->W; P.WW = ctx->WW;
-    const int variant = ctx->ncc_variant;          // 0: 128-px strips, 256 threads (two halves per column); 1: 128-px strips, thread = column; 2: 192-px
-    const bool wide = variant != 0;
-    const int tw = variant == 2 ? 192 : TW;
+    const int variant = ctx->ncc_variant;          // 1 (default): thread = column; 0: 256 threads, two tap halves per column (round 1)
+    const int tw = TW;
     const int strips = (ctx->W + tw - 1) / tw;
     // vertical segments cost LEAD halo steps each: split only while the grid is short of ~8 waves (296 or 444 CTA slots)
     const long long want = 4096;
@@ -707,10 +719,6 @@ template <int TL> cudaError_t launch(vbs_ctx *ctx, int batch, double st2) {
         auto kern = ncc_mask_wide_kernel<TL, 128>;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GeoW<TL, 128>::SMEM)) != cudaSuccess) return e;
         kern<<<dim3(strips, vsegs, batch), 128, GeoW<TL, 128>::SMEM, ctx->stream>>>(P);
-    } else if (variant == 2) {
-        auto kern = ncc_mask_wide_kernel<TL, 192>;
-        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GeoW<TL, 192>::SMEM)) != cudaSuccess) return e;
-        kern<<<dim3(strips, vsegs, batch), 192, GeoW<TL, 192>::SMEM, ctx->stream>>>(P);
     } else {
         auto kern = ncc_mask_kernel<TL>;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GeoR<TL>::SMEM)) != cudaSuccess) return e;

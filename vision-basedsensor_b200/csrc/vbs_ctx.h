@@ -116,7 +116,7 @@ struct vbs_ctx {
     // chunked two-stream pipeline
     cudaStream_t stream_b; cudaEvent_t ev_a[8], ev_b_done; int overlap_device;
     int no_branch_overlap;                      // 1: run the open-mask branch after the NCC instead of beside it
-    int ncc_variant;                            // VBS_NCC_VARIANT: 0 = two half-column threads per column (round 1), 1 / 2 = thread per column, 128- / 192-px strips
+    int ncc_variant;                            // VBS_NCC_VARIANT=0: round 1's kernel (two tap-half threads per column); default 1: thread per column
     double stage_ms[7]; int64_t stage_calls;
 };
 enum { VBS_NSTAGES = 7 };   // blur, ncc, morph, components, contours, track3d, output copies
