@@ -74,7 +74,10 @@ typedef enum vbs_stage {
     VBS_STAGE_MAXIMA = 2,     /* uint8 [B][H][W] {0,1}    maxima (MD:172-174)                  */
     VBS_STAGE_LABELS = 3,     /* int32 [B][H][W]          labeled (MD:176)                     */
     VBS_STAGE_OPENED = 4,     /* uint8 [B][H][W] {0,255}  area_mask after the 5x5 open (MD:195)*/
-    VBS_STAGE_RECHECKS = 5    /* int32 [B]                pixels re-decided in float64         */
+    VBS_STAGE_RECHECKS = 5,   /* int32 [B]                pixels re-decided in float64         */
+    VBS_STAGE_ELLIPSES = 6,   /* float64 [B][M][6]        per external contour of the opened mask, in cv2.findContours order (MD:196-220):
+                                                          cx, cy, major, minor, angle (+90 as MD:213-217), 1 = kept (>= 5 points, minor >= 5) */
+    VBS_STAGE_NCONTOURS = 7   /* int32 [B]                external contours of the opened mask  */
 } vbs_stage;
 
 /* lifetime ---------------------------------------------------------------------------------- */

@@ -860,3 +860,52 @@ def test_tensor_core_blur_whole_pipeline_1080p(monkeypatch):
     assert np.array_equal(a.n_markers, b.n_markers) and (a.n_markers == rows * cols).all()
     assert np.array_equal(a.marker_xy[:, : rows * cols], b.marker_xy[:, : rows * cols])
     assert np.array_equal(a.marker_axes[:, : rows * cols], b.marker_axes[:, : rows * cols])
+
+
+# ---------------------------------------------------------------------------------------------
+# 17. every ellipse the GPU fits (VBS_STAGE_ELLIPSES: one per external contour of the opened mask, cv2.findContours
+#     order) against cv2.fitEllipse - on the shapes that stress its conditioning (thin slivers, diagonal staircases, L / T /
+#     plus shapes, rings, frame contact) and on random opened blobs, incl. the 5-vertex contours cv2 routes through
+#     fitEllipseDirect.  See tests/test_oracle_cpu.py::test_fit_ellipse_retry_is_unreachable_and_five_point_contours.
+# ---------------------------------------------------------------------------------------------
+def test_ellipse_stage_equals_cv2_on_degenerate_and_random_shapes():
+    import cv2
+    from test_oracle_cpu import degenerate_shape_masks, random_opened_masks
+    H = W = 144
+    shapes = degenerate_shape_masks() + list(random_opened_masks(150, 23))
+    masks = np.zeros((len(shapes), H, W), np.uint8)
+    for i, m in enumerate(shapes):
+        masks[i, :m.shape[0], :m.shape[1]] = m
+    B = len(masks)
+    with pipeline.MarkerPipeline(H, W, 1, max_batch=B, max_markers=256, max_refs=1) as pipe:
+        pipe.marker_center(torch_cuda(np.zeros_like(masks)), torch_cuda(masks))
+        pipe.sync()
+        cells = pipe.debug_stage(capi.STAGE_ELLIPSES, B).cpu().numpy()
+        ncont = pipe.debug_stage(capi.STAGE_NCONTOURS, B).cpu().numpy()
+        opened = pipe.debug_stage(capi.STAGE_OPENED, B).cpu().numpy()
+    checked = skipped = 0
+    for f in range(B):
+        assert np.array_equal(opened[f], cv2.morphologyEx(masks[f], cv2.MORPH_OPEN, np.ones((5, 5), np.uint8)))
+        contours, _ = cv2.findContours(opened[f], cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
+        assert ncont[f] >= len(contours)                        # the GPU also numbers blobs nested in holes (no ellipse, like RETR_EXTERNAL)
+        want = []
+        for cnt in contours:
+            if len(cnt) < 5:                                    # MD:204
+                continue
+            refs = [cv2.fitEllipse(cnt) for _ in range(4 if len(cnt) == 5 else 1)]
+            (cx, cy), (ww, hh), ang = refs[0]
+            unstable = any(r != refs[0] for r in refs)          # cv2 re-fits randomly perturbed points: it does not agree with itself
+            if unstable:
+                want.append(None)
+            elif min(ww, hh) >= 5:                              # MD:219
+                want.append((cx, cy, max(ww, hh), min(ww, hh), ang if ww > hh else ang + 90.0))
+        got = [tuple(c[:5]) for c in cells[f, : int(ncont[f])] if c[5] != 0.0]
+        if any(w is None for w in want):
+            skipped += 1
+            continue
+        assert len(got) == len(want), (f, len(got), len(want))
+        for g, w in zip(got, want):
+            assert pu.f32_ulps(np.array(g[:4]), np.array(w[:4])).max() <= 2.0, (f, g, w)
+            assert pu.angle_ulps(g[4], w[4]) <= pu.ANGLE_TOL_ULP, (f, g, w)
+            checked += 1
+    assert checked > 400 and skipped < 10

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libvbs_b200.so")
 
 VBS_OK, VBS_ERR_BAD_ARG, VBS_ERR_CAPACITY, VBS_ERR_CUDA, VBS_ERR_STATE, VBS_ERR_INTERNAL = 0, -1, -2, -3, -4, -5
-STAGE_AREA_MASK, STAGE_MASK, STAGE_MAXIMA, STAGE_LABELS, STAGE_OPENED, STAGE_RECHECKS = range(6)
+STAGE_AREA_MASK, STAGE_MASK, STAGE_MAXIMA, STAGE_LABELS, STAGE_OPENED, STAGE_RECHECKS, STAGE_ELLIPSES, STAGE_NCONTOURS = range(8)
 
 
 class VbsConfig(C.Structure):

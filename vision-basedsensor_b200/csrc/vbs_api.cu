@@ -882,11 +882,14 @@ int vbs_debug_stage(vbs_ctx *ctx, int32_t stage, void *dst_device, size_t bytes)
     if (batch <= 0 || !ctx->image_ready) return fail(ctx, VBS_ERR_STATE, "no batch processed yet");
     VBS_ON_DEVICE(ctx);
     // the first frames of the most recent batch, as many as `bytes` holds (at least one)
-    const size_t per_frame = stage == VBS_STAGE_RECHECKS ? sizeof(int32_t) : (size_t)ctx->H * ctx->W * (stage == VBS_STAGE_LABELS ? 4 : 1);
+    const size_t per_frame = (stage == VBS_STAGE_RECHECKS || stage == VBS_STAGE_NCONTOURS) ? sizeof(int32_t)
+                             : stage == VBS_STAGE_ELLIPSES ? sizeof(double) * 6 * (size_t)ctx->M
+                                                           : (size_t)ctx->H * ctx->W * (stage == VBS_STAGE_LABELS ? 4 : 1);
     if (bytes < per_frame) return fail(ctx, VBS_ERR_BAD_ARG, "destination too small");
     if ((size_t)batch > bytes / per_frame) batch = (int)(bytes / per_frame);
-    if (stage == VBS_STAGE_RECHECKS) {
-        VBS_CUDA(cudaMemcpyAsync(dst_device, ctx->recheck_n, sizeof(int32_t) * batch, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (stage == VBS_STAGE_RECHECKS || stage == VBS_STAGE_NCONTOURS || stage == VBS_STAGE_ELLIPSES) {
+        const void *src = stage == VBS_STAGE_RECHECKS ? (const void *)ctx->recheck_n : stage == VBS_STAGE_NCONTOURS ? (const void *)ctx->d_ncont : (const void *)ctx->cell;
+        VBS_CUDA(cudaMemcpyAsync(dst_device, src, per_frame * batch, cudaMemcpyDeviceToDevice, ctx->stream));
         return VBS_OK;
     }
     VBS_CUDA(vbs_launch_unpack(ctx, stage, dst_device, batch));

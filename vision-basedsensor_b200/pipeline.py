@@ -410,8 +410,10 @@ class MarkerPipeline:
     def debug_stage(self, stage: int, batch: int):
         import torch
         dev = torch.device("cuda", self.device)
-        if stage == capi.STAGE_RECHECKS:
+        if stage in (capi.STAGE_RECHECKS, capi.STAGE_NCONTOURS):
             t = torch.empty((batch,), dtype=torch.int32, device=dev)
+        elif stage == capi.STAGE_ELLIPSES:
+            t = torch.empty((batch, self.M, 6), dtype=torch.float64, device=dev)
         elif stage == capi.STAGE_LABELS:
             t = torch.empty((batch, self.H, self.W), dtype=torch.int32, device=dev)
         else:
