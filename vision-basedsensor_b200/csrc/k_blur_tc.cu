@@ -22,6 +22,8 @@
 // One CTA = one 64-column strip of one frame, marching down in 64-row chunks: TMA warp, MMA warp (one thread
 // issues), 4 warps epilogue 1, 4 warps epilogue 2; accumulators in TMEM (D1 double-buffered), mbarrier hand-offs.
 #include <cuda.h>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "vbs_ctx.h"
@@ -32,20 +34,22 @@ constexpr int SW = 64;             // output columns per CTA
 constexpr int CHR = 64;            // image rows per chunk (pass 1 step) = K bytes per ring slab
 constexpr int BLK = 128;           // output rows per pass-2 block
 constexpr int KEXT = 256;          // K extent of both passes in bytes (two 128-byte swizzle slabs)
-constexpr int NSLAB = 6;           // ring of pass-1 results (4 are read by a block, 2 are being produced)
+constexpr int NSLAB = 5;           // ring of pass-1 results (4 are read by a block, 1 is being produced)
+constexpr int NSTAGE = 3;          // image-row stages in flight (TMA runs three chunks ahead of pass 1) and D1 accumulators
 constexpr int NTHREADS = 512;      // warp 0: TMA, 1: MMA, 2: TMEM allocator, 3: idle, 4-7: epilogue 1, 8-15: epilogue 2
 
 constexpr uint32_t OFF_A1 = 0;                         // [2 K-slabs][128 rows][128 B]            32 KB
 constexpr uint32_t OFF_A2 = 32768;                     // [2 blurs][2 K-slabs][128 rows][128 B]   64 KB
-constexpr uint32_t OFF_B1 = 98304;                     // [2 stages][2 K-slabs][64 rows][128 B]   32 KB
-constexpr uint32_t OFF_H = 131072;                     // [NSLAB][2 blurs][128 rows][64 B]        96 KB
+constexpr uint32_t OFF_B1 = 98304;                     // [NSTAGE][2 K-slabs][64 rows][128 B]     48 KB
+constexpr uint32_t OFF_H = OFF_B1 + NSTAGE * 16384;    // [NSLAB][2 blurs][128 rows][64 B]        80 KB
 constexpr uint32_t OFF_BAR = OFF_H + NSLAB * 16384;    // mbarriers + TMEM base + abort flag
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;  // + slack to align the base to 1024 B
 
-enum { BAR_A1 = 0, BAR_B1_FULL = 1, BAR_B1_EMPTY = 3, BAR_D1_FULL = 5, BAR_D1_EMPTY = 7, BAR_H_FULL = 9, BAR_BLK = 15, BAR_D2_FULL = 19,
-       BAR_D2_EMPTY = 20, BAR_A2 = 21, NBARS = 22 };
+enum { BAR_A1 = 0, BAR_A2 = 1, BAR_D2_FULL = 2, BAR_D2_EMPTY = 3, BAR_B1_FULL = 4, BAR_B1_EMPTY = BAR_B1_FULL + NSTAGE, BAR_D1_FULL = BAR_B1_EMPTY + NSTAGE,
+       BAR_D1_EMPTY = BAR_D1_FULL + NSTAGE, BAR_H_FULL = BAR_D1_EMPTY + NSTAGE, BAR_BLK = BAR_H_FULL + NSLAB, NBARS = BAR_BLK + 4 };
+static_assert(8 * NBARS + 8 <= 256, "barrier block");
 
-constexpr uint32_t TM_D1 = 0;      // TMEM columns: D1 stage s at 64 s
+__host__ __device__ constexpr uint32_t tm_d1(int st) { return st < 2 ? 64u * (uint32_t)st : 384u; }      // TMEM columns of D1 stage st (D2 sits at 128..383)
 constexpr uint32_t TM_D2 = 128;    // D2 of blur b at 128 + 128 b: columns [0,64) high bytes, [64,128) low bytes
 constexpr uint32_t TM_COLS = 512;
 
@@ -54,7 +58,9 @@ struct TcParams {
     int nreal, nchunks, nblocks;   // real chunks (image rows), chunk slots incl. the mirrored ones, blocks of 128 output rows
     int radius;                    // rows mirrored above row 0 and below row H-1 (radius of the large blur)
     uint32_t *area_bits, *area_count, *status;
+    long long *dbg;                // optional timeline of one CTA (VBS_TC_TIMELINE=1): clock64 at pipeline events
 };
+#define TC_DBG(id) do { if (P.dbg && blockIdx.x == 5 && blockIdx.y == 3) P.dbg[id] = clock64(); } while (0)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -109,6 +115,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
                    "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                  : "r"(taddr));
 }
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptor, K-major, swizzled (cute::UMMA::SmemDescriptor): start address and stride between
@@ -151,10 +163,11 @@ blur_area_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
     const int strip = blockIdx.x, f = blockIdx.y;
     const int x0 = strip * SW;
     const int CR = P.nreal, C = P.nchunks, NB = P.nblocks;    // chunk slot cc covers virtual rows [64 (cc - 1), 64 cc); real: 1 .. CR
+    if (tid == 0) TC_DBG(0);
 
     if (tid == 0) {
         mbar_init(bar(BAR_A1), 1); mbar_init(bar(BAR_A2), 1);
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < NSTAGE; ++i) {
             mbar_init(bar(BAR_B1_FULL + i), 1); mbar_init(bar(BAR_B1_EMPTY + i), 1);
             mbar_init(bar(BAR_D1_FULL + i), 1); mbar_init(bar(BAR_D1_EMPTY + i), 128);
         }
@@ -164,6 +177,11 @@ blur_area_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
         *abort_flag = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a1) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_img) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a2) : "memory");
+    }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void *)tmem_slot)), "r"(TM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -171,53 +189,73 @@ blur_area_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = *reinterpret_cast<const uint32_t *>(gen + OFF_BAR + 8 * NBARS);     // plain load at a uniform address: a uniform value
+    if (tid == 0) TC_DBG(1);
 
     if (warp == 0) {
-        // ================= TMA producer (one thread): operator matrices, then 64 image rows per chunk =================
-        if (lane == 0) {
-            mbar_expect_tx(bar(BAR_A1), 32768u);
-            for (int s = 0; s < 2; ++s) tma_load_2d(base + OFF_A1 + 16384u * s, &map_a1, 128 * s, 128 * strip, bar(BAR_A1));
-            for (int i = 0; i < CR; ++i) {                                      // real chunk i + 1 = image rows [64 i, 64 i + 64)
-                const int st = i & 1;
-                if (i >= 2 && !mbar_wait(bar(BAR_B1_EMPTY + st), ((i >> 1) - 1) & 1, abort_flag)) break;
-                const uint32_t dst = base + OFF_B1 + 16384u * st;
-                mbar_expect_tx(bar(BAR_B1_FULL + st), 16384u);                  // rows / columns outside the image arrive as zeros
-                tma_load_3d(dst, &map_img, x0 - 64, CHR * i, f, bar(BAR_B1_FULL + st));
-                tma_load_3d(dst + 8192u, &map_img, x0 + 64, CHR * i, f, bar(BAR_B1_FULL + st));
-                if (i == 1 || CR == 1) {                                        // pass 2 starts four chunks in: its matrices load behind the first rows
-                    mbar_expect_tx(bar(BAR_A2), 65536u);
-                    for (int b = 0; b < 2; ++b)
-                        for (int s = 0; s < 2; ++s) tma_load_2d(base + OFF_A2 + 32768u * b + 16384u * s, &map_a2, 128 * s, 128 * b, bar(BAR_A2));
+        // ================= TMA producer (warp-uniform control flow, one elected lane issues): operator matrices, then
+        // 64 image rows per chunk =================
+        {
+            if (elect_one()) {
+                mbar_expect_tx(bar(BAR_A1), 32768u);
+                for (int s = 0; s < 2; ++s) tma_load_2d(base + OFF_A1 + 16384u * s, &map_a1, 128 * s, 128 * strip, bar(BAR_A1));
+            }
+            __syncwarp();
+            bool ok = true;
+            int st = 0; uint32_t ph = 0;
+            for (int i = 0; i < CR && ok; ++i) {                                // real chunk i + 1 = image rows [64 i, 64 i + 64)
+                if (i >= NSTAGE) ok = __all_sync(0xffffffffu, mbar_wait(bar(BAR_B1_EMPTY + st), ph ^ 1u, abort_flag));
+                if (!ok) break;
+                if (elect_one()) {
+                    const uint32_t dst = base + OFF_B1 + 16384u * st;
+                    mbar_expect_tx(bar(BAR_B1_FULL + st), 16384u);              // rows / columns outside the image arrive as zeros
+                    tma_load_3d(dst, &map_img, x0 - 64, CHR * i, f, bar(BAR_B1_FULL + st));
+                    tma_load_3d(dst + 8192u, &map_img, x0 + 64, CHR * i, f, bar(BAR_B1_FULL + st));
+                    TC_DBG(120 + i);
+                    if (i == 1 || CR == 1) {                                    // pass 2 starts four chunks in: its matrices load behind the first rows
+                        mbar_expect_tx(bar(BAR_A2), 65536u);
+                        for (int b = 0; b < 2; ++b)
+                            for (int s = 0; s < 2; ++s) tma_load_2d(base + OFF_A2 + 32768u * b + 16384u * s, &map_a2, 128 * s, 128 * b, bar(BAR_A2));
+                    }
                 }
+                __syncwarp();
+                if (++st == NSTAGE) { st = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer (one thread).  Everything between two MMAs is scalar code of ONE thread, so the
-        // descriptors are built once and moved by constants; the K loops are unrolled over compile-time ranges. ==========
-        if (lane == 0) {
+        // descriptors are built once and moved by constants; the K loops are unrolled over compile-time ranges.  The WHOLE
+        // warp runs the (uniform) control flow and one elected lane issues: inside a divergent `lane == 0` region ptxas cannot
+        // keep the descriptors in uniform registers and wraps every MMA in a lane-serialising loop. ==========
+        {
             constexpr uint32_t ID1 = idesc_i8(128, 64, 0, 0);                   // taps (u8, <= 26) x pixels (u8)
             constexpr uint32_t ID2 = idesc_i8(128, 128, 1, 1);                  // taps (s8, <= 13) x sign-flipped bytes (s8)
             const uint64_t a1d = smem_desc(base + OFF_A1, 1024, 2), b1d = smem_desc(base + OFF_B1, 1024, 2);
             const uint64_t a2d = smem_desc(base + OFF_A2, 1024, 2), hd = smem_desc(base + OFF_H, 512, 4);
             int i1 = 0, b2 = 0, slab0 = 0;                                      // next real chunk, next block, ring slot of chunk 2 b2
+            int st1 = 0; uint32_t ph1 = 0;                                      // stage and phase parity of real chunk i1
             bool a2_ready = false;
             bool ok = mbar_wait(bar(BAR_A1), 0, abort_flag);
             int idle = 0;
             while (ok && (i1 < CR || b2 < NB)) {
                 bool progressed = false;
                 if (i1 < CR) {                                                  // pass 1 of real chunk i1 + 1
-                    const int st = i1 & 1;
-                    if (mbar_test(bar(BAR_B1_FULL + st), (i1 >> 1) & 1) && (i1 < 2 || mbar_test(bar(BAR_D1_EMPTY + st), ((i1 >> 1) - 1) & 1))) {
+                    const int st = st1;
+                    if (mbar_test(bar(BAR_B1_FULL + st), ph1) && (i1 < NSTAGE || mbar_test(bar(BAR_D1_EMPTY + st), ph1 ^ 1u))) {
                         tc_fence_after();
                         const uint64_t bd = b1d + (uint64_t)(1024u * st);
-                        const uint32_t dd = tmem + TM_D1 + 64u * st;
+                        const uint32_t dd = tmem + tm_d1(st);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int j = k1_lo(RL); j < k1_hi(RL); ++j)
-                            tc_mma_i8(dd, a1d + (uint64_t)(1024 * (j >> 2) + 2 * (j & 3)), bd + (uint64_t)(512 * (j >> 2) + 2 * (j & 3)), ID1, j > k1_lo(RL));
-                        tc_commit(bar(BAR_B1_EMPTY + st));
-                        tc_commit(bar(BAR_D1_FULL + st));
+                            for (int j = k1_lo(RL); j < k1_hi(RL); ++j)
+                                tc_mma_i8(dd, a1d + (uint64_t)(1024 * (j >> 2) + 2 * (j & 3)), bd + (uint64_t)(512 * (j >> 2) + 2 * (j & 3)), ID1, j > k1_lo(RL));
+                            tc_commit(bar(BAR_B1_EMPTY + st));
+                            tc_commit(bar(BAR_D1_FULL + st));
+                            TC_DBG(10 + i1);
+                        }
+                        __syncwarp();
                         ++i1;
+                        if (++st1 == NSTAGE) { st1 = 0; ph1 ^= 1u; }
                         progressed = true;
                     }
                 }
@@ -234,15 +272,19 @@ blur_area_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
                     }
                     if (ready && (b2 == 0 || mbar_test(bar(BAR_D2_EMPTY), (b2 - 1) & 1))) {
                         tc_fence_after();
+                        if (elect_one()) {
 #pragma unroll
-                        for (int j = k2_lo(RL); j < k2_hi(RL); ++j)
-                            tc_mma_i8(tmem + TM_D2, a2d + (uint64_t)(1024 * (j >> 2) + 2 * (j & 3)), hs[j >> 1] + (uint64_t)(2 * (j & 1)), ID2, j > k2_lo(RL));
+                            for (int j = k2_lo(RL); j < k2_hi(RL); ++j)
+                                tc_mma_i8(tmem + TM_D2, a2d + (uint64_t)(1024 * (j >> 2) + 2 * (j & 3)), hs[j >> 1] + (uint64_t)(2 * (j & 1)), ID2, j > k2_lo(RL));
 #pragma unroll
-                        for (int j = k2_lo(RS); j < k2_hi(RS); ++j)
-                            tc_mma_i8(tmem + TM_D2 + 128u, a2d + (uint64_t)(2048 + 1024 * (j >> 2) + 2 * (j & 3)), hs[j >> 1] + (uint64_t)(512 + 2 * (j & 1)), ID2,
-                                      j > k2_lo(RS));
-                        tc_commit(bar(BAR_BLK + (b2 & 3)));
-                        tc_commit(bar(BAR_D2_FULL));
+                            for (int j = k2_lo(RS); j < k2_hi(RS); ++j)
+                                tc_mma_i8(tmem + TM_D2 + 128u, a2d + (uint64_t)(2048 + 1024 * (j >> 2) + 2 * (j & 3)), hs[j >> 1] + (uint64_t)(512 + 2 * (j & 1)), ID2,
+                                          j > k2_lo(RS));
+                            tc_commit(bar(BAR_BLK + (b2 & 3)));
+                            tc_commit(bar(BAR_D2_FULL));
+                            TC_DBG(40 + b2);
+                        }
+                        __syncwarp();
                         ++b2;
                         slab0 += 2; if (slab0 >= NSLAB) slab0 -= NSLAB;
                         progressed = true;
@@ -250,6 +292,7 @@ blur_area_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
                 }
                 if (progressed) idle = 0;
                 else if (++idle > (1 << 22) || ((idle & 1023) == 0 && *abort_flag)) { *abort_flag = 1; ok = false; }
+                ok = __all_sync(0xffffffffu, ok);
             }
         }
     } else if (warp >= 4 && warp < 8) {
@@ -271,14 +314,15 @@ blur_area_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
         };
         bool ok = true;
         for (int i = 0; i < CR && ok; ++i) {
-            const int st = i & 1, cc = i + 1;
-            ok = mbar_wait(bar(BAR_D1_FULL + st), (i >> 1) & 1, abort_flag);
+            const int st = i % NSTAGE, cc = i + 1;
+            ok = mbar_wait(bar(BAR_D1_FULL + st), (i / NSTAGE) & 1, abort_flag);
             if (!ok) break;
             tc_fence_after();
             uint32_t v[4][16];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) tmem_ld16(tmem + ((uint32_t)(32 * q) << 16) + TM_D1 + 64u * st + 16u * g, v[g]);
+            for (int g = 0; g < 4; ++g) tmem_ld16(tmem + ((uint32_t)(32 * q) << 16) + tm_d1(st) + 16u * g, v[g]);
             tmem_ld_wait();
+            if (tid == 128) TC_DBG(150 + i);
             tc_fence_before();
             mbar_arrive(bar(BAR_D1_EMPTY + st));                // the accumulator stage may be overwritten
             if (!(ok = slot_free(cc))) break;
@@ -315,6 +359,7 @@ blur_area_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
             mbar_arrive(bar(BAR_H_FULL + cc % NSLAB));
             if (cc == CR)
                 for (int ct = CR + 1; ct < C; ++ct) mbar_arrive(bar(BAR_H_FULL + ct % NSLAB));
+            if (tid == 128) TC_DBG(60 + i);
         }
     } else if (warp >= 8) {
         // ================= epilogue 2: D2 -> rounding, wrapping DoG, inRange, 32 bits per thread and row =================
@@ -348,6 +393,7 @@ blur_area_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
                     bits |= (uint32_t)(d <= span) << (16 * g + i);
                 }
             }
+            if (tid == 256) TC_DBG(90 + b);
             const int y = BLK * b + r;
             if (y < P.H && wx < P.WW) {
                 bits &= colmask;
@@ -362,6 +408,7 @@ blur_area_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
 
     tc_fence_before();
     __syncthreads();
+    if (tid == 0) TC_DBG(2);
     if (tid == 0 && *abort_flag) atomicOr(P.status, VBS_DEV_TMA_TIMEOUT);
     if (warp == 2) {
         tc_fence_after();
@@ -467,10 +514,31 @@ cudaError_t vbs_launch_blur_tc(vbs_ctx *ctx, const uint8_t *frames, int batch, i
     P.nblocks = (H + BLK - 1) / BLK;
     P.radius = R;
     P.area_bits = ctx->area_bits; P.area_count = ctx->area_count; P.status = ctx->d_status;
+    P.dbg = nullptr;
+    static long long *dbg_buf = nullptr;
+    if (const char *env = getenv("VBS_TC_TIMELINE"); env && env[0] == '1') {
+        if (!dbg_buf) { cudaMalloc((void **)&dbg_buf, 256 * sizeof(long long)); }
+        cudaMemsetAsync(dbg_buf, 0, 256 * sizeof(long long), ctx->stream);
+        P.dbg = dbg_buf;
+    }
     auto kern = ctx->big ? blur_area_tc_kernel<50, 19> : blur_area_tc_kernel<17, 10>;
     if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES)) != cudaSuccess) return e;
     kern<<<dim3(nstrips, batch), NTHREADS, SMEM_BYTES, ctx->stream>>>(m_img, m_a1, m_a2, P);
     ctx->launches += 1;
     ctx->tc_launches += 1;
+    if (P.dbg) {                                                 // developer aid: print the timeline of CTA (5, 3) relative to its start
+        long long h[256];
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "tc timeline (cycles after CTA start): setup %lld end %lld\n", h[1] - h[0], h[2] - h[0]);
+        const char *names[5] = {"tma", "p1", "e1ld", "e1", "p2/e2"};
+        const int base[4] = {120, 10, 150, 60};
+        for (int i = 0; i < P.nreal; ++i) {
+            fprintf(stderr, "  chunk %2d:", i);
+            for (int k = 0; k < 4; ++k) fprintf(stderr, " %s %6lld", names[k], h[base[k] + i] ? h[base[k] + i] - h[0] : -1);
+            fprintf(stderr, "\n");
+        }
+        for (int b = 0; b < P.nblocks; ++b) fprintf(stderr, "  block %2d: p2 %6lld e2 %6lld\n", b, h[40 + b] - h[0], h[90 + b] - h[0]);
+    }
     return cudaGetLastError();
 }
