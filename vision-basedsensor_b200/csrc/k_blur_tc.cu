@@ -34,14 +34,18 @@ constexpr int SW = 64;             // output columns per CTA
 constexpr int CHR = 64;            // image rows per chunk (pass 1 step) = K bytes per ring slab
 constexpr int BLK = 128;           // output rows per pass-2 block
 constexpr int KEXT = 256;          // K extent of both passes in bytes (two 128-byte swizzle slabs)
-constexpr int NSLAB = 5;           // ring of pass-1 results (4 are read by a block, 1 is being produced)
-constexpr int NSTAGE = 3;          // image-row stages in flight (TMA runs three chunks ahead of pass 1) and D1 accumulators
-constexpr int NTHREADS = 512;      // warp 0: TMA, 1: MMA, 2: TMEM allocator, 3: idle, 4-7: epilogue 1, 8-15: epilogue 2
+constexpr int NSLAB = 6;           // ring of pass-1 results (4 are read by a block, 2 are being produced: epilogue 1 never waits for the block in flight)
+constexpr int NSTAGE = 3;          // image-row stages in flight and D1 accumulators (a TMA load takes ~3000 cycles from issue to arrival)
+constexpr int NTHREADS = 512;      // warp 0: TMA, 1: MMA pass 1, 2: TMEM allocator, 3: MMA pass 2, 4-7: epilogue 1, 8-15: epilogue 2
 
-constexpr uint32_t OFF_A1 = 0;                         // [2 K-slabs][128 rows][128 B]            32 KB
-constexpr uint32_t OFF_A2 = 32768;                     // [2 blurs][2 K-slabs][128 rows][128 B]   64 KB
-constexpr uint32_t OFF_B1 = 98304;                     // [NSTAGE][2 K-slabs][64 rows][128 B]     48 KB
-constexpr uint32_t OFF_H = OFF_B1 + NSTAGE * 16384;    // [NSLAB][2 blurs][128 rows][64 B]        80 KB
+// Pass 1 only has taps in K bytes 0..191 (image columns x0 - 64 .. x0 + 127), so its operands are a 128-byte slab
+// (SWIZZLE_128B) plus a 64-byte half slab (SWIZZLE_64B): three image stages fit where two full ones did.
+constexpr uint32_t OFF_A1 = 0;                         // [128 rows][128 B] + [128 rows][64 B]    24 KB
+constexpr uint32_t OFF_A1H = 16384;
+constexpr uint32_t OFF_A2 = 24576;                     // [2 blurs][2 K-slabs][128 rows][128 B]   64 KB
+constexpr uint32_t OFF_B1 = OFF_A2 + 65536;            // [NSTAGE]{[64 rows][128 B] + [64 rows][64 B]}   36 KB
+constexpr uint32_t B1_STAGE = 12288, B1_HALF = 8192;
+constexpr uint32_t OFF_H = OFF_B1 + NSTAGE * B1_STAGE; // [NSLAB][2 blurs][128 rows][64 B]        96 KB
 constexpr uint32_t OFF_BAR = OFF_H + NSLAB * 16384;    // mbarriers + TMEM base + abort flag
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;  // + slack to align the base to 1024 B
 
@@ -149,7 +153,8 @@ __device__ __forceinline__ uint32_t swz64(uint32_t row, uint32_t k) {
 // RL / RS: radii of the large / small blur (50 / 19 above 480 rows, 17 / 10 below: MD:117-126)
 template <int RL, int RS>
 __global__ void __launch_bounds__(NTHREADS, 1)
-blur_area_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant__ CUtensorMap map_a1,
+blur_area_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant__ CUtensorMap map_imgh,
+                    const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a1h,
                     const __grid_constant__ CUtensorMap map_a2, const TcParams P) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -180,6 +185,8 @@ blur_area_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a1) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_img) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_imgh) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a1h) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a2) : "memory");
     }
     if (warp == 2) {
@@ -197,8 +204,9 @@ blur_area_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
         // 64 image rows per chunk =================
         {
             if (elect_one()) {
-                mbar_expect_tx(bar(BAR_A1), 32768u);
-                for (int s = 0; s < 2; ++s) tma_load_2d(base + OFF_A1 + 16384u * s, &map_a1, 128 * s, 128 * strip, bar(BAR_A1));
+                mbar_expect_tx(bar(BAR_A1), 16384u + 8192u);
+                tma_load_2d(base + OFF_A1, &map_a1, 0, 128 * strip, bar(BAR_A1));
+                tma_load_2d(base + OFF_A1H, &map_a1h, 128, 128 * strip, bar(BAR_A1));
             }
             __syncwarp();
             bool ok = true;
@@ -207,10 +215,10 @@ blur_area_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
                 if (i >= NSTAGE) ok = __all_sync(0xffffffffu, mbar_wait(bar(BAR_B1_EMPTY + st), ph ^ 1u, abort_flag));
                 if (!ok) break;
                 if (elect_one()) {
-                    const uint32_t dst = base + OFF_B1 + 16384u * st;
-                    mbar_expect_tx(bar(BAR_B1_FULL + st), 16384u);              // rows / columns outside the image arrive as zeros
+                    const uint32_t dst = base + OFF_B1 + B1_STAGE * st;
+                    mbar_expect_tx(bar(BAR_B1_FULL + st), B1_STAGE);            // rows / columns outside the image arrive as zeros
                     tma_load_3d(dst, &map_img, x0 - 64, CHR * i, f, bar(BAR_B1_FULL + st));
-                    tma_load_3d(dst + 8192u, &map_img, x0 + 64, CHR * i, f, bar(BAR_B1_FULL + st));
+                    tma_load_3d(dst + B1_HALF, &map_imgh, x0 + 64, CHR * i, f, bar(BAR_B1_FULL + st));
                     TC_DBG(120 + i);
                     if (i == 1 || CR == 1) {                                    // pass 2 starts four chunks in: its matrices load behind the first rows
                         mbar_expect_tx(bar(BAR_A2), 65536u);
@@ -223,89 +231,81 @@ blur_area_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer (one thread).  Everything between two MMAs is scalar code of ONE thread, so the
-        // descriptors are built once and moved by constants; the K loops are unrolled over compile-time ranges.  The WHOLE
-        // warp runs the (uniform) control flow and one elected lane issues: inside a divergent `lane == 0` region ptxas cannot
-        // keep the descriptors in uniform registers and wraps every MMA in a lane-serialising loop. ==========
-        {
-            constexpr uint32_t ID1 = idesc_i8(128, 64, 0, 0);                   // taps (u8, <= 26) x pixels (u8)
-            constexpr uint32_t ID2 = idesc_i8(128, 128, 1, 1);                  // taps (s8, <= 13) x sign-flipped bytes (s8)
-            const uint64_t a1d = smem_desc(base + OFF_A1, 1024, 2), b1d = smem_desc(base + OFF_B1, 1024, 2);
-            const uint64_t a2d = smem_desc(base + OFF_A2, 1024, 2), hd = smem_desc(base + OFF_H, 512, 4);
-            int i1 = 0, b2 = 0, slab0 = 0;                                      // next real chunk, next block, ring slot of chunk 2 b2
-            int st1 = 0; uint32_t ph1 = 0;                                      // stage and phase parity of real chunk i1
-            bool a2_ready = false;
-            bool ok = mbar_wait(bar(BAR_A1), 0, abort_flag);
-            int idle = 0;
-            while (ok && (i1 < CR || b2 < NB)) {
-                bool progressed = false;
-                if (i1 < CR) {                                                  // pass 1 of real chunk i1 + 1
-                    const int st = st1;
-                    if (mbar_test(bar(BAR_B1_FULL + st), ph1) && (i1 < NSTAGE || mbar_test(bar(BAR_D1_EMPTY + st), ph1 ^ 1u))) {
-                        tc_fence_after();
-                        const uint64_t bd = b1d + (uint64_t)(1024u * st);
-                        const uint32_t dd = tmem + tm_d1(st);
-                        if (elect_one()) {
+        // ================= MMA issuer, pass 1 (warp-uniform control flow, one elected lane issues).  Everything between two
+        // MMAs is scalar code of one thread, so the descriptors are built once and moved by constants, the K loop is unrolled over
+        // a compile-time range, and the waits are the blocking kind (a poll is a ~150-cycle round trip: one warp polling for both
+        // passes paced the whole pipeline at ~900 cycles per issue - hence one issuing warp per pass). =================
+        constexpr uint32_t ID1 = idesc_i8(128, 64, 0, 0);                       // taps (u8, <= 26) x pixels (u8)
+        const uint64_t a1d = smem_desc(base + OFF_A1, 1024, 2), b1d = smem_desc(base + OFF_B1, 1024, 2);
+        const uint64_t a1hd = smem_desc(base + OFF_A1H, 512, 4), b1hd = smem_desc(base + OFF_B1 + B1_HALF, 512, 4);      // K bytes 128..191
+        bool ok = __all_sync(0xffffffffu, mbar_wait(bar(BAR_A1), 0, abort_flag));
+        int st = 0; uint32_t ph = 0;
+        for (int i = 0; i < CR && ok; ++i) {                                    // real chunk i + 1
+            ok = mbar_wait(bar(BAR_B1_FULL + st), ph, abort_flag);
+            if (ok && i >= NSTAGE) ok = mbar_wait(bar(BAR_D1_EMPTY + st), ph ^ 1u, abort_flag);
+            ok = __all_sync(0xffffffffu, ok);
+            if (!ok) break;
+            tc_fence_after();
+            const uint64_t so = (uint64_t)((B1_STAGE / 16) * st);
+            const uint32_t dd = tmem + tm_d1(st);
+            if (elect_one()) {
 #pragma unroll
-                            for (int j = k1_lo(RL); j < k1_hi(RL); ++j)
-                                tc_mma_i8(dd, a1d + (uint64_t)(1024 * (j >> 2) + 2 * (j & 3)), bd + (uint64_t)(512 * (j >> 2) + 2 * (j & 3)), ID1, j > k1_lo(RL));
-                            tc_commit(bar(BAR_B1_EMPTY + st));
-                            tc_commit(bar(BAR_D1_FULL + st));
-                            TC_DBG(10 + i1);
-                        }
-                        __syncwarp();
-                        ++i1;
-                        if (++st1 == NSTAGE) { st1 = 0; ph1 ^= 1u; }
-                        progressed = true;
-                    }
+                for (int j = k1_lo(RL); j < k1_hi(RL); ++j) {
+                    if (j < 4) tc_mma_i8(dd, a1d + (uint64_t)(2 * j), b1d + so + (uint64_t)(2 * j), ID1, j > k1_lo(RL));
+                    else tc_mma_i8(dd, a1hd + (uint64_t)(2 * (j - 4)), b1hd + so + (uint64_t)(2 * (j - 4)), ID1, j > k1_lo(RL));
                 }
-                if (b2 < NB) {                                                  // pass 2 of output rows [128 b2, 128 b2 + 128): chunk slots 2 b2 .. 2 b2 + 3
-                    bool ready = a2_ready || (a2_ready = mbar_test(bar(BAR_A2), 0));
-                    uint64_t hs[4];
-                    int sl = slab0, cc = 2 * b2;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        if (cc > C - 1) { hs[q] = hs[q - (q > 0)]; continue; }  // slots past the last one: taps there only feed rows that are never stored
-                        ready = ready && mbar_test(bar(BAR_H_FULL + sl), (uint32_t)(cc / NSLAB) & 1u);
-                        hs[q] = hd + (uint64_t)(1024u * sl);
-                        ++cc; if (++sl == NSLAB) sl = 0;
-                    }
-                    if (ready && (b2 == 0 || mbar_test(bar(BAR_D2_EMPTY), (b2 - 1) & 1))) {
-                        tc_fence_after();
-                        if (elect_one()) {
-#pragma unroll
-                            for (int j = k2_lo(RL); j < k2_hi(RL); ++j)
-                                tc_mma_i8(tmem + TM_D2, a2d + (uint64_t)(1024 * (j >> 2) + 2 * (j & 3)), hs[j >> 1] + (uint64_t)(2 * (j & 1)), ID2, j > k2_lo(RL));
-#pragma unroll
-                            for (int j = k2_lo(RS); j < k2_hi(RS); ++j)
-                                tc_mma_i8(tmem + TM_D2 + 128u, a2d + (uint64_t)(2048 + 1024 * (j >> 2) + 2 * (j & 3)), hs[j >> 1] + (uint64_t)(512 + 2 * (j & 1)), ID2,
-                                          j > k2_lo(RS));
-                            tc_commit(bar(BAR_BLK + (b2 & 3)));
-                            tc_commit(bar(BAR_D2_FULL));
-                            TC_DBG(40 + b2);
-                        }
-                        __syncwarp();
-                        ++b2;
-                        slab0 += 2; if (slab0 >= NSLAB) slab0 -= NSLAB;
-                        progressed = true;
-                    }
-                }
-                if (progressed) idle = 0;
-                else if (++idle > (1 << 22) || ((idle & 1023) == 0 && *abort_flag)) { *abort_flag = 1; ok = false; }
-                ok = __all_sync(0xffffffffu, ok);
+                tc_commit(bar(BAR_B1_EMPTY + st));
+                tc_commit(bar(BAR_D1_FULL + st));
+                TC_DBG(10 + i);
             }
+            __syncwarp();
+            if (++st == NSTAGE) { st = 0; ph ^= 1u; }
+        }
+    } else if (warp == 3) {
+        // ================= MMA issuer, pass 2: output rows [128 b, 128 b + 128) read chunk slots 2 b .. 2 b + 3 of the ring =================
+        constexpr uint32_t ID2 = idesc_i8(128, 128, 1, 1);                      // taps (s8, <= 13) x sign-flipped bytes (s8)
+        const uint64_t a2d = smem_desc(base + OFF_A2, 1024, 2), hd = smem_desc(base + OFF_H, 512, 4);
+        bool ok = __all_sync(0xffffffffu, mbar_wait(bar(BAR_A2), 0, abort_flag));
+        int slab0 = 0;                                                          // ring slot of chunk 2 b
+        for (int b2 = 0; b2 < NB && ok; ++b2) {
+            const int c_need = min(2 * b2 + 3, C - 1);                          // newest chunk slot the block reads (epilogue 1 finishes chunks in order)
+            int sl_need = slab0 + (c_need - 2 * b2); if (sl_need >= NSLAB) sl_need -= NSLAB;
+            ok = mbar_wait(bar(BAR_H_FULL + sl_need), (uint32_t)(c_need / NSLAB) & 1u, abort_flag);
+            if (ok && b2 >= 1) ok = mbar_wait(bar(BAR_D2_EMPTY), (uint32_t)(b2 - 1) & 1u, abort_flag);
+            ok = __all_sync(0xffffffffu, ok);
+            if (!ok) break;
+            uint64_t hs[4];
+            int sl = slab0, cc = 2 * b2;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (cc > C - 1) { hs[q] = hs[q - (q > 0)]; continue; }          // slots past the last one: taps there only feed rows that are never stored
+                hs[q] = hd + (uint64_t)(1024u * sl);
+                ++cc; if (++sl == NSLAB) sl = 0;
+            }
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+                for (int j = k2_lo(RL); j < k2_hi(RL); ++j)
+                    tc_mma_i8(tmem + TM_D2, a2d + (uint64_t)(1024 * (j >> 2) + 2 * (j & 3)), hs[j >> 1] + (uint64_t)(2 * (j & 1)), ID2, j > k2_lo(RL));
+#pragma unroll
+                for (int j = k2_lo(RS); j < k2_hi(RS); ++j)
+                    tc_mma_i8(tmem + TM_D2 + 128u, a2d + (uint64_t)(2048 + 1024 * (j >> 2) + 2 * (j & 3)), hs[j >> 1] + (uint64_t)(512 + 2 * (j & 1)), ID2,
+                              j > k2_lo(RS));
+                tc_commit(bar(BAR_BLK + (b2 & 3)));
+                tc_commit(bar(BAR_D2_FULL));
+                TC_DBG(40 + b2);
+            }
+            __syncwarp();
+            slab0 += 2; if (slab0 >= NSLAB) slab0 -= NSLAB;
         }
     } else if (warp >= 4 && warp < 8) {
         // ================= epilogue 1: D1 -> signed high / low bytes, K-major, into the ring =================
         const int q = warp & 3, row = 32 * q + lane;          // TMEM lane = (blur, column): blur = row / 64
         const int bl = row >> 6, n = row & 63;
         auto tile_of = [&](int cc) -> unsigned char * { return gen + OFF_H + 16384u * (uint32_t)(cc % NSLAB) + 8192u * (uint32_t)bl; };
-        // one byte of both planes: (chunk slot, k) <- (chunk slot, k); a thread only ever touches its own two rows
-        auto copy_byte = [&](int cs, int ks, int ct, int kt) {
-            const unsigned char *src = tile_of(cs);
-            unsigned char *dst = tile_of(ct);
-            dst[swz64((uint32_t)n, (uint32_t)kt)] = src[swz64((uint32_t)n, (uint32_t)ks)];
-            dst[swz64((uint32_t)(64 + n), (uint32_t)kt)] = src[swz64((uint32_t)(64 + n), (uint32_t)ks)];
+        // the four bytes of virtual rows t .. t + 3 (t % 4 == 0) of one of this thread's two ring rows
+        auto vword = [&](int prow, int t) -> uint32_t * {
+            return reinterpret_cast<uint32_t *>(tile_of((t >> 6) + 1) + swz64((uint32_t)prow, (uint32_t)(t & 63)));
         };
         auto slot_free = [&](int cc) -> bool {                 // the slot of chunk cc held chunk cc - NSLAB, last read by block min(NB-1, (cc-NSLAB)/2)
             if (cc < NSLAB) return true;
@@ -342,16 +342,47 @@ blur_area_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
                 *reinterpret_cast<uint4 *>(tile + 64u * (64 + n) + 16u * ch) = lo4;      // ((64 + n) / 2) & 3 == (n / 2) & 3
             }
             // REFLECT_101 in y: the horizontal pass commutes with it, so the virtual rows above row 0 and below row H-1 are
-            // COPIES of rows this thread has already written (its own two ring rows: no cross-thread hazard)
-            if (cc == 1) {                                      // rows -j <- rows j, j = 1 .. radius: chunk slot 0, k = 64 - j
-                for (int j = 1; j <= P.radius; ++j) copy_byte(1, j, 0, 64 - j);
+            // COPIES of rows this thread has just produced (its own two ring rows: no cross-thread hazard)
+            if (cc == 1) {                                      // rows -j <- rows j: chunk slot 0, k = 64 - j, straight from the registers
+                unsigned char *t0 = tile_of(0);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {                   // 16-byte chunk c of slot 0: k = 16 c .. 16 c + 15  <-  rows 64 - k
+                    uint32_t lw[4], hw[4];
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        constexpr int Z = 63;                   // (k = 0 would need row 64: never read, the taps end at 63 rows)
+                        const int y0 = 64 - 16 * c - 4 * w;
+                        const uint32_t va = v[(y0 > Z ? Z : y0) >> 4][(y0 > Z ? Z : y0) & 15], vb = v[(y0 - 1) >> 4][(y0 - 1) & 15];
+                        const uint32_t vc = v[(y0 - 2) >> 4][(y0 - 2) & 15], vd = v[(y0 - 3) >> 4][(y0 - 3) & 15];
+                        const uint32_t pa = __byte_perm(va, vb, 0x5140), pb = __byte_perm(vc, vd, 0x5140);
+                        lw[w] = __byte_perm(pa, pb, 0x5410) ^ 0x80808080u;
+                        hw[w] = __byte_perm(pa, pb, 0x7632) ^ 0x80808080u;
+                    }
+                    const uint32_t ch = (uint32_t)c ^ ((uint32_t)(n >> 1) & 3u);
+                    *reinterpret_cast<uint4 *>(t0 + 64u * n + 16u * ch) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                    *reinterpret_cast<uint4 *>(t0 + 64u * (64 + n) + 16u * ch) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                }
             }
-            if (cc == CR) {                                     // rows H + t <- rows H - 2 - t (the last ones may sit in the previous chunk)
+            if (cc == CR) {                                     // rows H + i <- rows H - 2 - i, i < radius (sources may sit in the previous chunk)
                 for (int ct = CR + 1; ct < C && ok; ++ct) ok = slot_free(ct);
                 if (!ok) break;
-                for (int t = 0; t < P.radius; ++t) {
-                    const int vt = P.H + t, vs = P.H - 2 - t;
-                    copy_byte((vs >> 6) + 1, vs & 63, (vt >> 6) + 1, vt & 63);
+                // word-wise: target bytes t0 .. t0 + 3 are source bytes M - t0 - 3 .. M - t0 reversed (M = 2 H - 2); the source span
+                // starts (M + 1) & 3 bytes into an aligned word, the same for every word
+                const int M2 = 2 * P.H - 2, sh = (M2 + 1) & 3;
+#pragma unroll 2
+                for (int t0 = P.H & ~3; t0 < P.H + P.radius; t0 += 4) {         // both planes per iteration: two independent chains
+                    const int a = (M2 - t0 - 3) & ~3;
+                    const uint32_t h0 = *vword(n, a), l0 = *vword(64 + n, a);
+                    const uint32_t h1 = sh ? *vword(n, a + 4) : 0u, l1 = sh ? *vword(64 + n, a + 4) : 0u;
+                    const uint32_t hrev = __byte_perm(__funnelshift_r(h0, h1, 8 * sh), 0u, 0x0123);
+                    const uint32_t lrev = __byte_perm(__funnelshift_r(l0, l1, 8 * sh), 0u, 0x0123);
+                    uint32_t *hd_ = vword(n, t0), *ld_ = vword(64 + n, t0);
+                    if (t0 >= P.H) { *hd_ = hrev; *ld_ = lrev; }
+                    else {                                      // the word that straddles row H: keep the real rows below H
+                        const uint32_t keep = (1u << (8 * (P.H - t0))) - 1u;
+                        *hd_ = (*hd_ & keep) | (hrev & ~keep);
+                        *ld_ = (*ld_ & keep) | (lrev & ~keep);
+                    }
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                  // generic writes -> visible to the tensor core's reads
@@ -433,12 +464,13 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-bool encode_u8(CUtensorMap *map, const void *ptr, int rank, const cuuint64_t *dims, const cuuint64_t *strides, const cuuint32_t *box) {
+bool encode_u8(CUtensorMap *map, const void *ptr, int rank, const cuuint64_t *dims, const cuuint64_t *strides, const cuuint32_t *box, bool sw64 = false) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return false;
     const cuuint32_t estr[3] = {1, 1, 1};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, (cuuint32_t)rank, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+               sw64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 int host_reflect101(int i, int n) {
@@ -494,17 +526,19 @@ cudaError_t vbs_launch_blur_tc(vbs_ctx *ctx, const uint8_t *frames, int batch, i
     cudaError_t e = vbs_blur_tc_setup(ctx);
     if (e != cudaSuccess) return e;
     const int H = ctx->H, W = ctx->W, nstrips = (W + SW - 1) / SW;
-    CUtensorMap m_img, m_a1, m_a2;
+    CUtensorMap m_img, m_imgh, m_a1, m_a1h, m_a2;
     {
         const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)batch};
         const cuuint64_t strides[2] = {(cuuint64_t)row_pitch, (cuuint64_t)frame_stride};
-        const cuuint32_t box[3] = {128, CHR, 1};
-        if (!encode_u8(&m_img, frames, 3, dims, strides, box)) return cudaErrorNotSupported;
+        const cuuint32_t box[3] = {128, CHR, 1}, boxh[3] = {64, CHR, 1};
+        if (!encode_u8(&m_img, frames, 3, dims, strides, box) || !encode_u8(&m_imgh, frames, 3, dims, strides, boxh, true)) return cudaErrorNotSupported;
     }
     {
         const cuuint64_t d1[2] = {KEXT, (cuuint64_t)128 * nstrips}, d2[2] = {KEXT, 256}, st[1] = {KEXT};
-        const cuuint32_t box[2] = {128, 128};
-        if (!encode_u8(&m_a1, ctx->tc_a1, 2, d1, st, box) || !encode_u8(&m_a2, ctx->tc_a2, 2, d2, st, box)) return cudaErrorNotSupported;
+        const cuuint32_t box[2] = {128, 128}, boxh[2] = {64, 128};
+        if (!encode_u8(&m_a1, ctx->tc_a1, 2, d1, st, box) || !encode_u8(&m_a1h, ctx->tc_a1, 2, d1, st, boxh, true) ||
+            !encode_u8(&m_a2, ctx->tc_a2, 2, d2, st, box))
+            return cudaErrorNotSupported;
     }
     const int R = ctx->br.kl / 2;
     TcParams P;
@@ -523,7 +557,7 @@ cudaError_t vbs_launch_blur_tc(vbs_ctx *ctx, const uint8_t *frames, int batch, i
     }
     auto kern = ctx->big ? blur_area_tc_kernel<50, 19> : blur_area_tc_kernel<17, 10>;
     if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES)) != cudaSuccess) return e;
-    kern<<<dim3(nstrips, batch), NTHREADS, SMEM_BYTES, ctx->stream>>>(m_img, m_a1, m_a2, P);
+    kern<<<dim3(nstrips, batch), NTHREADS, SMEM_BYTES, ctx->stream>>>(m_img, m_imgh, m_a1, m_a1h, m_a2, P);
     ctx->launches += 1;
     ctx->tc_launches += 1;
     if (P.dbg) {                                                 // developer aid: print the timeline of CTA (5, 3) relative to its start
