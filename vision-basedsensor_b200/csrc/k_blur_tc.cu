@@ -35,15 +35,17 @@ constexpr int CHR = 64;            // image rows per chunk (pass 1 step) = K byt
 constexpr int BLK = 128;           // output rows per pass-2 block
 constexpr int KEXT = 256;          // K extent of both passes in bytes (two 128-byte swizzle slabs)
 constexpr int NSLAB = 6;           // ring of pass-1 results (4 are read by a block, 2 are being produced: epilogue 1 never waits for the block in flight)
-constexpr int NSTAGE = 3;          // image-row stages in flight and D1 accumulators (a TMA load takes ~3000 cycles from issue to arrival)
+constexpr int NSTAGE = 3;          // image-row stages in flight and D1 accumulators (a TMA load takes ~3000 cycles from issue to arrival; a 4th stage measured no gain)
 constexpr int NTHREADS = 512;      // warp 0: TMA, 1: MMA pass 1, 2: TMEM allocator, 3: MMA pass 2, 4-7: epilogue 1, 8-15: epilogue 2
 
 // Pass 1 only has taps in K bytes 0..191 (image columns x0 - 64 .. x0 + 127), so its operands are a 128-byte slab
 // (SWIZZLE_128B) plus a 64-byte half slab (SWIZZLE_64B): three image stages fit where two full ones did.
 constexpr uint32_t OFF_A1 = 0;                         // [128 rows][128 B] + [128 rows][64 B]    24 KB
 constexpr uint32_t OFF_A1H = 16384;
-constexpr uint32_t OFF_A2 = 24576;                     // [2 blurs][2 K-slabs][128 rows][128 B]   64 KB
-constexpr uint32_t OFF_B1 = OFF_A2 + 65536;            // [NSTAGE]{[64 rows][128 B] + [64 rows][64 B]}   36 KB
+constexpr uint32_t OFF_A2 = 24576;                     // large blur: [2 K-slabs][128 rows][128 B]  32 KB
+constexpr uint32_t OFF_A2S = OFF_A2 + 32768;           // small blur, K bytes 32..223 only: [128 rows][128 B] + [128 rows][64 B]  24 KB
+constexpr uint32_t OFF_A2SH = OFF_A2S + 16384;
+constexpr uint32_t OFF_B1 = OFF_A2SH + 8192;           // [NSTAGE]{[64 rows][128 B] + [64 rows][64 B]}   48 KB
 constexpr uint32_t B1_STAGE = 12288, B1_HALF = 8192;
 constexpr uint32_t OFF_H = OFF_B1 + NSTAGE * B1_STAGE; // [NSLAB][2 blurs][128 rows][64 B]        96 KB
 constexpr uint32_t OFF_BAR = OFF_H + NSLAB * 16384;    // mbarriers + TMEM base + abort flag
@@ -53,7 +55,7 @@ enum { BAR_A1 = 0, BAR_A2 = 1, BAR_D2_FULL = 2, BAR_D2_EMPTY = 3, BAR_B1_FULL = 
        BAR_D1_EMPTY = BAR_D1_FULL + NSTAGE, BAR_H_FULL = BAR_D1_EMPTY + NSTAGE, BAR_BLK = BAR_H_FULL + NSLAB, NBARS = BAR_BLK + 4 };
 static_assert(8 * NBARS + 8 <= 256, "barrier block");
 
-__host__ __device__ constexpr uint32_t tm_d1(int st) { return st < 2 ? 64u * (uint32_t)st : 384u; }      // TMEM columns of D1 stage st (D2 sits at 128..383)
+__host__ __device__ constexpr uint32_t tm_d1(int st) { return st < 2 ? 64u * (uint32_t)st : 384u + 64u * (uint32_t)(st - 2); }      // TMEM columns of D1 stage st (D2 sits at 128..383)
 constexpr uint32_t TM_D2 = 128;    // D2 of blur b at 128 + 128 b: columns [0,64) high bytes, [64,128) low bytes
 constexpr uint32_t TM_COLS = 512;
 
@@ -155,7 +157,8 @@ template <int RL, int RS>
 __global__ void __launch_bounds__(NTHREADS, 1)
 blur_area_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant__ CUtensorMap map_imgh,
                     const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a1h,
-                    const __grid_constant__ CUtensorMap map_a2, const TcParams P) {
+                    const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a2h, const TcParams P) {
+    static_assert(k2_lo(RS) == 1 && k2_hi(RS) == 7, "the small blur's pass-2 matrix is stored for K steps 1..6");
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char *gen = smem_raw + (base - smem_u32(smem_raw));          // generic pointer to the aligned base
@@ -188,6 +191,7 @@ blur_area_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_imgh) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a1h) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a2) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a2h) : "memory");
     }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void *)tmem_slot)), "r"(TM_COLS) : "memory");
@@ -221,9 +225,10 @@ blur_area_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
                     tma_load_3d(dst + B1_HALF, &map_imgh, x0 + 64, CHR * i, f, bar(BAR_B1_FULL + st));
                     TC_DBG(120 + i);
                     if (i == 1 || CR == 1) {                                    // pass 2 starts four chunks in: its matrices load behind the first rows
-                        mbar_expect_tx(bar(BAR_A2), 65536u);
-                        for (int b = 0; b < 2; ++b)
-                            for (int s = 0; s < 2; ++s) tma_load_2d(base + OFF_A2 + 32768u * b + 16384u * s, &map_a2, 128 * s, 128 * b, bar(BAR_A2));
+                        mbar_expect_tx(bar(BAR_A2), 32768u + 16384u + 8192u);
+                        for (int s = 0; s < 2; ++s) tma_load_2d(base + OFF_A2 + 16384u * s, &map_a2, 128 * s, 0, bar(BAR_A2));
+                        tma_load_2d(base + OFF_A2S, &map_a2, 32, 128, bar(BAR_A2));             // small blur: K bytes 32..159
+                        tma_load_2d(base + OFF_A2SH, &map_a2h, 160, 128, bar(BAR_A2));          //             K bytes 160..223
                     }
                 }
                 __syncwarp();
@@ -265,6 +270,7 @@ blur_area_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
         // ================= MMA issuer, pass 2: output rows [128 b, 128 b + 128) read chunk slots 2 b .. 2 b + 3 of the ring =================
         constexpr uint32_t ID2 = idesc_i8(128, 128, 1, 1);                      // taps (s8, <= 13) x sign-flipped bytes (s8)
         const uint64_t a2d = smem_desc(base + OFF_A2, 1024, 2), hd = smem_desc(base + OFF_H, 512, 4);
+        const uint64_t a2sd = smem_desc(base + OFF_A2S, 1024, 2), a2shd = smem_desc(base + OFF_A2SH, 512, 4);
         bool ok = __all_sync(0xffffffffu, mbar_wait(bar(BAR_A2), 0, abort_flag));
         int slab0 = 0;                                                          // ring slot of chunk 2 b
         for (int b2 = 0; b2 < NB && ok; ++b2) {
@@ -289,7 +295,7 @@ blur_area_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
                     tc_mma_i8(tmem + TM_D2, a2d + (uint64_t)(1024 * (j >> 2) + 2 * (j & 3)), hs[j >> 1] + (uint64_t)(2 * (j & 1)), ID2, j > k2_lo(RL));
 #pragma unroll
                 for (int j = k2_lo(RS); j < k2_hi(RS); ++j)
-                    tc_mma_i8(tmem + TM_D2 + 128u, a2d + (uint64_t)(2048 + 1024 * (j >> 2) + 2 * (j & 3)), hs[j >> 1] + (uint64_t)(512 + 2 * (j & 1)), ID2,
+                    tc_mma_i8(tmem + TM_D2 + 128u, j < 5 ? a2sd + (uint64_t)(2 * (j - 1)) : a2shd + (uint64_t)(2 * (j - 5)), hs[j >> 1] + (uint64_t)(512 + 2 * (j & 1)), ID2,
                               j > k2_lo(RS));
                 tc_commit(bar(BAR_BLK + (b2 & 3)));
                 tc_commit(bar(BAR_D2_FULL));
@@ -526,7 +532,7 @@ cudaError_t vbs_launch_blur_tc(vbs_ctx *ctx, const uint8_t *frames, int batch, i
     cudaError_t e = vbs_blur_tc_setup(ctx);
     if (e != cudaSuccess) return e;
     const int H = ctx->H, W = ctx->W, nstrips = (W + SW - 1) / SW;
-    CUtensorMap m_img, m_imgh, m_a1, m_a1h, m_a2;
+    CUtensorMap m_img, m_imgh, m_a1, m_a1h, m_a2, m_a2h;
     {
         const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)batch};
         const cuuint64_t strides[2] = {(cuuint64_t)row_pitch, (cuuint64_t)frame_stride};
@@ -537,7 +543,7 @@ cudaError_t vbs_launch_blur_tc(vbs_ctx *ctx, const uint8_t *frames, int batch, i
         const cuuint64_t d1[2] = {KEXT, (cuuint64_t)128 * nstrips}, d2[2] = {KEXT, 256}, st[1] = {KEXT};
         const cuuint32_t box[2] = {128, 128}, boxh[2] = {64, 128};
         if (!encode_u8(&m_a1, ctx->tc_a1, 2, d1, st, box) || !encode_u8(&m_a1h, ctx->tc_a1, 2, d1, st, boxh, true) ||
-            !encode_u8(&m_a2, ctx->tc_a2, 2, d2, st, box))
+            !encode_u8(&m_a2, ctx->tc_a2, 2, d2, st, box) || !encode_u8(&m_a2h, ctx->tc_a2, 2, d2, st, boxh, true))
             return cudaErrorNotSupported;
     }
     const int R = ctx->br.kl / 2;
@@ -557,7 +563,7 @@ cudaError_t vbs_launch_blur_tc(vbs_ctx *ctx, const uint8_t *frames, int batch, i
     }
     auto kern = ctx->big ? blur_area_tc_kernel<50, 19> : blur_area_tc_kernel<17, 10>;
     if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES)) != cudaSuccess) return e;
-    kern<<<dim3(nstrips, batch), NTHREADS, SMEM_BYTES, ctx->stream>>>(m_img, m_imgh, m_a1, m_a1h, m_a2, P);
+    kern<<<dim3(nstrips, batch), NTHREADS, SMEM_BYTES, ctx->stream>>>(m_img, m_imgh, m_a1, m_a1h, m_a2, m_a2h, P);
     ctx->launches += 1;
     ctx->tc_launches += 1;
     if (P.dbg) {                                                 // developer aid: print the timeline of CTA (5, 3) relative to its start
