@@ -477,12 +477,12 @@ def main():
         blur_ms = stage["blur_dog_area"] / max(calls, 1)
         ach = B * b_alg / (blur_ms * 1e-3) / 1e9
         whole = B * b_alg / (ms / args.steps * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        traffic = traffic_tc = None
+        tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
         if os.path.exists(tp):
             t = json.load(open(tp)).get(args.workload)
             if t and t.get("batch") == B:
-                traffic = t.get("blur_area_kernel")
+                traffic, traffic_tc = t.get("blur_area_kernel"), t.get("blur_area_tc_kernel")
         line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8 (integer blur/labels) + f32/f64 (NCC, geometry)", "data": "synthetic", "config": config,
@@ -539,8 +539,8 @@ def main():
                                "kernel": "blur_area_tc_kernel (tcgen05.mma kind::i8 banded-Toeplitz GEMMs, TMEM accumulators, TMA operands)",
                                "kernel_ms": bms, "tc_launches": int(used), "records_equal_default_arm": bool(same),
                                "stage_ms_per_step": {k: v / max(calls_tc, 1) for k, v in stage_tc.items()},
-                               "roofline": {"bound": "hbm", "achieved": ach_tc, "peak": peak, "unit": "GB/s", "frac": ach_tc / peak,
-                                            "algorithmic_bytes_per_launch": B * b_alg},
+                               "roofline": {"bound": "hbm", "achieved": ach_tc, "peak": peak, "unit": "GB/s", "frac": ach_tc / peak, "traffic": traffic_tc,
+                                            "algorithmic_bytes_per_launch": B * b_alg, "kernel_ms": bms},
                                "note": "opt-in (VBS_BLUR_TC=1 / vbs_set_blur_tc); not the default because the north_star rules tensor cores out"}
 
     # ---- e2e: host frames -> records on the host (rank 0's host for N > 1) through the public API, all copies and the
