@@ -514,6 +514,7 @@ def main():
             step(s)
         pipe.sync()
         pipe.set_profiling(True)
+        stage_before, calls_before = pipe.stage_ms()       # the per-stage accumulators run on from the default arm: difference them
         barrier()
         t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0e.record(stream)
@@ -524,6 +525,8 @@ def main():
         ms_tc = t0e.elapsed_time(t1e)
         pipe.sync()
         stage_tc, calls_tc = pipe.stage_ms()
+        stage_tc = {k: v - stage_before[k] for k, v in stage_tc.items()}
+        calls_tc -= calls_before
         pipe.set_profiling(False)
         used = pipe.tc_launches - t0c
         same = all(bool(torch.equal(keep[k].contiguous().view(torch.uint8), outs[0][k].contiguous().view(torch.uint8))) for k in keep)

@@ -18,8 +18,19 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 H, W = 1080, 1920
 u = synth.workload_frames("1080p_20x20", 4, seed0=0)
 x = torch.from_numpy(np.tile(u, (B // 4, 1, 1))).cuda()
+REFS = os.environ.get("TC_PROBE_REFS", "0") == "1"
+SAME = os.environ.get("TC_PROBE_SAME_CTX", "0") == "1"
+shared = pipeline.MarkerPipeline(H, W, 1, max_batch=B, max_markers=1024, max_refs=512) if SAME else None
 for tc in (0, 1):
-    with pipeline.MarkerPipeline(H, W, 1, max_batch=B, max_markers=1024, max_refs=1) as p:
+    with (shared if SAME else pipeline.MarkerPipeline(H, W, 1, max_batch=B, max_markers=1024, max_refs=512)) as p:
+        if SAME:
+            p.__exit__ = lambda *a: None
+        if REFS and (tc == 0 or not SAME):
+            from vbs_b200 import reference_state
+            r0 = p.process(x[:1], 0); p.sync(); h0 = r0.to_host()
+            keys, xy = reference_state.grid_ids(h0.marker_xy[0, : int(h0.n_markers[0])], 20)
+            p.set_reference([k[0] for k in keys], [k[1] for k in keys], xy[:, 0], xy[:, 1], 20.0)
+            p.set_camera(*synth.synthetic_camera(), 2.0, 5.0, 50.0, warmup_frames=0)
         p.set_blur_tc(bool(tc))
         outs = p.alloc_outputs(B, True)
         for _ in range(2):
