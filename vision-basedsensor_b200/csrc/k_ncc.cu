@@ -460,18 +460,26 @@ __global__ void __launch_bounds__(TW2, TW2 == 128 ? 3 : 2) ncc_mask_wide_kernel(
     const bool warp_outside = x0 + (tid & ~31) >= W;                // this warp's 32 columns lie right of the image
 
     uint32_t pw[4] = {0, 0, 0, 0};
+    int woff[4]; uint32_t wmsk[4];                                  // the four words of the union window: step-invariant
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const bool ok = wi0 + i >= 0 && wi0 + i < WW;
+        woff[i] = ok ? wi0 + i : 0; wmsk[i] = ok ? 0xffffffffu : 0u;
+    }
     auto fetch = [&](int m) {
         const int p = ys - G::OFF + RB * m + hr;
         if (p >= 0 && p < H) {
             const uint32_t *row = abits + (size_t)p * WW;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) pw[i] = ld_bits(row, wi0 + i, WW);
+            for (int i = 0; i < 4; ++i) pw[i] = __ldg(row + woff[i]);     // masked where used: the load stays in flight for a whole step
         } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i) pw[i] = 0u;
         }
     };
     int s_prev = 0; uint32_t hb_m1 = 0;         // S of the previous output row and the box row that left the window
+    uint32_t s_lead = 0;                        // box sum of the lead groups = rows 0 .. 8 (TL / 8) - 1 of the first window
+    static_assert(G::LEAD == TL / 8 && TL % 8 <= 4, "first-window box sum is accumulated group by group during the lead steps");
 
     fetch(0);
     __syncthreads();
@@ -479,6 +487,8 @@ __global__ void __launch_bounds__(TW2, TW2 == 128 ? 3 : 2) ncc_mask_wide_kernel(
     for (int m = 0; m < nsteps; ++m) {
         // ---- H: horizontal pass on bits ------------------------------------------------------------
         {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pw[i] &= wmsk[i];
             uint32_t U0 = __funnelshift_r(pw[0], pw[1], bo);
             uint32_t U1 = __funnelshift_r(pw[1], pw[2], bo);
             uint32_t U2 = __funnelshift_r(pw[2], pw[3], bo);
@@ -489,8 +499,9 @@ __global__ void __launch_bounds__(TW2, TW2 == 128 ? 3 : 2) ncc_mask_wide_kernel(
             const uint32_t T1 = U1 ^ __funnelshift_l(U0, U1, 1);
             const uint32_t T2 = U2 ^ __funnelshift_l(U1, U2, 1);
             int acc[8];
+            uint32_t hb[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = 0;
+            for (int j = 0; j < 8; ++j) { acc[j] = 0; hb[j] = 0; }
             auto consume = [&](uint32_t T, uint32_t Uw, int base) {
                 while (T) {
                     const int b = __ffs(T) - 1;
@@ -503,17 +514,18 @@ __global__ void __launch_bounds__(TW2, TW2 == 128 ? 3 : 2) ncc_mask_wide_kernel(
                     acc[3] += sgn * hi.x; acc[2] += sgn * hi.y; acc[1] += sgn * hi.z; acc[0] += sgn * hi.w;
                 }
             };
-            consume(T0, U0, 0);
-            consume(T1, U1, 32);
-            if constexpr (G::UL > 64) consume(T2, U2, 64);
-            auto bit = [&](int t) -> uint32_t {
-                return t < 32 ? (U0 >> t) & 1u : t < 64 ? (U1 >> (t - 32)) & 1u : (U2 >> (t - 64)) & 1u;
-            };
-            uint32_t hb[8];
-            if constexpr (TL >= 64) hb[0] = __popc(U0) + __popc(U1) + __popc(U2 & ((1u << (TL - 64)) - 1u));
-            else hb[0] = __popc(U0) + __popc(U1 & ((1u << (TL - 32)) - 1u));
+            if (U0 | U1 | U2) {                                      // a window without area pixels leaves h = 0, box = 0
+                consume(T0, U0, 0);
+                consume(T1, U1, 32);
+                if constexpr (G::UL > 64) consume(T2, U2, 64);
+                auto bit = [&](int t) -> uint32_t {
+                    return t < 32 ? (U0 >> t) & 1u : t < 64 ? (U1 >> (t - 32)) & 1u : (U2 >> (t - 64)) & 1u;
+                };
+                if constexpr (TL >= 64) hb[0] = __popc(U0) + __popc(U1) + __popc(U2 & ((1u << (TL - 64)) - 1u));
+                else hb[0] = __popc(U0) + __popc(U1 & ((1u << (TL - 32)) - 1u));
 #pragma unroll
-            for (int j = 1; j < 8; ++j) hb[j] = hb[j - 1] + bit(j - 1 + TL) - bit(j - 1);
+                for (int j = 1; j < 8; ++j) hb[j] = hb[j - 1] + bit(j - 1 + TL) - bit(j - 1);
+            }
             float *dstH = reinterpret_cast<float *>(ringH + (gw * 2 + (hr >> 2)) * TWP2) + (hr & 3);
             unsigned char *dstB = reinterpret_cast<unsigned char *>(ringB + gw * TWP2) + hr;
 #pragma unroll
@@ -526,7 +538,11 @@ __global__ void __launch_bounds__(TW2, TW2 == 128 ? 3 : 2) ncc_mask_wide_kernel(
         __syncthreads();                                             // the only barrier of the step
 
         // ---- V + D: vertical pass and decision, thread = column ------------------------------------
-        if (m >= G::LEAD) {
+        if (m < G::LEAD) {                                           // lead: only the box sum of the first window grows
+            const uint2 b = ringB[gw * TWP2 + cp];
+            s_lead = __dp4a(b.x, 0x01010101u, s_lead);
+            s_lead = __dp4a(b.y, 0x01010101u, s_lead);
+        } else {
             const int k = m - G::LEAD;
             const int yb = ys + RB * k;
             int g0 = gw - G::LEAD; if (g0 < 0) g0 += G::NR;          // slot of step k
@@ -540,13 +556,9 @@ __global__ void __launch_bounds__(TW2, TW2 == 128 ? 3 : 2) ncc_mask_wide_kernel(
                     const uint32_t w = (idx % 8) < 4 ? b.x : b.y;
                     return (int)((w >> (8 * (idx % 4))) & 255u);
                 };
-                if (k == 0) {                   // first step of the segment: sum the whole window once (rolled: code size)
-                    int s = 0;
-#pragma unroll 1
-                    for (int t = 0; t < TL; ++t) {
-                        int gi = g0 + (t >> 3); if (gi >= G::NR) gi -= G::NR;
-                        s += reinterpret_cast<const unsigned char *>(ringB + gi * TWP2 + cp)[t & 7];
-                    }
+                if (k == 0) {                   // first step of the segment: the lead groups + the TL % 8 rows of this step's group
+                    int s = (int)s_lead;
+                    if constexpr (TL % 8 != 0) s += (int)__dp4a(ringB[gw * TWP2 + cp].x & ((1u << (8 * (TL % 8))) - 1u), 0x01010101u, 0u);
                     S8[0] = s;
                 } else {
                     S8[0] = s_prev + box_at(std::integral_constant<int, TL - 1>{}) - (int)hb_m1;
@@ -577,9 +589,8 @@ __global__ void __launch_bounds__(TW2, TW2 == 128 ? 3 : 2) ncc_mask_wide_kernel(
                 const float4 *b0 = ringH + ub * TWP2 + cp;
                 const float4 *b1 = b0 - 2 * G::NR * TWP2;
                 const int wrap_at = 2 * G::NR - ub;                             // first unit index that wraps
-                static_for<0, U1_ + 1>([&](auto U_) {
+                auto unit = [&](auto U_, const float4 v) {
                     constexpr int u = decltype(U_)::value;
-                    const float4 v = (u < wrap_at ? b0 : b1)[u * TWP2];
                     static_for<0, 2>([&](auto P_) {
                         constexpr int t = 4 * u + 2 * decltype(P_)::value;      // even ring row of the pair
                         const float2 hp = decltype(P_)::value ? make_float2(v.z, v.w) : make_float2(v.x, v.y);
@@ -594,6 +605,10 @@ __global__ void __launch_bounds__(TW2, TW2 == 128 ? 3 : 2) ncc_mask_wide_kernel(
                         if constexpr (t + 1 >= 0 && t + 1 < TL) o0 = fmaf(c_n32[TL == 80][t + 1], hp.y, o0);
                         if constexpr (t - 7 >= 0 && t - 7 < TL) o7 = fmaf(c_n32[TL == 80][t - 7], hp.x, o7);
                     });
+                };
+                static_for<0, U1_ + 1>([&](auto U_) {
+                    constexpr int u = decltype(U_)::value;
+                    unit(U_, (u < wrap_at ? b0 : b1)[u * TWP2]);
                 });
             }
             float acc[RB];
@@ -602,7 +617,9 @@ __global__ void __launch_bounds__(TW2, TW2 == 128 ? 3 : 2) ncc_mask_wide_kernel(
             // ---- D: decision --------------------------------------------------------------------------
             const int x = x0 + vcol;
             uint32_t onmask = 0, needmask = 0;        // bit r: row r of this column is on / needs the float64 pass
-            if (strip_interior && yb >= G::OFF && yb + RB - 1 + G::HI < H && yb + RB <= ye) {
+            if (empty) {
+                // S == 0 in the whole warp: off on every path (interior table entry 0 is +inf, border_decide returns 0)
+            } else if (strip_interior && yb >= G::OFF && yb + RB - 1 + G::HI < H && yb + RB <= ye) {
                 float thr[RB];                        // whole step inside the image: threshold is the table entry of the box sum
 #pragma unroll
                 for (int r = 0; r < RB; ++r) thr[r] = __ldg(P.thr_lut + S8[r]);
@@ -625,10 +642,12 @@ __global__ void __launch_bounds__(TW2, TW2 == 128 ? 3 : 2) ncc_mask_wide_kernel(
                 }
             }
             uint32_t myword = 0;
+            if (!empty) {
 #pragma unroll
-            for (int r = 0; r < RB; ++r) {
-                const uint32_t word = __ballot_sync(0xffffffffu, (onmask >> r) & 1u);
-                if (lane == r) myword = word;
+                for (int r = 0; r < RB; ++r) {
+                    const uint32_t word = __ballot_sync(0xffffffffu, (onmask >> r) & 1u);
+                    if (lane == r) myword = word;
+                }
             }
             while (needmask) {                        // float32 cannot decide: queue for the float64 pass (rare)
                 const int r = __ffs(needmask) - 1;
