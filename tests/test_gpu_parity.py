@@ -686,6 +686,34 @@ def test_branch_overlap_equals_sequential_schedule(monkeypatch):
     assert [len(w) for w in want] == a.n_markers.tolist()
 
 
+@pytest.mark.parametrize("h,w,n", [(300, 1000, 230), (500, 900, 230)])
+def test_mixed_segment_plan_equals_uniform_segments(monkeypatch, h, w, n):
+    """The strip-marching kernels (blur, NCC) run the first (frame, strip) items whole-height and only the tail of the
+    grid in row segments (VbsSegPlan, vbs_ctx.h).  Enough items here to have both kinds (>= 3 waves of 4 x 148 CTAs); the masks
+    must equal those of the uniform plan (VBS_SEG_PLAN=0, every item in the same segments) and cv2 / the port."""
+    import cv2
+    rng = np.random.default_rng(h)
+    radius = 6.0 if h <= 480 else 11.0
+    centres = synth.grid_layout(h, w, 4, 12, 60.0)
+    base = np.stack([synth.render_frame(h, w, centres, radius, seed=300 + i) for i in range(6)])
+    frames = np.ascontiguousarray(base[np.arange(n) % len(base)])
+    frames[:, ::7, ::5] ^= rng.integers(0, 64, frames[:, ::7, ::5].shape, dtype=np.uint8)      # make every frame different
+    x = torch_cuda(frames)
+
+    def run():
+        with pipeline.MarkerPipeline(h, w, 1, max_batch=n, max_markers=256, max_refs=1) as pipe:
+            pipe.process(x, 0); pipe.sync()
+            return pipe.debug_stage(capi.STAGE_AREA_MASK, n).cpu().numpy(), pipe.debug_stage(capi.STAGE_MASK, n).cpu().numpy()
+
+    a_area, a_mask = run()
+    monkeypatch.setenv("VBS_SEG_PLAN", "0")
+    b_area, b_mask = run()
+    assert np.array_equal(a_area, b_area) and np.array_equal(a_mask, b_mask)
+    for f in (0, n // 2, n - 1):                                  # first item (whole height), middle, last (row segments)
+        want_mask, want_area = port.detect_masks(frames[f])[:2]
+        assert np.array_equal(a_area[f] != 0, want_area != 0) and np.array_equal(a_mask[f] != 0, want_mask != 0), f
+
+
 # ---------------------------------------------------------------------------------------------
 # 14. K2 in isolation (vbs_ncc_mask): arbitrary area masks against the reference's three-FFT normxcorr2
 #     (MD:146-164) > 0.1, bit for bit - random blob fields, border-heavy content, near-empty and near-full

@@ -144,7 +144,7 @@ __device__ __forceinline__ void tma_load_tile(void *dst, const CUtensorMap *map,
 template <int KS, int KL, bool BGR>
 __global__ void __launch_bounds__(TW, 4)
 blur_area_kernel(const __grid_constant__ CUtensorMap tmap, int use_tma, const uint8_t *__restrict__ frames, int64_t frame_stride,
-                 int64_t row_pitch, int H, int W, int WW, int seg_rows, int lo, int hi, uint32_t *__restrict__ area_bits,
+                 int64_t row_pitch, int H, int W, int WW, VbsSegPlan plan, int strips, int lo, int hi, uint32_t *__restrict__ area_bits,
                  uint32_t *__restrict__ area_count, uint32_t *__restrict__ status) {
     using G = Geo<KS, KL>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -154,10 +154,16 @@ blur_area_kernel(const __grid_constant__ CUtensorMap tmap, int use_tma, const ui
     uint4 *ringS = ringL + G::NGL * TW;                                       // [NGS][TW]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int x0 = blockIdx.x * TW;
-    const int ys = blockIdx.y * seg_rows;
-    const int ye = min(H, ys + seg_rows);
-    const int f = blockIdx.z;
+    // CTA -> (frame, strip, row segment): whole-height items first, the tail of the grid in row segments (VbsSegPlan)
+    int item = blockIdx.x, ys = 0, ye = H;
+    if (item >= plan.n_full) {
+        const int j = item - plan.n_full, q = j / plan.vsegs;
+        item = plan.n_full + q;
+        ys = (j - q * plan.vsegs) * plan.seg_rows;
+        ye = min(H, ys + plan.seg_rows);
+    }
+    const int f = item / strips;
+    const int x0 = (item - f * strips) * TW;
     const uint8_t *fbase = frames + (size_t)f * frame_stride;
     const bool aligned4 = ((reinterpret_cast<uintptr_t>(fbase) | (uintptr_t)row_pitch) & 3) == 0;
     const int nk = (ye - ys + RB - 1) / RB;
@@ -381,12 +387,9 @@ template <int KS, int KL>
 cudaError_t launch(vbs_ctx *ctx, const uint8_t *frames, int batch, int64_t frame_stride, int64_t row_pitch) {
     using G = Geo<KS, KL>;
     const int strips = (ctx->W + TW - 1) / TW;
-    // enough CTAs for ~8 waves of 4 CTAs/SM, but at least 64 output rows per segment
-    int vsegs = 1;
-    while ((long long)strips * batch * vsegs < 4096 && (ctx->H + vsegs) / (vsegs + 1) >= 64) ++vsegs;
-    int seg_rows = ((ctx->H + vsegs - 1) / vsegs + RB - 1) / RB * RB;
-    vsegs = (ctx->H + seg_rows - 1) / seg_rows;
-    dim3 grid(strips, vsegs, batch), block(TW);
+    // 4 CTAs per SM are resident; a lead step runs the horizontal passes only (about a third of a full step)
+    const VbsSegPlan plan = vbs_seg_plan(ctx->H, (long long)strips * batch, 4 * ctx->sm_count, G::LEAD, RB, 0.35, ctx->seg_plan != 0);
+    dim3 grid(plan.ctas), block(TW);
     cudaError_t e;
     CUtensorMap map;
     std::memset(&map, 0, sizeof(map));
@@ -394,12 +397,12 @@ cudaError_t launch(vbs_ctx *ctx, const uint8_t *frames, int batch, int64_t frame
     if (ctx->C == 3) {
         auto kern = blur_area_kernel<KS, KL, true>;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM)) != cudaSuccess) return e;
-        kern<<<grid, block, G::SMEM, ctx->stream>>>(map, 0, frames, frame_stride, row_pitch, ctx->H, ctx->W, ctx->WW, seg_rows,
+        kern<<<grid, block, G::SMEM, ctx->stream>>>(map, 0, frames, frame_stride, row_pitch, ctx->H, ctx->W, ctx->WW, plan, strips,
                                                     ctx->br.lo, ctx->br.hi, ctx->area_bits, ctx->area_count, ctx->d_status);
     } else {
         auto kern = blur_area_kernel<KS, KL, false>;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM)) != cudaSuccess) return e;
-        kern<<<grid, block, G::SMEM, ctx->stream>>>(map, use_tma, frames, frame_stride, row_pitch, ctx->H, ctx->W, ctx->WW, seg_rows,
+        kern<<<grid, block, G::SMEM, ctx->stream>>>(map, use_tma, frames, frame_stride, row_pitch, ctx->H, ctx->W, ctx->WW, plan, strips,
                                                     ctx->br.lo, ctx->br.hi, ctx->area_bits, ctx->area_count, ctx->d_status);
     }
     ctx->launches += 1;

@@ -58,6 +58,7 @@ template <int TL> struct Geo {
 
 struct NccParams {
     int H, W, WW, seg_rows;
+    VbsSegPlan plan; int strips;                   // thread-per-column kernel: CTA -> (frame, strip, row segment)
     double st2, hw;
     const uint32_t *area_bits; const uint32_t *area_count;
     uint32_t *mask_bits;
@@ -438,10 +439,16 @@ __global__ void __launch_bounds__(TW2, TW2 == 128 ? 3 : 2) ncc_mask_wide_kernel(
     int4 *fx = reinterpret_cast<int4 *>(cn + G::CNX + (G::CNX & 1));             // [4][FXN/4] shifted fixed-point copies
 
     const int tid = threadIdx.x, lane = tid & 31;
-    const int x0 = blockIdx.x * TW2;
-    const int ys = blockIdx.y * P.seg_rows;
-    const int ye = min(P.H, ys + P.seg_rows);
-    const int f = blockIdx.z;
+    // CTA -> (frame, strip, row segment): whole-height items first, the tail of the grid in row segments (VbsSegPlan)
+    int item = blockIdx.x, ys = 0, ye = P.H;
+    if (item >= P.plan.n_full) {
+        const int j = item - P.plan.n_full, q = j / P.plan.vsegs;
+        item = P.plan.n_full + q;
+        ys = (j - q * P.plan.vsegs) * P.plan.seg_rows;
+        ye = min(P.H, ys + P.plan.seg_rows);
+    }
+    const int f = item / P.strips;
+    const int x0 = (item - f * P.strips) * TW2;
     const int H = P.H, W = P.W, WW = P.WW;
     const uint32_t *abits = P.area_bits + (size_t)f * H * WW;
     const double mfrac64 = (double)P.area_count[f] / P.hw;
@@ -735,9 +742,12 @@ template <int TL> cudaError_t launch(vbs_ctx *ctx, int batch, double st2) {
     cudaError_t e = cudaMemsetAsync(ctx->recheck_n, 0, sizeof(uint32_t) * batch, ctx->stream);
     if (e != cudaSuccess) return e;
     if (variant == 1) {
+        // 3 CTAs per SM are resident; a lead step runs the horizontal pass only
+        P.strips = strips;
+        P.plan = vbs_seg_plan(ctx->H, (long long)strips * batch, 3 * ctx->sm_count, Geo<TL>::LEAD, RB, 0.4, ctx->seg_plan != 0);
         auto kern = ncc_mask_wide_kernel<TL, 128>;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GeoW<TL, 128>::SMEM)) != cudaSuccess) return e;
-        kern<<<dim3(strips, vsegs, batch), 128, GeoW<TL, 128>::SMEM, ctx->stream>>>(P);
+        kern<<<dim3(P.plan.ctas), 128, GeoW<TL, 128>::SMEM, ctx->stream>>>(P);
     } else {
         auto kern = ncc_mask_kernel<TL>;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GeoR<TL>::SMEM)) != cudaSuccess) return e;

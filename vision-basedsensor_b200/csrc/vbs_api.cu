@@ -402,6 +402,9 @@ int vbs_create(vbs_ctx **out, const vbs_config *cfg) {
     ctx->min_dist = 20.0;
     { const char *e = getenv("VBS_NO_TMA"); ctx->no_tma = (e && e[0] == '1') ? 1 : 0; }
     { const char *e = getenv("VBS_NCC_VARIANT"); ctx->ncc_variant = (e && e[0] == '0') ? 0 : 1; }
+    { const char *e = getenv("VBS_SEG_PLAN"); ctx->seg_plan = (e && e[0] == '0') ? 0 : 1; }
+    ctx->sm_count = 148;
+    { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess && v > 0) ctx->sm_count = v; }
     { const char *e = getenv("VBS_BLUR_TC"); ctx->blur_tc = (e && e[0] == '1') ? 1 : 0; }      // opt-in tensor-core blur
     // The open-mask branch (5x5 open, blobs, border following, ellipse fits) needs K1 only and runs on a second,
     // high-priority stream beside the NCC: the NCC stretches from 3.0 to 3.7 ms but the 0.9 ms of small latency-bound
