@@ -19,8 +19,14 @@
 //        32768 and the sign flips cancel: sum(taps) = 256, so sum tap*(v-128) = sum tap*v - 32768, and the two
 //        constants are equal for both blurs)  ->  dog = uint8(b_large - b_small + 15), lo <= dog <= hi, 64 bits per row.
 //
-// One CTA = one 64-column strip of one frame, marching down in 64-row chunks: TMA warp, MMA warp (one thread
-// issues), 4 warps epilogue 1, 4 warps epilogue 2; accumulators in TMEM (D1 double-buffered), mbarrier hand-offs.
+// A work item = one 64-column strip of one frame, marched down in 64-row chunks; persistent CTAs (one per SM) run a
+// contiguous range of items without draining the pipeline in between.  Roles: TMA warp, one MMA-issuing warp per pass,
+// 4 warps epilogue 1, 8 warps epilogue 2; accumulators in TMEM (D1 x3 stages, D2), mbarrier hand-offs.
+// What bounds it (per-CTA timeline, VBS_TC_TIMELINE=1): a kind::i8 MMA reads 32 K-bytes of both operands from shared
+// memory, (4 KB + N x 32 B) per instruction, and at N <= 128 that - not the multipliers - sets its duration (N = 64:
+// 48.9 cycles = 6 KB at 128 B/clk, N = 128: 64.6 cycles); both passes together read 92 KB per chunk, epilogue 1 and TMA
+// write another 28 KB, so the shared-memory ports allow ~0.94 k cycles per chunk (~0.5 ms per 256 1080p frames) and the
+// kernel runs at ~1.3 k.
 #include <cuda.h>
 #include <cstdio>
 #include <cstdlib>
@@ -35,7 +41,8 @@ constexpr int CHR = 64;            // image rows per chunk (pass 1 step) = K byt
 constexpr int BLK = 128;           // output rows per pass-2 block
 constexpr int KEXT = 256;          // K extent of both passes in bytes (two 128-byte swizzle slabs)
 constexpr int NSLAB = 6;           // ring of pass-1 results (4 are read by a block, 2 are being produced: epilogue 1 never waits for the block in flight)
-constexpr int NSTAGE = 3;          // image-row stages in flight and D1 accumulators (a TMA load takes ~3000 cycles from issue to arrival; a 4th stage measured no gain)
+constexpr int NSTAGE = 3;          // image-row stages in flight and D1 accumulators (a TMA load takes ~3000 cycles from issue to arrival; a 4th stage
+                                   // and an L2 prefetch 8 chunks ahead measured no gain: epilogue 1 and the shared-memory ports set the pace)
 constexpr int NTHREADS = 512;      // warp 0: TMA, 1: MMA pass 1, 2: TMEM allocator, 3: MMA pass 2, 4-7: epilogue 1, 8-15: epilogue 2
 
 // Pass 1 only has taps in K bytes 0..191 (image columns x0 - 64 .. x0 + 127), so its operands are a 128-byte slab
@@ -63,10 +70,13 @@ struct TcParams {
     int H, W, WW, lo, hi;
     int nreal, nchunks, nblocks;   // real chunks (image rows), chunk slots incl. the mirrored ones, blocks of 128 output rows
     int radius;                    // rows mirrored above row 0 and below row H-1 (radius of the large blur)
+    int batch, nstrips, total;     // work items = (strip, frame) pairs; CTA c runs items [total c / grid, total (c + 1) / grid)
+    int strip_major;               // 1: item e = strip * batch + frame (persistent CTAs keep their operator matrix), 0: frame * nstrips + strip
+    int dbg_item;                  // which of the CTA's items the timeline records
     uint32_t *area_bits, *area_count, *status;
     long long *dbg;                // optional timeline of one CTA (VBS_TC_TIMELINE=1): clock64 at pipeline events
 };
-#define TC_DBG(id) do { if (P.dbg && blockIdx.x == 5 && blockIdx.y == 3) P.dbg[id] = clock64(); } while (0)
+#define TC_DBG(id) do { if (dbg_on) P.dbg[id] = clock64(); } while (0)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -168,9 +178,16 @@ blur_area_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
     auto bar = [&](int i) -> uint32_t { return bars + 8u * (uint32_t)i; };
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int strip = blockIdx.x, f = blockIdx.y;
-    const int x0 = strip * SW;
     const int CR = P.nreal, C = P.nchunks, NB = P.nblocks;    // chunk slot cc covers virtual rows [64 (cc - 1), 64 cc); real: 1 .. CR
+    // Persistent CTA: a contiguous range of work items.  Every role walks the same item sequence and keeps RUNNING
+    // counters (g1: real chunks, gc0: chunk slots, gb0: blocks) from which all stage indices and barrier parities
+    // follow, so the pipeline never drains between items: the loads and pass 1 of item n+1 run under pass 2 and the
+    // epilogues of item n.
+    const int e0 = (int)((long long)P.total * blockIdx.x / gridDim.x), e1 = (int)((long long)P.total * (blockIdx.x + 1) / gridDim.x);
+    auto item_strip = [&](int e) -> int { return P.strip_major ? e / P.batch : e % P.nstrips; };
+    auto item_frame = [&](int e) -> int { return P.strip_major ? e % P.batch : e / P.nstrips; };
+    const bool dbg_cta = P.dbg != nullptr && blockIdx.x == 5;
+    bool dbg_on = dbg_cta;
     if (tid == 0) TC_DBG(0);
 
     if (tid == 0) {
@@ -207,16 +224,28 @@ blur_area_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
         // ================= TMA producer (warp-uniform control flow, one elected lane issues): operator matrices, then
         // 64 image rows per chunk =================
         {
-            if (elect_one()) {
-                mbar_expect_tx(bar(BAR_A1), 16384u + 8192u);
-                tma_load_2d(base + OFF_A1, &map_a1, 0, 128 * strip, bar(BAR_A1));
-                tma_load_2d(base + OFF_A1H, &map_a1h, 128, 128 * strip, bar(BAR_A1));
-            }
-            __syncwarp();
             bool ok = true;
             int st = 0; uint32_t ph = 0;
-            for (int i = 0; i < CR && ok; ++i) {                                // real chunk i + 1 = image rows [64 i, 64 i + 64)
-                if (i >= NSTAGE) ok = __all_sync(0xffffffffu, mbar_wait(bar(BAR_B1_EMPTY + st), ph ^ 1u, abort_flag));
+            int g1 = 0, cur_strip = -1;
+            for (int e = e0; e < e1 && ok; ++e) {
+            const int strip = item_strip(e), f = item_frame(e), x0 = strip * SW;
+            dbg_on = dbg_cta && e - e0 == P.dbg_item;
+            if (strip != cur_strip) {                                           // a new operator matrix: every pass-1 MMA that reads the old one must be done
+                if (g1 > 0) {
+                    const int gl = g1 - 1;                                      // the last chunk issued commits to its stage's EMPTY barrier
+                    ok = __all_sync(0xffffffffu, mbar_wait(bar(BAR_B1_EMPTY + gl % NSTAGE), (uint32_t)(gl / NSTAGE) & 1u, abort_flag));
+                    if (!ok) break;
+                }
+                if (elect_one()) {
+                    mbar_expect_tx(bar(BAR_A1), 16384u + 8192u);
+                    tma_load_2d(base + OFF_A1, &map_a1, 0, 128 * strip, bar(BAR_A1));
+                    tma_load_2d(base + OFF_A1H, &map_a1h, 128, 128 * strip, bar(BAR_A1));
+                }
+                __syncwarp();
+                cur_strip = strip;
+            }
+            for (int i = 0; i < CR && ok; ++i, ++g1) {                          // real chunk i + 1 = image rows [64 i, 64 i + 64)
+                if (g1 >= NSTAGE) ok = __all_sync(0xffffffffu, mbar_wait(bar(BAR_B1_EMPTY + st), ph ^ 1u, abort_flag));
                 if (!ok) break;
                 if (elect_one()) {
                     const uint32_t dst = base + OFF_B1 + B1_STAGE * st;
@@ -224,7 +253,7 @@ blur_area_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
                     tma_load_3d(dst, &map_img, x0 - 64, CHR * i, f, bar(BAR_B1_FULL + st));
                     tma_load_3d(dst + B1_HALF, &map_imgh, x0 + 64, CHR * i, f, bar(BAR_B1_FULL + st));
                     TC_DBG(120 + i);
-                    if (i == 1 || CR == 1) {                                    // pass 2 starts four chunks in: its matrices load behind the first rows
+                    if (e == e0 && (i == 1 || CR == 1)) {                       // pass 2 starts four chunks in: its matrices load behind the first rows
                         mbar_expect_tx(bar(BAR_A2), 32768u + 16384u + 8192u);
                         for (int s = 0; s < 2; ++s) tma_load_2d(base + OFF_A2 + 16384u * s, &map_a2, 128 * s, 0, bar(BAR_A2));
                         tma_load_2d(base + OFF_A2S, &map_a2, 32, 128, bar(BAR_A2));             // small blur: K bytes 32..159
@@ -233,6 +262,7 @@ blur_area_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
                 }
                 __syncwarp();
                 if (++st == NSTAGE) { st = 0; ph ^= 1u; }
+            }
             }
         }
     } else if (warp == 1) {
@@ -243,11 +273,20 @@ blur_area_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
         constexpr uint32_t ID1 = idesc_i8(128, 64, 0, 0);                       // taps (u8, <= 26) x pixels (u8)
         const uint64_t a1d = smem_desc(base + OFF_A1, 1024, 2), b1d = smem_desc(base + OFF_B1, 1024, 2);
         const uint64_t a1hd = smem_desc(base + OFF_A1H, 512, 4), b1hd = smem_desc(base + OFF_B1 + B1_HALF, 512, 4);      // K bytes 128..191
-        bool ok = __all_sync(0xffffffffu, mbar_wait(bar(BAR_A1), 0, abort_flag));
+        bool ok = true;
         int st = 0; uint32_t ph = 0;
-        for (int i = 0; i < CR && ok; ++i) {                                    // real chunk i + 1
+        int g1 = 0, cur_strip = -1; uint32_t a1_loads = 0;
+        for (int e = e0; e < e1 && ok; ++e) {
+        const int strip = item_strip(e);
+        dbg_on = dbg_cta && e - e0 == P.dbg_item;
+        if (strip != cur_strip) {
+            ok = __all_sync(0xffffffffu, mbar_wait(bar(BAR_A1), a1_loads & 1u, abort_flag));
+            ++a1_loads; cur_strip = strip;
+            if (!ok) break;
+        }
+        for (int i = 0; i < CR && ok; ++i, ++g1) {                              // real chunk i + 1
             ok = mbar_wait(bar(BAR_B1_FULL + st), ph, abort_flag);
-            if (ok && i >= NSTAGE) ok = mbar_wait(bar(BAR_D1_EMPTY + st), ph ^ 1u, abort_flag);
+            if (ok && g1 >= NSTAGE) ok = mbar_wait(bar(BAR_D1_EMPTY + st), ph ^ 1u, abort_flag);
             ok = __all_sync(0xffffffffu, ok);
             if (!ok) break;
             tc_fence_after();
@@ -266,18 +305,22 @@ blur_area_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
             __syncwarp();
             if (++st == NSTAGE) { st = 0; ph ^= 1u; }
         }
+        }
     } else if (warp == 3) {
         // ================= MMA issuer, pass 2: output rows [128 b, 128 b + 128) read chunk slots 2 b .. 2 b + 3 of the ring =================
         constexpr uint32_t ID2 = idesc_i8(128, 128, 1, 1);                      // taps (s8, <= 13) x sign-flipped bytes (s8)
         const uint64_t a2d = smem_desc(base + OFF_A2, 1024, 2), hd = smem_desc(base + OFF_H, 512, 4);
         const uint64_t a2sd = smem_desc(base + OFF_A2S, 1024, 2), a2shd = smem_desc(base + OFF_A2SH, 512, 4);
         bool ok = __all_sync(0xffffffffu, mbar_wait(bar(BAR_A2), 0, abort_flag));
-        int slab0 = 0;                                                          // ring slot of chunk 2 b
+        for (int e = e0; e < e1 && ok; ++e) {
+        const int gc0 = (e - e0) * C, gb0 = (e - e0) * NB;                      // running chunk-slot / block numbers of this item's first
+        dbg_on = dbg_cta && e - e0 == P.dbg_item;
+        int slab0 = gc0 % NSLAB;                                                // ring slot of chunk 2 b
         for (int b2 = 0; b2 < NB && ok; ++b2) {
+            const int gb = gb0 + b2;
             const int c_need = min(2 * b2 + 3, C - 1);                          // newest chunk slot the block reads (epilogue 1 finishes chunks in order)
-            int sl_need = slab0 + (c_need - 2 * b2); if (sl_need >= NSLAB) sl_need -= NSLAB;
-            ok = mbar_wait(bar(BAR_H_FULL + sl_need), (uint32_t)(c_need / NSLAB) & 1u, abort_flag);
-            if (ok && b2 >= 1) ok = mbar_wait(bar(BAR_D2_EMPTY), (uint32_t)(b2 - 1) & 1u, abort_flag);
+            ok = mbar_wait(bar(BAR_H_FULL + (gc0 + c_need) % NSLAB), (uint32_t)((gc0 + c_need) / NSLAB) & 1u, abort_flag);
+            if (ok && gb >= 1) ok = mbar_wait(bar(BAR_D2_EMPTY), (uint32_t)(gb - 1) & 1u, abort_flag);
             ok = __all_sync(0xffffffffu, ok);
             if (!ok) break;
             uint64_t hs[4];
@@ -297,31 +340,45 @@ blur_area_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
                 for (int j = k2_lo(RS); j < k2_hi(RS); ++j)
                     tc_mma_i8(tmem + TM_D2 + 128u, j < 5 ? a2sd + (uint64_t)(2 * (j - 1)) : a2shd + (uint64_t)(2 * (j - 5)), hs[j >> 1] + (uint64_t)(512 + 2 * (j & 1)), ID2,
                               j > k2_lo(RS));
-                tc_commit(bar(BAR_BLK + (b2 & 3)));
+                tc_commit(bar(BAR_BLK + (gb & 3)));
                 tc_commit(bar(BAR_D2_FULL));
                 TC_DBG(40 + b2);
             }
             __syncwarp();
             slab0 += 2; if (slab0 >= NSLAB) slab0 -= NSLAB;
         }
+        }
     } else if (warp >= 4 && warp < 8) {
         // ================= epilogue 1: D1 -> signed high / low bytes, K-major, into the ring =================
         const int q = warp & 3, row = 32 * q + lane;          // TMEM lane = (blur, column): blur = row / 64
         const int bl = row >> 6, n = row & 63;
-        auto tile_of = [&](int cc) -> unsigned char * { return gen + OFF_H + 16384u * (uint32_t)(cc % NSLAB) + 8192u * (uint32_t)bl; };
+        int gc0 = 0, gb0 = 0;                                  // running chunk-slot / block numbers of the current item's first
+        auto tile_of = [&](int cc) -> unsigned char * { return gen + OFF_H + 16384u * (uint32_t)((gc0 + cc) % NSLAB) + 8192u * (uint32_t)bl; };
         // the four bytes of virtual rows t .. t + 3 (t % 4 == 0) of one of this thread's two ring rows
         auto vword = [&](int prow, int t) -> uint32_t * {
             return reinterpret_cast<uint32_t *>(tile_of((t >> 6) + 1) + swz64((uint32_t)prow, (uint32_t)(t & 63)));
         };
-        auto slot_free = [&](int cc) -> bool {                 // the slot of chunk cc held chunk cc - NSLAB, last read by block min(NB-1, (cc-NSLAB)/2)
-            if (cc < NSLAB) return true;
-            const int bdone = min(NB - 1, (cc - NSLAB) >> 1);
-            return mbar_wait(bar(BAR_BLK + (bdone & 3)), (bdone >> 2) & 1, abort_flag);
+        // the slot of chunk cc held the chunk NSLAB slots earlier (of this item or the previous one), last read by block
+        // min(NB - 1, chunk / 2) of that item (a block reads chunks 2 b .. 2 b + 3)
+        int blk_known = -1;                                    // newest block known complete (blocks complete in order; a wait is a ~150-cycle round trip)
+        auto slot_free = [&](int cc) -> bool {
+            const int g = gc0 + cc - NSLAB;
+            if (g < 0) return true;
+            int pc = cc - NSLAB, pb0 = gb0;
+            while (pc < 0) { pc += C; pb0 -= NB; }              // (frames of fewer than NSLAB chunk slots: further back)
+            const int bdone = pb0 + min(NB - 1, pc >> 1);
+            if (bdone <= blk_known) return true;
+            if (!mbar_wait(bar(BAR_BLK + (bdone & 3)), (uint32_t)(bdone >> 2) & 1u, abort_flag)) return false;
+            blk_known = bdone;
+            return true;
         };
         bool ok = true;
-        for (int i = 0; i < CR && ok; ++i) {
-            const int st = i % NSTAGE, cc = i + 1;
-            ok = mbar_wait(bar(BAR_D1_FULL + st), (i / NSTAGE) & 1, abort_flag);
+        int g1 = 0;
+        for (int e = e0; e < e1 && ok; ++e, gc0 += C, gb0 += NB) {
+        dbg_on = dbg_cta && e - e0 == P.dbg_item;
+        for (int i = 0; i < CR && ok; ++i, ++g1) {
+            const int st = g1 % NSTAGE, cc = i + 1;
+            ok = mbar_wait(bar(BAR_D1_FULL + st), (uint32_t)(g1 / NSTAGE) & 1u, abort_flag);
             if (!ok) break;
             tc_fence_after();
             uint32_t v[4][16];
@@ -331,7 +388,9 @@ blur_area_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
             if (tid == 128) TC_DBG(150 + i);
             tc_fence_before();
             mbar_arrive(bar(BAR_D1_EMPTY + st));                // the accumulator stage may be overwritten
+            if (cc == 1 && !(ok = slot_free(0))) break;         // the top mirror goes into the slot before this chunk's
             if (!(ok = slot_free(cc))) break;
+            if (tid == 128) TC_DBG(170 + i);
             unsigned char *tile = tile_of(cc);                  // [128 rows][64 B]: rows 0..63 high bytes, 64..127 low bytes
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -391,25 +450,31 @@ blur_area_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
                     }
                 }
             }
+            if (tid == 128) TC_DBG(190 + i);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                  // generic writes -> visible to the tensor core's reads
-            if (cc == 1) mbar_arrive(bar(BAR_H_FULL + 0));
-            mbar_arrive(bar(BAR_H_FULL + cc % NSLAB));
+            if (cc == 1) mbar_arrive(bar(BAR_H_FULL + gc0 % NSLAB));
+            mbar_arrive(bar(BAR_H_FULL + (gc0 + cc) % NSLAB));
             if (cc == CR)
-                for (int ct = CR + 1; ct < C; ++ct) mbar_arrive(bar(BAR_H_FULL + ct % NSLAB));
+                for (int ct = CR + 1; ct < C; ++ct) mbar_arrive(bar(BAR_H_FULL + (gc0 + ct) % NSLAB));
             if (tid == 128) TC_DBG(60 + i);
+        }
         }
     } else if (warp >= 8) {
         // ================= epilogue 2: D2 -> rounding, wrapping DoG, inRange, 32 bits per thread and row =================
         const int q = warp & 3, half = (warp - 8) >> 2, r = 32 * q + lane;     // TMEM lane = output row within the block; columns 32 half ..
         const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16) + TM_D2 + 32u * half;
-        const uint32_t span = (uint32_t)(P.hi - P.lo), bias = (uint32_t)(15 - P.lo);
+        const uint32_t bias16 = (uint32_t)(15 - P.lo) << 16, lim16 = (uint32_t)(P.hi - P.lo + 1) << 16;
+        bool ok = true;
+        int gb = 0;
+        for (int e = e0; e < e1 && ok; ++e) {
+        const int f = item_frame(e), x0 = item_strip(e) * SW;
+        dbg_on = dbg_cta && e - e0 == P.dbg_item;
         const int nvalid = min(32, P.W - x0 - 32 * half);       // columns of this half strip inside the image
         const uint32_t colmask = nvalid >= 32 ? ~0u : nvalid > 0 ? ((1u << nvalid) - 1u) : 0u;
         const int wx = (x0 >> 5) + half;
         uint32_t count = 0;
-        bool ok = true;
-        for (int b = 0; b < NB && ok; ++b) {
-            ok = mbar_wait(bar(BAR_D2_FULL), b & 1, abort_flag);
+        for (int b = 0; b < NB && ok; ++b, ++gb) {
+            ok = mbar_wait(bar(BAR_D2_FULL), (uint32_t)gb & 1u, abort_flag);
             if (!ok) break;
             tc_fence_after();
             uint32_t bits = 0;
@@ -422,13 +487,18 @@ blur_area_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
                 tmem_ld16(lane_addr + 192u + 16u * g, lS);
                 tmem_ld_wait();
                 if (g == 1) { tc_fence_before(); mbar_arrive(bar(BAR_D2_EMPTY)); }      // this thread's part of D2 is in registers
+                uint32_t bitsg = 0;
+                // uint8(b_large - b_small + 15) (MD:128) only needs the blurs mod 256 = byte 2 of u = 256 hi + lo; subtracting the
+                // small blur with its low half cleared leaves the difference in byte 2 (no borrow from below), the bias is added
+                // in place, and `in range` (MD:129) becomes the sign of (byte 2) - (span + 1), shifted into the row word
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int uL = (int)hL[i] * 256 + (int)lL[i];
-                    const int uS = (int)hS[i] * 256 + (int)lS[i];
-                    const uint32_t d = ((uint32_t)((uL >> 16) - (uS >> 16)) + bias) & 255u;       // uint8 wrap (MD:128), inRange (MD:129)
-                    bits |= (uint32_t)(d <= span) << (16 * g + i);
+                for (int i = 15; i >= 0; --i) {
+                    const uint32_t uL = (uint32_t)((int)hL[i] * 256 + (int)lL[i]);
+                    const uint32_t uS = (uint32_t)((int)hS[i] * 256 + (int)lS[i]);
+                    const uint32_t x = (uL - (uS & 0xffff0000u) + bias16) & 0x00ff0000u;         // d << 16
+                    bitsg = __funnelshift_l(x - lim16, bitsg, 1);                                 // bit 31 of (d - span - 1) << 16: d <= span
                 }
+                bits |= (bitsg & 0xffffu) << (16 * g);
             }
             if (tid == 256) TC_DBG(90 + b);
             const int y = BLK * b + r;
@@ -441,10 +511,12 @@ blur_area_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
         if (lane == 0 && count) atomicAdd(P.area_count + f, count);              // mean of area_mask for the NCC (MD:153)
+        }
     }
 
     tc_fence_before();
     __syncthreads();
+    dbg_on = dbg_cta;
     if (tid == 0) TC_DBG(2);
     if (tid == 0 && *abort_flag) atomicOr(P.status, VBS_DEV_TMA_TIMEOUT);
     if (warp == 2) {
@@ -553,6 +625,15 @@ cudaError_t vbs_launch_blur_tc(vbs_ctx *ctx, const uint8_t *frames, int batch, i
     P.nchunks = (H - 1 + R) / CHR + 2;                           // slots for virtual rows [-64, H + radius)
     P.nblocks = (H + BLK - 1) / BLK;
     P.radius = R;
+    // persistent CTAs, one per SM, over strip-major items (a CTA changes its operator matrix at most a few times); neighbouring
+    // strips of a frame are still in flight at about the same time, so their halo columns meet in L2.  VBS_TC_PERSIST=0: one
+    // CTA per item, frame-major.
+    const char *pe = getenv("VBS_TC_PERSIST");
+    const bool persist = !(pe && pe[0] == '0');
+    P.batch = batch; P.nstrips = nstrips; P.total = nstrips * batch;
+    P.strip_major = persist ? 1 : 0;
+    const int grid = persist ? (P.total < ctx->sm_count ? P.total : ctx->sm_count) : P.total;
+    P.dbg_item = (P.total / grid) > 1 ? 1 : 0;
     P.area_bits = ctx->area_bits; P.area_count = ctx->area_count; P.status = ctx->d_status;
     P.dbg = nullptr;
     static long long *dbg_buf = nullptr;
@@ -563,19 +644,19 @@ cudaError_t vbs_launch_blur_tc(vbs_ctx *ctx, const uint8_t *frames, int batch, i
     }
     auto kern = ctx->big ? blur_area_tc_kernel<50, 19> : blur_area_tc_kernel<17, 10>;
     if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES)) != cudaSuccess) return e;
-    kern<<<dim3(nstrips, batch), NTHREADS, SMEM_BYTES, ctx->stream>>>(m_img, m_imgh, m_a1, m_a1h, m_a2, m_a2h, P);
+    kern<<<dim3(grid), NTHREADS, SMEM_BYTES, ctx->stream>>>(m_img, m_imgh, m_a1, m_a1h, m_a2, m_a2h, P);
     ctx->launches += 1;
     ctx->tc_launches += 1;
-    if (P.dbg) {                                                 // developer aid: print the timeline of CTA (5, 3) relative to its start
+    if (P.dbg) {                                                 // developer aid: print the timeline of one item of CTA 5 relative to the CTA's start
         long long h[256];
         cudaStreamSynchronize(ctx->stream);
         cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
         fprintf(stderr, "tc timeline (cycles after CTA start): setup %lld end %lld\n", h[1] - h[0], h[2] - h[0]);
-        const char *names[5] = {"tma", "p1", "e1ld", "e1", "p2/e2"};
-        const int base[4] = {120, 10, 150, 60};
+        const char *names[6] = {"tma", "p1", "e1ld", "slot", "stored", "e1"};
+        const int base[6] = {120, 10, 150, 170, 190, 60};
         for (int i = 0; i < P.nreal; ++i) {
             fprintf(stderr, "  chunk %2d:", i);
-            for (int k = 0; k < 4; ++k) fprintf(stderr, " %s %6lld", names[k], h[base[k] + i] ? h[base[k] + i] - h[0] : -1);
+            for (int k = 0; k < 6; ++k) fprintf(stderr, " %s %6lld", names[k], h[base[k] + i] ? h[base[k] + i] - h[0] : -1);
             fprintf(stderr, "\n");
         }
         for (int b = 0; b < P.nblocks; ++b) fprintf(stderr, "  block %2d: p2 %6lld e2 %6lld\n", b, h[40 + b] - h[0], h[90 + b] - h[0]);
