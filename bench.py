@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--overlap", action="store_true", help="two-stream chunk pipelining for device-resident batches (default off)")
     ap.add_argument("--undistort", action="store_true", help="side measurement: lens correction (MD:93-109) active on the CUDA arm; not the headline workload")
     ap.add_argument("--no-tc", action="store_true", help="skip the opt-in tensor-core blur arm (reported beside the default arm as `tc_blur`)")
+    ap.add_argument("--no-balance", action="store_true", help="N > 1: skip the e2e mode that splits the global batch by measured host-to-device link rates")
     ap.add_argument("--host-chunk", type=int, default=0, help="frames per chunk of the host path copy/compute overlap (0 = library default)")
     return ap.parse_args()
 
@@ -594,6 +595,77 @@ def main():
         chunk = args.host_chunk or 64
         modes = {"whole_batch": timed(0), f"chunked_{chunk}": timed(chunk)}
         pipe.set_host_chunk(args.host_chunk)
+
+        # N > 1: the host feeds the GPUs at different rates when every rank copies at once (8 ranks on this pool's boxes:
+        # 23 .. 36 GB/s per link, tools/h2d_concurrent.py), and with an equal split the slowest link sets the step time.
+        # Balanced split: the same global batch (world x B frames per step) is cut in proportion to the link rates
+        # measured here, each rank submits its share through the same API, the records are gathered (padded to the
+        # largest share) and land on rank 0's host as before.
+        balance = None
+        if world > 1 and not args.no_balance:
+            cap = (B * 3 // 2 + 7) // 8 * 8
+            probe = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            probe.copy_(pin, non_blocking=True)
+            barrier()
+            ev0.record(stream)
+            for _ in range(3):
+                probe.copy_(pin, non_blocking=True)
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            bw = torch.tensor([3 * pin.numel() / (ev0.elapsed_time(ev1) * 1e-3) / 1e9], device=dev, dtype=torch.float64)
+            bws = [torch.empty_like(bw) for _ in range(world)]
+            dist.all_gather(bws, bw)
+            bws = [float(x.item()) for x in bws]
+            del probe
+            share = [min(cap, max(8, int(round(world * B * x / sum(bws) / 8)) * 8)) for x in bws]
+            i = 0
+            while sum(share) != world * B and i < 64 * world:        # hand the rounding remainder out in steps of 8, fastest links first
+                order = sorted(range(world), key=lambda r: -bws[r])
+                r = order[i % world]
+                d = 8 if sum(share) < world * B else -8
+                if 8 <= share[r] + d <= cap:
+                    share[r] += d
+                i += 1
+            if sum(share) == world * B:
+                nb = share[rank]
+                cap = max(share)                              # rows every rank contributes to the gather (NCCL wants equal blocks)
+                reps_b = (cap + len(frames_u) - 1) // len(frames_u)
+                pin_b = torch.from_numpy(np.ascontiguousarray(np.tile(frames_u, (reps_b, 1, 1))[:cap])).pin_memory()
+                pipe_b, _, _, _ = setup_pipe(args, frames_u, H, W, rows, cols, local, cap)
+                bouts = [pipe_b.alloc_outputs(cap, True, compact=True) for _ in range(2)]
+                if rank == 0:
+                    hgb = {k: torch.empty((world * v.shape[0],) + tuple(v.shape[1:]), dtype=v.dtype).pin_memory() for k, v in bouts[0][0].items() if k in REC}
+
+                def land_b(s):
+                    g = gather(bouts[s & 1][0])
+                    if rank == 0:
+                        for k, v in g.items():
+                            hgb[k].copy_(v, non_blocking=True)
+
+                def run_b(nsteps, s0):
+                    pipe_b.submit_host_ptr(pin_b.data_ptr(), nb, H * W, W, s0 * nb, bouts[s0 & 1])
+                    for s in range(s0 + 1, s0 + nsteps):
+                        pipe_b.submit_host_ptr(pin_b.data_ptr(), nb, H * W, W, s * nb, bouts[s & 1])
+                        pipe_b.wait_host()
+                        land_b(s - 1)
+                    pipe_b.wait_host()
+                    land_b(s0 + nsteps - 1)
+                    torch.cuda.current_stream().synchronize()
+
+                pipe_b.reset_sequence()
+                pipe_b.set_host_chunk(chunk)
+                run_b(2, 0)
+                barrier()
+                t0 = time.perf_counter()
+                run_b(args.steps, 2)
+                torch.cuda.synchronize()
+                d = time.perf_counter() - t0
+                tt = torch.tensor([d], device=dev, dtype=torch.float64)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                modes[f"balanced_chunked_{chunk}"] = world * B * args.steps / float(tt.item())
+                balance = {"h2d_gbs_per_rank": [round(x, 1) for x in bws], "frames_per_rank": share, "padded_to": cap}
+                pipe_b.close()
         # the synchronous call (one batch in, results out, nothing in flight afterwards) for comparison
         souts = pipe.alloc_outputs(B, False, compact=True)
         for s in range(2):
@@ -611,10 +683,12 @@ def main():
             best = max(modes, key=modes.get)
             d2h = sum(int(a.numel() * a.element_size()) if hasattr(a, "numel") else a.nbytes for a in houts[0][0].values())
             line["e2e"] = {"value": modes[best], "unit": UNIT, "h2d_bytes_per_step": int(B * H * W), "d2h_bytes_per_step": int(d2h),
-                           "mode": best, "modes": modes,
+                           "mode": best, "modes": modes, "balance": balance,
                            "api": "MarkerPipeline.submit_host_ptr / wait_host -> vbs_submit_host / vbs_wait_host (pinned host frames in, compact record "
                                   "block out, two batches in flight); the copy schedule (whole batch vs chunks, vbs_set_host_chunk) is picked by "
-                                  "measuring both" + ("; records gathered to rank 0 over NCCL and copied to its pinned host memory every step" if on_dev else ""),
+                                  "measuring both" + ("; records gathered to rank 0 over NCCL and copied to its pinned host memory every step; `balanced_*`: the "
+                                                      "global batch of world x B frames is split across the ranks in proportion to their measured "
+                                                      "host-to-device rates instead of equally" if on_dev else ""),
                            "synchronous_call_value": world * B / dts,
                            "synchronous_api": "MarkerPipeline.process_host_ptr -> vbs_process_host (chunked copy/compute overlap inside one call, per-rank host results)"}
 
