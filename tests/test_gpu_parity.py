@@ -867,6 +867,35 @@ def test_tensor_core_blur_equals_cv2_and_default_kernel(name):
         assert len(bad) == 0, (name, "tc" if tc else "idp", len(bad), bad[:8].tolist(), bad[-4:].tolist())
 
 
+@pytest.mark.parametrize("h,w,n,persist", [(300, 368, 130, "1"), (100, 256, 200, "1"), (563, 645, 40, "1"), (300, 368, 130, "0")])
+def test_tensor_core_blur_persistent_ctas_many_items(monkeypatch, h, w, n, persist):
+    """More (frame, strip) items than SMs: every persistent CTA runs several items back to back (running stage / ring /
+    block counters, operator-matrix reload when its strip changes; 100 rows = fewer chunk slots per item than the ring
+    has).  All frames equal the default kernel, three of them cv2.  persist = "0": one CTA per item (VBS_TC_PERSIST=0)."""
+    import torch
+    rng = np.random.default_rng(h * 1000 + w)
+    frames = rng.integers(0, 256, (n, h, w), dtype=np.uint8)
+    frames[::3] = np.clip(rng.normal(120, 60, (len(frames[::3]), h, w)), 0, 255).astype(np.uint8)
+    frames[1::5, : h // 2] = 255
+    Wp = (w + 15) // 16 * 16
+    buf = torch.zeros((n, h, Wp), dtype=torch.uint8, device="cuda")
+    buf[:, :, :w] = torch_cuda(frames)
+    monkeypatch.setenv("VBS_TC_PERSIST", persist)
+    got = {}
+    for tc in (0, 1):
+        with pipeline.MarkerPipeline(h, w, 1, max_batch=n, max_markers=4096, max_refs=1) as pipe:
+            pipe.set_blur_tc(bool(tc))
+            pipe._follow_torch_stream()
+            capi.check(pipe._ctx, capi.lib.vbs_find_markers(pipe._ctx, buf.data_ptr(), n, h * Wp, Wp))
+            pipe.sync()
+            got[tc] = pipe.debug_stage(capi.STAGE_AREA_MASK, n).cpu().numpy()
+            assert (pipe.tc_launches >= 1) == bool(tc)
+    bad = np.argwhere(got[0] != got[1])
+    assert len(bad) == 0, (len(bad), bad[:8].tolist(), bad[-4:].tolist())
+    for f in (0, n // 2, n - 1):
+        assert np.array_equal(got[1][f], cv2_area_mask(frames[f])), f
+
+
 def test_tensor_core_blur_whole_pipeline_1080p(monkeypatch):
     """VBS_BLUR_TC=1 end to end at the headline geometry: every table equals the default path's."""
     name, U = "1080p_20x20", 6
