@@ -524,6 +524,40 @@ def test_async_host_api_equals_synchronous_calls():
         assert (sync_res[2]["pos_flags"] & 4).any()
 
 
+def test_chunked_async_batches_with_changing_chunk_size():
+    """Chunked submit_host with another chunk size per batch while the batch before is still in flight: chunk c of
+    the new batch covers another scratch range than chunk c of the old one, so the per-chunk-index events alone do
+    not order the reuse (enqueue_host_chunks waits for every live chunk when the size changes)."""
+    import torch
+    h, w, rows, cols = 560, 640, 6, 8
+    centres = synth.grid_layout(h, w, rows, cols, 60.0)
+    seq = synth.compression_sequence(h, w, centres, 11.0, 36, tilt=0.3, depth=1.0, seed0=710)
+    keys, xy = pu.grid_reference(port.find_markers_frame(seq[0]), cols)
+    K, D, R, T = synth.synthetic_camera()
+    pin = torch.from_numpy(seq).pin_memory()
+    B = 12
+    with pipeline.MarkerPipeline(h, w, 1, max_batch=B, max_markers=256, max_refs=len(keys)) as pipe:
+        pipe.set_reference([k[0] for k in keys], [k[1] for k in keys], xy[:, 0], xy[:, 1], 20.0)
+        pipe.set_camera(K, D, R, T, 2.0, 5.0, 50.0, warmup_frames=0)
+        sync_res = []
+        for s in range(3):
+            o = pipe.alloc_outputs(B, False)
+            pipe.process_host_ptr(pin.data_ptr() + s * B * h * w, B, h * w, w, s * B, o)
+            sync_res.append({k: np.copy(v) for k, v in o[0].items()})
+        for rep in range(4):
+            pipe.reset_sequence()
+            outs = [pipe.alloc_outputs(B, False) for _ in range(3)]
+            for s, ch in enumerate((2, 5, 3)):
+                pipe.set_host_chunk(ch)
+                if s == 2:
+                    pipe.wait_host()
+                pipe.submit_host_ptr(pin.data_ptr() + s * B * h * w, B, h * w, w, s * B, outs[s])
+            pipe.wait_host(); pipe.wait_host()
+            for s in range(3):
+                for k, v in sync_res[s].items():
+                    assert np.array_equal(outs[s][0][k], v, equal_nan=True), (rep, s, k)
+
+
 # ---------------------------------------------------------------------------------------------
 # 10. BASELINE.json config 3: vertical / tilted compression sequences on the sensor's 65-marker ring
 #     layout -> tracking -> 3D displacement -> deviation against the vertical baseline -> plane tilt

@@ -657,6 +657,13 @@ int enqueue_host_chunks(vbs_ctx *ctx, const uint8_t *frames, int batch, int64_t 
     const size_t half = ctx->frames_bytes / 2;
     const int nchunks = (batch + CH - 1) / CH;
     if (ctx->profiling && (rc = prof_collect(ctx)) != VBS_OK) return rc;
+    if (CH != ctx->last_chunk_frames) {
+        // another chunk size than the batch before: chunk c no longer covers the scratch range chunk c covered, so
+        // the per-index events below do not order the reuse - wait for every chunk that may still be in stage B
+        for (int c = 0; c < VBS_MAX_CHUNKS; ++c)
+            if (ctx->bchunk_live[c]) { VBS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_bchunk[c], 0)); ctx->bchunk_live[c] = 0; }
+        ctx->last_chunk_frames = CH;
+    }
     // the copy stream runs one chunk ahead of stage A; stage B of the previous chunk runs beside stage A
     auto upload = [&](int c) -> int {
         const int off = c * CH, n = batch - off < CH ? batch - off : CH;

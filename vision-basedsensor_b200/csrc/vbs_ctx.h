@@ -58,6 +58,7 @@ struct vbs_ctx {
     // asynchronous host path: two whole-batch staging slots
     uint8_t *d_slots; cudaEvent_t ev_slot_in[2], ev_slot_free[2], ev_slot_done[2]; uint32_t *h_slot_status;
     int64_t submitted; int inflight; int slot_used[2];
+    int last_chunk_frames;                       // frames per chunk of the latest chunked batch (scratch ranges of chunk c depend on it)
     int64_t chunk_seq;                           // chunks uploaded so far (staging buffer = chunk_seq & 1, across calls)
     cudaEvent_t ev_bchunk[8]; int bchunk_live[8];    // end of stage B of chunk c of the latest chunked batch
     // bit images [B][H][WW]
