@@ -337,7 +337,7 @@ def stream_main(args, rank, world, local):
                                        f"(warm-up 100 frames, last-seen exchange across shards) -> plane tilt; one NCCL gather of the record blobs + tilt to rank 0, shard boundaries patched there, all in the timed region",
                            "batch_per_gpu": B, "frames": N, "l2_policy": "inputs larger than L2 (batch of frames = %.0f MB/GPU)" % (B * H * W / 1e6),
                            "parallelism": f"frame-sharded x{world}", "gathered_bytes": rec_bytes},
-                "roofline": {"bound": "hbm", "kernel": "blur_area_kernel<39,101> (gray -> DoG -> area mask)", "achieved": ach, "peak": peak, "unit": "GB/s",
+                "roofline": {"bound": "hbm", "kernel": "blur_area_cs_kernel<39,101> (gray -> DoG -> area mask)", "achieved": ach, "peak": peak, "unit": "GB/s",
                              "frac": ach / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": frames_per_launch * b_alg,
                              "kernel_ms": blur_ms, "note": "ALU-bound path, see DESIGN.md"},
                 "stage_ms_per_batch": {k: v / max(calls, 1) for k, v in stage.items()}, "gpu_launches": int(launches), "clocks": clk.summary(),
@@ -483,11 +483,11 @@ def main():
         if os.path.exists(tp):
             t = json.load(open(tp)).get(args.workload)
             if t and t.get("batch") == B:
-                traffic, traffic_tc = t.get("blur_area_kernel"), t.get("blur_area_tc_kernel")
+                traffic, traffic_tc = t.get("blur_area_cs_kernel"), t.get("blur_area_tc_kernel")
         line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8 (integer blur/labels) + f32/f64 (NCC, geometry)", "data": "synthetic", "config": config,
-                "roofline": {"bound": "hbm", "kernel": "blur_area_kernel<39,101> (gray -> DoG -> area mask)", "achieved": ach, "peak": peak,
+                "roofline": {"bound": "hbm", "kernel": "blur_area_cs_kernel<39,101> (gray -> DoG -> area mask)", "achieved": ach, "peak": peak,
                              "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": B * b_alg, "kernel_ms": blur_ms,
                              "whole_path_achieved": whole, "whole_path_frac": whole / peak,
@@ -495,15 +495,19 @@ def main():
                 "stage_ms_per_step": {k: v / max(calls, 1) for k, v in stage.items()},
                 "gpu_launches": int(launches), "clocks": clk.summary(), "markers_per_frame": found,
                 "checks": {"periodic_records": periodic, "ok": bool(all(periodic.values()) and found == (n_markers, n_markers))}}
-        # the binding roofline of the dominant kernel: integer-dot-product issue rate
+        # the binding roofline of the dominant kernel: instruction issue.  blur_area_cs_kernel spreads
+        # its work over the fma pipe (integer dot products) and the ALU pipe (column-sum adds); ncu: 4672 warp instructions
+        # per 8-row step of a 128-px strip, 148 steps per 135 output steps of a whole-height CTA at 1080p
         csum = line["clocks"]
         if H > 480 and csum.get("sm_mhz"):
-            idp_per_px = (284 + 544) / 8.0          # IDP.4A + IDP.2A per pixel of blur_area_kernel<39,101> (k_blur.cu)
+            winstr_per_px = 4672.0 / 1024.0 * (H / 8.0 + 13.0) / (H / 8.0)
             sms = torch.cuda.get_device_properties(local).multi_processor_count
-            rate = idp_per_px * B * H * W / (blur_ms * 1e-3 * sms * csum["sm_mhz"] * 1e6)
-            line["roofline"]["alu"] = {"pipe": "IDP.4A/IDP.2A (fma pipe, half rate)", "achieved": rate, "peak": 62.8, "unit": "lane-instr/clk/SM",
-                                       "frac": rate / 62.8, "peak_source": "measured, profiles/r01_ubench_pipe_rates.txt",
-                                       "instr_per_pixel": idp_per_px}
+            rate = winstr_per_px * B * H * W / (blur_ms * 1e-3 * sms * csum["sm_mhz"] * 1e6)
+            line["roofline"]["alu"] = {"pipe": "instruction issue (IDP.4A/IDP.2A on the fma pipe, three-input adds on the ALU pipe)", "achieved": rate,
+                                       "peak": 4.0, "unit": "warp-instr/clk/SM", "frac": rate / 4.0,
+                                       "peak_source": "4 schedulers x 1 instruction per clock; ncu profiles/r02_ncu_full_blur_cs_batch64.txt: issue active 73 %, "
+                                                      "fma pipe 72 % and ALU pipe 82 % of their half-rate peaks",
+                                       "instr_per_pixel": winstr_per_px}
 
     # ---- opt-in arm: the same step with the two blurs on the tensor cores (vbs_set_blur_tc).  The default
     #      arm above is the headline (north_star: no tensor cores); this one is reported beside it.

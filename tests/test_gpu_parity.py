@@ -525,33 +525,35 @@ def test_async_host_api_equals_synchronous_calls():
 
 
 def test_chunked_async_batches_with_changing_chunk_size():
-    """Chunked submit_host with another chunk size per batch while the batch before is still in flight: chunk c of
-    the new batch covers another scratch range than chunk c of the old one, so the per-chunk-index events alone do
-    not order the reuse (enqueue_host_chunks waits for every live chunk when the size changes)."""
+    """Chunked submit_host with batches of different sizes in flight: the chunk size follows the batch (at most 8 chunks
+    per batch), so chunk c of the new batch covers another scratch range than chunk c of the one before and the
+    per-chunk-index events alone do not order the reuse (enqueue_host_chunks waits for every live chunk when the size
+    changes)."""
     import torch
     h, w, rows, cols = 560, 640, 6, 8
+    sizes = (12, 24, 16)                                           # chunk sizes 2, 3, 2 with vbs_set_host_chunk(2)
     centres = synth.grid_layout(h, w, rows, cols, 60.0)
-    seq = synth.compression_sequence(h, w, centres, 11.0, 36, tilt=0.3, depth=1.0, seed0=710)
+    seq = synth.compression_sequence(h, w, centres, 11.0, sum(sizes), tilt=0.3, depth=1.0, seed0=710)
     keys, xy = pu.grid_reference(port.find_markers_frame(seq[0]), cols)
     K, D, R, T = synth.synthetic_camera()
     pin = torch.from_numpy(seq).pin_memory()
-    B = 12
-    with pipeline.MarkerPipeline(h, w, 1, max_batch=B, max_markers=256, max_refs=len(keys)) as pipe:
+    starts = np.concatenate([[0], np.cumsum(sizes)[:-1]])
+    with pipeline.MarkerPipeline(h, w, 1, max_batch=max(sizes), max_markers=256, max_refs=len(keys)) as pipe:
         pipe.set_reference([k[0] for k in keys], [k[1] for k in keys], xy[:, 0], xy[:, 1], 20.0)
         pipe.set_camera(K, D, R, T, 2.0, 5.0, 50.0, warmup_frames=0)
+        pipe.set_host_chunk(2)
         sync_res = []
-        for s in range(3):
-            o = pipe.alloc_outputs(B, False)
-            pipe.process_host_ptr(pin.data_ptr() + s * B * h * w, B, h * w, w, s * B, o)
+        for n, f0 in zip(sizes, starts):
+            o = pipe.alloc_outputs(n, False)
+            pipe.process_host_ptr(pin.data_ptr() + int(f0) * h * w, n, h * w, w, int(f0), o)
             sync_res.append({k: np.copy(v) for k, v in o[0].items()})
         for rep in range(4):
             pipe.reset_sequence()
-            outs = [pipe.alloc_outputs(B, False) for _ in range(3)]
-            for s, ch in enumerate((2, 5, 3)):
-                pipe.set_host_chunk(ch)
+            outs = [pipe.alloc_outputs(n, False) for n in sizes]
+            for s, (n, f0) in enumerate(zip(sizes, starts)):
                 if s == 2:
                     pipe.wait_host()
-                pipe.submit_host_ptr(pin.data_ptr() + s * B * h * w, B, h * w, w, s * B, outs[s])
+                pipe.submit_host_ptr(pin.data_ptr() + int(f0) * h * w, n, h * w, w, int(f0), outs[s])
             pipe.wait_host(); pipe.wait_host()
             for s in range(3):
                 for k, v in sync_res[s].items():
@@ -951,6 +953,60 @@ def test_tensor_core_blur_whole_pipeline_1080p(monkeypatch):
     assert np.array_equal(a.n_markers, b.n_markers) and (a.n_markers == rows * cols).all()
     assert np.array_equal(a.marker_xy[:, : rows * cols], b.marker_xy[:, : rows * cols])
     assert np.array_equal(a.marker_axes[:, : rows * cols], b.marker_axes[:, : rows * cols])
+
+
+# ---------------------------------------------------------------------------------------------
+# 16b. column-sum form of the 101-tap vertical pass (k_blur.cu: blur_area_cs_kernel, the default for gray frames of
+#      the > 480 branch) against cv2 and the all-dot-product kernel (VBS_BLUR_VARIANT=0): the tensor-core blur's cases
+#      where that branch applies, TMA and generic loader, padded and unaligned pitches, more items than resident
+#      CTAs (whole-height CTAs + row segments)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["markers_560x640", "ragged_563x645", "noise_520x704", "narrow_700x130"])
+def test_column_sum_blur_equals_cv2(monkeypatch, name):
+    import torch
+    frames = tc_blur_cases()[name]
+    B, H, W = frames.shape
+    want = np.stack([cv2_area_mask(f) for f in frames])
+    monkeypatch.delenv("VBS_BLUR_VARIANT", raising=False)
+    for pitch, no_tma in (((W + 15) // 16 * 16, "0"), (W + 3, "0"), ((W + 15) // 16 * 16, "1")):     # TMA where a tile is interior / generic loader
+        monkeypatch.setenv("VBS_NO_TMA", no_tma)
+        buf = torch.zeros((B, H, pitch), dtype=torch.uint8, device="cuda")
+        buf[:, :, :W] = torch_cuda(frames)
+        with pipeline.MarkerPipeline(H, W, 1, max_batch=B, max_markers=4096, max_refs=1) as pipe:
+            pipe._follow_torch_stream()
+            capi.check(pipe._ctx, capi.lib.vbs_find_markers(pipe._ctx, buf.data_ptr(), B, H * pitch, pitch))
+            pipe.sync()
+            got = pipe.debug_stage(capi.STAGE_AREA_MASK, B).cpu().numpy()
+        bad = np.argwhere(got != want)
+        assert len(bad) == 0, (name, pitch, no_tma, len(bad), bad[:8].tolist(), bad[-4:].tolist())
+
+
+@pytest.mark.parametrize("h,w,n", [(563, 645, 160), (1080, 1920, 64)])
+def test_column_sum_blur_many_items_equals_dot_product_kernel(monkeypatch, h, w, n):
+    """Grids of several waves: whole-height CTAs and row segments (VbsSegPlan with two resident CTAs per SM), segment
+    starts inside the image (the column sums start from zero at row ys - 50), frames of full-range noise and of markers."""
+    import torch
+    rng = np.random.default_rng(h + w + n)
+    frames = rng.integers(0, 256, (n, h, w), dtype=np.uint8)
+    frames[::3] = np.clip(rng.normal(120, 60, (len(frames[::3]), h, w)), 0, 255).astype(np.uint8)
+    frames[1::5, : h // 2] = 255
+    if (h, w) == (1080, 1920):
+        frames[2::4] = synth.workload_frames("1080p_20x20", len(frames[2::4]), seed0=5)
+    Wp = (w + 15) // 16 * 16
+    buf = torch.zeros((n, h, Wp), dtype=torch.uint8, device="cuda")
+    buf[:, :, :w] = torch_cuda(frames)
+    got = {}
+    for v in ("0", "1"):
+        monkeypatch.setenv("VBS_BLUR_VARIANT", v)
+        with pipeline.MarkerPipeline(h, w, 1, max_batch=n, max_markers=4096, max_refs=1) as pipe:
+            pipe._follow_torch_stream()
+            capi.check(pipe._ctx, capi.lib.vbs_find_markers(pipe._ctx, buf.data_ptr(), n, h * Wp, Wp))
+            pipe.sync()
+            got[v] = pipe.debug_stage(capi.STAGE_AREA_MASK, n).cpu().numpy()
+    bad = np.argwhere(got["0"] != got["1"])
+    assert len(bad) == 0, (len(bad), bad[:8].tolist(), bad[-4:].tolist())
+    for f in (0, 2, n - 1):
+        assert np.array_equal(got["1"][f], cv2_area_mask(frames[f])), f
 
 
 # ---------------------------------------------------------------------------------------------

@@ -352,6 +352,319 @@ blur_area_kernel(const __grid_constant__ CUtensorMap tmap, int use_tma, const ui
     if (lane == 0 && count) atomicAdd(area_count + f, count);
 }
 
+// ---- K1, column-sum form of the large vertical pass (default for gray frames of the > 480 branch) --------------
+// The 8.8 fixed-point taps of the 101-tap kernel are small integers (0..6) that change by at most one from tap to tap,
+// so with the running column sum P[q] = sum_{q' <= q} h[q'] of the horizontal results
+//     sum_j k[j] h[q + j] = sum_t (k[t] - k[t+1]) P[q + t]
+// has 56 terms of weight +-1 instead of 101 multiply-adds: per 8 output rows of a column 237 three-input integer adds
+// (ALU pipe) instead of 404 IDP.2A (fma pipe, half rate).  All sums are taken mod 2^32 and the true value is below
+// 2^24: exact.  The column sums are private to the thread that owns the column.  The ring holds 32-bit sums (56 KB
+// instead of 28 KB of u16 pairs), so two CTAs are resident per SM instead of four, and each pipe gets its own warps:
+//   warps 0-3  (warp = row pair, lane = pixel quad) load the tiles and run both horizontal passes of step i (IDP.4A),
+//   warps 4-7  (thread = column) take step i - 1: its 8 rows join the column sums, then the large vertical pass as adds;
+//              the eight sums of each column cross to the last role through shared memory,
+//   warps 8-11 (thread = column) take step i - 2: small vertical pass (IDP.2A), rounding, DoG, inRange, ballot.
+// One CTA barrier per step; the large horizontal results cross through a double-buffered stage, the small ring has two
+// slots more than the last role reads so the producers' next group never lands on a live one.
+// Measured (256 1080p frames): 3.83 -> 3.43 ms.  The kernel executes about as many instructions as blur_area_kernel
+// (5.5 vs 5.7 warp instructions per pixel: the adds, the wider ring loads and the hand-over replace the dot products
+// one for one) but spreads them over both pipes; it issues on 73 % of the cycles (ncu: profiles/r02_ncu_full_blur_cs_batch64.txt),
+// blur_area_kernel on 65 % with the fma pipe at 85 % of its IDP rate.  Tried on the way: the same arithmetic in the
+// four-warp CTA of blur_area_kernel with the adds written between the dot products (ptxas schedules them after the dot
+// products anyway: 4.08 ms), two roles instead of three (3.53 ms), and the small horizontal pass moved from the first to
+// the third role to even out the roles (3.44 against 3.46 ms: the sum of the work, not its split, sets the pace).
+template <int KL> struct DTaps {                                    // D[t] = k[t] - k[t+1], t = -1 .. KL-1
+    static __host__ __device__ constexpr int at(int t) { return Taps<KL>::at(t) - Taps<KL>::at(t + 1); }
+    static __host__ __device__ constexpr bool unit() {
+        for (int t = -1; t < KL; ++t)
+            if (at(t) > 1 || at(t) < -1) return false;
+        return at(-1) == 0;
+    }
+    // e-index (0..7) of the n-th non-zero term of ring group g for output row r, -1 when there is none
+    static __host__ __device__ constexpr int term(int g, int r, int n) {
+        int c = 0;
+        for (int e = 0; e < RB; ++e)
+            if (at(RB * g + e - r) != 0) {
+                if (c == n) return e;
+                ++c;
+            }
+        return -1;
+    }
+};
+
+// acc[r] += sum_e D[8g + e - r] * p[e] for the 8 output rows, two terms per add
+template <int KL, int g>
+__device__ __forceinline__ void psum_group(uint32_t (&acc)[RB], const uint32_t (&p)[RB]) {
+    static_for<0, RB>([&](auto R_) {
+        constexpr int r = decltype(R_)::value;
+        static_for<0, RB / 2>([&](auto N_) {
+            constexpr int n = decltype(N_)::value;
+            constexpr int e1 = DTaps<KL>::term(g, r, 2 * n), e2 = DTaps<KL>::term(g, r, 2 * n + 1);
+            if constexpr (e1 >= 0 && e2 >= 0) {
+                constexpr int s1 = DTaps<KL>::at(RB * g + e1 - r), s2 = DTaps<KL>::at(RB * g + e2 - r);
+                if constexpr (s1 > 0 && s2 > 0) acc[r] = acc[r] + p[e1] + p[e2];
+                else if constexpr (s1 > 0 && s2 < 0) acc[r] = acc[r] + p[e1] - p[e2];
+                else if constexpr (s1 < 0 && s2 > 0) acc[r] = acc[r] - p[e1] + p[e2];
+                else acc[r] = acc[r] - p[e1] - p[e2];
+            } else if constexpr (e1 >= 0) {
+                constexpr int s1 = DTaps<KL>::at(RB * g + e1 - r);
+                if constexpr (s1 > 0) acc[r] += p[e1];
+                else acc[r] -= p[e1];
+            }
+        });
+    });
+}
+
+template <int KS, int KL> struct GeoCS : Geo<KS, KL> {
+    using G = Geo<KS, KL>;
+    static constexpr int NT = 2;                                                 // tile buffers
+    static constexpr int NGSW = G::NGS + 2;
+    static constexpr int OFFSLOT = (NGSW - (G::LEAD - G::GS0) % NGSW) % NGSW;    // slot of step m - LEAD + GS0, relative to m % NGSW
+    static constexpr size_t SMEM = NT * (size_t)G::TILE_BYTES + 128 + 2 * (size_t)TW * 16 + 4 * (size_t)TW * 16 + (size_t)G::NGL * 2 * TW * 16 + (size_t)NGSW * TW * 16;
+};
+
+__device__ __forceinline__ void role_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 producer warps only
+
+template <int KS, int KL>
+__global__ void __launch_bounds__(3 * TW, 2)
+blur_area_cs_kernel(const __grid_constant__ CUtensorMap tmap, int use_tma, const uint8_t *__restrict__ frames, int64_t frame_stride,
+                    int64_t row_pitch, int H, int W, int WW, VbsSegPlan plan, int strips, int lo, int hi, uint32_t *__restrict__ area_bits,
+                    uint32_t *__restrict__ area_count, uint32_t *__restrict__ status) {
+    using G = GeoCS<KS, KL>;
+    static_assert(DTaps<KL>::unit(), "the column-sum vertical pass needs taps that change by at most one and start at zero");
+    static_assert(G::PL == G::RL, "ring row q of output row r and tap j is q = r + j");
+    static_assert(TW == 128, "bar.sync 1, 128 names the producer warps");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint32_t *tiles = reinterpret_cast<uint32_t *>(smem_raw);                 // [NT][RB][TSTRIDE] staged input rows
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + G::NT * G::TILE_BYTES);   // [NT] TMA completion barriers
+    uint4 *stage = reinterpret_cast<uint4 *>(smem_raw + G::NT * G::TILE_BYTES + 128);  // [2][TW] large horizontal results of a step
+    uint4 *sumsL = stage + 2 * TW;                                            // [2][2][TW] large vertical sums of a step, rows 0-3 / 4-7
+    uint4 *ringP = sumsL + 4 * TW;                                            // [NGL][2][TW] column sums, rows 0-3 / 4-7 of a group
+    uint4 *ringS = ringP + G::NGL * 2 * TW;                                   // [NGSW][TW]
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool producer = warp < 4, summer = warp < 8;
+    const int tid = threadIdx.x & (TW - 1);                                   // index within the role
+    int item = blockIdx.x, ys = 0, ye = H;
+    if (item >= plan.n_full) {
+        const int j = item - plan.n_full, q = j / plan.vsegs;
+        item = plan.n_full + q;
+        ys = (j - q * plan.vsegs) * plan.seg_rows;
+        ye = min(H, ys + plan.seg_rows);
+    }
+    const int f = item / strips;
+    const int x0 = (item - f * strips) * TW;
+    const int nk = (ye - ys + RB - 1) / RB;
+    const int nsteps = nk + G::LEAD;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int b = 0; b < G::NT; ++b) mbar_init(&mbar[b], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (producer) {
+        // =========================== producers: tiles + horizontal passes ===========================
+        const uint8_t *fbase = frames + (size_t)f * frame_stride;
+        const bool aligned4 = ((reinterpret_cast<uintptr_t>(fbase) | (uintptr_t)row_pitch) & 3) == 0;
+        uint32_t pre[G::PRE];
+        int lrow[G::PRE], lcol[G::PRE], lslot[G::PRE];
+        bool lfast[G::PRE];
+#pragma unroll
+        for (int i = 0; i < G::PRE; ++i) {
+            const int wi = tid + i * TW;
+            lrow[i] = wi / G::TWORDS;
+            lcol[i] = x0 - G::HL + 4 * (wi - lrow[i] * G::TWORDS);
+            lslot[i] = lrow[i] * G::TSTRIDE + G::OFFW + (wi - lrow[i] * G::TWORDS);
+            lfast[i] = aligned4 && lcol[i] >= 0 && lcol[i] + 3 < W;
+        }
+        auto fetch = [&](int m) {
+            const int p0 = ys - G::PL + RB * m;
+#pragma unroll
+            for (int i = 0; i < G::PRE; ++i) {
+                if (tid + i * TW < RB * G::TWORDS) {
+                    const int p = p0 + lrow[i];
+                    const int pr = (p >= 0 && p < H) ? p : reflect101(p, H);
+                    const uint8_t *row = fbase + (size_t)pr * row_pitch;
+                    if (lfast[i]) pre[i] = __ldg(reinterpret_cast<const uint32_t *>(row + lcol[i]));
+                    else pre[i] = load_word<false>(row, lcol[i], W, false);
+                }
+            }
+        };
+        auto stash = [&](uint32_t *tile) {
+#pragma unroll
+            for (int i = 0; i < G::PRE; ++i)
+                if (tid + i * TW < RB * G::TWORDS) tile[lslot[i]] = pre[i];
+        };
+        const bool x_inside = use_tma && x0 - G::HL >= 0 && x0 - G::HL + G::TWORDS * 4 <= W;
+        auto by_tma = [&](int m) -> bool {
+            const int p0 = ys - G::PL + RB * m;
+            return x_inside && p0 >= 0 && p0 + RB <= H;
+        };
+        uint32_t phase = 0;
+        auto issue = [&](int m) {
+            if (by_tma(m)) {
+                if (tid == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_expect_tx(&mbar[m % G::NT], G::TILE_BYTES);
+                    tma_load_tile(tiles + (m % G::NT) * (G::TILE_BYTES / 4), &tmap, x0 - G::HLA, ys - G::PL + RB * m, f, &mbar[m % G::NT]);
+                }
+            } else {
+                fetch(m);
+            }
+        };
+        issue(0);
+        int gs = 0;                                          // small-ring slot of step i: i % NGSW
+        for (int i = 0; i <= nsteps + 1; ++i) {
+            if (i < nsteps) {
+                const int tb = i % G::NT;
+                uint32_t *tile = tiles + tb * (G::TILE_BYTES / 4);
+                const bool tma_now = by_tma(i);
+                if (!tma_now) stash(tile);
+                role_barrier();                              // tile visible to the four producer warps
+                if (tma_now) {
+                    if (!mbar_wait(&mbar[tb], (phase >> tb) & 1u) && tid == 0) atomicOr(status, VBS_DEV_TMA_TIMEOUT);
+                    phase ^= 1u << tb;
+                }
+                if (i + 1 < nsteps) issue(i + 1);            // its buffer was last read an iteration ago, before the CTA barrier
+                uint32_t outL[4], outS[4];
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const uint32_t *trow = tile + (2 * warp + half) * G::TSTRIDE + G::OFFW + lane;
+                    uint32_t x[G::NW];
+#pragma unroll
+                    for (int w = 0; w < G::NW; ++w) x[w] = trow[w];
+                    uint32_t aL[4] = {0, 0, 0, 0}, aS[4] = {0, 0, 0, 0};
+                    static_for<0, 4>([&](auto S_) {
+                        constexpr int s = decltype(S_)::value;
+                        static_for<0, G::NW>([&](auto W_) {
+                            constexpr int w = decltype(W_)::value;
+                            constexpr uint32_t wl = pack4<KL>(4 * w - (G::HL - G::RL) - s);
+                            constexpr uint32_t ws = pack4<KS>(4 * w - (G::HL - G::RS) - s);
+                            if constexpr (wl != 0) aL[s] = __dp4a(x[w], wl, aL[s]);
+                            if constexpr (ws != 0) aS[s] = __dp4a(x[w], ws, aS[s]);
+                        });
+                    });
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        if (half == 0) { outL[s] = aL[s]; outS[s] = aS[s]; }
+                        else { outL[s] |= aL[s] << 16; outS[s] |= aS[s] << 16; }
+                    }
+                }
+                uint32_t *dstL = reinterpret_cast<uint32_t *>(stage + (i & 1) * TW) + warp;
+                uint32_t *dstS = reinterpret_cast<uint32_t *>(ringS + gs * TW) + warp;
+                const int swz = (lane >> 1) & 3;
+#pragma unroll
+                for (int sft = 0; sft < 4; ++sft) {
+                    const int c = (4 * lane + sft) ^ swz;
+                    dstL[c * 4] = outL[sft];
+                    dstS[c * 4] = outS[sft];
+                }
+                if (++gs == G::NGSW) gs = 0;
+            }
+            __syncthreads();
+        }
+    } else if (summer) {
+        // =========================== column sums + large vertical pass (step i - 1) ===========================
+        uint32_t prun = 0;                                   // column sum up to the last row of the previous step
+        int gl = 0;                                          // slot of step m: m % NGL
+        const int vcol = tid ^ ((tid >> 3) & 3);             // swizzle of the producers' stores
+        __syncthreads();                                     // iteration 0: nothing to consume yet
+        for (int m = 0; m < nsteps; ++m) {
+            uint32_t pn[RB];
+            {
+                const uint4 v = stage[(m & 1) * TW + vcol];
+                pn[0] = prun + (v.x & 0xffffu);  pn[1] = pn[0] + (v.x >> 16);
+                pn[2] = pn[1] + (v.y & 0xffffu); pn[3] = pn[2] + (v.y >> 16);
+                pn[4] = pn[3] + (v.z & 0xffffu); pn[5] = pn[4] + (v.z >> 16);
+                pn[6] = pn[5] + (v.w & 0xffffu); pn[7] = pn[6] + (v.w >> 16);
+                prun = pn[7];
+                uint4 *dst = ringP + gl * 2 * TW + tid;
+                dst[0] = make_uint4(pn[0], pn[1], pn[2], pn[3]);
+                dst[TW] = make_uint4(pn[4], pn[5], pn[6], pn[7]);
+            }
+            if (m >= G::LEAD) {
+                uint32_t accL[RB];
+#pragma unroll
+                for (int r = 0; r < RB; ++r) accL[r] = 32768u;
+                // oldest live group of the sum ring is (gl + 1) % NGL (step m - LEAD); the newest is still in registers
+                int g0 = gl + 1; if (g0 >= G::NGL) g0 -= G::NGL;
+                const uint4 *bP0 = ringP + g0 * 2 * TW + tid, *bP1 = bP0 - G::NGL * 2 * TW;
+                const int wrapL = G::NGL - g0;
+                static_for<0, G::NGL - 1>([&](auto G_) {
+                    constexpr int g = decltype(G_)::value;
+                    const uint4 *src = (g < wrapL ? bP0 : bP1) + g * 2 * TW;
+                    const uint4 a = src[0], b = src[TW];
+                    const uint32_t p[RB] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                    psum_group<KL, g>(accL, p);
+                });
+                psum_group<KL, G::NGL - 1>(accL, pn);
+                uint4 *dst = sumsL + (m & 1) * 2 * TW + tid;
+                dst[0] = make_uint4(accL[0], accL[1], accL[2], accL[3]);
+                dst[TW] = make_uint4(accL[4], accL[5], accL[6], accL[7]);
+            }
+            if (++gl == G::NGL) gl = 0;
+            __syncthreads();
+        }
+        __syncthreads();                                     // iteration nsteps + 1
+    } else {
+        // =========================== small vertical pass + decision (step i - 2) ===========================
+        uint32_t count = 0;
+        int gs = 0;                                          // slot of step m: m % NGSW
+        const int vcol = tid ^ ((tid >> 3) & 3);
+        const bool col_ok = (x0 + tid) < W;
+        const int wx = (x0 >> 5) + (warp - 8);
+        __syncthreads();                                     // iterations 0 and 1: nothing to consume yet
+        __syncthreads();
+        for (int m = 0; m < nsteps; ++m) {                   // iteration m + 2
+            if (m >= G::LEAD) {
+                const int k = m - G::LEAD;
+                const int yb = ys + RB * k;
+                uint32_t accS[RB];
+#pragma unroll
+                for (int r = 0; r < RB; ++r) accS[r] = 32768u;
+                int s0 = gs + G::OFFSLOT; if (s0 >= G::NGSW) s0 -= G::NGSW;      // slot of step k + GS0
+                const uint4 *bS0 = ringS + s0 * TW + vcol, *bS1 = bS0 - G::NGSW * TW;
+                const int wrapS = G::NGSW - s0;
+                static_for<G::GS0, G::GS1 + 1>([&](auto G_) {
+                    constexpr int g = decltype(G_)::value;                 // group index relative to step k
+                    const uint4 v = ((g - G::GS0) < wrapS ? bS0 : bS1)[(g - G::GS0) * TW];
+                    static_for<0, RB>([&](auto R_) {
+                        constexpr int r = decltype(R_)::value;
+                        constexpr uint32_t w01 = pack4<KS>(2 * (4 * g - G::OFFS) - r - G::PS + G::RS);
+                        constexpr uint32_t w23 = pack4<KS>(2 * (4 * g + 2 - G::OFFS) - r - G::PS + G::RS);
+                        if constexpr ((w01 & 0xffffu) != 0) accS[r] = __dp2a_lo(v.x, w01, accS[r]);
+                        if constexpr ((w01 >> 16) != 0) accS[r] = __dp2a_hi(v.y, w01, accS[r]);
+                        if constexpr ((w23 & 0xffffu) != 0) accS[r] = __dp2a_lo(v.z, w23, accS[r]);
+                        if constexpr ((w23 >> 16) != 0) accS[r] = __dp2a_hi(v.w, w23, accS[r]);
+                    });
+                });
+                const uint4 *src = sumsL + (m & 1) * 2 * TW + tid;
+                const uint4 la = src[0], lb = src[TW];
+                const uint32_t accL[RB] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
+                uint32_t myword = 0;
+#pragma unroll
+                for (int r = 0; r < RB; ++r) {
+                    const uint32_t bl = accL[r] >> 16, bs = accS[r] >> 16;
+                    const uint32_t dog = (bl - bs + 15u) & 255u;             // uint8 wrap, MD:128
+                    const bool in = col_ok && dog >= (uint32_t)lo && dog <= (uint32_t)hi;
+                    const uint32_t word = __ballot_sync(0xffffffffu, in);
+                    if (lane == r) myword = word;
+                }
+                if (lane < RB && yb + lane < ye && wx < WW) {
+                    area_bits[((size_t)f * H + (yb + lane)) * WW + wx] = myword;
+                    count += __popc(myword);
+                }
+            }
+            if (++gs == G::NGSW) gs = 0;
+            __syncthreads();
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
+        if (lane == 0 && count) atomicAdd(area_count + f, count);
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -405,6 +718,25 @@ cudaError_t launch(vbs_ctx *ctx, const uint8_t *frames, int batch, int64_t frame
         kern<<<grid, block, G::SMEM, ctx->stream>>>(map, use_tma, frames, frame_stride, row_pitch, ctx->H, ctx->W, ctx->WW, plan, strips,
                                                     ctx->br.lo, ctx->br.hi, ctx->area_bits, ctx->area_count, ctx->d_status);
     }
+    ctx->launches += 1;
+    ctx->tma_launches += use_tma;
+    return cudaGetLastError();
+}
+
+// column-sum kernel: producer / summer / decider warps, 2 CTAs per SM; during a lead step only the producers work
+cudaError_t launch_cs(vbs_ctx *ctx, const uint8_t *frames, int batch, int64_t frame_stride, int64_t row_pitch) {
+    using G = GeoCS<39, 101>;
+    const int strips = (ctx->W + TW - 1) / TW;
+    const VbsSegPlan plan = vbs_seg_plan(ctx->H, (long long)strips * batch, 2 * ctx->sm_count, G::LEAD, RB, 0.75, ctx->seg_plan != 0);
+    dim3 grid(plan.ctas), block(3 * TW);
+    cudaError_t e;
+    CUtensorMap map;
+    std::memset(&map, 0, sizeof(map));
+    const int use_tma = (!ctx->no_tma && make_frame_map(&map, frames, ctx->W, ctx->H, batch, row_pitch, frame_stride, G::BOXW)) ? 1 : 0;
+    auto kern = blur_area_cs_kernel<39, 101>;
+    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM)) != cudaSuccess) return e;
+    kern<<<grid, block, G::SMEM, ctx->stream>>>(map, use_tma, frames, frame_stride, row_pitch, ctx->H, ctx->W, ctx->WW, plan, strips,
+                                                ctx->br.lo, ctx->br.hi, ctx->area_bits, ctx->area_count, ctx->d_status);
     ctx->launches += 1;
     ctx->tma_launches += use_tma;
     return cudaGetLastError();
@@ -464,6 +796,7 @@ cudaError_t vbs_launch_blur(vbs_ctx *ctx, const uint8_t *frames, int batch, int6
         e = vbs_launch_blur_tc(ctx, frames, batch, frame_stride, row_pitch);
         if (e != cudaErrorNotSupported) return e;
     }                                           // BGR input / frames the TMA unit cannot describe: integer-dot-product kernel
+    if (ctx->big && ctx->C == 1 && ctx->blur_variant != 0) return launch_cs(ctx, frames, batch, frame_stride, row_pitch);
     if (ctx->big) return launch<39, 101>(ctx, frames, batch, frame_stride, row_pitch);
     return launch<21, 35>(ctx, frames, batch, frame_stride, row_pitch);
 }

@@ -402,6 +402,7 @@ int vbs_create(vbs_ctx **out, const vbs_config *cfg) {
     ctx->min_dist = 20.0;
     { const char *e = getenv("VBS_NO_TMA"); ctx->no_tma = (e && e[0] == '1') ? 1 : 0; }
     { const char *e = getenv("VBS_NCC_VARIANT"); ctx->ncc_variant = (e && e[0] == '0') ? 0 : 1; }
+    { const char *e = getenv("VBS_BLUR_VARIANT"); ctx->blur_variant = (e && e[0] == '0') ? 0 : 1; }
     { const char *e = getenv("VBS_SEG_PLAN"); ctx->seg_plan = (e && e[0] == '0') ? 0 : 1; }
     ctx->sm_count = 148;
     { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess && v > 0) ctx->sm_count = v; }
