@@ -1,7 +1,7 @@
 #!/usr/bin/env python
-"""Times the blur stage (per-stage events of vbs_process_device) for every VBS_BLUR_VARIANT and checks that the area
-masks of all variants are equal.
-    python tools/blur_probe.py [batch] [reps] [variants, e.g. 0123]"""
+"""Times the blur stage (per-stage events of vbs_process_device) for the given VBS_BLUR_VARIANT values (0 = all-dot-product
+kernel, 1 = column-sum kernel, the default) and checks that the area masks of all of them are equal.
+    python tools/blur_probe.py [batch] [reps] [variants, e.g. 01]"""
 import os
 import sys
 
@@ -15,7 +15,7 @@ from vbs_b200 import capi, pipeline, synth
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
-variants = sys.argv[3] if len(sys.argv) > 3 else "0123"
+variants = sys.argv[3] if len(sys.argv) > 3 else "01"
 H, W = 1080, 1920
 u = synth.workload_frames("1080p_20x20", 8, seed0=0)
 x = torch.from_numpy(np.tile(u, (B // 8, 1, 1))).cuda()
