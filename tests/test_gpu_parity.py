@@ -823,6 +823,24 @@ def test_ncc_random_area_masks(h, w, seed0):
     assert rechecks.max() < 16384                          # the recheck list never overflowed
 
 
+@pytest.mark.parametrize("h,w", [(520, 600), (300, 357)])
+def test_ncc_kernel_variants_agree(monkeypatch, h, w):
+    """The three matched-filter kernels (VBS_NCC_VARIANT = 0: round 1, 1: thread per column, 2: thread per column with
+    horizontal / vertical warp roles, the default) decide every pixel of the stress masks alike and queue the same number
+    of float64 re-decisions."""
+    n = 24
+    masks = torch_cuda(np.stack([ncc_stress_masks(h, w, 500 + i) for i in range(n)]))
+    res = {}
+    for v in ("2", "1", "0"):
+        monkeypatch.setenv("VBS_NCC_VARIANT", v)
+        with pipeline.MarkerPipeline(h, w, 1, max_batch=n, max_markers=64, max_refs=1) as pipe:
+            got, rechecks = pipe.ncc_mask(masks)
+            res[v] = (got.cpu().numpy(), rechecks.cpu().numpy())
+    for v in ("1", "0"):
+        assert np.array_equal(res["2"][0], res[v][0]), v
+    assert np.array_equal(res["2"][1], res["1"][1])        # same float32 filter in both thread-per-column kernels
+
+
 # ---------------------------------------------------------------------------------------------
 # 15. 3D position with a camera whose f_avg^2 is NOT exactly representable in float32: the reference squares
 #     an np.float32 scalar (R3:219), so that term is rounded to float32 before it meets the float64 radius

@@ -671,6 +671,261 @@ __global__ void __launch_bounds__(TW2, TW2 == 128 ? 3 : 2) ncc_mask_wide_kernel(
     }
 }
 
+// ---- column-per-thread variant with warp roles -----------------------------------------------------------------
+// Same arithmetic and ring as ncc_mask_wide_kernel, twice the threads: warps 0-3 run the horizontal pass (integer adds,
+// table loads) of step i while warps 4-7 run the vertical pass (FFMA2) and the decision of step i - 1; the ring's spare
+// group already keeps the two apart, so there is still one CTA barrier per step.  24 warps per SM instead of 12.
+template <int TL, int TW2>
+__global__ void __launch_bounds__(2 * TW2, 3) ncc_mask_roles_kernel(NccParams P) {
+    using G = GeoW<TL, TW2>;
+    constexpr int NT = TW2, TWP2 = G::TWP2, OCT = TW2 / 8;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4 *ringH = reinterpret_cast<float4 *>(smem_raw);                        // [NR*2][TWP2]
+    uint2 *ringB = reinterpret_cast<uint2 *>(ringH + G::NR * 2 * TWP2);          // [NR][TWP2]
+    double *cn = reinterpret_cast<double *>(ringB + G::NR * TWP2);               // [CNX] float64 prefix sums (border formula)
+    int4 *fx = reinterpret_cast<int4 *>(cn + G::CNX + (G::CNX & 1));             // [4][FXN/4] shifted fixed-point copies
+
+    const int tid = threadIdx.x % TW2, lane = tid & 31;              // index within the role
+    const bool hrole = threadIdx.x < TW2;                            // warps 0..: horizontal pass of step i; the others: vertical pass of step i - 1
+    // CTA -> (frame, strip, row segment): whole-height items first, the tail of the grid in row segments (VbsSegPlan)
+    int item = blockIdx.x, ys = 0, ye = P.H;
+    if (item >= P.plan.n_full) {
+        const int j = item - P.plan.n_full, q = j / P.plan.vsegs;
+        item = P.plan.n_full + q;
+        ys = (j - q * P.plan.vsegs) * P.plan.seg_rows;
+        ye = min(P.H, ys + P.plan.seg_rows);
+    }
+    const int f = item / P.strips;
+    const int x0 = (item - f * P.strips) * TW2;
+    const int H = P.H, W = P.W, WW = P.WW;
+    const uint32_t *abits = P.area_bits + (size_t)f * H * WW;
+    const double mfrac64 = (double)P.area_count[f] / P.hw;
+    const float mfrac = (float)mfrac64, mcomp = (float)(1.0 - mfrac64);   // mean(area_mask)/255 and its complement
+    for (int i = threadIdx.x; i < G::CNX; i += 2 * NT) cn[i] = P.cn64[i];
+    for (int i = threadIdx.x; i < 4 * FXN; i += 2 * NT) reinterpret_cast<int *>(fx)[i] = P.cnfix[i];
+
+    const int nk = (ye - ys + RB - 1) / RB;
+    const int nsteps = nk + G::LEAD;
+    const int hr = tid / OCT, ho = tid - hr * OCT;                  // horizontal role: row hr of the step, pixel octet ho
+    const int sb = x0 + 8 * ho - G::OFF;                            // first bit of the union window
+    const int wi0 = sb >> 5, bo = sb & 31;                          // arithmetic shift: floor
+    const int vcol = tid;                                           // vertical role: one column
+    const int cp = vcol + (vcol >> 3);
+    const bool strip_interior = x0 >= G::OFF && x0 + TW2 - 1 + G::HI < W;
+    const bool warp_outside = x0 + (tid & ~31) >= W;                // this warp's 32 columns lie right of the image
+
+    uint32_t pw[4] = {0, 0, 0, 0};
+    int woff[4]; uint32_t wmsk[4];                                  // the four words of the union window: step-invariant
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const bool ok = wi0 + i >= 0 && wi0 + i < WW;
+        woff[i] = ok ? wi0 + i : 0; wmsk[i] = ok ? 0xffffffffu : 0u;
+    }
+    auto fetch = [&](int m) {
+        const int p = ys - G::OFF + RB * m + hr;
+        if (p >= 0 && p < H) {
+            const uint32_t *row = abits + (size_t)p * WW;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pw[i] = __ldg(row + woff[i]);     // masked where used: the load stays in flight for a whole step
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pw[i] = 0u;
+        }
+    };
+    int s_prev = 0; uint32_t hb_m1 = 0;         // S of the previous output row and the box row that left the window
+    uint32_t s_lead = 0;                        // box sum of the lead groups = rows 0 .. 8 (TL / 8) - 1 of the first window
+    static_assert(G::LEAD == TL / 8 && TL % 8 <= 4, "first-window box sum is accumulated group by group during the lead steps");
+
+    __syncthreads();                             // tables loaded
+    int gw = 0;                                  // ring slot written by step m (m % NR)
+    if (hrole) {
+      fetch(0);
+      for (int m = 0; m <= nsteps; ++m) {        // iteration m: H of step m beside V of step m - 1; the ring's spare group keeps them apart
+        // ---- H: horizontal pass on bits ------------------------------------------------------------
+        if (m < nsteps) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pw[i] &= wmsk[i];
+            uint32_t U0 = __funnelshift_r(pw[0], pw[1], bo);
+            uint32_t U1 = __funnelshift_r(pw[1], pw[2], bo);
+            uint32_t U2 = __funnelshift_r(pw[2], pw[3], bo);
+            if (m + 1 < nsteps) fetch(m + 1);
+            if constexpr (G::UL <= 64) { U2 = 0; U1 &= (G::UL == 64) ? 0xffffffffu : ((1u << (G::UL - 32)) - 1u); }
+            else { U2 &= (1u << (G::UL - 64)) - 1u; }
+            const uint32_t T0 = U0 ^ (U0 << 1);
+            const uint32_t T1 = U1 ^ __funnelshift_l(U0, U1, 1);
+            const uint32_t T2 = U2 ^ __funnelshift_l(U1, U2, 1);
+            int acc[8];
+            uint32_t hb[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { acc[j] = 0; hb[j] = 0; }
+            auto consume = [&](uint32_t T, uint32_t Uw, int base) {
+                while (T) {
+                    const int b = __ffs(T) - 1;
+                    T &= T - 1;
+                    const int sgn = ((Uw >> b) & 1u) ? -1 : 1;       // run start: -Cn, run end: +Cn
+                    const int i0 = base + b + 1;                     // table index of d = t - 7 (pixel j = 7)
+                    const int4 *src = fx + (i0 & 3) * (FXN / 4) + (i0 >> 2);
+                    const int4 lo = src[0], hi = src[1];
+                    acc[7] += sgn * lo.x; acc[6] += sgn * lo.y; acc[5] += sgn * lo.z; acc[4] += sgn * lo.w;
+                    acc[3] += sgn * hi.x; acc[2] += sgn * hi.y; acc[1] += sgn * hi.z; acc[0] += sgn * hi.w;
+                }
+            };
+            if (U0 | U1 | U2) {                                      // a window without area pixels leaves h = 0, box = 0
+                consume(T0, U0, 0);
+                consume(T1, U1, 32);
+                if constexpr (G::UL > 64) consume(T2, U2, 64);
+                auto bit = [&](int t) -> uint32_t {
+                    return t < 32 ? (U0 >> t) & 1u : t < 64 ? (U1 >> (t - 32)) & 1u : (U2 >> (t - 64)) & 1u;
+                };
+                if constexpr (TL >= 64) hb[0] = __popc(U0) + __popc(U1) + __popc(U2 & ((1u << (TL - 64)) - 1u));
+                else hb[0] = __popc(U0) + __popc(U1 & ((1u << (TL - 32)) - 1u));
+#pragma unroll
+                for (int j = 1; j < 8; ++j) hb[j] = hb[j - 1] + bit(j - 1 + TL) - bit(j - 1);
+            }
+            float *dstH = reinterpret_cast<float *>(ringH + (gw * 2 + (hr >> 2)) * TWP2) + (hr & 3);
+            unsigned char *dstB = reinterpret_cast<unsigned char *>(ringB + gw * TWP2) + hr;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = 9 * ho + j;                            // (8 ho + j) + (8 ho + j) / 8
+                dstH[c * 4] = (float)acc[j];                         // 2^30 h; the scale lives in the vertical weights
+                dstB[c * 8] = (unsigned char)hb[j];
+            }
+            if (++gw == G::NR) gw = 0;
+        }
+        __syncthreads();                                             // the only barrier of the step
+      }
+    } else {
+      __syncthreads();                                               // iteration 0: nothing to consume yet
+      for (int m = 0; m < nsteps; ++m) {
+        // ---- V + D: vertical pass and decision, thread = column ------------------------------------
+        if (m < G::LEAD) {                                           // lead: only the box sum of the first window grows
+            const uint2 b = ringB[gw * TWP2 + cp];
+            s_lead = __dp4a(b.x, 0x01010101u, s_lead);
+            s_lead = __dp4a(b.y, 0x01010101u, s_lead);
+        } else {
+            const int k = m - G::LEAD;
+            const int yb = ys + RB * k;
+            int g0 = gw - G::LEAD; if (g0 < 0) g0 += G::NR;          // slot of step k
+            int S8[RB];
+            bool empty;
+            {
+                auto box_at = [&](auto I_) -> int {
+                    constexpr int idx = decltype(I_)::value;
+                    int gi = g0 + idx / 8; if (gi >= G::NR) gi -= G::NR;
+                    const uint2 b = ringB[gi * TWP2 + cp];
+                    const uint32_t w = (idx % 8) < 4 ? b.x : b.y;
+                    return (int)((w >> (8 * (idx % 4))) & 255u);
+                };
+                if (k == 0) {                   // first step of the segment: the lead groups + the TL % 8 rows of this step's group
+                    int s = (int)s_lead;
+                    if constexpr (TL % 8 != 0) s += (int)__dp4a(ringB[gw * TWP2 + cp].x & ((1u << (8 * (TL % 8))) - 1u), 0x01010101u, 0u);
+                    S8[0] = s;
+                } else {
+                    S8[0] = s_prev + box_at(std::integral_constant<int, TL - 1>{}) - (int)hb_m1;
+                }
+                static_for<1, RB>([&](auto R_) {
+                    constexpr int r = decltype(R_)::value;
+                    S8[r] = S8[r - 1] + box_at(std::integral_constant<int, r + TL - 1>{}) - box_at(std::integral_constant<int, r - 1>{});
+                });
+                s_prev = S8[RB - 1]; hb_m1 = (uint32_t)box_at(std::integral_constant<int, RB - 1>{});
+                int any = 0;
+#pragma unroll
+                for (int r = 0; r < RB; ++r) any |= S8[r];
+                // S == 0 <=> no area pixel in the whole L x L window <=> G == 0 and mask == 0: when that holds
+                // for all 8 rows of all 32 columns of the warp, the L-tap column sums are skipped (exact)
+                empty = warp_outside || !__any_sync(0xffffffffu, any != 0);
+            }
+            // Gaussian column sums of the 8 rows, packed: ring rows come as float4 = two aligned pairs (h_t, h_t+1),
+            // accumulators are paired as (row r, row r+1), one FFMA2 applies one tap to two rows
+            float2 E[4], O[3];
+            float o0 = 0.f, o7 = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) E[q] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) O[q] = make_float2(0.f, 0.f);
+            if (!empty) {
+                constexpr int U1_ = (TL - 1 + RB - 1) / 4;                       // last ring unit touched
+                const int ub = 2 * g0;
+                const float4 *b0 = ringH + ub * TWP2 + cp;
+                const float4 *b1 = b0 - 2 * G::NR * TWP2;
+                const int wrap_at = 2 * G::NR - ub;                             // first unit index that wraps
+                auto unit = [&](auto U_, const float4 v) {
+                    constexpr int u = decltype(U_)::value;
+                    static_for<0, 2>([&](auto P_) {
+                        constexpr int t = 4 * u + 2 * decltype(P_)::value;      // even ring row of the pair
+                        const float2 hp = decltype(P_)::value ? make_float2(v.z, v.w) : make_float2(v.x, v.y);
+                        static_for<0, 4>([&](auto Q_) {
+                            constexpr int a = t - 2 * decltype(Q_)::value;
+                            if constexpr (a >= 0 && a < TL) ffma2(E[decltype(Q_)::value], hp, c_n32[TL == 80][a]);
+                        });
+                        static_for<0, 3>([&](auto Q_) {
+                            constexpr int a = t - 2 * decltype(Q_)::value - 1;
+                            if constexpr (a >= 0 && a < TL) ffma2(O[decltype(Q_)::value], hp, c_n32[TL == 80][a]);
+                        });
+                        if constexpr (t + 1 >= 0 && t + 1 < TL) o0 = fmaf(c_n32[TL == 80][t + 1], hp.y, o0);
+                        if constexpr (t - 7 >= 0 && t - 7 < TL) o7 = fmaf(c_n32[TL == 80][t - 7], hp.x, o7);
+                    });
+                };
+                static_for<0, U1_ + 1>([&](auto U_) {
+                    constexpr int u = decltype(U_)::value;
+                    unit(U_, (u < wrap_at ? b0 : b1)[u * TWP2]);
+                });
+            }
+            float acc[RB];
+            acc[0] = E[0].x + o0;     acc[1] = E[0].y + O[0].x; acc[2] = E[1].x + O[0].y; acc[3] = E[1].y + O[1].x;
+            acc[4] = E[2].x + O[1].y; acc[5] = E[2].y + O[2].x; acc[6] = E[3].x + O[2].y; acc[7] = E[3].y + o7;
+            // ---- D: decision --------------------------------------------------------------------------
+            const int x = x0 + vcol;
+            uint32_t onmask = 0, needmask = 0;        // bit r: row r of this column is on / needs the float64 pass
+            if (empty) {
+                // S == 0 in the whole warp: off on every path (interior table entry 0 is +inf, border_decide returns 0)
+            } else if (strip_interior && yb >= G::OFF && yb + RB - 1 + G::HI < H && yb + RB <= ye) {
+                float thr[RB];                        // whole step inside the image: threshold is the table entry of the box sum
+#pragma unroll
+                for (int r = 0; r < RB; ++r) thr[r] = __ldg(P.thr_lut + S8[r]);
+#pragma unroll
+                for (int r = 0; r < RB; ++r) {
+                    const float d = acc[r] - thr[r];
+                    const bool need = fabsf(d) <= BAND;
+                    onmask |= (uint32_t)(d > 0.f && !need) << r;
+                    needmask |= (uint32_t)need << r;
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < RB; ++r) {
+                    const int y = yb + r;
+                    if (x < W && y < ye) {
+                        const int dec = border_decide<TL>(y, x, H, W, S8[r], acc[r], mfrac, mcomp, P.st2, P.thr_lut, cn);
+                        onmask |= (uint32_t)(dec == 1) << r;
+                        needmask |= (uint32_t)(dec == 2) << r;
+                    }
+                }
+            }
+            uint32_t myword = 0;
+            if (!empty) {
+#pragma unroll
+                for (int r = 0; r < RB; ++r) {
+                    const uint32_t word = __ballot_sync(0xffffffffu, (onmask >> r) & 1u);
+                    if (lane == r) myword = word;
+                }
+            }
+            while (needmask) {                        // float32 cannot decide: queue for the float64 pass (rare)
+                const int r = __ffs(needmask) - 1;
+                needmask &= needmask - 1;
+                const uint32_t slot = atomicAdd(P.recheck_n + f, 1u);
+                if (slot < (uint32_t)P.recheck_cap) P.recheck[(size_t)f * P.recheck_cap + slot] = make_int2(x, yb + r);
+                else atomicOr(P.status, VBS_DEV_RECHECK_OVERFLOW);
+            }
+            const int wx = (x0 >> 5) + (vcol >> 5);
+            const int yw = yb + lane;
+            if (lane < RB && yw < ye && wx < WW) P.mask_bits[((size_t)f * H + yw) * WW + wx] = myword;
+        }
+        if (++gw == G::NR) gw = 0;
+        __syncthreads();
+      }
+    }
+}
+
 // float64 re-decision of queued pixels with the reference's literal formula (MD:152-163).
 // One warp per pixel: lanes split the window rows; fixed-order butterfly keeps it deterministic.
 template <int TL>
@@ -725,7 +980,7 @@ __global__ void ncc_recheck_kernel(NccParams P, const double *__restrict__ n64, 
 template <int TL> cudaError_t launch(vbs_ctx *ctx, int batch, double st2) {
     NccParams P;
     P.H = ctx->H; P.W = ctx->W; P.WW = ctx->WW;
-    const int variant = ctx->ncc_variant;          // 1 (default): thread = column; 0: 256 threads, two tap halves per column (round 1)
+    const int variant = ctx->ncc_variant;          // 2 (default): thread = column, warp roles; 1: thread = column; 0: 256 threads, two tap halves per column (round 1)
     const int tw = TW;
     const int strips = (ctx->W + tw - 1) / tw;
     // vertical segments cost LEAD halo steps each: split only while the grid is short of ~8 waves (296 or 444 CTA slots)
@@ -741,7 +996,13 @@ template <int TL> cudaError_t launch(vbs_ctx *ctx, int batch, double st2) {
     P.status = ctx->d_status;
     cudaError_t e = cudaMemsetAsync(ctx->recheck_n, 0, sizeof(uint32_t) * batch, ctx->stream);
     if (e != cudaSuccess) return e;
-    if (variant == 1) {
+    if (variant == 2) {
+        P.strips = strips;
+        P.plan = vbs_seg_plan(ctx->H, (long long)strips * batch, 3 * ctx->sm_count, Geo<TL>::LEAD, RB, 0.4, ctx->seg_plan != 0);
+        auto kern = ncc_mask_roles_kernel<TL, 128>;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GeoW<TL, 128>::SMEM)) != cudaSuccess) return e;
+        kern<<<dim3(P.plan.ctas), 256, GeoW<TL, 128>::SMEM, ctx->stream>>>(P);
+    } else if (variant == 1) {
         // 3 CTAs per SM are resident; a lead step runs the horizontal pass only
         P.strips = strips;
         P.plan = vbs_seg_plan(ctx->H, (long long)strips * batch, 3 * ctx->sm_count, Geo<TL>::LEAD, RB, 0.4, ctx->seg_plan != 0);

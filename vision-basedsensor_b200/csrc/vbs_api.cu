@@ -401,7 +401,7 @@ int vbs_create(vbs_ctx **out, const vbs_config *cfg) {
     ctx->br = ctx->big ? VbsBranch{39, 101, 80, 13.0, 20, 200, 14} : VbsBranch{21, 35, 33, 7.4, 35, 180, 8};
     ctx->min_dist = 20.0;
     { const char *e = getenv("VBS_NO_TMA"); ctx->no_tma = (e && e[0] == '1') ? 1 : 0; }
-    { const char *e = getenv("VBS_NCC_VARIANT"); ctx->ncc_variant = (e && e[0] == '0') ? 0 : 1; }
+    { const char *e = getenv("VBS_NCC_VARIANT"); ctx->ncc_variant = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2; }
     { const char *e = getenv("VBS_BLUR_VARIANT"); ctx->blur_variant = (e && e[0] == '0') ? 0 : 1; }
     { const char *e = getenv("VBS_SEG_PLAN"); ctx->seg_plan = (e && e[0] == '0') ? 0 : 1; }
     ctx->sm_count = 148;

@@ -120,7 +120,7 @@ struct vbs_ctx {
     int sm_count;                               // multiprocessors of the context's device (grid planning)
     int seg_plan;                               // VBS_SEG_PLAN=0: every (frame, strip) split into the same number of row segments (round 1)
     int blur_variant;                           // VBS_BLUR_VARIANT=0: every vertical tap an integer dot product (blur_area_kernel); default 1: column sums for the 101-tap pass (blur_area_cs_kernel)
-    int ncc_variant;                            // VBS_NCC_VARIANT=0: round 1's kernel (two tap-half threads per column); default 1: thread per column
+    int ncc_variant;                            // VBS_NCC_VARIANT: 0 = round 1's kernel (two tap-half threads per column), 1 = thread per column, default 2 = thread per column with horizontal / vertical warp roles
     double stage_ms[7]; int64_t stage_calls;
 };
 enum { VBS_NSTAGES = 7 };   // blur, ncc, morph, components, contours, track3d, output copies
