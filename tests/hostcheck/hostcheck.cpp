@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstring>
 #include "../../vision-basedsensor_b200/csrc/vbs_geom.h"
+#include "../../vision-basedsensor_b200/csrc/vbs_segplan.h"
 
 using namespace vbs;
 
@@ -111,4 +112,9 @@ void hc_undistort_normalized(const double *K, const double *D, int nd, const dou
     for (int i = 0; i < n; ++i) undistort_normalized(c, uv[2 * i], uv[2 * i + 1], out[2 * i], out[2 * i + 1]);
 }
 
+// grid plan of the strip-marching kernels: out = {n_full, vsegs, seg_rows, ctas}
+void hc_seg_plan(int H, long long items, int slots, int lead, int rb, double lead_cost, int mixed, int out[4]) {
+    const VbsSegPlan p = vbs_seg_plan(H, items, slots, lead, rb, lead_cost, mixed != 0);
+    out[0] = p.n_full; out[1] = p.vsegs; out[2] = p.seg_rows; out[3] = p.ctas;
+}
 }  // extern "C"
