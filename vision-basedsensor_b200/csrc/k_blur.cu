@@ -356,8 +356,9 @@ blur_area_kernel(const __grid_constant__ CUtensorMap tmap, int use_tma, const ui
 // The 8.8 fixed-point taps of the 101-tap kernel are small integers (0..6) that change by at most one from tap to tap,
 // so with the running column sum P[q] = sum_{q' <= q} h[q'] of the horizontal results
 //     sum_j k[j] h[q + j] = sum_t (k[t] - k[t+1]) P[q + t]
-// has 56 terms of weight +-1 instead of 101 multiply-adds: per 8 output rows of a column 237 three-input integer adds
-// (ALU pipe) instead of 404 IDP.2A (fma pipe, half rate).  All sums are taken mod 2^32 and the true value is below
+// has 56 terms of weight +-1 instead of 101 multiply-adds: per 8 output rows of a column 233 integer adds (two thirds of
+// them three-input, after common sub-sums) instead of 404 IDP.2A (fma pipe, half rate); the compiler spreads the adds over
+// the ALU pipe (IADD3) and, for a third of them, the fma pipe (IMAD.IADD).  All sums are taken mod 2^32 and the true value is below
 // 2^24: exact.  The column sums are private to the thread that owns the column.  The ring holds 32-bit sums (56 KB
 // instead of 28 KB of u16 pairs), so two CTAs are resident per SM instead of four, and each pipe gets its own warps:
 //   warps 0-3  (warp = row pair, lane = pixel quad) load the tiles and run both horizontal passes of step i (IDP.4A),
